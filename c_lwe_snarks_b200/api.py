@@ -1,0 +1,257 @@
+"""ctypes binding of include/mfb200.h.
+
+Host-flavour methods take and return numpy arrays; ``*_dev`` methods take raw device pointers (ints, e.g.
+``tensor.data_ptr()``) and a CUDA stream handle, and are asynchronous.  PyTorch is only plumbing here
+(device memory, streams, torch.distributed); nothing in this module imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+N, NC, NCP, L64 = 1470, 1471, 1472, 11
+CT_BYTES = 92
+CTR_CT = CT_BYTES * N
+P = 0xFFFFFFFB
+ENT_BYTES = 70
+FLAT_CT_U64 = NC * L64
+FLAT_SK_U64 = N * L64
+PLANAR_U64 = L64 * NCP
+ALGO_BYTES_PER_MAC = NC * 88
+
+
+class MfbError(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return PKG / "lib" / "libmfb200.so"
+
+
+def build_library(verbose: bool = False) -> Path:
+    """Compile the CUDA sources for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", str(PKG / "csrc"), "-j4"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise MfbError("building libmfb200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return library_path()
+
+
+_u8p, _u32p, _u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+
+_SIGS = {
+    "mfb_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "mfb_ctx_destroy": (None, [_vp]),
+    "mfb_last_error": (C.c_char_p, []),
+    "mfb_device_sm_count": (C.c_int, [_vp]),
+    "mfb_launch_count": (C.c_uint64, [_vp]),
+    "mfb_sync": (C.c_int, [_vp]),
+    "mfb_stream": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t]),
+    "mfb_stream_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp]),
+    "mfb_expand_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp, _vp]),
+    "mfb_lincomb_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_lincomb": (C.c_int, [_vp, _u64p, _u32p, C.c_size_t, _u64p]),
+    "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
+    "mfb_region_destroy": (None, [_vp, _vp]),
+    "mfb_region_lincomb": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, C.c_size_t, _u64p]),
+    "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mfb_eval_poly": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u32p, C.c_size_t, _u64p]),
+    "mfb_eval_poly_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_encrypt": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p]),
+    "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
+    "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
+    "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_flat_to_planar_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, _vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load lib/libmfb200.so.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not path.exists():
+            raise MfbError(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C c_lwe_snarks_b200/csrc`); there is no CPU fallback")
+        lib = C.CDLL(str(path))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _p8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+def _p32(a):
+    return a.ctypes.data_as(_u32p)
+
+
+def _p64(a):
+    return a.ctypes.data_as(_u64p)
+
+
+def _seed(seed) -> np.ndarray:
+    s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    if s.size != 40:
+        raise ValueError("seed is 40 bytes: nonce(8) || key(32)")
+    return s
+
+
+def _arr(a, dtype) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Region:
+    """A CRS region expanded into HBM (planar layout) and kept resident."""
+
+    def __init__(self, ctx: "Context", handle: int, count: int):
+        self.ctx, self.handle, self.count = ctx, handle, count
+
+    def lincomb(self, coeffs, first: int = 0, rop=None) -> np.ndarray:
+        co = _arr(coeffs, np.uint32)
+        r = np.zeros((NC, L64), np.uint64) if rop is None else _arr(rop, np.uint64).copy()
+        self.ctx._ck(self.ctx.lib.mfb_region_lincomb(self.ctx.h, self.handle, first, _p32(co), co.size, _p64(r)))
+        return r
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.mfb_region_destroy(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.mfb_ctx_create(C.byref(h), device)
+        if rc != 0:
+            raise MfbError(f"mfb_ctx_create({device}) failed ({rc}): {self.lib.mfb_last_error().decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mfb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise MfbError(f"mfb call failed ({rc}): {self.lib.mfb_last_error().decode()}")
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.mfb_device_sm_count(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mfb_launch_count(self.h))
+
+    def sync(self):
+        self._ck(self.lib.mfb_sync(self.h))
+
+    # ---------------------------------------------------------------- host flavour
+    def stream(self, seed, offset: int, nbytes: int) -> np.ndarray:
+        s, out = _seed(seed), np.zeros(nbytes, np.uint8)
+        self._ck(self.lib.mfb_stream(self.h, _p8(s), offset, _p8(out), nbytes))
+        return out
+
+    def eval_poly(self, seed, offset: int, c8, coeffs, rop=None, idx=None) -> np.ndarray:
+        s, rec, co = _seed(seed), _arr(c8, np.uint8), _arr(coeffs, np.uint64)
+        ix = None if idx is None else _arr(idx, np.uint32)
+        r = np.zeros((NC, L64), np.uint64) if rop is None else _arr(rop, np.uint64).copy()
+        need = (int(ix.max()) + 1 if ix is not None and ix.size else co.size) * CT_BYTES
+        if rec.size < need:
+            raise ValueError("record array shorter than the ciphertext indices used")
+        self._ck(self.lib.mfb_eval_poly(self.h, _p8(s), offset, _p8(rec), _p64(co), None if ix is None else _p32(ix),
+                                        co.size, _p64(r)))
+        return r
+
+    def lincomb(self, cts_flat, coeffs, rop=None) -> np.ndarray:
+        cts, co = _arr(cts_flat, np.uint64), _arr(coeffs, np.uint32)
+        if cts.size != co.size * FLAT_CT_U64:
+            raise ValueError("cts_flat must be (d, 1471, 11) uint64")
+        r = np.zeros((NC, L64), np.uint64) if rop is None else _arr(rop, np.uint64).copy()
+        self._ck(self.lib.mfb_lincomb(self.h, _p64(cts), _p32(co), co.size, _p64(r)))
+        return r
+
+    def region(self, seed, offset: int, c8) -> Region:
+        s, rec = _seed(seed), _arr(c8, np.uint8)
+        count = rec.size // CT_BYTES
+        h = _vp()
+        self._ck(self.lib.mfb_region_create(self.h, _p8(s), offset, _p8(rec), count, C.byref(h)))
+        return Region(self, h, count)
+
+    def encrypt(self, seed, offset: int, sk_flat, msg, ent, ent_stride: int = ENT_BYTES,
+                ent_nbytes: int = ENT_BYTES - 1) -> np.ndarray:
+        s, sk, m, e = _seed(seed), _arr(sk_flat, np.uint64), _arr(msg, np.uint64), _arr(ent, np.uint8)
+        if sk.size != FLAT_SK_U64:
+            raise ValueError("sk_flat must be (1470, 11) uint64")
+        if e.size < m.size * ent_stride:
+            raise ValueError("entropy buffer too short")
+        out = np.zeros((m.size, CT_BYTES), np.uint8)
+        self._ck(self.lib.mfb_encrypt(self.h, _p8(s), offset, _p64(sk), _p64(m), _p8(e), ent_stride, ent_nbytes,
+                                      m.size, _p8(out)))
+        return out
+
+    def decrypt(self, sk_flat, cts_flat, b_neg=None, want_dot: bool = False):
+        sk, cts = _arr(sk_flat, np.uint64), _arr(cts_flat, np.uint64)
+        count = cts.size // FLAT_CT_U64
+        neg = None if b_neg is None else _arr(np.asarray(b_neg, dtype=bool), np.uint8)
+        m = np.zeros(count, np.uint64)
+        dot = np.zeros((count, L64), np.uint64) if want_dot else None
+        self._ck(self.lib.mfb_decrypt(self.h, _p64(sk), _p64(cts), None if neg is None else _p8(neg), count, _p64(m),
+                                      None if dot is None else _p64(dot)))
+        return (m, dot) if want_dot else m
+
+    # ---------------------------------------------------------------- device flavour (raw pointers)
+    def stream_dev(self, seed, offset: int, out_ptr: int, nbytes: int, stream: int = 0):
+        self._ck(self.lib.mfb_stream_dev(self.h, _p8(_seed(seed)), offset, out_ptr, nbytes, stream))
+
+    def expand_dev(self, seed, offset: int, c8_ptr: int, count: int, cts_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_expand_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, count, cts_ptr, stream))
+
+    def lincomb_dev(self, cts_ptr: int, coeffs_ptr: int, d: int, rop_in_ptr, rop_out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_lincomb_dev(self.h, cts_ptr, coeffs_ptr, d, rop_in_ptr, rop_out_ptr, stream))
+
+    def eval_poly_dev(self, seed, offset: int, c8_ptr: int, coeffs_ptr: int, idx_ptr, d: int, rop_in_ptr,
+                      rop_out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_eval_poly_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, coeffs_ptr, idx_ptr, d, rop_in_ptr,
+                                            rop_out_ptr, stream))
+
+    def columns_split_dev(self, flat_ptr: int, cols_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_columns_split_dev(self.h, flat_ptr, cols_ptr, stream))
+
+    def columns_carry_dev(self, cols_ptr: int, c0: int, ncoord: int, flat_in_ptr, flat_out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_columns_carry_dev(self.h, cols_ptr, c0, ncoord, flat_in_ptr, flat_out_ptr, stream))
+
+    def encrypt_dev(self, seed, offset: int, sk_planar_ptr: int, msg_ptr: int, ent_ptr: int, ent_stride: int,
+                    ent_nbytes: int, count: int, out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_encrypt_dev(self.h, _p8(_seed(seed)), offset, sk_planar_ptr, msg_ptr, ent_ptr, ent_stride,
+                                          ent_nbytes, count, out_ptr, stream))
+
+    def decrypt_dev(self, sk_planar_ptr: int, cts_flat_ptr: int, b_neg_ptr, count: int, out_m_ptr: int, out_dot_ptr,
+                    stream: int = 0):
+        self._ck(self.lib.mfb_decrypt_dev(self.h, sk_planar_ptr, cts_flat_ptr, b_neg_ptr, count, out_m_ptr, out_dot_ptr,
+                                          stream))
+
+    def flat_to_planar_dev(self, flat_ptr: int, n: int, count: int, planar_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_flat_to_planar_dev(self.h, flat_ptr, n, count, planar_ptr, stream))

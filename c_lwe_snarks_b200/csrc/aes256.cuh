@@ -1,0 +1,179 @@
+// AES-256-CTR keystream for the a-vectors (replaces aes.c:49-144 + entropy.c:46-61 on the device).
+//
+// Stream definition (aes.c:122-133, entropy.c:58-61): with seed = nonce(8 B) || key(32 B),
+//   keystream block k = AES256_Enc(key, nonce || LE64(k)),   stream byte p = byte p%16 of block p/16.
+//
+// Device formulation: FIPS-197 rounds through one 32-bit "T-table" in a little-endian column
+// convention (column word = bytes 4c..4c+3 of the block, byte r = row r):
+//   T0[x] = 2S | S<<8 | S<<16 | 3S<<24          (S = sbox[x]; contribution of a row-0 byte to its column)
+//   T2[x] = rotl(T0[x], 16)                     (row-2 byte);   rows 1 and 3 are rotl8 of T0 / T2.
+// Both tables sit in shared memory REPLICATED ACROSS THE 32 BANKS: entry x occupies 256 B,
+//   [x*256 + 4*lane]       = T0[x]     and     [x*256 + 128 + 4*lane] = T2[x],
+// so lane L only ever touches bank L: every lookup is conflict-free whatever the data
+// (64 KB per CTA).  A lookup address is one PRMT: (byte << 8) | (lane << 2).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace mfb {
+
+constexpr int AES_TAB_BYTES = 256 * 256;  // 64 KB
+
+struct AesKey {
+  uint32_t rk[60];   // 15 round keys x 4 little-endian column words
+  uint32_t nonce[2]; // block bytes 0..7
+};
+
+// ----------------------------------------------------------------------------------- host side
+namespace aes_host {
+
+inline uint8_t gmul(uint8_t a, uint8_t b) {
+  uint8_t r = 0;
+  while (b) {
+    if (b & 1) r ^= a;
+    a = (uint8_t)((a << 1) ^ ((a & 0x80) ? 0x1b : 0));
+    b >>= 1;
+  }
+  return r;
+}
+
+inline const uint8_t *sbox() {
+  static uint8_t S[256];
+  static bool ready = false;
+  if (!ready) {
+    // multiplicative inverse via the generator 3, then the FIPS-197 affine map
+    uint8_t p = 1, q = 1;
+    do {
+      p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));  // p *= 3
+      q ^= (uint8_t)(q << 1);                                  // q /= 3
+      q ^= (uint8_t)(q << 2);
+      q ^= (uint8_t)(q << 4);
+      if (q & 0x80) q ^= 0x09;
+      uint8_t x = (uint8_t)(q ^ (q << 1 | q >> 7) ^ (q << 2 | q >> 6) ^ (q << 3 | q >> 5) ^ (q << 4 | q >> 4));
+      S[p] = (uint8_t)(x ^ 0x63);
+    } while (p != 1);
+    S[0] = 0x63;
+    ready = true;
+  }
+  return S;
+}
+
+// seed = nonce(8) || key(32)  (entropy.c:58-61)
+inline void expand(const uint8_t seed[40], AesKey *out) {
+  const uint8_t *S = sbox();
+  const uint8_t *key = seed + 8;
+  uint8_t w[60][4];
+  std::memcpy(w, key, 32);
+  uint8_t rcon = 1;
+  for (int i = 8; i < 60; i++) {
+    uint8_t t[4] = {w[i - 1][0], w[i - 1][1], w[i - 1][2], w[i - 1][3]};
+    if (i % 8 == 0) {
+      uint8_t t0 = t[0];
+      t[0] = (uint8_t)(S[t[1]] ^ rcon);
+      t[1] = S[t[2]];
+      t[2] = S[t[3]];
+      t[3] = S[t0];
+      rcon = gmul(rcon, 2);
+    } else if (i % 8 == 4) {
+      for (int k = 0; k < 4; k++) t[k] = S[t[k]];
+    }
+    for (int k = 0; k < 4; k++) w[i][k] = (uint8_t)(w[i - 8][k] ^ t[k]);
+  }
+  for (int i = 0; i < 60; i++)
+    out->rk[i] = (uint32_t)w[i][0] | (uint32_t)w[i][1] << 8 | (uint32_t)w[i][2] << 16 | (uint32_t)w[i][3] << 24;
+  std::memcpy(out->nonce, seed, 8);
+}
+
+inline void t0_table(uint32_t T0[256]) {
+  const uint8_t *S = sbox();
+  for (int x = 0; x < 256; x++) {
+    uint32_t s = S[x], s2 = gmul((uint8_t)s, 2), s3 = s2 ^ s;
+    T0[x] = s2 | s << 8 | s << 16 | s3 << 24;
+  }
+}
+
+}  // namespace aes_host
+
+// ----------------------------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+// Fill the bank-replicated tables of this CTA from the 1 KB global T0 table.  `tab` is 64 KB, 256-B aligned.
+__device__ __forceinline__ void aes_tables_init(uint8_t *tab, const uint32_t *__restrict__ t0_global, int tid,
+                                                int nthreads) {
+  for (int w = tid; w < 256 * 64; w += nthreads) {
+    const int x = w >> 6, slot = w & 63;
+    uint32_t t = __ldg(t0_global + x);
+    if (slot >= 32) t = __byte_perm(t, 0, 0x1032);  // rotl 16
+    reinterpret_cast<uint32_t *>(tab)[w] = t;
+  }
+}
+
+// Lookup addressing.  The tables live at a 64 KB-ALIGNED address of the CTA's shared window, so the
+// full address  tab | (byte << 8) | (lane << 2)  is composed by ONE PRMT from
+//   lanebase = tab | 4*lane        (bytes: [0] = 4*lane, [1] = 0, [2..3] = tab >> 16)
+// and the state word; T2 is reached with the LDS immediate offset +128.  No adds on the lookup path.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32_t2(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+128];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int K>
+__device__ __forceinline__ uint32_t aes_addr(uint32_t w, uint32_t lanebase) {
+  // __byte_perm(x, y, s): nibble i of s selects result byte i from {x.b0..b3 = 0..3, y.b0..b3 = 4..7}
+  return __byte_perm(lanebase, w, 0x3200 | ((4 + K) << 4));
+}
+__device__ __forceinline__ uint32_t rotl8(uint32_t x) { return __byte_perm(x, 0, 0x2103); }
+
+struct AesState {
+  uint32_t w0, w1, w2, w3;
+};
+
+// One full AES-256 encryption of block (nonce || LE64(ctr)); lb = lanebase (see aes_addr).
+__device__ __forceinline__ AesState aes256_ctr_block(const AesKey &k, uint64_t ctr, uint32_t lb) {
+  uint32_t s0 = k.nonce[0] ^ k.rk[0];
+  uint32_t s1 = k.nonce[1] ^ k.rk[1];
+  uint32_t s2 = (uint32_t)ctr ^ k.rk[2];
+  uint32_t s3 = (uint32_t)(ctr >> 32) ^ k.rk[3];
+#pragma unroll
+  for (int r = 1; r < 14; r++) {
+    // column c: T0[b0(s_c)] ^ rotl8(T0[b1(s_{c+1})]) ^ T2[b2(s_{c+2})] ^ rotl8(T2[b3(s_{c+3})]) ^ rk
+    uint32_t a0 = lds32(aes_addr<0>(s0, lb)), a1 = lds32(aes_addr<1>(s1, lb));
+    uint32_t a2 = lds32_t2(aes_addr<2>(s2, lb)), a3 = lds32_t2(aes_addr<3>(s3, lb));
+    uint32_t b0 = lds32(aes_addr<0>(s1, lb)), b1 = lds32(aes_addr<1>(s2, lb));
+    uint32_t b2 = lds32_t2(aes_addr<2>(s3, lb)), b3 = lds32_t2(aes_addr<3>(s0, lb));
+    uint32_t c0 = lds32(aes_addr<0>(s2, lb)), c1 = lds32(aes_addr<1>(s3, lb));
+    uint32_t c2 = lds32_t2(aes_addr<2>(s0, lb)), c3 = lds32_t2(aes_addr<3>(s1, lb));
+    uint32_t d0 = lds32(aes_addr<0>(s3, lb)), d1 = lds32(aes_addr<1>(s0, lb));
+    uint32_t d2 = lds32_t2(aes_addr<2>(s1, lb)), d3 = lds32_t2(aes_addr<3>(s2, lb));
+    s0 = a0 ^ a2 ^ k.rk[4 * r + 0] ^ rotl8(a1 ^ a3);
+    s1 = b0 ^ b2 ^ k.rk[4 * r + 1] ^ rotl8(b1 ^ b3);
+    s2 = c0 ^ c2 ^ k.rk[4 * r + 2] ^ rotl8(c1 ^ c3);
+    s3 = d0 ^ d2 ^ k.rk[4 * r + 3] ^ rotl8(d1 ^ d3);
+  }
+  // last round: SubBytes + ShiftRows only.  S sits in byte 0 of T2 (=S,3S,2S,S), byte 1 and 2 of
+  // T0 (=2S,S,S,3S) and byte 3 of T2, i.e. already at the byte position where it is needed.
+  AesState o;
+  {
+    uint32_t a0 = lds32_t2(aes_addr<0>(s0, lb)), a1 = lds32(aes_addr<1>(s1, lb));
+    uint32_t a2 = lds32(aes_addr<2>(s2, lb)), a3 = lds32_t2(aes_addr<3>(s3, lb));
+    uint32_t b0 = lds32_t2(aes_addr<0>(s1, lb)), b1 = lds32(aes_addr<1>(s2, lb));
+    uint32_t b2 = lds32(aes_addr<2>(s3, lb)), b3 = lds32_t2(aes_addr<3>(s0, lb));
+    uint32_t c0 = lds32_t2(aes_addr<0>(s2, lb)), c1 = lds32(aes_addr<1>(s3, lb));
+    uint32_t c2 = lds32(aes_addr<2>(s0, lb)), c3 = lds32_t2(aes_addr<3>(s1, lb));
+    uint32_t d0 = lds32_t2(aes_addr<0>(s3, lb)), d1 = lds32(aes_addr<1>(s0, lb));
+    uint32_t d2 = lds32(aes_addr<2>(s1, lb)), d3 = lds32_t2(aes_addr<3>(s2, lb));
+    o.w0 = ((a0 & 0x000000ffu) | (a1 & 0x0000ff00u) | (a2 & 0x00ff0000u) | (a3 & 0xff000000u)) ^ k.rk[56];
+    o.w1 = ((b0 & 0x000000ffu) | (b1 & 0x0000ff00u) | (b2 & 0x00ff0000u) | (b3 & 0xff000000u)) ^ k.rk[57];
+    o.w2 = ((c0 & 0x000000ffu) | (c1 & 0x0000ff00u) | (c2 & 0x00ff0000u) | (c3 & 0xff000000u)) ^ k.rk[58];
+    o.w3 = ((d0 & 0x000000ffu) | (d1 & 0x0000ff00u) | (d2 & 0x00ff0000u) | (d3 & 0xff000000u)) ^ k.rk[59];
+  }
+  return o;
+}
+
+#endif  // __CUDACC__
+}  // namespace mfb

@@ -1,0 +1,386 @@
+// K2 — AES-256-CTR expansion of the a-vectors, standalone and fused into its consumers.
+//
+//   k_stream_bytes   raw keystream bytes                          (aesctr_prg aes.c:104-144, rng_seek entropy.c:46-56)
+//   k_expand         AES -> planar resident ciphertext array      (ct_import lwe.c:122-126, mpz2_urandomb entropy.c:11-26)
+//   k_evalpoly       AES -> 704-bit MAC, a never touches HBM       (eval_poly lwe.c:176-186)
+//   k_encrypt        AES -> <a, sk> + e*p + m -> 92-byte record    (regev_encrypt2 lwe.c:78-97 + ct_export :115-119)
+//
+// Stream geometry (snark.h:8-12, entropy.h:62-66): coordinate j of the ciphertext whose a-vector starts at stream
+// byte `off` is the little-endian integer of the 92 bytes at off + 92*j; only its low 88 bytes survive modq.
+//
+// CTA shape: 512 threads, one CTA per SM.  Shared memory: 64 KB bank-replicated T-tables at a 64 KB-aligned
+// address (aes256.cuh) and two keystream buffers of one coordinate tile each (double buffered, one
+// __syncthreads per work item): the MAC/store phase of item t and the AES phase of item t+1 overlap
+// across warps.  The bound is the shared-memory lookup rate: 224 conflict-free LDS per AES block.
+#include "aes256.cuh"
+#include "mfb_common.cuh"
+
+namespace mfb {
+
+constexpr int KS_THREADS = 512;
+constexpr int KS_TILE = 490;                            // coordinates per tile; 1470 = 3 * 490
+constexpr int KS_NTILES = N / KS_TILE;                  // 3
+constexpr int KS_TILE_BYTES = KS_TILE * CT_BYTES;       // 45080
+constexpr int KS_MAX_BLK = (KS_TILE_BYTES + 15 + 15) / 16;  // 2819 blocks cover a tile at any byte alignment
+constexpr int KS_BUF_BYTES = KS_MAX_BLK * 16 + 16;      // + one word of slack for the funnel read
+constexpr int KS_SMEM_BYTES = 0x20000 + KS_BUF_BYTES;   // [pad/buffer A | 64 KB tables | buffer B]
+
+struct KsSmem {
+  uint32_t tab;   // shared address of the tables (64 KB aligned)
+  uint32_t buf[2];
+  uint32_t lb;    // tab | 4*lane
+};
+
+__device__ __forceinline__ KsSmem ks_smem_setup(uint8_t *dyn, const uint32_t *__restrict__ t0_global) {
+  KsSmem s;
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(dyn);
+  s.tab = (s0 + 0xffffu) & ~0xffffu;
+  // buffer A lives in the alignment pad below the tables when it fits there, else above buffer B
+  if (s.tab - s0 < (uint32_t)KS_BUF_BYTES) __trap();  // dynamic smem starts within 20 KB of the window base
+  s.buf[0] = s0;
+  s.buf[1] = s.tab + AES_TAB_BYTES;
+  s.lb = s.tab | ((threadIdx.x & 31) << 2);
+  aes_tables_init(dyn + (s.tab - s0), t0_global, threadIdx.x, blockDim.x);
+  return s;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const AesState &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.w0), "r"(v.w1), "r"(v.w2), "r"(v.w3)
+               : "memory");
+}
+
+// keystream blocks [first, first + nblk) -> shared buffer
+__device__ __forceinline__ void ks_fill(const AesKey &key, uint64_t first, int nblk, uint32_t buf, uint32_t lb) {
+  for (int b = threadIdx.x; b < nblk; b += KS_THREADS) sts128(buf + 16u * b, aes256_ctr_block(key, first + b, lb));
+}
+
+// the 22 live limbs of the coordinate that starts at byte `pos` of the shared buffer
+__device__ __forceinline__ void ks_read_coord(uint32_t buf, uint32_t pos, uint32_t (&a)[22]) {
+  const uint32_t w = buf + (pos & ~3u);
+  const uint32_t sh = (pos & 3u) * 8;
+  uint32_t lo = lds32(w);
+#pragma unroll
+  for (int l = 0; l < 22; l++) {
+    const uint32_t hi = lds32(w + 4 * (l + 1));
+    a[l] = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+  }
+}
+
+struct TileGeom {
+  uint64_t first;  // first AES block
+  int nblk;
+  uint32_t delta;  // byte offset of the tile's first coordinate inside block `first`
+};
+__device__ __forceinline__ TileGeom tile_geom(uint64_t ct_off, int tile) {
+  const uint64_t off = ct_off + (uint64_t)tile * KS_TILE_BYTES;
+  TileGeom g;
+  g.first = off >> 4;
+  g.delta = (uint32_t)(off & 15);
+  g.nblk = (int)((g.delta + KS_TILE_BYTES + 15) >> 4);
+  return g;
+}
+
+// ------------------------------------------------------------------------------------ raw bytes
+// out[0..nbytes) = stream bytes [offset, offset + nbytes).  One AES block per thread iteration.
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_stream_bytes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+               uint8_t *__restrict__ out, size_t nbytes) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  __syncthreads();
+  const uint64_t first = offset >> 4;
+  const uint64_t end = offset + nbytes;
+  const uint64_t nblk = ((end + 15) >> 4) - first;
+  for (uint64_t b = (uint64_t)blockIdx.x * KS_THREADS + threadIdx.x; b < nblk; b += (uint64_t)gridDim.x * KS_THREADS) {
+    const AesState v = aes256_ctr_block(key, first + b, s.lb);
+    const uint64_t p0 = (first + b) << 4;  // stream position of this block's byte 0
+    const uint32_t w[4] = {v.w0, v.w1, v.w2, v.w3};
+    if (p0 >= offset && p0 + 16 <= end && (((uintptr_t)(out + (p0 - offset))) & 15) == 0) {
+      *reinterpret_cast<uint4 *>(out + (p0 - offset)) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint64_t p = p0 + i;
+        if (p >= offset && p < end) out[p - offset] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ expand
+// cts[k] (planar) <- a-vector of the ciphertext at stream offset + k*CTR_CT, b from the wire record c8[k].
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+         const uint8_t *__restrict__ c8, size_t count, uint64_t *__restrict__ cts) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  const size_t nitems = count * KS_NTILES;
+  size_t it = blockIdx.x;
+  int ph = 0;
+  __syncthreads();  // tables ready
+  if (it < nitems) {
+    const TileGeom g = tile_geom(offset + (it / KS_NTILES) * (uint64_t)CTR_CT, (int)(it % KS_NTILES));
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+  }
+  __syncthreads();
+  for (; it < nitems; it += gridDim.x, ph ^= 1) {
+    const size_t k = it / KS_NTILES;
+    const int tile = (int)(it % KS_NTILES);
+    const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+    uint64_t *dst = cts + k * PLANAR_U64;
+    if (threadIdx.x < KS_TILE) {
+      uint32_t a[22];
+      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
+      const int c = tile * KS_TILE + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < L64; j++) dst[(size_t)j * NCP + c] = (uint64_t)a[2 * j] | (uint64_t)a[2 * j + 1] << 32;
+    } else if (tile == 0 && threadIdx.x < KS_TILE + L64) {
+      // b coordinate: low 88 bytes of the wire record (ct_import lwe.c:125); padding coordinate: 0
+      const int j = threadIdx.x - KS_TILE;
+      const uint8_t *rec = c8 + k * CT_BYTES + 8 * j;
+      uint64_t v = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) v |= (uint64_t)rec[i] << (8 * i);
+      dst[(size_t)j * NCP + N] = v;
+      dst[(size_t)j * NCP + N + 1] = 0;
+    }
+    const size_t nx = it + gridDim.x;
+    if (nx < nitems) {
+      const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ fused eval_poly
+// partial[chunk] (planar, canonical) = sum over this CTA's ciphertexts of coeff * CT, for the CTA's tile.
+// Work item m of the list: ciphertext index idx[m] (or m), scalar coeffs[m]; CTA (tile, chunk) walks
+// m = chunk, chunk + nchunks, ...  The b coordinate (1470) is handled by thread KS_TILE of the tile-0 CTAs,
+// straight from the wire records.
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+           const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs, const uint32_t *__restrict__ idx,
+           size_t d, int nchunks, uint64_t *__restrict__ partial) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  const int tile = blockIdx.x % KS_NTILES;
+  const int chunk = blockIdx.x / KS_NTILES;
+
+  Acc704 acc;
+  acc_zero(acc);
+  const bool is_b = (tile == 0 && threadIdx.x == KS_TILE);
+
+  size_t m = chunk;
+  int ph = 0;
+  __syncthreads();  // tables ready
+  if (m < d) {
+    const size_t k = idx ? idx[m] : m;
+    const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+  }
+  __syncthreads();
+  for (; m < d; m += nchunks, ph ^= 1) {
+    const size_t k = idx ? idx[m] : m;
+    const uint32_t h = coeffs[m];
+    if (threadIdx.x < KS_TILE) {
+      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+      uint32_t a[22];
+      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
+      acc_mad(acc, a, h);
+    } else if (is_b) {
+      const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + k * CT_BYTES);  // 92 % 4 == 0
+      uint32_t a[22];
+#pragma unroll
+      for (int l = 0; l < 22; l++) a[l] = rec[l];
+      acc_mad(acc, a, h);
+    }
+    const size_t nx = m + nchunks;
+    if (nx < d) {
+      const size_t kn = idx ? idx[nx] : nx;
+      const TileGeom gn = tile_geom(offset + kn * (uint64_t)CTR_CT, tile);
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+    }
+    __syncthreads();
+  }
+
+  uint64_t *out = partial + (size_t)chunk * PLANAR_U64;
+  if (threadIdx.x < KS_TILE || is_b) {
+    uint32_t r[22];
+    acc_fold(acc, r);
+    const int c = is_b ? N : tile * KS_TILE + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+  } else if (tile == 0 && threadIdx.x == KS_TILE + 1) {
+#pragma unroll
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + N + 1] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------ Regev encryption
+// One CTA per ciphertext k (grid-stride): b_k = (e_k * p + <sk, a_k> + m_k) mod 2^704, written as the
+// 92-byte wire record.  sk is planar [11][1472].  e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes)
+// (69 noise bytes of errdist_uniform lwe.c:60-63; the sign byte that follows is consumed by the host
+// protocol and never used, lwe.c:86-87).
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+          const uint64_t *__restrict__ sk, const uint64_t *__restrict__ msg, const uint8_t *__restrict__ ent,
+          int ent_stride, int ent_nbytes, size_t count, uint8_t *__restrict__ out_c8) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  __shared__ uint32_t red[KS_THREADS / 32][44];
+  __shared__ unsigned long long cols[22];
+  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  const size_t nitems = count * KS_NTILES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  Acc704 acc;
+  acc_zero(acc);
+  size_t it = (size_t)blockIdx.x * KS_NTILES;  // a CTA takes whole ciphertexts: items 3k, 3k+1, 3k+2
+  int ph = 0;
+  __syncthreads();  // tables ready
+  if (it < nitems) {
+    const TileGeom g = tile_geom(offset + (it / KS_NTILES) * (uint64_t)CTR_CT, 0);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+  }
+  __syncthreads();
+  while (it < nitems) {
+    const size_t k = it / KS_NTILES;
+    const int tile = (int)(it % KS_NTILES);
+    // next item of this CTA: next tile of the same ciphertext, else tile 0 of ciphertext k + gridDim.x
+    const size_t nx = (tile + 1 < KS_NTILES) ? it + 1 : (k + gridDim.x) * KS_NTILES;
+    if (threadIdx.x < KS_TILE) {
+      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+      uint32_t a[22], b[22];
+      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
+      const int c = tile * KS_TILE + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < L64; j++) {
+        const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
+        b[2 * j] = (uint32_t)v;
+        b[2 * j + 1] = (uint32_t)(v >> 32);
+      }
+      acc_mul(acc, a, b);
+    }
+    if (nx < nitems) {
+      const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+    }
+    if (tile == KS_NTILES - 1) {
+      // block-reduce the per-thread sums: 16-bit halves so that warp REDUX sums cannot overflow
+      uint32_t r[22];
+      acc_fold(acc, r);
+      acc_zero(acc);
+#pragma unroll
+      for (int l = 0; l < 22; l++) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, r[l] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, r[l] >> 16);
+        if (lane == 0) {
+          red[warp][2 * l] = lo;
+          red[warp][2 * l + 1] = hi;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 22) {
+        unsigned long long lo = 0, hi = 0;
+        for (int w = 0; w < KS_THREADS / 32; w++) {
+          lo += red[w][2 * threadIdx.x];
+          hi += red[w][2 * threadIdx.x + 1];
+        }
+        cols[threadIdx.x] = lo + (hi << 16);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        // b = sum_l cols[l] << 32l  +  e * p  +  m      (mod 2^704)
+        const uint8_t *e8 = ent + k * (size_t)ent_stride;
+        const uint64_t mm = msg[k];
+        uint64_t carry = 0;  // < 2^34 throughout
+        uint8_t *rec = out_c8 + k * CT_BYTES;
+        for (int l = 0; l < 22; l++) {
+          uint32_t el = 0;
+          for (int i = 0; i < 4; i++) {
+            const int byte = 4 * l + i;
+            if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
+          }
+          uint64_t t = cols[l] + carry;  // < 2^44
+          if (l == 0) t += mm & 0xffffffffu;
+          if (l == 1) t += mm >> 32;
+          const uint64_t prod = (uint64_t)el * P;
+          const uint64_t sum = t + prod;
+          const uint64_t c_out = sum < prod ? 1 : 0;
+          carry = (sum >> 32) + (c_out << 32);
+          const uint32_t limb = (uint32_t)sum;
+          rec[4 * l + 0] = (uint8_t)limb;
+          rec[4 * l + 1] = (uint8_t)(limb >> 8);
+          rec[4 * l + 2] = (uint8_t)(limb >> 16);
+          rec[4 * l + 3] = (uint8_t)(limb >> 24);
+        }
+        rec[88] = rec[89] = rec[90] = rec[91] = 0;
+      }
+    }
+    __syncthreads();
+    it = nx;
+    ph ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+static cudaError_t ks_attr(const void *fn) {
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_SMEM_BYTES);
+}
+
+cudaError_t launch_stream_bytes(const AesKey &key, const uint32_t *t0, uint64_t offset, uint8_t *out, size_t nbytes,
+                                int sm_count, cudaStream_t st) {
+  if (nbytes == 0) return cudaSuccess;
+  cudaError_t e = ks_attr((const void *)k_stream_bytes);
+  if (e != cudaSuccess) return e;
+  const size_t nblk = (nbytes + 31) / 16;
+  size_t grid = (nblk + KS_THREADS - 1) / KS_THREADS;
+  if (grid > (size_t)sm_count) grid = sm_count;
+  k_stream_bytes<<<(unsigned)grid, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, out, nbytes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expand(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8, size_t count,
+                          uint64_t *cts, int sm_count, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  cudaError_t e = ks_attr((const void *)k_expand);
+  if (e != cudaSuccess) return e;
+  size_t grid = count * KS_NTILES;
+  if (grid > (size_t)sm_count) grid = sm_count;
+  k_expand<<<(unsigned)grid, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, count, cts);
+  return cudaGetLastError();
+}
+
+int evalpoly_nchunks(size_t d, int sm_count) {
+  size_t n = sm_count / KS_NTILES;
+  if (n < 1) n = 1;
+  if (n > d) n = d;
+  return (int)(n ? n : 1);
+}
+
+// writes `nchunks` canonical planar partial sums to partial_ws
+cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
+                                     uint64_t *partial_ws, cudaStream_t st) {
+  if (d == 0 || nchunks == 0) return cudaSuccess;
+  cudaError_t e = ks_attr((const void *)k_evalpoly);
+  if (e != cudaSuccess) return e;
+  k_evalpoly<<<nchunks * KS_NTILES, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, idx, d, nchunks,
+                                                                     partial_ws);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
+                           const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
+                           uint8_t *out_c8, int sm_count, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  cudaError_t e = ks_attr((const void *)k_encrypt);
+  if (e != cudaSuccess) return e;
+  size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
+  k_encrypt<<<(unsigned)grid, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
+                                                               count, out_c8);
+  return cudaGetLastError();
+}
+
+}  // namespace mfb

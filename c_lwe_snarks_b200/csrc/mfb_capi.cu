@@ -1,0 +1,462 @@
+// C-ABI of include/mfb200.h: context, scratch management, host<->device staging and kernel launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/mfb200.h"
+#include "aes256.cuh"
+#include "mfb_common.cuh"
+
+namespace mfb {
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int fail(cudaError_t e, const char *what, const char *file, int line) {
+  return set_err(MFB_ECUDA, "%s:%d: %s -> %s (%s)", file, line, what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// kernels / launchers (k_*.cu)
+int lincomb_nchunks(size_t d, int sm_count);
+cudaError_t launch_lincomb(const uint64_t *cts, const uint32_t *coeffs, size_t d, const uint64_t *rop_in,
+                           uint64_t *rop_out, uint64_t *partial_ws, int nchunks, cudaStream_t st);
+cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                                  cudaStream_t st);
+cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
+cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
+                                 cudaStream_t st);
+cudaError_t launch_stream_bytes(const AesKey &key, const uint32_t *t0, uint64_t offset, uint8_t *out, size_t nbytes,
+                                int sm_count, cudaStream_t st);
+cudaError_t launch_expand(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8, size_t count,
+                          uint64_t *cts, int sm_count, cudaStream_t st);
+int evalpoly_nchunks(size_t d, int sm_count);
+cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
+                                     uint64_t *partial_ws, cudaStream_t st);
+cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
+                           const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
+                           uint8_t *out_c8, int sm_count, cudaStream_t st);
+cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
+                           uint64_t *out_m, uint64_t *out_dot, cudaStream_t st);
+cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, cudaStream_t st);
+
+constexpr int MAX_CHUNKS = 256;
+constexpr int NSLOTS = 8;
+
+}  // namespace mfb
+
+using namespace mfb;
+
+struct mfb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;   // the context's own stream (host flavour)
+  uint32_t *t0_dev = nullptr;      // 256-entry T0 table
+  uint64_t *partial_ws = nullptr;  // MAX_CHUNKS planar partial sums
+  void *slot[NSLOTS] = {};         // growable device scratch for the host flavour
+  size_t slot_cap[NSLOTS] = {};
+  uint64_t launches = 0;
+};
+
+struct mfb_region {
+  uint64_t *cts = nullptr;  // planar
+  size_t count = 0;
+};
+
+static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->slot_cap[i] < bytes) {
+    if (ctx->slot[i]) MFB_CUDA_TRY(cudaFree(ctx->slot[i]));
+    ctx->slot[i] = nullptr;
+    ctx->slot_cap[i] = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc(&ctx->slot[i], cap);
+    if (e != cudaSuccess) return set_err(MFB_ENOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+    ctx->slot_cap[i] = cap;
+  }
+  *out = ctx->slot[i];
+  return MFB_OK;
+}
+
+#define MFB_TRY(expr)              \
+  do {                             \
+    int _r = (expr);               \
+    if (_r != MFB_OK) return _r;   \
+  } while (0)
+
+#define MFB_CHECK_CTX(ctx)                                     \
+  do {                                                         \
+    if (!(ctx)) return set_err(MFB_EARG, "null context");      \
+    MFB_CUDA_TRY(cudaSetDevice((ctx)->device));                \
+  } while (0)
+
+extern "C" {
+
+const char *mfb_last_error(void) { return g_err; }
+
+int mfb_ctx_create(mfb_ctx **out, int device) {
+  if (!out) return set_err(MFB_EARG, "null out");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return set_err(MFB_ENODEV, "no CUDA device (%s); this library has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_err(MFB_EARG, "device %d out of range [0, %d)", device, n);
+  MFB_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MFB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_err(MFB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                   prop.minor);
+  mfb_ctx *ctx = new (std::nothrow) mfb_ctx();
+  if (!ctx) return set_err(MFB_ENOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  uint32_t t0[256];
+  aes_host::t0_table(t0);
+  int rc = MFB_OK;
+  do {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&ctx->t0_dev, sizeof(t0))) != cudaSuccess) break;
+    if ((e = cudaMemcpy(ctx->t0_dev, t0, sizeof(t0), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&ctx->partial_ws, (size_t)MAX_CHUNKS * PLANAR_U64 * 8)) != cudaSuccess) break;
+  } while (0);
+  if (e != cudaSuccess) {
+    rc = fail(e, "context setup", __FILE__, __LINE__);
+    mfb_ctx_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return MFB_OK;
+}
+
+void mfb_ctx_destroy(mfb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  for (int i = 0; i < NSLOTS; i++)
+    if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+  if (ctx->t0_dev) cudaFree(ctx->t0_dev);
+  if (ctx->partial_ws) cudaFree(ctx->partial_ws);
+  delete ctx;
+}
+
+int mfb_device_sm_count(mfb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t mfb_launch_count(mfb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int mfb_sync(mfb_ctx *ctx) {
+  MFB_CHECK_CTX(ctx);
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+/* ------------------------------------------------------------------------------------ _dev flavour */
+
+int mfb_stream_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *out_dev, size_t nbytes,
+                   void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || (!out_dev && nbytes)) return set_err(MFB_EARG, "mfb_stream_dev: null pointer");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  MFB_CUDA_TRY(launch_stream_bytes(key, ctx->t0_dev, offset, out_dev, nbytes, ctx->sm_count, (cudaStream_t)stream));
+  if (nbytes) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_expand_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev, size_t count,
+                   uint64_t *cts_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || (count && (!c8_dev || !cts_dev))) return set_err(MFB_EARG, "mfb_expand_dev: null pointer");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  MFB_CUDA_TRY(launch_expand(key, ctx->t0_dev, offset, c8_dev, count, cts_dev, ctx->sm_count, (cudaStream_t)stream));
+  if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
+                    const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!rop_out_dev || (d && (!cts_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_lincomb_dev: null pointer");
+  int nchunks = lincomb_nchunks(d, ctx->sm_count);
+  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
+  MFB_CUDA_TRY(launch_lincomb(cts_dev, coeffs_dev, d, rop_in_dev, rop_out_dev, ctx->partial_ws, nchunks,
+                              (cudaStream_t)stream));
+  ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
+int mfb_columns_split_dev(mfb_ctx *ctx, const uint64_t *flat_dev, uint64_t *cols_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!flat_dev || !cols_dev) return set_err(MFB_EARG, "mfb_columns_split_dev: null pointer");
+  MFB_CUDA_TRY(launch_columns_split(flat_dev, cols_dev, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_columns_carry_dev(mfb_ctx *ctx, const uint64_t *cols_dev, int c0, int ncoord, const uint64_t *flat_in_dev,
+                          uint64_t *flat_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!cols_dev || !flat_out_dev || c0 < 0 || ncoord < 0) return set_err(MFB_EARG, "mfb_columns_carry_dev: bad argument");
+  if (ncoord == 0) return MFB_OK;
+  MFB_CUDA_TRY(launch_columns_carry(cols_dev, c0, ncoord, flat_in_dev, flat_out_dev, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                      const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
+                      uint64_t *rop_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || !rop_out_dev || (d && (!c8_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_eval_poly_dev: null pointer");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
+  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
+  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
+                                        ctx->partial_ws, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, (cudaStream_t)stream));
+  ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
+int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
+                    const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride, int ent_nbytes, size_t count,
+                    uint8_t *out_c8_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || (count && (!sk_planar_dev || !msg_dev || !ent_dev || !out_c8_dev)))
+    return set_err(MFB_EARG, "mfb_encrypt_dev: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes)
+    return set_err(MFB_EARG, "mfb_encrypt_dev: need 0 <= ent_nbytes <= 88 and ent_stride >= ent_nbytes");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  MFB_CUDA_TRY(launch_encrypt(key, ctx->t0_dev, offset, sk_planar_dev, msg_dev, ent_dev, ent_stride, ent_nbytes, count,
+                              out_c8_dev, ctx->sm_count, (cudaStream_t)stream));
+  if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const uint64_t *cts_flat_dev,
+                    const uint8_t *b_neg_dev, size_t count, uint64_t *out_m_dev, uint64_t *out_dot_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (count && (!sk_planar_dev || !cts_flat_dev || !out_m_dev)) return set_err(MFB_EARG, "mfb_decrypt_dev: null pointer");
+  MFB_CUDA_TRY(launch_decrypt(sk_planar_dev, cts_flat_dev, b_neg_dev, count, out_m_dev, out_dot_dev, (cudaStream_t)stream));
+  if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
+                           void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (count && (!flat_dev || !planar_dev)) return set_err(MFB_EARG, "mfb_flat_to_planar_dev: null pointer");
+  if (n < 0 || n > NCP) return set_err(MFB_EARG, "mfb_flat_to_planar_dev: n out of range");
+  MFB_CUDA_TRY(launch_flat_to_planar(flat_dev, n, count, planar_dev, (cudaStream_t)stream));
+  if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+/* ------------------------------------------------------------------------------------ host flavour */
+
+int mfb_stream(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *out, size_t nbytes) {
+  MFB_CHECK_CTX(ctx);
+  if (nbytes == 0) return MFB_OK;
+  if (!out) return set_err(MFB_EARG, "mfb_stream: null out");
+  void *d;
+  MFB_TRY(scratch(ctx, 0, nbytes, &d));
+  MFB_TRY(mfb_stream_dev(ctx, seed, offset, (uint8_t *)d, nbytes, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(out, d, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+static int narrow_coeffs(const uint64_t *coeffs, size_t d, uint32_t *out) {
+  for (size_t i = 0; i < d; i++) {
+    if (coeffs[i] >> 32) return set_err(MFB_EARG, "coefficient %zu = %llu does not fit 32 bits", i,
+                                        (unsigned long long)coeffs[i]);
+    out[i] = (uint32_t)coeffs[i];
+  }
+  return MFB_OK;
+}
+
+int mfb_eval_poly(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs,
+                  const uint32_t *idx, size_t d, uint64_t *rop_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || !rop_flat_inout || (d && (!c8 || !coeffs))) return set_err(MFB_EARG, "mfb_eval_poly: null pointer");
+  // the record array is indexed by ciphertext number: with idx it spans max(idx) + 1 records
+  size_t nrec = d;
+  if (idx) {
+    nrec = 0;
+    for (size_t i = 0; i < d; i++)
+      if ((size_t)idx[i] + 1 > nrec) nrec = (size_t)idx[i] + 1;
+  }
+  void *d_c8, *d_co, *d_idx = nullptr, *d_rop;
+  MFB_TRY(scratch(ctx, 0, nrec * CT_BYTES, &d_c8));
+  MFB_TRY(scratch(ctx, 1, d * 4, &d_co));
+  MFB_TRY(scratch(ctx, 2, MFB_FLAT_CT_U64 * 8, &d_rop));
+  if (idx) MFB_TRY(scratch(ctx, 3, d * 4, &d_idx));
+  uint32_t *co32 = (uint32_t *)malloc(d ? d * 4 : 4);
+  if (!co32) return set_err(MFB_ENOMEM, "out of host memory");
+  int rc = narrow_coeffs(coeffs, d, co32);
+  if (rc == MFB_OK) {
+    cudaError_t e = cudaSuccess;
+    do {
+      if (d && (e = cudaMemcpyAsync(d_c8, c8, nrec * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if (d && (e = cudaMemcpyAsync(d_co, co32, d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if (idx && d && (e = cudaMemcpyAsync(d_idx, idx, d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(d_rop, rop_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
+  }
+  if (rc == MFB_OK)
+    rc = mfb_eval_poly_dev(ctx, seed, offset, (const uint8_t *)d_c8, (const uint32_t *)d_co, (const uint32_t *)d_idx, d,
+                           (const uint64_t *)d_rop, (uint64_t *)d_rop, ctx->stream);
+  if (rc == MFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(e, "D2H", __FILE__, __LINE__);
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  free(co32);
+  return rc;
+}
+
+int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, size_t d, uint64_t *rop_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!rop_flat_inout || (d && (!cts_flat || !coeffs))) return set_err(MFB_EARG, "mfb_lincomb: null pointer");
+  void *d_flat, *d_planar, *d_co, *d_rop;
+  MFB_TRY(scratch(ctx, 0, d * MFB_FLAT_CT_U64 * 8, &d_flat));
+  MFB_TRY(scratch(ctx, 4, d * PLANAR_U64 * 8, &d_planar));
+  MFB_TRY(scratch(ctx, 1, d * 4, &d_co));
+  MFB_TRY(scratch(ctx, 2, MFB_FLAT_CT_U64 * 8, &d_rop));
+  if (d) {
+    MFB_CUDA_TRY(cudaMemcpyAsync(d_flat, cts_flat, d * MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MFB_CUDA_TRY(cudaMemcpyAsync(d_co, coeffs, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_rop, rop_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_flat, NC, d, (uint64_t *)d_planar, ctx->stream));
+  MFB_TRY(mfb_lincomb_dev(ctx, (const uint64_t *)d_planar, (const uint32_t *)d_co, d, (const uint64_t *)d_rop,
+                          (uint64_t *)d_rop, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                      mfb_region **out) {
+  MFB_CHECK_CTX(ctx);
+  if (!out || !seed || (count && !c8)) return set_err(MFB_EARG, "mfb_region_create: null pointer");
+  *out = nullptr;
+  mfb_region *r = new (std::nothrow) mfb_region();
+  if (!r) return set_err(MFB_ENOMEM, "out of host memory");
+  r->count = count;
+  cudaError_t e = cudaMalloc(&r->cts, (count ? count : 1) * PLANAR_U64 * 8);
+  if (e != cudaSuccess) {
+    delete r;
+    return set_err(MFB_ENOMEM, "cudaMalloc of %zu resident ciphertexts failed: %s", count, cudaGetErrorString(e));
+  }
+  void *d_c8;
+  int rc = scratch(ctx, 0, count * CT_BYTES, &d_c8);
+  if (rc == MFB_OK && count) {
+    e = cudaMemcpyAsync(d_c8, c8, count * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
+  }
+  if (rc == MFB_OK) rc = mfb_expand_dev(ctx, seed, offset, (const uint8_t *)d_c8, count, r->cts, ctx->stream);
+  if (rc == MFB_OK) {
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(e, "sync", __FILE__, __LINE__);
+  }
+  if (rc != MFB_OK) {
+    cudaFree(r->cts);
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return MFB_OK;
+}
+
+void mfb_region_destroy(mfb_ctx *ctx, mfb_region *r) {
+  if (!r) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (r->cts) cudaFree(r->cts);
+  delete r;
+}
+
+int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs, size_t d,
+                       uint64_t *rop_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!r || !rop_flat_inout || (d && !coeffs)) return set_err(MFB_EARG, "mfb_region_lincomb: null pointer");
+  if (first > r->count || d > r->count - first) return set_err(MFB_EARG, "mfb_region_lincomb: range exceeds the region");
+  void *d_co, *d_rop;
+  MFB_TRY(scratch(ctx, 1, d * 4, &d_co));
+  MFB_TRY(scratch(ctx, 2, MFB_FLAT_CT_U64 * 8, &d_rop));
+  if (d) MFB_CUDA_TRY(cudaMemcpyAsync(d_co, coeffs, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_rop, rop_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_lincomb_dev(ctx, r->cts + first * PLANAR_U64, (const uint32_t *)d_co, d, (const uint64_t *)d_rop,
+                          (uint64_t *)d_rop, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+  MFB_CHECK_CTX(ctx);
+  if (count == 0) return MFB_OK;
+  if (!seed || !sk_flat || !msg || !ent || !out_c8) return set_err(MFB_EARG, "mfb_encrypt: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes)
+    return set_err(MFB_EARG, "mfb_encrypt: need 0 <= ent_nbytes <= 88 and ent_stride >= ent_nbytes");
+  void *d_skf, *d_skp, *d_msg, *d_ent, *d_out;
+  MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
+  MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
+  MFB_TRY(scratch(ctx, 1, count * 8, &d_msg));
+  MFB_TRY(scratch(ctx, 3, count * (size_t)ent_stride, &d_ent));
+  MFB_TRY(scratch(ctx, 5, count * CT_BYTES, &d_out));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_msg, msg, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_ent, ent, count * (size_t)ent_stride, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_skf, N, 1, (uint64_t *)d_skp, ctx->stream));
+  MFB_TRY(mfb_encrypt_dev(ctx, seed, offset, (const uint64_t *)d_skp, (const uint64_t *)d_msg, (const uint8_t *)d_ent,
+                          ent_stride, ent_nbytes, count, (uint8_t *)d_out, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
+                uint64_t *out_m, uint64_t *out_dot) {
+  MFB_CHECK_CTX(ctx);
+  if (count == 0) return MFB_OK;
+  if (!sk_flat || !cts_flat || !out_m) return set_err(MFB_EARG, "mfb_decrypt: null pointer");
+  void *d_skf, *d_skp, *d_cts, *d_neg = nullptr, *d_m, *d_dot = nullptr;
+  MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
+  MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
+  MFB_TRY(scratch(ctx, 5, count * MFB_FLAT_CT_U64 * 8, &d_cts));
+  MFB_TRY(scratch(ctx, 1, count * 8, &d_m));
+  if (b_neg) MFB_TRY(scratch(ctx, 3, count, &d_neg));
+  if (out_dot) MFB_TRY(scratch(ctx, 6, count * L64 * 8, &d_dot));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_cts, cts_flat, count * MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (b_neg) MFB_CUDA_TRY(cudaMemcpyAsync(d_neg, b_neg, count, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_skf, N, 1, (uint64_t *)d_skp, ctx->stream));
+  MFB_TRY(mfb_decrypt_dev(ctx, (const uint64_t *)d_skp, (const uint64_t *)d_cts, (const uint8_t *)d_neg, count,
+                          (uint64_t *)d_m, (uint64_t *)d_dot, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(out_m, d_m, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_dot) MFB_CUDA_TRY(cudaMemcpyAsync(out_dot, d_dot, count * L64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+}  // extern "C"

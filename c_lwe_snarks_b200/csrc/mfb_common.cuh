@@ -1,0 +1,156 @@
+// Shared definitions for the sm_100a kernels of the SSP-SNARK hot path.
+//
+// Parameter set = the reference's only one (lwe.h:23-31): n = 1470, log q = 736 with the *effective*
+// modulus 2^704 that modq() (lwe.h:108-118) implements, p = 2^32 - 5.  All arithmetic is unsigned
+// multi-limb integer; "reduction mod q" is truncation to 22 x 32-bit limbs.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mfb {
+
+constexpr int N = 1470;            // GAMMA_N (lwe.h:23)
+constexpr int NC = N + 1;          // coordinates per ciphertext: a_0..a_1469, b
+constexpr int NCP = 1472;          // coordinates padded to a multiple of 64 (23 x 64) for the planar layout
+constexpr int L32 = 22;            // live 32-bit limbs per coordinate (704 bit)
+constexpr int L64 = 11;            // live 64-bit limbs per coordinate
+constexpr int CT_BYTES = 92;       // wire width of one coordinate (LOGQ_BYTES, lwe.h:29)
+constexpr int CTR_CT = CT_BYTES * N;  // stream bytes per ciphertext (snark.h:8) = 135240
+constexpr uint32_t P = 0xfffffffbu;   // GAMMA_P (lwe.h:25)
+constexpr int NOISE_BYTES = 69;    // (GAMMA_LOG_SIGMA + 3) / 8 (lwe.c:62, entropy.c:32)
+constexpr int ENT_BYTES = 70;      // noise bytes + the sign byte that is drawn and discarded (lwe.c:87)
+
+// "planar" resident layout of a ciphertext array in HBM: ct i, 64-bit limb row j, coordinate c at
+//   cts[(i * L64 + j) * NCP + c]
+// so that a warp reading one limb row touches 256 contiguous bytes.  Coordinate 1470 is b, 1471 is 0.
+constexpr size_t PLANAR_U64 = (size_t)L64 * NCP;  // 16192 u64 = 129536 B per ciphertext
+
+// ---------------------------------------------------------------------------------------------
+// 704-bit multiply-accumulate with in-thread carry chains.
+//
+// acc (mod 2^704) is kept as two interleaved accumulators so that every product lands on a 64-bit
+// boundary of one of them and a whole row is one carry chain:
+//   E[0..21]  holds sum of  s*a[2k]   << 64k      (k = 0..10)
+//   O[0..20]  holds sum of  s*a[2k+1] << 64k      (k = 0..10, the last one low half only),
+//             worth O << 32 in the final value.
+// value = (E + (O << 32)) mod 2^704.  Carries out of the top are dropped: that IS modq.
+// The lo/hi pairs below are fused by ptxas into IMAD.WIDE.U32 with carry-in/-out (one per limb).
+// ---------------------------------------------------------------------------------------------
+struct Acc704 {
+  uint32_t E[22];
+  uint32_t O[21];
+};
+
+__device__ __forceinline__ void acc_zero(Acc704 &x) {
+#pragma unroll
+  for (int i = 0; i < 22; i++) x.E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 21; i++) x.O[i] = 0;
+}
+
+// acc += s * a   (a = 22 limbs, s < 2^32), mod 2^704
+__device__ __forceinline__ void acc_mad(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(x.E[0]), "+r"(x.E[1]) : "r"(a[0]), "r"(s));
+#pragma unroll
+  for (int k = 1; k < 10; k++)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(x.E[2 * k]), "+r"(x.E[2 * k + 1]) : "r"(a[2 * k]), "r"(s));
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+               : "+r"(x.E[20]), "+r"(x.E[21]) : "r"(a[20]), "r"(s));
+
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(x.O[0]), "+r"(x.O[1]) : "r"(a[1]), "r"(s));
+#pragma unroll
+  for (int k = 1; k < 10; k++)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(x.O[2 * k]), "+r"(x.O[2 * k + 1]) : "r"(a[2 * k + 1]), "r"(s));
+  asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[21]), "r"(s));
+}
+
+// acc += (a * b) mod 2^704 for two 22-limb operands (schoolbook low half, 253 limb products).
+// Row KB adds a[0..21-KB] * b[KB] at limb offset KB as two carry chains (l even, l odd).  A product at
+// limb position pos = l + KB goes to E[pos], E[pos+1] when pos is even and to O[pos-1], O[pos] when
+// pos is odd; along a chain pos keeps its parity and advances by 2, so consecutive products occupy
+// consecutive 64-bit slots of one accumulator and the carry flag links them.  One chain of every row
+// ends at pos 20 (E[20], E[21]), the other at pos 21 (low half into O[20]): both reach the top, where
+// the carry is dropped (that is modq).
+template <int KB, int Lx, bool FIRST>
+__device__ __forceinline__ void acc_mul_chain(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
+  constexpr int pos = Lx + KB;
+  if constexpr (pos <= 21) {
+    if constexpr ((pos & 1) == 0) {
+      if constexpr (FIRST)
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(x.E[pos]), "+r"(x.E[pos + 1]) : "r"(a[Lx]), "r"(s));
+      else
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(x.E[pos]), "+r"(x.E[pos + 1]) : "r"(a[Lx]), "r"(s));
+    } else if constexpr (pos < 21) {
+      if constexpr (FIRST)
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(x.O[pos - 1]), "+r"(x.O[pos]) : "r"(a[Lx]), "r"(s));
+      else
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(x.O[pos - 1]), "+r"(x.O[pos]) : "r"(a[Lx]), "r"(s));
+    } else {
+      if constexpr (FIRST)
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[Lx]), "r"(s));
+      else
+        asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[Lx]), "r"(s));
+    }
+    acc_mul_chain<KB, Lx + 2, false>(x, a, s);
+  }
+}
+
+template <int KB>
+__device__ __forceinline__ void acc_mul_rows(Acc704 &x, const uint32_t (&a)[22], const uint32_t (&b)[22]) {
+  if constexpr (KB <= 21) {
+    acc_mul_chain<KB, 0, true>(x, a, b[KB]);
+    acc_mul_chain<KB, 1, true>(x, a, b[KB]);
+    acc_mul_rows<KB + 1>(x, a, b);
+  }
+}
+
+__device__ __forceinline__ void acc_mul(Acc704 &x, const uint32_t (&a)[22], const uint32_t (&b)[22]) {
+  acc_mul_rows<0>(x, a, b);
+}
+
+// r[0..21] = (E + (O << 32)) mod 2^704
+__device__ __forceinline__ void acc_fold(const Acc704 &x, uint32_t (&r)[22]) {
+  r[0] = x.E[0];
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[1]) : "r"(x.E[1]), "r"(x.O[0]));
+#pragma unroll
+  for (int i = 2; i < 21; i++)
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(x.E[i]), "r"(x.O[i - 1]));
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r[21]) : "r"(x.E[21]), "r"(x.O[20]));
+}
+
+// r += b (22 limbs), mod 2^704
+__device__ __forceinline__ void add704(uint32_t (&r)[22], const uint32_t (&b)[22]) {
+  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r[0]) : "r"(b[0]));
+#pragma unroll
+  for (int i = 1; i < 21; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b[i]));
+  asm volatile("addc.u32 %0, %0, %1;" : "+r"(r[21]) : "r"(b[21]));
+}
+
+// r = a - b (22 limbs) mod 2^704; returns 1 when a < b (borrow out of the top)
+__device__ __forceinline__ uint32_t sub704(uint32_t (&r)[22], const uint32_t (&a)[22], const uint32_t (&b)[22]) {
+  uint32_t borrow;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(a[0]), "r"(b[0]));
+#pragma unroll
+  for (int i = 1; i < 22; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(a[i]), "r"(b[i]));
+  asm volatile("subc.u32 %0, 0, 0;" : "=r"(borrow));
+  return borrow & 1u;
+}
+
+#define MFB_CUDA_TRY(expr)                         \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return mfb::fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+int fail(cudaError_t e, const char *what, const char *file, int line);  // mfb_capi.cu
+
+}  // namespace mfb

@@ -1,0 +1,151 @@
+/* mfb200.h — C-ABI of the B200 (sm_100a) kernels behind the SSP-SNARK hot path of mmaker/c-lwe-snarks.
+ *
+ * This is the device boundary: plain pointers and sizes, C linkage, no torch / GMP / FLINT types.
+ * The reference has no FFI layer — its "plugin interface" is its own C headers — so each entry point
+ * below names the reference function (path:line under the reference's src/) whose inner loop it
+ * replaces; the drop-in C layer that keeps the reference's mpz_t-typed signatures (include/mangiafuoco/
+ * lwe.h, snark.h, entropy.h) is a thin adapter over these calls.
+ *
+ * Formats (all little-endian, all unsigned):
+ *   seed      40 bytes: nonce(8) || AES-256 key(32)                         entropy.h:35, entropy.c:58-61
+ *   record    92 bytes: the b coordinate as ct_export writes it            lwe.c:115-119 (top 4 bytes are 0)
+ *   flat ct   MFB_NC (1471) coordinates x MFB_L64 (11) uint64 limbs, coordinate-major: the value of every
+ *             coordinate mod 2^704 — the modulus modq() really implements    lwe.h:108-118
+ *   flat sk   MFB_N (1470) coordinates x 11 uint64 limbs (bits >= 704 of a key never reach any output)
+ *   planar    resident (HBM) layout of a ciphertext array: ct i, limb row j, coordinate c at
+ *             u64 index (i*11 + j)*1472 + c; coordinate 1470 is b, 1471 is zero padding
+ *   scalars   uint32 < p = 2^32 - 5 (nmod_poly coefficients; any uint32 is computed exactly)
+ *
+ * Every function returns 0 on success or a negative MFB_E* code; mfb_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device mfb_ctx_create fails.
+ *
+ * Two flavours:
+ *   host flavour  (no suffix)  host pointers in, host pointers out; copies + kernels on the context's own
+ *                              stream; returns after the result is in host memory.
+ *   _dev flavour               device pointers, asynchronous on the caller's stream (a cudaStream_t passed
+ *                              as void*; NULL = the legacy default stream); no allocation, no sync.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB_N 1470
+#define MFB_NC 1471
+#define MFB_NCP 1472
+#define MFB_L64 11
+#define MFB_CT_BYTES 92
+#define MFB_CTR_CT (MFB_CT_BYTES * MFB_N) /* 135240 stream bytes per ciphertext, snark.h:8 */
+#define MFB_P 0xfffffffbu
+#define MFB_FLAT_CT_U64 ((size_t)MFB_NC * MFB_L64)   /* 16181 */
+#define MFB_FLAT_SK_U64 ((size_t)MFB_N * MFB_L64)    /* 16170 */
+#define MFB_PLANAR_U64 ((size_t)MFB_L64 * MFB_NCP)   /* 16192 u64 = 129536 B per resident ciphertext */
+#define MFB_ENT_BYTES 70 /* per encryption: 69 noise bytes (lwe.c:62) + 1 sign byte (lwe.c:54,87) */
+#define MFB_ALGO_BYTES_PER_MAC 129448 /* 1471 x 88: algorithmic HBM bytes of one ciphertext-MAC */
+
+#define MFB_OK 0
+#define MFB_ECUDA (-1)   /* a CUDA call failed */
+#define MFB_EARG (-2)    /* bad argument */
+#define MFB_ENODEV (-3)  /* no usable CUDA device */
+#define MFB_ENOMEM (-4)
+
+#if defined(__GNUC__)
+#define MFB_API __attribute__((visibility("default")))
+#else
+#define MFB_API
+#endif
+
+typedef struct mfb_ctx mfb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
+MFB_API void mfb_ctx_destroy(mfb_ctx *ctx);
+MFB_API const char *mfb_last_error(void);
+MFB_API int mfb_device_sm_count(mfb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+MFB_API uint64_t mfb_launch_count(mfb_ctx *ctx);
+MFB_API int mfb_sync(mfb_ctx *ctx);
+
+/* ---- K2: AES-256-CTR stream -------------------------------------------------------------- */
+/* out[0..nbytes) = stream bytes [offset, offset+nbytes) of `seed`.
+ * Replaces rng_init + rng_seek + rng_gen / aesctr_prg (entropy.c:46-61, aes.c:104-144). */
+MFB_API int mfb_stream(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *out, size_t nbytes);
+MFB_API int mfb_stream_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *out_dev, size_t nbytes,
+                   void *stream);
+
+/* cts_dev[k] (planar) <- ct_import(rng at offset + k*MFB_CTR_CT, c8[k]) for k < count (lwe.c:122-126):
+ * the a-vector from the stream, b from the 92-byte record.  This is how a CRS region is made resident. */
+MFB_API int mfb_expand_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev, size_t count,
+                   uint64_t *cts_dev, void *stream);
+
+/* ---- K1: ciphertext linear combination over resident ciphertexts -------------------------- */
+/* rop = (rop_in + sum_{i<d} coeffs[i] * cts[i]) mod 2^704, coordinate-wise: the loop of eval_poly
+ * (lwe.c:176-186) = d x ct_addmul_ui (lwe.c:141-149) with modq (lwe.h:108-118); also ct_mul_ui and ct_add
+ * (lwe.c:131-157) as the d = 1, 2 cases.  rop_in may be NULL (zero) or equal to rop_out. */
+MFB_API int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
+                    const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
+/* host flavour over flat host ciphertexts (d small: ct_add / ct_mul_ui / ct_addmul_ui on ct_t objects) */
+MFB_API int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, size_t d, uint64_t *rop_flat_inout);
+
+/* Resident CRS region: expand once, reuse for every proof.  handle is owned by the context. */
+typedef struct mfb_region mfb_region;
+MFB_API int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                      mfb_region **out);
+MFB_API void mfb_region_destroy(mfb_ctx *ctx, mfb_region *r);
+/* rop += sum_i coeffs[i] * region[first + i], i < d; coeffs/rop in host memory */
+MFB_API int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs, size_t d,
+                       uint64_t *rop_flat_inout);
+
+/* ---- multi-GPU exchange helpers (one process per GPU; the collective itself is NCCL) ------ */
+/* cols_dev[1472][22] u64 <- the 32-bit limbs of flat_dev, widened, so that an elementwise integer sum over
+ * ranks is exact; carry: flat_out[c] = (flat_in[c] + sum_l cols[c - c0][l] << 32l) mod 2^704 for the
+ * ncoord coordinates this rank owns after the reduce-scatter. */
+MFB_API int mfb_columns_split_dev(mfb_ctx *ctx, const uint64_t *flat_dev, uint64_t *cols_dev, void *stream);
+MFB_API int mfb_columns_carry_dev(mfb_ctx *ctx, const uint64_t *cols_dev, int c0, int ncoord, const uint64_t *flat_in_dev,
+                          uint64_t *flat_out_dev, void *stream);
+
+/* ---- K2+K1 fused: eval_poly with a regenerated in-kernel ----------------------------------- */
+/* rop += sum_{m<d} coeffs[m] * CT_{k(m)},  k(m) = idx ? idx[m] : m, where CT_k = ct_import(stream at
+ * offset + k*MFB_CTR_CT, c8[k]).  Exactly eval_poly (lwe.c:176-186) with the rng positioned at `offset`;
+ * with idx it is also the prover's b_w loop (snark.c:143-155), which skips unset witness bits.
+ * Coefficients are uint64 as nmod_poly stores them; they must be < 2^32. */
+MFB_API int mfb_eval_poly(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs,
+                  const uint32_t *idx, size_t d, uint64_t *rop_flat_inout);
+MFB_API int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                      const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
+                      uint64_t *rop_out_dev, void *stream);
+
+/* ---- K3+K5: Regev encryption -------------------------------------------------------------- */
+/* out_c8[k] = ct_export(regev_encrypt2(rng at offset + k*MFB_CTR_CT, sk, msg[k], e_k)) for k < count
+ * (lwe.c:78-97, 115-119): b = (e*p + <sk, a> + m) mod 2^704.  e_k is the little-endian integer of
+ * ent[k*ent_stride .. +ent_nbytes): pass the raw entropy of the reference's two getrandom calls per
+ * encryption (stride 70, nbytes 69 — errdist_uniform lwe.c:60-63; the sign byte is drawn and unused,
+ * lwe.c:86-87) or an explicit noise value for a custom chi (stride = nbytes <= 88). */
+MFB_API int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
+MFB_API int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
+                    const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride, int ent_nbytes, size_t count,
+                    uint8_t *out_c8_dev, void *stream);
+
+/* ---- K4: batched decryption ---------------------------------------------------------------- */
+/* out_m[k] = regev_decrypt(sk, ct_k) (lwe.c:105-111) = (b - (<a, sk> mod 2^704)) floor-mod p, where the b
+ * coordinate of ct_k is -(its stored magnitude) when b_neg[k] != 0 (ct_smudge can leave it negative,
+ * lwe.c:65-76).  out_dot (nullable) receives <a, sk> mod 2^704 as 11 u64 (mpz_dotp, lwe.h:57-61). */
+MFB_API int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
+                uint64_t *out_m, uint64_t *out_dot);
+MFB_API int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const uint64_t *cts_flat_dev,
+                    const uint8_t *b_neg_dev, size_t count, uint64_t *out_m_dev, uint64_t *out_dot_dev, void *stream);
+
+/* flat [count][n][11] -> planar [count][11][1472] on the device (n = 1470 for keys, 1471 for ciphertexts) */
+MFB_API int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
+                           void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */
