@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the prover's ciphertext linear combination (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2d 16]
+
+One *step* = one pass of the hot path over one batch of synthetic input: rop = sum_i h_i * CT_i mod 2^704
+over D = 2^16 Regev ciphertexts per GPU (n = 1470, log q = 736 / effective 704), i.e. one eval_poly
+(lwe.c:176-186).  Unit = ciphertext-MAC.
+
+  value     whole-job ciphertext-MAC/s with the ciphertexts RESIDENT in HBM (planar layout, expanded once
+            from the CRS seed by the AES-CTR kernel before the timed region), K1 = k_lincomb + k_lincomb_finish;
+            CUDA events on the launching stream, max over ranks.
+  roofline  k_lincomb alone (events recorded around that launch inside the library, mfb_profile_*):
+            algorithmic bytes = D * 129448 per launch against MEASURED_PEAKS.json's HBM copy bandwidth.
+  e2e       the same eval_poly through the host-flavour C-ABI call mfb_eval_poly with HOST buffers (seed, 92-byte
+            records, coefficients, accumulator), as the reference's eval_poly(rop, rng, c8, coeffs, d) is called:
+            H2D of records + scalars + rop, AES-CTR regeneration of every a-vector in-kernel (nothing is
+            resident), fused MAC, D2H of the result — all inside the timed region.
+  cpu_baseline  the compiled reference (oracle/_ref, unmodified lwe.c/entropy.c/aes.c) on one host core, over a
+            bounded prefix of the same ciphertexts.
+  N > 1     weak scaling: every rank holds its own 2^16 ciphertexts (global D = N * 2^16); a step adds the
+            exchange of SURVEY §8e: widen partial sums to u64 columns, NCCL reduce-scatter, carry-propagate +
+            truncate on the owner, all-gather.
+
+`--impl reference` times the reference's own CPU eval_poly with every host core (one process per core over disjoint
+ciphertext ranges positioned with rng_seek, partials folded with ct_add), each step a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ciphertext-MAC/s"
+SEED = bytes(range(40))
+N, NC, L64, CT_BYTES, CTR_CT, P = 1470, 1471, 11, 92, 92 * 1470, 0xFFFFFFFB
+ALGO_BYTES = NC * 88
+PLANAR_BYTES = L64 * 1472 * 8
+
+
+def synth_inputs(d: int, rank: int = 0):
+    """Seeded synthetic instance: 92-byte b records (top 4 bytes zero) and scalars uniform in [0, p)."""
+    rng = np.random.Generator(np.random.PCG64(20181018 + rank))
+    c8 = rng.integers(0, 256, size=(d, CT_BYTES), dtype=np.uint8)
+    c8[:, 88:] = 0
+    h = (rng.integers(0, 2**63, size=d, dtype=np.uint64) % np.uint64(P)).astype(np.uint64)
+    return c8, h
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def ref_lib(d_hint: int = 256):
+    from oracle.loader import Reference
+    return Reference(256, 64)
+
+
+def cpu_baseline_single(sample: int):
+    """The compiled reference's eval_poly on ONE core over the first `sample` ciphertexts of the workload."""
+    ref = ref_lib()
+    c8, h = synth_inputs(sample)
+    secs, _rop, t_imp, t_mac = ref.time_eval_poly(SEED, 0, c8, h, split=True)
+    return {"value": sample / secs, "unit": METRIC, "cores": 1, "kind": "reference",
+            "sample": f"first {sample} of the 2^16 ciphertexts, eval_poly of oracle/_ref (unmodified lwe.c) in {secs:.2f} s; "
+                      f"per ciphertext: ct_import (AES regen) {t_imp * 1e6:.0f} us, ct_addmul_ui (GMP) {t_mac * 1e6:.1f} us"}
+
+
+def _ref_worker(args):
+    first, count, reps = args
+    ref = ref_lib()
+    c8, h = synth_inputs(first + count)
+    out = []
+    for _ in range(reps):
+        t, rop = ref.time_eval_poly(SEED, first * CTR_CT, c8[first:first + count], h[first:first + count])
+        out.append(t)
+    return out, rop
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU eval_poly on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, min(cores, 64))
+    steps, warm = args.steps, args.warmup
+    # ~2 ms per ciphertext-MAC per core; keep the whole run near two minutes
+    per_core = max(16, min(2048, int(120.0 / (steps + warm) / 2.1e-3)))
+    total = per_core * cores
+    ranges = [(k * per_core, per_core, steps + warm) for k in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, ranges)
+    wall = time.perf_counter() - t0
+    ref = ref_lib()
+    # fold the partial sums as the reference would (ct_add), once; its cost is included in the step time below
+    t1 = time.perf_counter()
+    acc = res[0][1]
+    for _, rop in res[1:]:
+        acc = ref.ct_add(acc, rop)
+    fold = time.perf_counter() - t1
+    # a step ends when its slowest worker ends
+    step_times = [max(res[k][0][s] for k in range(cores)) + fold for s in range(warm, warm + steps)]
+    t = sum(step_times)
+    value = total * steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts, n=1470, logq=736 "
+                                   f"(eff. 704); CPU sample {total} ciphertexts per step",
+                       "sample_ciphertexts_per_step": total},
+            "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
+                             "sample": f"{total} ciphertexts per step ({per_core} per core x {cores} processes over disjoint "
+                                       f"ranges via rng_seek, partials folded with ct_add); wall {wall:.1f} s"},
+            "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import c_lwe_snarks_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = m.Context(local)
+    D = 1 << args.log2d
+    steps, warm = args.steps, max(3, args.warmup)
+    st = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic instance, made resident (untimed): expand the rank's ciphertext range from the seed
+    c8, h = synth_inputs(D, rank)
+    stream_off = rank * D * CTR_CT  # rank r owns ciphertext indices [r*D, (r+1)*D) of the global stream
+    d_c8 = torch.from_numpy(c8.reshape(-1)).cuda()
+    d_h = torch.from_numpy(h.astype(np.uint32).view(np.int32)).cuda()
+    d_cts = torch.empty(D * PLANAR_BYTES, dtype=torch.uint8, device="cuda")
+    ctx.expand_dev(SEED, stream_off, d_c8.data_ptr(), D, d_cts.data_ptr(), st)
+    d_rop = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")  # flat, padded to 1472 coordinates
+    d_part = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
+    d_cols = torch.zeros(1472 * 22, dtype=torch.int64, device="cuda")
+    own = 1472 // world
+    d_cols_own = torch.zeros(own * 22, dtype=torch.int64, device="cuda")
+    d_own_flat = torch.zeros(own * L64, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step():
+        if world == 1:
+            ctx.lincomb_dev(d_cts.data_ptr(), d_h.data_ptr(), D, None, d_rop.data_ptr(), st)
+        else:
+            ctx.lincomb_dev(d_cts.data_ptr(), d_h.data_ptr(), D, None, d_part.data_ptr(), st)
+            ctx.columns_split_dev(d_part.data_ptr(), d_cols.data_ptr(), st)
+            dist.reduce_scatter_tensor(d_cols_own, d_cols, op=dist.ReduceOp.SUM)
+            d_own_flat.zero_()
+            ctx.columns_carry_dev(d_cols_own.data_ptr(), rank * own, own, None,
+                                  d_own_flat.data_ptr() - rank * own * L64 * 8, st)
+            dist.all_gather_into_tensor(d_rop, d_own_flat)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launches
+    ctx.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    k_ms, k_n = ctx.profile_end()
+    launches = ctx.launches - l0 + (3 * steps if world > 1 else 0)  # + zero_ / NCCL kernels are not ours: not counted
+    launches = ctx.launches - l0
+    t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms = float(t_all.item())
+    result = d_rop.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64).copy()
+
+    # ---- e2e: host buffers through mfb_eval_poly (fused AES regeneration), every rank its own range
+    e2e_steps = max(2, min(steps, 5))
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    p_c8, p_h = pin(c8.reshape(-1).copy()), pin(h.copy())
+    p_rop = torch.zeros(NC * L64, dtype=torch.int64).pin_memory()
+    np_c8, np_h, np_rop = p_c8.numpy(), p_h.numpy(), p_rop.numpy().view(np.uint64).reshape(NC, L64)
+
+    def e2e_step():
+        np_rop[:] = 0
+        rc = ctx.lib.mfb_eval_poly(ctx.h, m.api._p8(np.frombuffer(SEED, np.uint8).copy()), stream_off, m.api._p8(np_c8),
+                                   m.api._p64(np_h), None, D, m.api._p64(np_rop))
+        ctx._ck(rc)
+
+    e2e_step()
+    fused_result = np_rop.copy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_all = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_all.item())
+    clocks = sampler.stop() if sampler else None
+
+    # ---- sanity outside the timed regions: resident path == fused path (two independent kernels), N=1 only
+    check = None
+    if world == 1:
+        check = bool(np.array_equal(result, fused_result))
+        if not check:
+            raise SystemExit("bench.py: resident lincomb and fused eval_poly disagree — numbers withheld")
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch_ms = k_ms / max(1, k_n)
+        achieved = D * ALGO_BYTES / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "k_lincomb_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            except (ValueError, OSError):
+                traffic = None
+        line = {
+            "metric": METRIC, "value": world * D * steps / (ms * 1e-3), "unit": METRIC, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts per GPU resident in HBM "
+                                   f"({D * PLANAR_BYTES / 1e9:.2f} GB planar), n=1470, logq=736 (eff. 704), p=2^32-5",
+                       "ciphertexts_per_gpu": D, "l2": "inputs (8.49 GB per step) exceed the 126 MB L2; no flush needed",
+                       "exchange": "none" if world == 1 else "u64-column reduce-scatter + carry + all-gather (NCCL)",
+                       "parity_check": check},
+            "roofline": {"bound": "hbm", "kernel": "k_lincomb", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": D * ALGO_BYTES, "kernel_ms": per_launch_ms, "launches_timed": k_n},
+            "e2e": {"value": world * D * e2e_steps / e2e_s, "unit": METRIC,
+                    "h2d_bytes_per_step": D * (CT_BYTES + 4) + NC * 88, "d2h_bytes_per_step": NC * 88,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "path": "mfb_eval_poly (host buffers; a regenerated by AES-256-CTR in-kernel, nothing resident)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2d", type=int, default=16, help="ciphertexts per GPU = 2^log2d (BASELINE configs[1]: 16)")
+    ap.add_argument("--cpu-sample", type=int, default=6000, help="ciphertexts timed by the 1-core cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,8 @@ _SIGS = {
     "mfb_device_sm_count": (C.c_int, [_vp]),
     "mfb_launch_count": (C.c_uint64, [_vp]),
     "mfb_sync": (C.c_int, [_vp]),
+    "mfb_profile_begin": (C.c_int, [_vp]),
+    "mfb_profile_end": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "mfb_stream": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t]),
     "mfb_stream_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp]),
     "mfb_expand_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp, _vp]),
@@ -167,6 +169,15 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.mfb_sync(self.h))
+
+    def profile_begin(self):
+        self._ck(self.lib.mfb_profile_begin(self.h))
+
+    def profile_end(self):
+        """(summed ms of the dominant kernel, number of launches timed) since profile_begin."""
+        ms, n = C.c_double(0), C.c_int(0)
+        self._ck(self.lib.mfb_profile_end(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     # ---------------------------------------------------------------- host flavour
     def stream(self, seed, offset: int, nbytes: int) -> np.ndarray:

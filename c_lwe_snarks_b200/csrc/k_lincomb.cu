@@ -161,16 +161,20 @@ int lincomb_nchunks(size_t d, int sm_count) {
   return (int)(n ? n : 1);
 }
 
-cudaError_t launch_lincomb(const uint64_t *cts, const uint32_t *coeffs, size_t d, const uint64_t *rop_in,
-                           uint64_t *rop_out, uint64_t *partial_ws, int nchunks, cudaStream_t st) {
-  if (d == 0) nchunks = 0;
+typedef void (*mark_fn)(void *, int, cudaStream_t);
+// launches the main kernel only; *nchunks_inout returns the number of partial sums written
+cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
+                                    int *nchunks_inout, cudaStream_t st, mark_fn mark, void *mark_arg) {
+  int nchunks = d ? *nchunks_inout : 0;
   if (nchunks > 0) {
     const size_t chunk_len = (d + nchunks - 1) / nchunks;
     nchunks = (int)((d + chunk_len - 1) / chunk_len);
     dim3 grid(NCP / LC_TILE, nchunks);
+    if (mark) mark(mark_arg, 0, st);
     k_lincomb<2><<<grid, LC_TILE, 0, st>>>(cts, coeffs, d, chunk_len, partial_ws);
+    if (mark) mark(mark_arg, 1, st);
   }
-  k_lincomb_finish<<<(NC + 127) / 128, 128, 0, st>>>(partial_ws, nchunks, rop_in, rop_out);
+  *nchunks_inout = nchunks;
   return cudaGetLastError();
 }
 

@@ -27,8 +27,9 @@ int fail(cudaError_t e, const char *what, const char *file, int line) {
 
 // kernels / launchers (k_*.cu)
 int lincomb_nchunks(size_t d, int sm_count);
-cudaError_t launch_lincomb(const uint64_t *cts, const uint32_t *coeffs, size_t d, const uint64_t *rop_in,
-                           uint64_t *rop_out, uint64_t *partial_ws, int nchunks, cudaStream_t st);
+typedef void (*mark_fn)(void *, int, cudaStream_t);
+cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
+                                    int *nchunks_inout, cudaStream_t st, mark_fn mark, void *mark_arg);
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
@@ -65,7 +66,18 @@ struct mfb_ctx {
   void *slot[NSLOTS] = {};         // growable device scratch for the host flavour
   size_t slot_cap[NSLOTS] = {};
   uint64_t launches = 0;
+  // optional per-kernel timing of the dominant kernel of lincomb / eval_poly calls (bench.py's roofline)
+  bool profiling = false;
+  int prof_n = 0;
+  cudaEvent_t prof_ev[2 * 1024] = {};
 };
+
+static const int PROF_MAX = 1024;
+static void prof_mark(mfb_ctx *ctx, int which, cudaStream_t st) {
+  if (!ctx->profiling || ctx->prof_n >= PROF_MAX) return;
+  cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + which], st);
+  if (which == 1) ctx->prof_n++;
+}
 
 struct mfb_region {
   uint64_t *cts = nullptr;  // planar
@@ -151,6 +163,8 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
     if (ctx->slot[i]) cudaFree(ctx->slot[i]);
   if (ctx->t0_dev) cudaFree(ctx->t0_dev);
   if (ctx->partial_ws) cudaFree(ctx->partial_ws);
+  for (int i = 0; i < 2 * PROF_MAX; i++)
+    if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;
 }
 
@@ -159,6 +173,30 @@ uint64_t mfb_launch_count(mfb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int mfb_sync(mfb_ctx *ctx) {
   MFB_CHECK_CTX(ctx);
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_profile_begin(mfb_ctx *ctx) {
+  MFB_CHECK_CTX(ctx);
+  for (int i = 0; i < 2 * PROF_MAX; i++)
+    if (!ctx->prof_ev[i]) MFB_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[i]));
+  ctx->prof_n = 0;
+  ctx->profiling = true;
+  return MFB_OK;
+}
+
+int mfb_profile_end(mfb_ctx *ctx, double *sum_ms, int *count) {
+  MFB_CHECK_CTX(ctx);
+  ctx->profiling = false;
+  double sum = 0;
+  for (int i = 0; i < ctx->prof_n; i++) {
+    MFB_CUDA_TRY(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+    float ms = 0;
+    MFB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    sum += ms;
+  }
+  if (sum_ms) *sum_ms = sum;
+  if (count) *count = ctx->prof_n;
   return MFB_OK;
 }
 
@@ -192,8 +230,9 @@ int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeff
   if (!rop_out_dev || (d && (!cts_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_lincomb_dev: null pointer");
   int nchunks = lincomb_nchunks(d, ctx->sm_count);
   if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
-  MFB_CUDA_TRY(launch_lincomb(cts_dev, coeffs_dev, d, rop_in_dev, rop_out_dev, ctx->partial_ws, nchunks,
-                              (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, d, ctx->partial_ws, &nchunks, (cudaStream_t)stream,
+                                       [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }
@@ -225,8 +264,10 @@ int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   aes_host::expand(seed, &key);
   int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
   if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
+  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
   MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
                                         ctx->partial_ws, (cudaStream_t)stream));
+  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
   MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;

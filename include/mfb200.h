@@ -70,6 +70,11 @@ MFB_API int mfb_device_sm_count(mfb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 MFB_API uint64_t mfb_launch_count(mfb_ctx *ctx);
 MFB_API int mfb_sync(mfb_ctx *ctx);
+/* Per-kernel timing for the roofline: between begin and end every lincomb / eval_poly call brackets its
+ * dominant kernel (k_lincomb / k_evalpoly) with CUDA events on the launching stream; end waits for them and
+ * returns the summed duration and the number of launches timed (at most 1024). */
+MFB_API int mfb_profile_begin(mfb_ctx *ctx);
+MFB_API int mfb_profile_end(mfb_ctx *ctx, double *sum_ms, int *count);
 
 /* ---- K2: AES-256-CTR stream -------------------------------------------------------------- */
 /* out[0..nbytes) = stream bytes [offset, offset+nbytes) of `seed`.
