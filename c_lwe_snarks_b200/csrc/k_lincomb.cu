@@ -75,24 +75,19 @@ __global__ void __launch_bounds__(LC_TILE) k_lincomb(const uint64_t *__restrict_
 }
 
 // rop[c] = (rop_in[c] + sum_k partial[k][c]) mod 2^704.  rop is "flat": [1471][11] u64, coordinate-major.
-// One thread per coordinate; nparts is a few hundred at most.
-__global__ void k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts,
-                                 const uint64_t *rop_in, uint64_t *rop_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= NC) return;
+// CTA = 64 coordinates x FIN_SLICES slices of the partial index: each thread adds every FIN_SLICES-th partial
+// (loads of successive partials are independent, so several are in flight), the slices meet in shared memory.
+constexpr int FIN_SLICES = 8;
+__global__ void __launch_bounds__(64 * FIN_SLICES)
+k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out) {
+  __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
+  const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
   uint32_t r[22];
-  if (rop_in) {
 #pragma unroll
-    for (int j = 0; j < L64; j++) {
-      const uint64_t v = rop_in[(size_t)c * L64 + j];
-      r[2 * j] = (uint32_t)v;
-      r[2 * j + 1] = (uint32_t)(v >> 32);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 22; j++) r[j] = 0;
-  }
-  for (int k = 0; k < nparts; k++) {
+  for (int j = 0; j < 22; j++) r[j] = 0;
+#pragma unroll 2
+  for (int k = slice; k < nparts; k += FIN_SLICES) {
     uint32_t b[22];
 #pragma unroll
     for (int j = 0; j < L64; j++) {
@@ -102,8 +97,31 @@ __global__ void k_lincomb_finish(const uint64_t *__restrict__ partial, int npart
     }
     add704(r, b);
   }
+  if (slice > 0) {
 #pragma unroll
-  for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+    for (int j = 0; j < 22; j++) sm[slice - 1][j][cl] = r[j];
+  }
+  __syncthreads();
+  if (slice == 0 && c < NC) {
+    for (int s2 = 0; s2 < FIN_SLICES - 1; s2++) {
+      uint32_t b[22];
+#pragma unroll
+      for (int j = 0; j < 22; j++) b[j] = sm[s2][j][cl];
+      add704(r, b);
+    }
+    if (rop_in) {
+      uint32_t b[22];
+#pragma unroll
+      for (int j = 0; j < L64; j++) {
+        const uint64_t v = rop_in[(size_t)c * L64 + j];
+        b[2 * j] = (uint32_t)v;
+        b[2 * j + 1] = (uint32_t)(v >> 32);
+      }
+      add704(r, b);
+    }
+#pragma unroll
+    for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+  }
 }
 
 // --- multi-GPU exchange helpers --------------------------------------------------
@@ -180,7 +198,7 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs,
 
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   cudaStream_t st) {
-  k_lincomb_finish<<<(NC + 127) / 128, 128, 0, st>>>(partial_ws, nparts, rop_in, rop_out);
+  k_lincomb_finish<<<NCP / 64, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,112 @@
+/* Device context, instance size, entropy source and mpz <-> limb conversions for the drop-in layer. */
+#include "mf_internal.h"
+
+#include <pthread.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------ instance size (lwe.h:14-21 made run-time) */
+static size_t g_d = 0, g_m = 0;       /* explicit (mf_set_instance) */
+static size_t g_def_d = 0, g_def_m = 0; /* first compile-time default registered by a caller */
+
+void mf_set_instance(size_t D, size_t M) {
+  g_d = D;
+  g_m = M;
+}
+size_t mf_gamma_d(size_t def) {
+  if (g_d) return g_d;
+  if (!g_def_d) g_def_d = def;
+  return g_def_d;
+}
+size_t mf_gamma_m(size_t def) {
+  if (g_m) return g_m;
+  if (!g_def_m) g_def_m = def;
+  return g_def_m;
+}
+
+/* ------------------------------------------------------------------ entropy */
+static mf_entropy_fn g_ent_fn = NULL;
+static void *g_ent_arg = NULL;
+
+void mf_set_entropy_source(mf_entropy_fn fn, void *arg) {
+  g_ent_fn = fn;
+  g_ent_arg = arg;
+}
+
+void mf_entropy(void *buf, size_t len) {
+  if (g_ent_fn) {
+    g_ent_fn(buf, len, g_ent_arg);
+    return;
+  }
+  uint8_t *p = buf;
+  while (len) { /* getrandom(2) hands out at most 32 MiB - 1 per call and may be interrupted */
+    long r = syscall(SYS_getrandom, p, len, 0);
+    if (r <= 0) mf_die("getrandom(2)");
+    p += r;
+    len -= (size_t)r;
+  }
+}
+
+/* ------------------------------------------------------------------ device context */
+static mfb_ctx *g_ctx = NULL;
+static int g_device = -1;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+void mf_die(const char *what) {
+  fprintf(stderr, "mangiafuoco_b200: %s failed: %s\n", what, mfb_last_error());
+  abort();
+}
+
+void mf_set_device(int device) { g_device = device; }
+
+mfb_ctx *mf_gpu(void) {
+  if (g_ctx) return g_ctx;
+  pthread_mutex_lock(&g_lock);
+  if (!g_ctx) {
+    int dev = g_device;
+    if (dev < 0) {
+      const char *e = getenv("MF_B200_DEVICE");
+      dev = e ? atoi(e) : 0;
+    }
+    mfb_ctx *c = NULL;
+    if (mfb_ctx_create(&c, dev) != MFB_OK) mf_die("mfb_ctx_create (no CPU fallback exists)");
+    g_ctx = c;
+  }
+  pthread_mutex_unlock(&g_lock);
+  return g_ctx;
+}
+
+uint64_t mf_gpu_launches(void) { return g_ctx ? mfb_launch_count(g_ctx) : 0; }
+
+/* ------------------------------------------------------------------ conversions */
+int mf_to_flat(uint64_t out[MF_LIMBS], mpz_srcptr z) {
+  const int n = abs(SIZ(z));
+  for (int i = 0; i < MF_LIMBS; i++) out[i] = i < n ? PTR(z)[i] : 0;
+  return SIZ(z) < 0;
+}
+
+void mf_from_flat(mpz_ptr z, const uint64_t in[MF_LIMBS]) { mpz_import(z, MF_LIMBS, -1, sizeof(uint64_t), 0, 0, in); }
+
+void mf_ct_to_flat(uint64_t *out, ct_t ct, const char *who) {
+  for (size_t i = 0; i <= GAMMA_N; i++)
+    if (mf_to_flat(out + i * MF_LIMBS, ct[i])) {
+      fprintf(stderr, "mangiafuoco_b200: %s: coordinate %zu is negative (the reference asserts SIZ >= 0 here)\n", who, i);
+      abort();
+    }
+}
+
+void mf_ct_from_flat(ct_t ct, const uint64_t *in) {
+  for (size_t i = 0; i <= GAMMA_N; i++) mf_from_flat(ct[i], in + i * MF_LIMBS);
+}
+
+void mf_bytes_to_mpz(mpz_ptr z, const uint8_t *bytes, size_t n) { mpz_import(z, n, -1, 1, -1, 0, bytes); }
+
+/* lwe.h:108-118: SIZ > 11 -> keep limbs 0..10 (limb 11 is masked and then dropped), normalise */
+void modq(mpz_t a) {
+  const int pos = GAMMA_LOGQ / 64;
+  if (SIZ(a) > pos) {
+    int n = pos;
+    while (n > 0 && PTR(a)[n - 1] == 0) n--;
+    SIZ(a) = n;
+  }
+}

@@ -1,0 +1,293 @@
+/* snark.h of the reference: setup / prover / verifier orchestration over the GPU kernels.
+ *
+ * The protocol steps, their order, the stream regions (snark.h:8-12) and the order of entropy draws are the
+ * reference's; what changes is that each loop over ciphertexts is ONE batched device call:
+ *   setup     2D + M Regev encryptions            -> one mfb_encrypt   (snark.c:75-110)
+ *   prover    b_w = delta*CT_t + sum_{w_i} CT_v_i -> one mfb_eval_poly with an index list (snark.c:143-155)
+ *             v_w, hat_v, h, hat_h                 -> four mfb_eval_poly, or resident lincombs after
+ *                                                    mf_crs_make_resident (snark.c:157-174)
+ *   verifier  5 decryptions + the test-error dot  -> one mfb_decrypt   (snark.c:204-208, 238)
+ * Polynomial arithmetic over F_p (FLINT in the reference) stays on the host.
+ */
+#include "mf_internal.h"
+
+#define FLAT_CT (MFB_FLAT_CT_U64)
+
+void proof_init(proof_t pi) {
+  ct_init(pi->h);
+  ct_init(pi->hat_h);
+  ct_init(pi->hat_v);
+  ct_init(pi->v_w);
+  ct_init(pi->b_w);
+}
+
+void proof_clear(proof_t pi) {
+  ct_clear(pi->h);
+  ct_clear(pi->hat_h);
+  ct_clear(pi->hat_v);
+  ct_clear(pi->v_w);
+  ct_clear(pi->b_w);
+}
+
+/* ------------------------------------------------------------------ resident CRS regions (addition) */
+struct resident {
+  struct crs *owner;
+  mfb_region *s, *as;
+  size_t d;
+  struct resident *next;
+};
+static struct resident *g_resident = NULL;
+
+static struct resident *resident_find(struct crs *crs) {
+  for (struct resident *r = g_resident; r; r = r->next)
+    if (r->owner == crs) return r;
+  return NULL;
+}
+
+void mf_crs_release(crs_t crs) {
+  struct resident **pp = &g_resident;
+  while (*pp) {
+    struct resident *r = *pp;
+    if (r->owner == crs) {
+      mfb_region_destroy(mf_gpu(), r->s);
+      mfb_region_destroy(mf_gpu(), r->as);
+      *pp = r->next;
+      free(r);
+    } else {
+      pp = &r->next;
+    }
+  }
+}
+
+void mf_crs_make_resident(crs_t crs) {
+  mf_crs_release(crs);
+  struct resident *r = calloc(1, sizeof(*r));
+  if (!r) mf_die("malloc");
+  r->owner = crs;
+  r->d = GAMMA_D;
+  MF_GPU(mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s));
+  MF_GPU(mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as));
+  r->next = g_resident;
+  g_resident = r;
+}
+
+void crs_init(crs_t crs) { /* snark.c:35-48 */
+  mf_entropy(crs->seed, sizeof(rseed_t));
+  crs->s = malloc(CT_BYTES * GAMMA_D);
+  crs->as = malloc(CT_BYTES * GAMMA_D);
+  crs->v = malloc(CT_BYTES * GAMMA_M);
+  crs->t = malloc(CT_BYTES);
+  if (!crs->s || !crs->as || !crs->v || !crs->t) perror("Error allocating memory");
+}
+
+void crs_clear(crs_t crs) {
+  mf_crs_release(crs);
+  free(crs->s);
+  free(crs->as);
+  free(crs->v);
+  free(crs->t);
+}
+
+/* ------------------------------------------------------------------ setup (snark.c:57-115) */
+void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
+  const size_t D = GAMMA_D, M = GAMMA_M, count = 2 * D + M;
+  vrs->alpha = rand_modp();
+  vrs->beta = rand_modp();
+  vrs->s = rand_modp();
+  key_gen(vrs->sk);
+
+  /* plaintexts in stream order (snark.h:8-12): s^i, alpha*s^i, beta*t(s), beta*v_i(s) for i = 1..M-1 */
+  uint64_t *msg = malloc(count * 8);
+  if (!msg) mf_die("malloc");
+  uint64_t x = 1;
+  for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[i] = x;
+  x = vrs->alpha;
+  for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[D + i] = x;
+  nmod_poly_t v_i;
+  nmod_poly_init(v_i, GAMMA_P);
+  nmod_poly_import(&v_i, &ssp[ssp_t_offset], D);
+  msg[2 * D] = (nmod_poly_evaluate_nmod(v_i, vrs->s) * vrs->beta) % GAMMA_P;
+  for (size_t i = 1; i < M; i++) {
+    nmod_poly_import(&v_i, &ssp[ssp_v_offset(i)], D);
+    msg[2 * D + i] = (nmod_poly_evaluate_nmod(v_i, vrs->s) * vrs->beta) % GAMMA_P;
+  }
+  nmod_poly_clear(v_i);
+
+  /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order */
+  uint8_t *ent = malloc(count * MFB_ENT_BYTES), *recs = malloc(count * CT_BYTES);
+  uint64_t *skf = malloc(MFB_FLAT_SK_U64 * 8);
+  if (!ent || !recs || !skf) mf_die("malloc");
+  mf_entropy(ent, count * MFB_ENT_BYTES);
+  for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
+  MF_GPU(mfb_encrypt(mf_gpu(), crs->seed, 0, skf, msg, ent, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+  memcpy(crs->s, recs, D * CT_BYTES);
+  memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);
+  memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
+  memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
+  memset(ent, 0, count * MFB_ENT_BYTES);
+  free(ent);
+  free(recs);
+  free(skf);
+  free(msg);
+}
+
+/* ------------------------------------------------------------------ prover (snark.c:117-190) */
+static void lincomb_region(ct_t rop, crs_t crs, int which_as, nmod_poly_t poly) {
+  const size_t D = GAMMA_D;
+  uint64_t *acc = malloc(FLAT_CT * 8);
+  if (!acc) mf_die("malloc");
+  mf_ct_to_flat(acc, rop, "prover"); /* eval_poly adds into rop (0 after proof_init) */
+  struct resident *r = resident_find(crs);
+  if (r && r->d == D) {
+    uint32_t *co = malloc(D * 4);
+    if (!co) mf_die("malloc");
+    for (size_t i = 0; i < D; i++) co[i] = (uint32_t)nmod_poly_get_coeff_ui(poly, (slong)i);
+    MF_GPU(mfb_region_lincomb(mf_gpu(), which_as ? r->as : r->s, 0, co, D, acc));
+    free(co);
+  } else {
+    uint64_t *co = malloc(D * 8);
+    if (!co) mf_die("malloc");
+    for (size_t i = 0; i < D; i++) co[i] = nmod_poly_get_coeff_ui(poly, (slong)i);
+    MF_GPU(mfb_eval_poly(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S,
+                         (const uint8_t *)(which_as ? crs->as : crs->s), co, NULL, D, acc));
+    free(co);
+  }
+  mf_ct_from_flat(rop, acc);
+  free(acc);
+}
+
+void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
+  const size_t D = GAMMA_D, M = GAMMA_M;
+  nmod_poly_t t, v_i, w, h, one;
+  nmod_poly_init(t, GAMMA_P);
+  nmod_poly_init(v_i, GAMMA_P);
+  nmod_poly_init(w, GAMMA_P);
+  nmod_poly_init(h, GAMMA_P);
+  nmod_poly_init(one, GAMMA_P);
+  nmod_poly_set_coeff_ui(one, 0, 1);
+
+  nmod_poly_import(&t, &ssp[ssp_t_offset], D);
+  const uint64_t delta = rand_modp();
+  nmod_poly_scalar_mul_nmod(w, t, delta);
+
+  /* b_w = delta * CT_t + sum_{witness bit i-1} CT_v[i-1]: ciphertext k of the region at CTR_BT is t for k = 0
+   * and v[k-1] after it.  The reference regenerates every a-vector to advance its stream; only the selected
+   * ones contribute, so only those are expanded here. */
+  uint8_t *recs = malloc(M * CT_BYTES);
+  uint64_t *co = malloc(M * 8);
+  uint32_t *idx = malloc(M * 4);
+  if (!recs || !co || !idx) mf_die("malloc");
+  memcpy(recs, crs->t, CT_BYTES);
+  memcpy(recs + CT_BYTES, crs->v, (M - 1) * CT_BYTES);
+  size_t nsel = 0;
+  co[nsel] = delta;
+  idx[nsel++] = 0;
+  for (size_t i = 1; i < M; i++) {
+    if (mpz_tstbit(witness, i - 1)) {
+      nmod_poly_import(&v_i, &ssp[ssp_v_offset(i)], D);
+      nmod_poly_add(w, w, v_i);
+      co[nsel] = 1;
+      idx[nsel++] = (uint32_t)i;
+    }
+  }
+  {
+    uint64_t *acc = calloc(FLAT_CT, 8); /* ct_import overwrites pi->b_w: start from zero */
+    if (!acc) mf_die("malloc");
+    MF_GPU(mfb_eval_poly(mf_gpu(), crs->seed, CTR_BT, recs, co, idx, nsel, acc));
+    mf_ct_from_flat(pi->b_w, acc);
+    free(acc);
+  }
+  free(recs);
+  free(co);
+  free(idx);
+
+  lincomb_region(pi->v_w, crs, 0, w);
+
+  /* l_u = 0: v(x) = v_0(x) + w(x) */
+  nmod_poly_import(&v_i, &ssp[ssp_v_offset(0)], D);
+  nmod_poly_add(w, w, v_i);
+  lincomb_region(pi->hat_v, crs, 1, w);
+
+  /* h = (v^2 - 1) / t */
+  nmod_poly_set(h, w);
+  nmod_poly_pow(h, h, 2);
+  nmod_poly_sub(h, h, one);
+  nmod_poly_div(h, h, t);
+
+  lincomb_region(pi->h, crs, 0, h);
+  lincomb_region(pi->hat_h, crs, 1, h);
+
+  nmod_poly_clear(h);
+  nmod_poly_clear(v_i);
+  nmod_poly_clear(w);
+  nmod_poly_clear(one);
+  nmod_poly_clear(t);
+
+  /* smudging, in the reference's order: v_w twice, b_w never (snark.c:185-189) */
+  ct_smudge(pi->h);
+  ct_smudge(pi->hat_h);
+  ct_smudge(pi->hat_v);
+  ct_smudge(pi->v_w);
+  ct_smudge(pi->v_w);
+}
+
+/* ------------------------------------------------------------------ verifier (snark.c:192-250) */
+bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi) {
+  const size_t D = GAMMA_D;
+  const uint64_t p = GAMMA_P;
+  nmod_poly_t pp;
+  nmod_poly_init(pp, GAMMA_P);
+  nmod_poly_import(&pp, &ssp[ssp_t_offset], D);
+  const uint64_t t_s = nmod_poly_evaluate_nmod(pp, vrs->s);
+  nmod_poly_import(&pp, &ssp[ssp_v_offset(0)], D);
+  const uint64_t v0_s = nmod_poly_evaluate_nmod(pp, vrs->s);
+  nmod_poly_clear(pp);
+
+  /* one batch: decrypt h, hat_h, hat_v, v_w, b_w; the dot product of b_w is also the test-error input */
+  mpz_t *elems[5] = {pi->h, pi->hat_h, pi->hat_v, pi->v_w, pi->b_w};
+  uint64_t *cts = malloc(5 * FLAT_CT * 8), *skf = malloc(MFB_FLAT_SK_U64 * 8);
+  if (!cts || !skf) mf_die("malloc");
+  uint8_t neg[5];
+  for (int k = 0; k < 5; k++) {
+    for (size_t i = 0; i < GAMMA_N; i++)
+      if (mf_to_flat(cts + k * FLAT_CT + i * MF_LIMBS, elems[k][i])) {
+        fprintf(stderr, "mangiafuoco_b200: verifier: negative a coordinate in proof element %d\n", k);
+        abort();
+      }
+    neg[k] = (uint8_t)mf_to_flat(cts + k * FLAT_CT + (size_t)GAMMA_N * MF_LIMBS, elems[k][GAMMA_N]);
+  }
+  for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
+  uint64_t dec[5], dots[5 * MF_LIMBS];
+  MF_GPU(mfb_decrypt(mf_gpu(), skf, cts, neg, 5, dec, dots));
+  free(cts);
+  free(skf);
+  const uint64_t h_s = dec[0], hath_s = dec[1], hatv_s = dec[2], w_s = dec[3], b_s = dec[4];
+  const uint64_t v_s = (v0_s + w_s) % p;
+
+  bool result = false;
+  /* eq-pke */
+  if ((unsigned __int128)h_s * vrs->alpha % p != hath_s) goto end;
+  if ((unsigned __int128)v_s * vrs->alpha % p != hatv_s) goto end;
+  /* eq-div: v_s^2 - 1 - h_s*t_s == 0 mod p */
+  {
+    const uint64_t lhs = (uint64_t)((unsigned __int128)v_s * v_s % p);
+    const uint64_t rhs = (uint64_t)(((unsigned __int128)h_s * t_s + 1) % p);
+    if (lhs != rhs) goto end;
+  }
+  /* eq-lin */
+  if ((unsigned __int128)w_s * vrs->beta % p != b_s) goto end;
+  /* test-error (snark.c:237-241): -<b_w, sk> ceil-divided by p; the size comparison is the reference's */
+  {
+    mpz_t test;
+    mpz_init(test);
+    mf_from_flat(test, dots + 4 * MF_LIMBS);
+    mpz_neg(test, test);
+    mpz_cdiv_q_ui(test, test, GAMMA_P);
+    const bool too_big = SIZ(test) >= GAMMA_LOG_SMUDGING / 8;
+    mpz_clear(test);
+    if (too_big) goto end;
+  }
+  result = true;
+end:
+  return result;
+}

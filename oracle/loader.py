@@ -82,6 +82,16 @@ def build_reference(D: int = 256, M: int = 64, ref_src: str = "/root/reference/s
     return out
 
 
+def build_dropin() -> Path:
+    """Compile ref_shim.c against the PRODUCT's drop-in headers/library (oracle/_dropin/libmfdropin.so)."""
+    out = HERE / "_dropin" / "libmfdropin.so"
+    lib = HERE.parent / "c_lwe_snarks_b200" / "lib" / "libmangiafuoco_b200.so"
+    newest = max(p.stat().st_mtime for p in [HERE / "ref_shim.c", HERE / "Makefile", lib] if p.exists())
+    if not out.exists() or out.stat().st_mtime < newest:
+        subprocess.run(["make", "-s", "-C", str(HERE), "dropin"], check=True)
+    return out
+
+
 class Oracle:
     """Our CPU restatement.  Stateless; entropy is passed explicitly per call."""
 
@@ -210,11 +220,18 @@ class Reference:
         if path is None or not Path(path).exists():
             raise FileNotFoundError(f"reference build for D={D}, M={M} not available")
         self.lib = L = C.CDLL(str(path))
+        self._bind(D, M)
+
+    def _bind(self, D: int, M: int):
+        L = self.lib
         self._entropy = None
         L.ref_param.argtypes = [C.c_char_p]
         L.ref_param.restype = C.c_uint64
+        if hasattr(L, "ref_set_instance"):
+            L.ref_set_instance.argtypes = [C.c_size_t, C.c_size_t]
+            L.ref_set_instance(D, M)
         self.D, self.M = int(L.ref_param(b"D")), int(L.ref_param(b"M"))
-        assert (self.D, self.M) == (D, M) or path is not None
+        assert (self.D, self.M) == (D, M), "instance size of the loaded library differs from the request"
         L.ref_set_entropy.argtypes = [_u8p, C.c_size_t]
         L.ref_entropy_consumed.restype = C.c_size_t
         L.ref_entropy_calls.restype = C.c_uint64
@@ -398,3 +415,35 @@ class Reference:
         secs = (C.c_double * 3)()
         ok = self.lib.ref_benchmark_snark(secs)
         return float(secs[0]), float(secs[1]), float(secs[2]), bool(ok)
+
+
+class DropIn(Reference):
+    """The PRODUCT behind the reference's own C interface: ref_shim.c compiled against include/mangiafuoco and
+    linked with libmangiafuoco_b200.so (GPU kernels).  Same methods and formats as :class:`Reference`, so a
+    parity test is `DropIn(...).f(x) == Reference(...).f(x)`.  The instance size is a run-time value here."""
+
+    kind = "dropin"
+
+    def __init__(self, D: int = 256, M: int = 64):
+        path = build_dropin()
+        self.lib = C.CDLL(str(path))
+        self._bind(D, M)
+        self.lib.ref_gpu_launches.restype = C.c_uint64
+        if hasattr(self.lib, "ref_prover_resident"):
+            self.lib.ref_prover_resident.argtypes = self.lib.ref_prover.argtypes
+
+    def set_instance(self, D: int, M: int):
+        self.lib.ref_set_instance(D, M)
+        self.D, self.M = D, M
+
+    def gpu_launches(self) -> int:
+        return int(self.lib.ref_gpu_launches())
+
+    def prover_resident(self, ssp, crs: dict, witness_limbs):
+        """prover() after mf_crs_make_resident(): the s / as regions are expanded into HBM first."""
+        s, wl = _u8(ssp), _u64(witness_limbs)
+        proof = np.zeros((5, NC, LIMBS), np.uint64)
+        siz = np.zeros((5, NC), np.int32)
+        self.lib.ref_prover_resident(_p8(s), _p8(_u8(crs["seed"])), _p8(_u8(crs["s"])), _p8(_u8(crs["as_"])),
+                                     _p8(_u8(crs["v"])), _p8(_u8(crs["t"])), _p64(wl), wl.size, _p64(proof), _p32(siz))
+        return proof, siz

@@ -44,11 +44,22 @@ static const uint8_t *g_ent = NULL;
 static size_t g_ent_len = 0, g_ent_pos = 0;
 static uint64_t g_ent_calls = 0;
 
+#ifdef MFB200_DROPIN
+/* The same shim over the PRODUCT's drop-in library (libmangiafuoco_b200.so): entropy goes through the
+ * library's own hook instead of a compile-time getrandom interposer, the instance size is a run-time value. */
+static void dropin_entropy(void *buf, size_t len, void *arg);
+void ref_set_instance(size_t D, size_t M) { mf_set_instance(D, M); }
+uint64_t ref_gpu_launches(void) { return mf_gpu_launches(); }
+#endif
+
 void ref_set_entropy(const uint8_t *buf, size_t len) {
   g_ent = buf;
   g_ent_len = len;
   g_ent_pos = 0;
   g_ent_calls = 0;
+#ifdef MFB200_DROPIN
+  mf_set_entropy_source(buf ? dropin_entropy : NULL, NULL);
+#endif
 }
 size_t ref_entropy_consumed(void) { return g_ent_pos; }
 uint64_t ref_entropy_calls(void) { return g_ent_calls; }
@@ -65,6 +76,13 @@ ssize_t ref_getrandom(void *buf, size_t len, unsigned int flags) {
   g_ent_pos += len;
   return (ssize_t)len;
 }
+
+#ifdef MFB200_DROPIN
+static void dropin_entropy(void *buf, size_t len, void *arg) {
+  (void)arg;
+  ref_getrandom(buf, len, 0);
+}
+#endif
 
 /* ------------------------------------------------------------------ zeroing allocator */
 
@@ -84,7 +102,11 @@ static void z_free(void *p, size_t n) {
   free(p);
 }
 __attribute__((constructor)) static void ref_shim_init(void) {
+#ifndef MFB200_DROPIN
   mp_set_memory_functions(z_alloc, z_realloc, z_free);
+#else
+  (void)z_alloc; (void)z_realloc; (void)z_free;
+#endif
 }
 
 /* ------------------------------------------------------------------ parameters */
@@ -443,6 +465,33 @@ void ref_prover(const uint8_t *ssp, const uint8_t seed[40], const uint8_t *crs_s
   proof_clear(pi);
   mpz_clear(w);
 }
+
+#ifdef MFB200_DROPIN
+/* product-only: the same prover call with the two big CRS regions made resident in HBM first */
+void ref_prover_resident(const uint8_t *ssp, const uint8_t seed[40], const uint8_t *crs_s,
+                         const uint8_t *crs_as, const uint8_t *crs_v, const uint8_t *crs_tb,
+                         const uint64_t *witness_limbs, size_t witness_nlimbs, uint64_t *proof_flat,
+                         int32_t *siz) {
+  crs_t crs;
+  proof_t pi;
+  mpz_t w;
+  mpz_init(w);
+  mpz_from_limbs(w, witness_limbs, (int)witness_nlimbs);
+  crs_from_wire(crs, seed, crs_s, crs_as, crs_v, crs_tb);
+  mf_crs_make_resident(crs);
+  proof_init(pi);
+  prover(pi, crs, (ssp_t)ssp, w);
+  mf_crs_release(crs);
+  const size_t stride = REF_NC * REF_LIMBS;
+  ct_to_flat(proof_flat + 0 * stride, siz ? siz + 0 * REF_NC : NULL, pi->h);
+  ct_to_flat(proof_flat + 1 * stride, siz ? siz + 1 * REF_NC : NULL, pi->hat_h);
+  ct_to_flat(proof_flat + 2 * stride, siz ? siz + 2 * REF_NC : NULL, pi->hat_v);
+  ct_to_flat(proof_flat + 3 * stride, siz ? siz + 3 * REF_NC : NULL, pi->v_w);
+  ct_to_flat(proof_flat + 4 * stride, siz ? siz + 4 * REF_NC : NULL, pi->b_w);
+  proof_clear(pi);
+  mpz_clear(w);
+}
+#endif
 
 /* snark.c:192-250 */
 int ref_verifier(const uint8_t *ssp, const uint64_t abs_in[3], const uint64_t *sk_flat,

@@ -1,0 +1,161 @@
+"""The product behind the reference's OWN C interface (include/mangiafuoco, libmangiafuoco_b200.so).
+
+Three kinds of evidence, all on the GPU:
+  1. the full SNARK (random_ssp -> crs_init -> setup -> prover -> verifier) under injected entropy reproduces the
+     golden vectors that the compiled reference emitted (tests/golden/make_golden.py): CRS, proof and accept bit;
+  2. the same run beside the compiled reference itself (oracle/_ref/libmfref_*.so on the host CPU), larger instance;
+  3. the reference's five test programs, UNMODIFIED, compiled against the drop-in headers and linked with the
+     product (oracle/Makefile `dropin-tests`), exit 0.
+"""
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import SEED, sha, xof, xof_records, xof_scalars
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = json.loads((Path(__file__).parent / "golden" / "vectors.json").read_text())
+N, CT_BYTES, CTR_CT, P = 1470, 92, 92 * 1470, 0xFFFFFFFB
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    from oracle.loader import DropIn
+    return DropIn(64, 16)
+
+
+def hexs(a) -> str:
+    return np.ascontiguousarray(a).tobytes().hex()
+
+
+def snark_entropy_len(D, M):
+    return (M // 8 + M * 8 * D) + 40 + 24 + N * CT_BYTES + (2 * D + M) * 70 + 8 + 5 * 81
+
+
+def run_snark(lib, D, M, ent):
+    lib.set_entropy(ent)
+    ssp, wit = lib.random_ssp()
+    crs = lib.setup(ssp)
+    proof, siz = lib.prover(ssp, crs, wit)
+    used = lib.entropy_consumed()
+    ok = lib.verifier(ssp, crs, proof)
+    bad = proof.copy()
+    bad[0, N, 0] ^= np.uint64(1 << 40)
+    ok_bad = lib.verifier(ssp, crs, bad)
+    lib.clear_entropy()
+    return dict(ssp=ssp, wit=wit, crs=crs, proof=proof, siz=siz, used=used, ok=ok, ok_bad=ok_bad)
+
+
+def test_full_snark_golden(dropin):
+    g = GOLD["snark_d64_m16"]
+    D, M = g["D"], g["M"]
+    dropin.set_instance(D, M)
+    ent = xof("snark-entropy-d64-m16", g["entropy_bytes"])
+    launches0 = dropin.gpu_launches()
+    r = run_snark(dropin, D, M, ent)
+    assert r["used"] == g["entropy_bytes"], "entropy draws differ from the reference's sequence"
+    assert sha(r["ssp"]) == g["ssp_sha"] and hexs(r["wit"]) == g["witness"]
+    crs = r["crs"]
+    assert hexs(crs["seed"]) == g["seed"]
+    assert (crs["alpha"], crs["beta"], crs["s_point"]) == (g["alpha"], g["beta"], g["s_point"])
+    assert sha(crs["sk"]) == g["sk_sha"]
+    assert hexs(crs["s"][0]) == g["crs_s0"]
+    assert sha(crs["s"]) == g["crs_s_sha"] and sha(crs["as_"]) == g["crs_as_sha"]
+    assert sha(crs["v"][: M - 1]) == g["crs_v_sha"] and hexs(crs["t"]) == g["crs_t"]
+    for k in range(5):
+        assert hexs(r["proof"][k][N]) == g["proof_b"][k], f"proof element {k}: b differs"
+        assert sha(r["proof"][k]) == g["proof_sha"][k], f"proof element {k} differs"
+        assert bool(r["siz"][k][N] < 0) == g["proof_negative"][k]
+    assert r["ok"] == g["accept"] and r["ok_bad"] == g["accept_tampered"]
+    assert r["ok"] and not r["ok_bad"]
+    assert dropin.gpu_launches() > launches0, "no GPU kernel ran: the drop-in must not compute on the CPU"
+
+
+def test_prover_with_resident_crs_is_identical(dropin):
+    g = GOLD["snark_d64_m16"]
+    D, M = g["D"], g["M"]
+    dropin.set_instance(D, M)
+    ent = xof("snark-entropy-d64-m16", g["entropy_bytes"])
+    dropin.set_entropy(ent)
+    ssp, wit = dropin.random_ssp()
+    crs = dropin.setup(ssp)
+    proof, _ = dropin.prover_resident(ssp, crs, wit)
+    dropin.clear_entropy()
+    for k in range(5):
+        assert sha(proof[k]) == g["proof_sha"][k]
+
+
+def test_full_snark_beside_compiled_reference(dropin, reference):
+    D, M = reference.D, reference.M  # 256, 64
+    dropin.set_instance(D, M)
+    ent = xof("snark-entropy-d256-m64", snark_entropy_len(D, M))
+    a = run_snark(dropin, D, M, ent)
+    b = run_snark(reference, D, M, ent)
+    assert a["used"] == b["used"] == ent.size
+    assert np.array_equal(a["ssp"], b["ssp"]) and np.array_equal(a["wit"], b["wit"])
+    for key in ("seed", "s", "as_", "t", "sk"):
+        assert np.array_equal(a["crs"][key], b["crs"][key]), key
+    assert np.array_equal(a["crs"]["v"][: M - 1], b["crs"]["v"][: M - 1])
+    assert (a["crs"]["alpha"], a["crs"]["beta"], a["crs"]["s_point"]) == (b["crs"]["alpha"], b["crs"]["beta"], b["crs"]["s_point"])
+    assert np.array_equal(a["proof"], b["proof"]) and np.array_equal(a["siz"] < 0, b["siz"] < 0)
+    assert a["ok"] and b["ok"] and not a["ok_bad"] and not b["ok_bad"]
+    # cross-verification: each side accepts the other's proof
+    assert reference.verifier(b["ssp"], b["crs"], a["proof"]) and dropin.verifier(a["ssp"], a["crs"], b["proof"])
+
+
+def test_lwe_api_beside_compiled_reference(dropin, reference):
+    """ct_import / eval_poly / ct_mul_ui / ct_add / ct_addmul_ui / encrypt / decrypt / dotp / smudge / urandomb / modq."""
+    dropin.set_instance(256, 64)
+    d, off = 40, 3 * CTR_CT + 8
+    c8, h = xof_records("api-c8", d), xof_scalars("api-h", d)
+    for lib in (dropin, reference):
+        lib.clear_entropy()
+    assert np.array_equal(dropin.stream(SEED, 11, 1000), reference.stream(SEED, 11, 1000))
+    assert np.array_equal(dropin.stream(SEED, 0, 5000, chunk=92), reference.stream(SEED, 0, 5000, chunk=92))
+    for nbits in (64, 1, 5, 32, 40, 520, 512, 700, 736, 751):
+        assert dropin.urandomb(SEED, 11, nbits)[1] == reference.urandomb(SEED, 11, nbits)[1]
+        assert np.array_equal(dropin.urandomb(SEED, 11, nbits)[0], reference.urandomb(SEED, 11, nbits)[0])
+    for k, nl in enumerate([5, 11, 12, 13, 14]):
+        x = xof(f"modq{k}", 8 * nl).view("<u8")
+        assert np.array_equal(dropin.modq(x)[0], reference.modq(x)[0]) and dropin.modq(x)[1] == reference.modq(x)[1]
+    x = reference.ct_import(SEED, off, c8[0])
+    assert np.array_equal(dropin.ct_import(SEED, off, c8[0]), x)  # full 736-bit a_j
+    y = reference.ct_import(SEED, off + CTR_CT, c8[1])
+    assert np.array_equal(dropin.ct_export(x), reference.ct_export(x))
+    assert np.array_equal(dropin.eval_poly(SEED, off, c8, h), reference.eval_poly(SEED, off, c8, h))
+    assert np.array_equal(dropin.ct_mul_ui(x, int(h[0])), reference.ct_mul_ui(x, int(h[0])))
+    assert np.array_equal(dropin.ct_add(x, y), reference.ct_add(x, y))
+    assert np.array_equal(dropin.ct_addmul_ui(x, y, int(h[1])), reference.ct_addmul_ui(x, y, int(h[1])))
+    cnt = 3
+    ent = xof("api-ent", N * CT_BYTES + cnt * 70 + 81)
+    m = xof_scalars("api-m", cnt)
+    out = {}
+    for lib in (dropin, reference):
+        lib.set_entropy(ent)
+        sk = lib.key_gen()
+        recs, cts = lib.encrypt(SEED, off, sk, m, want_ct=True)
+        dec = [lib.decrypt(sk, cts[i]) for i in range(cnt)]
+        dot = lib.dotp(cts[0][:N], sk)
+        sm, neg = lib.ct_smudge(cts[0])
+        dec_sm = lib.decrypt(sk, sm)
+        assert lib.entropy_consumed() == ent.size
+        lib.clear_entropy()
+        out[lib.kind] = (sk, recs, cts, dec, dot, sm, neg, dec_sm)
+    a, b = out["dropin"], out["reference"]
+    for i in (0, 1, 2, 4, 5):
+        assert np.array_equal(a[i], b[i]), i
+    assert a[3] == b[3] == [int(v) for v in m] and a[6] == b[6] and a[7] == b[7] == int(m[0])
+
+
+@pytest.mark.parametrize("name", ["aes", "entropy", "ssp", "lwe", "snark"])
+def test_reference_test_programs_against_the_dropin(name):
+    exe = ROOT / "oracle" / "_ref" / f"dropin_test_{name}"
+    if not exe.exists():
+        pytest.skip("built only where the reference sources are present (oracle/Makefile dropin-tests)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
