@@ -10,6 +10,11 @@
 #ifndef MFB200_COMPAT_FLINT_NMOD_POLY_H
 #define MFB200_COMPAT_FLINT_NMOD_POLY_H
 
+/* FLINT's own headers pull these in; programs written against it (the reference's tests) rely on that */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <gmp.h>
 
 #ifdef __cplusplus

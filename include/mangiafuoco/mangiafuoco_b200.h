@@ -21,7 +21,9 @@
 #include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <strings.h>
 #include <sys/types.h>
+#include <unistd.h>
 
 #include <flint/nmod_poly.h>
 #include <gmp.h>
