@@ -205,25 +205,15 @@ def run_gpu_arm(args):
     d_h = torch.from_numpy(h.astype(np.uint32).view(np.int32)).cuda()
     d_cts = torch.empty(D * PLANAR_BYTES, dtype=torch.uint8, device="cuda")
     ctx.expand_dev(SEED, stream_off, d_c8.data_ptr(), D, d_cts.data_ptr(), st)
-    d_rop = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")  # flat, padded to 1472 coordinates
-    d_part = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
-    d_cols = torch.zeros(1472 * 22, dtype=torch.int64, device="cuda")
-    own = 1472 // world
-    d_cols_own = torch.zeros(own * 22, dtype=torch.int64, device="cuda")
-    d_own_flat = torch.zeros(own * L64, dtype=torch.int64, device="cuda")
+    from c_lwe_snarks_b200.sharding import DeviceOps, ShardedLincomb, ShardPlan
+    plan = ShardPlan(world, rank)
+    assert plan.ct_range(world * D) == (rank * D, D)
+    sl = ShardedLincomb(plan, DeviceOps(ctx, torch), dist, lambda n: torch.zeros(n, dtype=torch.int64, device="cuda"))
+    d_rop = sl.result
     torch.cuda.synchronize()
 
     def step():
-        if world == 1:
-            ctx.lincomb_dev(d_cts.data_ptr(), d_h.data_ptr(), D, None, d_rop.data_ptr(), st)
-        else:
-            ctx.lincomb_dev(d_cts.data_ptr(), d_h.data_ptr(), D, None, d_part.data_ptr(), st)
-            ctx.columns_split_dev(d_part.data_ptr(), d_cols.data_ptr(), st)
-            dist.reduce_scatter_tensor(d_cols_own, d_cols, op=dist.ReduceOp.SUM)
-            d_own_flat.zero_()
-            ctx.columns_carry_dev(d_cols_own.data_ptr(), rank * own, own, None,
-                                  d_own_flat.data_ptr() - rank * own * L64 * 8, st)
-            dist.all_gather_into_tensor(d_rop, d_own_flat)
+        sl.step(d_cts, d_h, D)
 
     def barrier():
         if world > 1:
@@ -245,8 +235,7 @@ def run_gpu_arm(args):
     barrier()
     ms = e0.elapsed_time(e1)
     k_ms, k_n = ctx.profile_end()
-    launches = ctx.launches - l0 + (3 * steps if world > 1 else 0)  # + zero_ / NCCL kernels are not ours: not counted
-    launches = ctx.launches - l0
+    launches = ctx.launches - l0  # our kernels only (NCCL's and torch's zero_ are not counted)
     t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)

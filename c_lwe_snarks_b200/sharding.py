@@ -1,0 +1,97 @@
+"""Multi-GPU sharding of the prover lincomb by ciphertext index, one process per GPU.
+
+Each rank holds a contiguous range of the ciphertexts and produces a canonical partial sum mod 2^704 with K1;
+exact sums mod 2^704 are associative, so adding the partials in any order is bit-identical to the reference's
+sequential fold.  The ONE exchange per proof element:
+
+    partial (1472 x 11 u64)  --columns_split-->  1472 x 22 u64 columns, each < 2^32        (local kernel)
+    reduce-scatter(SUM) by coordinate: rank r receives the summed columns of coordinates [r*1472/W, (r+1)*1472/W)
+    columns_carry: carry-propagate + truncate to 704 bit for the owned coordinates        (local kernel)
+    all-gather of the owned slices -> the full result on every rank
+
+An elementwise integer sum of W <= 2^31 values below 2^32 cannot overflow int64, which is what makes a plain
+NCCL SUM exact.  The messages are 259 KB in / 129 KB out: latency-bound, so NCCL's collectives are used as is.
+
+The kernels are reached through an `ops` object (DeviceOps = the CUDA path); the collectives through
+torch.distributed.  The CPU test-suite drives the same code with gloo and a stand-in `ops`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+NCP, L64, L32 = 1472, 11, 22
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    world: int
+    rank: int
+
+    def __post_init__(self):
+        if self.world < 1 or not (0 <= self.rank < self.world):
+            raise ValueError("bad rank / world size")
+        if NCP % self.world:
+            raise ValueError(f"world size must divide {NCP} (= 2^6 * 23): 1, 2, 4, 8, 16, 23, ...")
+
+    def ct_range(self, d_total: int):
+        """Contiguous slice [first, first + count) of the ciphertext indices; the remainder goes to the low ranks."""
+        base, extra = divmod(d_total, self.world)
+        first = self.rank * base + min(self.rank, extra)
+        return first, base + (1 if self.rank < extra else 0)
+
+    @property
+    def coords_per_rank(self) -> int:
+        return NCP // self.world
+
+    @property
+    def first_coord(self) -> int:
+        return self.rank * self.coords_per_rank
+
+
+class DeviceOps:
+    """The CUDA kernels behind include/mfb200.h, on torch int64 CUDA tensors (raw pointers, current stream)."""
+
+    def __init__(self, ctx, torch):
+        self.ctx, self.torch = ctx, torch
+
+    def _st(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def lincomb(self, cts, coeffs, d, out_flat):
+        self.ctx.lincomb_dev(cts.data_ptr(), coeffs.data_ptr(), d, None, out_flat.data_ptr(), self._st())
+
+    def columns_split(self, flat, cols):
+        self.ctx.columns_split_dev(flat.data_ptr(), cols.data_ptr(), self._st())
+
+    def columns_carry(self, cols_own, first_coord, ncoord, out_own_flat):
+        # the kernel indexes its output by absolute coordinate: bias the pointer so that it lands in the slice
+        self.ctx.columns_carry_dev(cols_own.data_ptr(), first_coord, ncoord, None,
+                                   out_own_flat.data_ptr() - first_coord * L64 * 8, self._st())
+
+
+class ShardedLincomb:
+    """Buffers + the per-step exchange for one rank.  `new_i64(n)` allocates a zeroed int64 tensor of n elements
+    on the rank's device."""
+
+    def __init__(self, plan: ShardPlan, ops, dist, new_i64):
+        self.plan, self.ops, self.dist = plan, ops, dist
+        own = plan.coords_per_rank
+        self.partial = new_i64(NCP * L64)      # this rank's canonical partial sum, flat, padded to 1472 coordinates
+        self.cols = new_i64(NCP * L32)
+        self.cols_own = new_i64(own * L32)
+        self.own_flat = new_i64(own * L64)
+        self.result = new_i64(NCP * L64)       # full result, every rank
+
+    def step(self, cts, coeffs, d_local):
+        """result <- sum over ALL ranks' ciphertexts; returns the flat [1472][11] tensor (coordinate 1471 is padding)."""
+        p = self.plan
+        if p.world == 1:
+            self.ops.lincomb(cts, coeffs, d_local, self.result)
+            return self.result
+        self.ops.lincomb(cts, coeffs, d_local, self.partial)
+        self.ops.columns_split(self.partial, self.cols)
+        self.dist.reduce_scatter_tensor(self.cols_own, self.cols, op=self.dist.ReduceOp.SUM)
+        self.own_flat.zero_()
+        self.ops.columns_carry(self.cols_own, p.first_coord, p.coords_per_rank, self.own_flat)
+        self.dist.all_gather_into_tensor(self.result, self.own_flat)
+        return self.result
