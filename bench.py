@@ -177,6 +177,35 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def snark_latency(log2d: int, M: int):
+    """BASELINE configs[2]: full setup + prove + verify of a 2^log2d-constraint SSP through the drop-in C interface
+    (setup/prover/verifier of snark.h:44-51, OS entropy, random degenerate SSP of ssp.c:37-77).  Wall-clock of each
+    call, host polynomial arithmetic included.  `prove_ms` regenerates every a-vector from AES (as the reference
+    does); `prove_resident_ms` is the same call after mf_crs_make_resident (regions s / as kept in HBM)."""
+    from c_lwe_snarks_b200.snark import Snark
+    D = 1 << log2d
+    sn = Snark(D, M)
+    try:
+        sn.random_ssp()
+        t_setup = sn.setup()
+        sn.prove()  # warm-up (scratch allocation)
+        t_prove = min(sn.prove() for _ in range(3))
+        ok, t_verify = sn.verify()
+        t0 = time.perf_counter()
+        sn.make_resident()
+        t_res = time.perf_counter() - t0
+        sn.prove()
+        t_prove_res = min(sn.prove() for _ in range(3))
+        ok2, _ = sn.verify()
+        sn.tamper()
+        bad, _ = sn.verify()
+    finally:
+        sn.close()
+    return {"D": D, "M": M, "setup_ms": 1e3 * t_setup, "prove_ms": 1e3 * t_prove, "verify_ms": 1e3 * t_verify,
+            "make_resident_ms": 1e3 * t_res, "prove_resident_ms": 1e3 * t_prove_res, "accept": bool(ok and ok2),
+            "tampered_accept": bool(bad), "entropy": "getrandom(2)", "api": "setup/prover/verifier (snark.h:44-51) via libmangiafuoco_b200.so"}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
     import torch
@@ -269,12 +298,22 @@ def run_gpu_arm(args):
     e2e_s = float(t_all.item())
     clocks = sampler.stop() if sampler else None
 
-    # ---- sanity outside the timed regions: resident path == fused path (two independent kernels), N=1 only
-    check = None
-    if world == 1:
-        check = bool(np.array_equal(result, fused_result))
-        if not check:
-            raise SystemExit("bench.py: resident lincomb and fused eval_poly disagree — numbers withheld")
+    # ---- sanity outside the timed regions: resident path (+ exchange) == sum of the ranks' fused results
+    # (two independent kernels; the sum over ranks is done here with Python integers)
+    if world > 1:
+        gathered = [torch.zeros(NC * L64, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(fused_result.reshape(-1).view(np.int64)).cuda())
+        parts = [g.cpu().numpy().view(np.uint64).reshape(NC, L64) for g in gathered]
+    else:
+        parts = [fused_result]
+    want = np.zeros((NC, L64), np.uint64)
+    if rank == 0:
+        for c in range(NC):
+            v = sum(int.from_bytes(p[c].tobytes(), "little") for p in parts) % (1 << 704)
+            want[c] = np.frombuffer(v.to_bytes(88, "little"), "<u8")
+    check = bool(np.array_equal(result, want)) if rank == 0 else None
+    if rank == 0 and not check:
+        raise SystemExit("bench.py: resident lincomb and fused eval_poly disagree — numbers withheld")
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -306,6 +345,8 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_snark:
+            line["snark"] = snark_latency(args.log2d, 64)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
         print(json.dumps(line), flush=True)
@@ -323,6 +364,7 @@ def main():
     ap.add_argument("--log2d", type=int, default=16, help="ciphertexts per GPU = 2^log2d (BASELINE configs[1]: 16)")
     ap.add_argument("--cpu-sample", type=int, default=6000, help="ciphertexts timed by the 1-core cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-snark", action="store_true", help="skip the full setup/prove/verify latency leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

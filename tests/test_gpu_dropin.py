@@ -159,3 +159,23 @@ def test_reference_test_programs_against_the_dropin(name):
         pytest.skip("built only where the reference sources are present (oracle/Makefile dropin-tests)")
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_python_snark_binding_roundtrip():
+    """c_lwe_snarks_b200.snark.Snark (ctypes over the drop-in's own structs) with OS entropy: accept, then reject."""
+    from c_lwe_snarks_b200.snark import Snark
+    sn = Snark(128, 16)
+    try:
+        sn.random_ssp()
+        sn.setup()
+        sn.prove()
+        ok, _ = sn.verify()
+        assert ok
+        sn.make_resident()
+        sn.prove()
+        assert sn.verify()[0]
+        sn.tamper()
+        assert not sn.verify()[0]
+        assert sn.gpu_launches() > 0
+    finally:
+        sn.close()
