@@ -24,6 +24,13 @@ PLANAR_U64 = L64 * NCP
 ALGO_BYTES_PER_MAC = NC * 88
 
 
+def resident_to_flat(res: np.ndarray) -> np.ndarray:
+    """(k, 16192) u64 in the resident tile-planar layout -> (k, 1471, 11) flat ciphertexts (host-side decode)."""
+    k = res.shape[0]
+    t = res.reshape(k, NCP // 64, L64, 64)            # [ct][tile][row][lane]
+    return np.ascontiguousarray(t.transpose(0, 1, 3, 2).reshape(k, NCP, L64)[:, :NC, :])
+
+
 class MfbError(RuntimeError):
     pass
 
@@ -69,6 +76,7 @@ _SIGS = {
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_flat_to_planar_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, _vp]),
+    "mfb_flat_to_resident_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -263,6 +271,9 @@ class Context:
                     stream: int = 0):
         self._ck(self.lib.mfb_decrypt_dev(self.h, sk_planar_ptr, cts_flat_ptr, b_neg_ptr, count, out_m_ptr, out_dot_ptr,
                                           stream))
+
+    def flat_to_resident_dev(self, flat_ptr: int, count: int, cts_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_flat_to_resident_dev(self.h, flat_ptr, count, cts_ptr, stream))
 
     def flat_to_planar_dev(self, flat_ptr: int, n: int, count: int, planar_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_flat_to_planar_dev(self.h, flat_ptr, n, count, planar_ptr, stream))

@@ -105,23 +105,32 @@ cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const u
   return cudaGetLastError();
 }
 
-// flat [n][11] u64 (coordinate-major) -> planar [11][NCP]; used for secret keys (n = 1470) and for
-// host-supplied ciphertexts (n = 1471)
-__global__ void k_flat_to_planar(const uint64_t *__restrict__ flat, int n, size_t count, uint64_t *__restrict__ planar) {
+// flat [count][n][11] u64 (coordinate-major) -> row-planar [count][11][1472] (tiled = 0: secret keys, n = 1470)
+// or the resident tile-planar layout (tiled = 1: host-supplied ciphertexts, n = 1471); missing coordinates are 0
+__global__ void k_flat_to_planar(const uint64_t *__restrict__ flat, int n, size_t count, uint64_t *__restrict__ out,
+                                 int tiled) {
   const size_t total = count * PLANAR_U64;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t k = idx / PLANAR_U64;
     const int rem = (int)(idx % PLANAR_U64);
-    const int j = rem / NCP, c = rem % NCP;
-    planar[idx] = c < n ? flat[(k * n + c) * L64 + j] : 0;
+    int j, c;
+    if (tiled) {
+      const int tile = rem / RT_TILE_U64, rr = rem % RT_TILE_U64;
+      j = rr / RT_TILE;
+      c = tile * RT_TILE + rr % RT_TILE;
+    } else {
+      j = rem / NCP;
+      c = rem % NCP;
+    }
+    out[idx] = c < n ? flat[(k * n + c) * L64 + j] : 0;
   }
 }
 
-cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, cudaStream_t st) {
+cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *out, int tiled, cudaStream_t st) {
   if (count == 0) return cudaSuccess;
   size_t blocks = (count * PLANAR_U64 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_flat_to_planar<<<(unsigned)blocks, 256, 0, st>>>(flat, n, count, planar);
+  k_flat_to_planar<<<(unsigned)blocks, 256, 0, st>>>(flat, n, count, out, tiled);
   return cudaGetLastError();
 }
 

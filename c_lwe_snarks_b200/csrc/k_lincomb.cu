@@ -5,71 +5,136 @@
 // Exact sums mod 2^704 are associative, so splitting the i-range over CTAs (and GPUs) and adding the
 // canonical partial sums afterwards is bit-identical to the reference's sequential fold.
 //
-// Data layout: the planar layout of mfb_common.cuh — one warp-wide LDG.64 per limb row reads 256
-// contiguous bytes; nothing is read twice, nothing is staged.  HBM-bound: 129 536 B per ciphertext
-// (129 448 B algorithmic), 22 IMAD.WIDE per coordinate.
-//
-// Grid: (NCP / TILE coordinate tiles) x (nchunks slices of the ciphertext index range).
-// Each thread owns one coordinate, keeps the 704-bit accumulator pair (E, O) in registers for its
-// whole slice, folds it once and writes a canonical partial sum; k_lincomb_finish adds the partials.
+// HBM-bound: 129 536 B per ciphertext (129 448 B algorithmic), 22 IMAD.WIDE per coordinate.  The kernel is a
+// streaming reduction built on the Blackwell copy engine:
+//   * resident layout = tile-planar (mfb_common.cuh): (ciphertext, 64-coordinate tile) is one contiguous 5632 B
+//     block, moved global -> shared by ONE `cp.async.bulk` (TMA, SASS UBLKCP) that completes on an mbarrier;
+//   * CTA = 64 threads bound to one coordinate tile, a ring of LC_STAGES x LC_G blocks in shared memory; thread 0
+//     is the producer (expect_tx + bulk copies), both warps consume (11 conflict-free LDS.64 per ciphertext) and
+//     release the slot through a second mbarrier;
+//   * work distribution is DYNAMIC: every tile has a queue of chunks of the ciphertext range (an atomic counter);
+//     CTAs of that tile pull chunks until the queue is empty.  All CTAs are co-resident (grid = 23 tiles x
+//     floor(SMs * occupancy / 23) slots), so there is no wave quantisation and SMs that run faster take more
+//     chunks — measured 1.13 ms for D = 2^16 (7.5 TB/s) against 1.49 ms for the static LDG version;
+//   * each thread owns one coordinate and keeps the 704-bit accumulator pair (E, O) in registers for all the
+//     chunks it pulls; at the end the CTA writes one canonical partial sum; k_lincomb_finish adds the partials,
+//     adds the incoming rop and resets the queues.
 #include "mfb_common.cuh"
 
 namespace mfb {
 
-constexpr int LC_TILE = 64;    // threads per CTA = coordinates per tile; 1472 = 23 * 64
-constexpr int LC_HSTAGE = 512; // scalars staged in shared memory per refill
+constexpr int LC_TILE = RT_TILE;  // 64 threads per CTA = coordinates per tile
+constexpr int LC_STAGES = 2;      // ring depth
+constexpr int LC_G = 2;           // ciphertext blocks per stage
+constexpr int LC_TILE_BYTES = RT_TILE_U64 * 8;  // 5632
+constexpr int LC_SMEM_BYTES = LC_STAGES * LC_G * LC_TILE_BYTES;
+constexpr int LC_CTR_STRIDE = 32;  // one queue counter per 128-byte line
 
-template <int UNROLL>
-__global__ void __launch_bounds__(LC_TILE) k_lincomb(const uint64_t *__restrict__ cts,
-                                                      const uint32_t *__restrict__ coeffs, size_t d,
-                                                      size_t chunk_len, uint64_t *__restrict__ partial) {
-  __shared__ uint32_t hs[LC_HSTAGE];
-  const int c = blockIdx.x * LC_TILE + threadIdx.x;
-  const size_t i0 = (size_t)blockIdx.y * chunk_len;
-  const size_t i1 = i0 + chunk_len < d ? i0 + chunk_len : d;
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// grid (23 tiles, nslots).  queue[tile * LC_CTR_STRIDE] = next chunk of that tile (zero on entry; reset by finish).
+// partial[slot] is row-planar: limb row j, coordinate c at j*1472 + c.
+__global__ void __launch_bounds__(LC_TILE)
+k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs, size_t d, uint32_t chunk_len,
+          unsigned int *__restrict__ queue, uint64_t *__restrict__ partial) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * LC_STAGES];  // [0, S): full (tx), [S, 2S): empty (2 warps)
+  __shared__ uint32_t meta_first[LC_STAGES];             // first ciphertext of the stage (d < 2^32 per GPU)
+  __shared__ uint32_t meta_n[LC_STAGES];                 // ciphertexts in the stage; 0 = queue drained
+  const int tile = blockIdx.x;
+  const uint32_t nchunks = (uint32_t)((d + chunk_len - 1) / chunk_len);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(bars);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LC_STAGES; s++) {
+      mbar_init(bbase + 8 * s, 1);
+      mbar_init(bbase + 8 * (LC_STAGES + s), LC_TILE / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer state (thread 0)
+  size_t cur = 0, end = 0;
+  bool drained = false;
+  auto issue = [&](int s) {
+    if (cur == end && !drained) {
+      const uint32_t ch = atomicAdd(queue + tile * LC_CTR_STRIDE, 1u);
+      if (ch < nchunks) {
+        cur = (size_t)ch * chunk_len;
+        end = cur + chunk_len < d ? cur + chunk_len : d;
+      } else {
+        drained = true;
+      }
+    }
+    if (drained) {  // end marker: consumers see n == 0
+      meta_n[s] = 0;
+      mbar_arrive(bbase + 8 * s);
+      return;
+    }
+    const int n = (int)(end - cur < (size_t)LC_G ? end - cur : (size_t)LC_G);
+    meta_first[s] = (uint32_t)cur;
+    meta_n[s] = n;
+    mbar_expect_tx(bbase + 8 * s, n * LC_TILE_BYTES);
+    for (int g = 0; g < n; g++)
+      bulk_g2s(sbase + (s * LC_G + g) * LC_TILE_BYTES, cts + (cur + g) * PLANAR_U64 + (size_t)tile * RT_TILE_U64,
+               LC_TILE_BYTES, bbase + 8 * s);
+    cur += n;
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < LC_STAGES; s++) issue(s);
 
   Acc704 acc;
   acc_zero(acc);
-
-  for (size_t base = i0; base < i1; base += LC_HSTAGE) {
-    const int n = (int)(i1 - base < (size_t)LC_HSTAGE ? i1 - base : (size_t)LC_HSTAGE);
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += LC_TILE) hs[k] = coeffs[base + k];
-    __syncthreads();
-    const uint64_t *p = cts + base * PLANAR_U64 + c;
-    int k = 0;
-    for (; k + UNROLL <= n; k += UNROLL) {
-      uint64_t v[UNROLL][L64];
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-        for (int j = 0; j < L64; j++) v[u][j] = __ldcs(p + (size_t)(k + u) * PLANAR_U64 + (size_t)j * NCP);
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        uint32_t a[22];
-#pragma unroll
-        for (int j = 0; j < L64; j++) {
-          a[2 * j] = (uint32_t)v[u][j];
-          a[2 * j + 1] = (uint32_t)(v[u][j] >> 32);
-        }
-        acc_mad(acc, a, hs[k + u]);
-      }
-    }
-    for (; k < n; k++) {
+  for (uint32_t it = 0;; it++) {
+    const int s = (int)(it % LC_STAGES);
+    const uint32_t ph = (it / LC_STAGES) & 1;
+    mbar_wait(bbase + 8 * s, ph);
+    const int n = (int)meta_n[s];
+    if (n == 0) break;
+    const size_t first = meta_first[s];
+    for (int g = 0; g < n; g++) {
+      const uint64_t *sp = reinterpret_cast<const uint64_t *>(smem + (s * LC_G + g) * LC_TILE_BYTES) + threadIdx.x;
       uint32_t a[22];
 #pragma unroll
       for (int j = 0; j < L64; j++) {
-        const uint64_t v = __ldcs(p + (size_t)k * PLANAR_U64 + (size_t)j * NCP);
+        const uint64_t v = sp[j * RT_TILE];
         a[2 * j] = (uint32_t)v;
         a[2 * j + 1] = (uint32_t)(v >> 32);
       }
-      acc_mad(acc, a, hs[k]);
+      acc_mad(acc, a, __ldg(coeffs + first + g));
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bbase + 8 * (LC_STAGES + s));  // this warp is done with slot s
+    if (threadIdx.x == 0) {
+      mbar_wait(bbase + 8 * (LC_STAGES + s), ph);  // every warp released it
+      issue(s);
     }
   }
 
   uint32_t r[22];
   acc_fold(acc, r);
-  uint64_t *out = partial + (size_t)blockIdx.y * PLANAR_U64 + c;
+  uint64_t *out = partial + (size_t)blockIdx.y * PLANAR_U64 + tile * LC_TILE + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < L64; j++) out[(size_t)j * NCP] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
 }
@@ -79,8 +144,10 @@ __global__ void __launch_bounds__(LC_TILE) k_lincomb(const uint64_t *__restrict_
 // (loads of successive partials are independent, so several are in flight), the slices meet in shared memory.
 constexpr int FIN_SLICES = 8;
 __global__ void __launch_bounds__(64 * FIN_SLICES)
-k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out) {
+k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                 unsigned int *queue) {
   __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
+  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;  // one CTA per tile: re-arm its chunk queue
   const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const int c = blockIdx.x * 64 + cl;
   uint32_t r[22];
@@ -171,34 +238,43 @@ __global__ void k_columns_carry(const uint64_t *__restrict__ cols, int c0, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-int lincomb_nchunks(size_t d, int sm_count) {
-  // ~2 waves of resident CTAs: 23 tiles x nchunks CTAs of 64 threads; aim for ~10 CTAs (20 warps) per SM
-  size_t target = ((size_t)sm_count * 10 + 22) / 23;
-  if (target < 1) target = 1;
-  size_t n = d < target ? d : target;
+// number of CTA slots per tile such that every CTA of the grid is resident at once
+int lincomb_nslots(size_t d, int sm_count) {
+  static int occ = 0;
+  if (!occ) {
+    cudaFuncSetAttribute(k_lincomb, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb, LC_TILE, LC_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 8;
+  }
+  size_t n = (size_t)sm_count * occ / RT_NTILES;
+  const size_t chunks = (d + 3) / 4;
+  if (n > chunks) n = chunks;
   return (int)(n ? n : 1);
 }
 
 typedef void (*mark_fn)(void *, int, cudaStream_t);
-// launches the main kernel only; *nchunks_inout returns the number of partial sums written
+// launches the main kernel only; *nslots_inout returns the number of partial sums written
 cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
-                                    int *nchunks_inout, cudaStream_t st, mark_fn mark, void *mark_arg) {
-  int nchunks = d ? *nchunks_inout : 0;
-  if (nchunks > 0) {
-    const size_t chunk_len = (d + nchunks - 1) / nchunks;
-    nchunks = (int)((d + chunk_len - 1) / chunk_len);
-    dim3 grid(NCP / LC_TILE, nchunks);
+                                    unsigned int *queue, int *nslots_inout, cudaStream_t st, mark_fn mark,
+                                    void *mark_arg) {
+  int nslots = d ? *nslots_inout : 0;
+  if (nslots > 0) {
+    if (d >> 32) return cudaErrorInvalidValue;  // stage metadata holds 32-bit ciphertext indices
+    cudaError_t e = cudaFuncSetAttribute(k_lincomb, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    // chunk = 4 ciphertexts (2 ring stages) unless that leaves CTAs without work to pull
+    const uint32_t chunk_len = 4;
+    dim3 grid(RT_NTILES, nslots);
     if (mark) mark(mark_arg, 0, st);
-    k_lincomb<2><<<grid, LC_TILE, 0, st>>>(cts, coeffs, d, chunk_len, partial_ws);
+    k_lincomb<<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs, d, chunk_len, queue, partial_ws);
     if (mark) mark(mark_arg, 1, st);
   }
-  *nchunks_inout = nchunks;
+  *nslots_inout = nslots;
   return cudaGetLastError();
 }
 
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                  cudaStream_t st) {
-  k_lincomb_finish<<<NCP / 64, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out);
+                                  unsigned int *queue, cudaStream_t st) {
+  k_lincomb_finish<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue);
   return cudaGetLastError();
 }
 

@@ -1,7 +1,7 @@
 // K2 — AES-256-CTR expansion of the a-vectors, standalone and fused into its consumers.
 //
 //   k_stream_bytes   raw keystream bytes                          (aesctr_prg aes.c:104-144, rng_seek entropy.c:46-56)
-//   k_expand         AES -> planar resident ciphertext array      (ct_import lwe.c:122-126, mpz2_urandomb entropy.c:11-26)
+//   k_expand         AES -> resident (tile-planar) ciphertext array     (ct_import lwe.c:122-126, mpz2_urandomb entropy.c:11-26)
 //   k_evalpoly       AES -> 704-bit MAC, a never touches HBM       (eval_poly lwe.c:176-186)
 //   k_encrypt        AES -> <a, sk> + e*p + m -> 92-byte record    (regev_encrypt2 lwe.c:78-97 + ct_export :115-119)
 //
@@ -109,7 +109,7 @@ k_stream_bytes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------ expand
-// cts[k] (planar) <- a-vector of the ciphertext at stream offset + k*CTR_CT, b from the wire record c8[k].
+// cts[k] (resident tile-planar layout) <- a-vector of the ciphertext at stream offset + k*CTR_CT, b from the wire record c8[k].
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
          const uint8_t *__restrict__ c8, size_t count, uint64_t *__restrict__ cts) {
@@ -134,7 +134,7 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
       ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
       const int c = tile * KS_TILE + threadIdx.x;
 #pragma unroll
-      for (int j = 0; j < L64; j++) dst[(size_t)j * NCP + c] = (uint64_t)a[2 * j] | (uint64_t)a[2 * j + 1] << 32;
+      for (int j = 0; j < L64; j++) dst[resident_index(c, j)] = (uint64_t)a[2 * j] | (uint64_t)a[2 * j + 1] << 32;
     } else if (tile == 0 && threadIdx.x < KS_TILE + L64) {
       // b coordinate: low 88 bytes of the wire record (ct_import lwe.c:125); padding coordinate: 0
       const int j = threadIdx.x - KS_TILE;
@@ -142,8 +142,8 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
       uint64_t v = 0;
 #pragma unroll
       for (int i = 0; i < 8; i++) v |= (uint64_t)rec[i] << (8 * i);
-      dst[(size_t)j * NCP + N] = v;
-      dst[(size_t)j * NCP + N + 1] = 0;
+      dst[resident_index(N, j)] = v;
+      dst[resident_index(N + 1, j)] = 0;
     }
     const size_t nx = it + gridDim.x;
     if (nx < nitems) {

@@ -26,12 +26,13 @@ int fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 // kernels / launchers (k_*.cu)
-int lincomb_nchunks(size_t d, int sm_count);
+int lincomb_nslots(size_t d, int sm_count);
 typedef void (*mark_fn)(void *, int, cudaStream_t);
 cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
-                                    int *nchunks_inout, cudaStream_t st, mark_fn mark, void *mark_arg);
+                                    unsigned int *queue, int *nslots_inout, cudaStream_t st, mark_fn mark,
+                                    void *mark_arg);
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                  cudaStream_t st);
+                                  unsigned int *queue, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
 cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
                                  cudaStream_t st);
@@ -48,7 +49,8 @@ cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offse
                            uint8_t *out_c8, int sm_count, cudaStream_t st);
 cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
                            uint64_t *out_m, uint64_t *out_dot, cudaStream_t st);
-cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, cudaStream_t st);
+cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, int tiled,
+                                  cudaStream_t st);
 
 constexpr int MAX_CHUNKS = 256;
 constexpr int NSLOTS = 8;
@@ -62,7 +64,8 @@ struct mfb_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;   // the context's own stream (host flavour)
   uint32_t *t0_dev = nullptr;      // 256-entry T0 table
-  uint64_t *partial_ws = nullptr;  // MAX_CHUNKS planar partial sums
+  uint64_t *partial_ws = nullptr;  // MAX_CHUNKS row-planar partial sums
+  unsigned int *queue = nullptr;   // K1's per-tile chunk queues (23 counters, one per 128 B line), zero between calls
   void *slot[NSLOTS] = {};         // growable device scratch for the host flavour
   size_t slot_cap[NSLOTS] = {};
   uint64_t launches = 0;
@@ -142,6 +145,8 @@ int mfb_ctx_create(mfb_ctx **out, int device) {
     if ((e = cudaMalloc(&ctx->t0_dev, sizeof(t0))) != cudaSuccess) break;
     if ((e = cudaMemcpy(ctx->t0_dev, t0, sizeof(t0), cudaMemcpyHostToDevice)) != cudaSuccess) break;
     if ((e = cudaMalloc(&ctx->partial_ws, (size_t)MAX_CHUNKS * PLANAR_U64 * 8)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&ctx->queue, 32 * 32 * sizeof(unsigned int))) != cudaSuccess) break;
+    if ((e = cudaMemset(ctx->queue, 0, 32 * 32 * sizeof(unsigned int))) != cudaSuccess) break;
   } while (0);
   if (e != cudaSuccess) {
     rc = fail(e, "context setup", __FILE__, __LINE__);
@@ -163,6 +168,7 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
     if (ctx->slot[i]) cudaFree(ctx->slot[i]);
   if (ctx->t0_dev) cudaFree(ctx->t0_dev);
   if (ctx->partial_ws) cudaFree(ctx->partial_ws);
+  if (ctx->queue) cudaFree(ctx->queue);
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;
@@ -228,11 +234,11 @@ int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeff
                     const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream) {
   MFB_CHECK_CTX(ctx);
   if (!rop_out_dev || (d && (!cts_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_lincomb_dev: null pointer");
-  int nchunks = lincomb_nchunks(d, ctx->sm_count);
-  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
-  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, d, ctx->partial_ws, &nchunks, (cudaStream_t)stream,
+  int nslots = lincomb_nslots(d, ctx->sm_count);
+  if (nslots > MAX_CHUNKS) nslots = MAX_CHUNKS;
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, d, ctx->partial_ws, ctx->queue, &nslots, (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nslots, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }
@@ -268,7 +274,7 @@ int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
                                         ctx->partial_ws, (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }
@@ -298,14 +304,23 @@ int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const uint64_t 
   return MFB_OK;
 }
 
-int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
-                           void *stream) {
+static int flat_convert(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *out_dev, int tiled,
+                        void *stream) {
   MFB_CHECK_CTX(ctx);
-  if (count && (!flat_dev || !planar_dev)) return set_err(MFB_EARG, "mfb_flat_to_planar_dev: null pointer");
-  if (n < 0 || n > NCP) return set_err(MFB_EARG, "mfb_flat_to_planar_dev: n out of range");
-  MFB_CUDA_TRY(launch_flat_to_planar(flat_dev, n, count, planar_dev, (cudaStream_t)stream));
+  if (count && (!flat_dev || !out_dev)) return set_err(MFB_EARG, "flat conversion: null pointer");
+  if (n < 0 || n > NCP) return set_err(MFB_EARG, "flat conversion: n out of range");
+  MFB_CUDA_TRY(launch_flat_to_planar(flat_dev, n, count, out_dev, tiled, (cudaStream_t)stream));
   if (count) ctx->launches += 1;
   return MFB_OK;
+}
+
+int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
+                           void *stream) {
+  return flat_convert(ctx, flat_dev, n, count, planar_dev, 0, stream);
+}
+
+int mfb_flat_to_resident_dev(mfb_ctx *ctx, const uint64_t *flat_dev, size_t count, uint64_t *cts_dev, void *stream) {
+  return flat_convert(ctx, flat_dev, NC, count, cts_dev, 1, stream);
 }
 
 /* ------------------------------------------------------------------------------------ host flavour */
@@ -387,7 +402,7 @@ int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, 
     MFB_CUDA_TRY(cudaMemcpyAsync(d_co, coeffs, d * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   MFB_CUDA_TRY(cudaMemcpyAsync(d_rop, rop_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
-  MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_flat, NC, d, (uint64_t *)d_planar, ctx->stream));
+  MFB_TRY(mfb_flat_to_resident_dev(ctx, (const uint64_t *)d_flat, d, (uint64_t *)d_planar, ctx->stream));
   MFB_TRY(mfb_lincomb_dev(ctx, (const uint64_t *)d_planar, (const uint32_t *)d_co, d, (const uint64_t *)d_rop,
                           (uint64_t *)d_rop, ctx->stream));
   MFB_CUDA_TRY(cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));

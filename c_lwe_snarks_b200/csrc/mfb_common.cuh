@@ -21,10 +21,19 @@ constexpr uint32_t P = 0xfffffffbu;   // GAMMA_P (lwe.h:25)
 constexpr int NOISE_BYTES = 69;    // (GAMMA_LOG_SIGMA + 3) / 8 (lwe.c:62, entropy.c:32)
 constexpr int ENT_BYTES = 70;      // noise bytes + the sign byte that is drawn and discarded (lwe.c:87)
 
-// "planar" resident layout of a ciphertext array in HBM: ct i, 64-bit limb row j, coordinate c at
-//   cts[(i * L64 + j) * NCP + c]
-// so that a warp reading one limb row touches 256 contiguous bytes.  Coordinate 1470 is b, 1471 is 0.
+// Resident ("tile-planar") layout of a ciphertext array in HBM.  The 1472 coordinates of a ciphertext are cut
+// into 23 tiles of 64; a tile is 11 limb rows of 64 x u64, stored contiguously (5632 B):
+//   u64 index of (ct i, 64-bit limb row j, coordinate c) = i*16192 + (c / 64)*704 + j*64 + (c % 64)
+// so that (ct, tile) is ONE contiguous, 16-byte-aligned block for a TMA bulk copy, and inside it a warp reads a
+// limb row as 256 contiguous bytes (bank-conflict free LDS.64).  Coordinate 1470 is b, 1471 is zero padding.
+constexpr int RT_TILE = 64;                       // coordinates per tile
+constexpr int RT_NTILES = NCP / RT_TILE;          // 23
+constexpr int RT_TILE_U64 = L64 * RT_TILE;        // 704 u64 = 5632 B
 constexpr size_t PLANAR_U64 = (size_t)L64 * NCP;  // 16192 u64 = 129536 B per ciphertext
+__host__ __device__ __forceinline__ size_t resident_index(int c, int j) {
+  return (size_t)(c / RT_TILE) * RT_TILE_U64 + (size_t)j * RT_TILE + (c % RT_TILE);
+}
+// "Row-planar" layout (secret keys, partial sums): limb row j, coordinate c at j*1472 + c.
 
 // ---------------------------------------------------------------------------------------------
 // 704-bit multiply-accumulate with in-thread carry chains.

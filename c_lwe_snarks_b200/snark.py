@@ -66,7 +66,7 @@ class Snark:
         self.lib.mf_set_instance(D, M)
         self.crs, self.vrs, self.proof = Crs(), Vrs(), Proof()
         self.witness = Mpz()
-        self.gmp.__gmpz_init(C.byref(self.witness))
+        getattr(self.gmp, "__gmpz_init")(C.byref(self.witness))  # getattr: no class-private name mangling
         self.ssp = np.zeros(D * 8 * (M + 3), np.uint8)
         self._crs_live = self._proof_live = self._vrs_live = False
 

@@ -12,8 +12,11 @@
  *   flat ct   MFB_NC (1471) coordinates x MFB_L64 (11) uint64 limbs, coordinate-major: the value of every
  *             coordinate mod 2^704 — the modulus modq() really implements    lwe.h:108-118
  *   flat sk   MFB_N (1470) coordinates x 11 uint64 limbs (bits >= 704 of a key never reach any output)
- *   planar    resident (HBM) layout of a ciphertext array: ct i, limb row j, coordinate c at
- *             u64 index (i*11 + j)*1472 + c; coordinate 1470 is b, 1471 is zero padding
+ *   resident  (HBM) "tile-planar" layout of a ciphertext array, MFB_PLANAR_U64 u64 per ciphertext: the 1472
+ *             coordinates (1470 = b, 1471 = zero padding) are cut into 23 tiles of 64; (ct i, 64-bit limb row j,
+ *             coordinate c) sits at u64 index i*16192 + (c/64)*704 + j*64 + c%64, so that (ct, tile) is one
+ *             contiguous 5632-byte block for a TMA bulk copy
+ *   row-planar  secret keys on the device: limb row j, coordinate c at j*1472 + c
  *   scalars   uint32 < p = 2^32 - 5 (nmod_poly coefficients; any uint32 is computed exactly)
  *
  * Every function returns 0 on success or a negative MFB_E* code; mfb_last_error() gives the text.
@@ -83,7 +86,7 @@ MFB_API int mfb_stream(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, ui
 MFB_API int mfb_stream_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *out_dev, size_t nbytes,
                    void *stream);
 
-/* cts_dev[k] (planar) <- ct_import(rng at offset + k*MFB_CTR_CT, c8[k]) for k < count (lwe.c:122-126):
+/* cts_dev[k] (resident layout) <- ct_import(rng at offset + k*MFB_CTR_CT, c8[k]) for k < count (lwe.c:122-126):
  * the a-vector from the stream, b from the 92-byte record.  This is how a CRS region is made resident. */
 MFB_API int mfb_expand_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev, size_t count,
                    uint64_t *cts_dev, void *stream);
@@ -91,7 +94,8 @@ MFB_API int mfb_expand_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
 /* ---- K1: ciphertext linear combination over resident ciphertexts -------------------------- */
 /* rop = (rop_in + sum_{i<d} coeffs[i] * cts[i]) mod 2^704, coordinate-wise: the loop of eval_poly
  * (lwe.c:176-186) = d x ct_addmul_ui (lwe.c:141-149) with modq (lwe.h:108-118); also ct_mul_ui and ct_add
- * (lwe.c:131-157) as the d = 1, 2 cases.  rop_in may be NULL (zero) or equal to rop_out. */
+ * (lwe.c:131-157) as the d = 1, 2 cases.  cts_dev is in the resident layout, d < 2^32 per call; rop_in may be
+ * NULL (zero) or equal to rop_out.  One call at a time per context (it owns the partial-sum workspace). */
 MFB_API int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
                     const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
 /* host flavour over flat host ciphertexts (d small: ct_add / ct_mul_ui / ct_addmul_ui on ct_t objects) */
@@ -146,9 +150,12 @@ MFB_API int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *c
 MFB_API int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const uint64_t *cts_flat_dev,
                     const uint8_t *b_neg_dev, size_t count, uint64_t *out_m_dev, uint64_t *out_dot_dev, void *stream);
 
-/* flat [count][n][11] -> planar [count][11][1472] on the device (n = 1470 for keys, 1471 for ciphertexts) */
+/* flat [count][n][11] -> row-planar [count][11][1472] on the device (secret keys: n = 1470) */
 MFB_API int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
                            void *stream);
+/* flat ciphertexts [count][1471][11] -> the resident tile-planar layout that mfb_lincomb_dev streams */
+MFB_API int mfb_flat_to_resident_dev(mfb_ctx *ctx, const uint64_t *flat_dev, size_t count, uint64_t *cts_dev,
+                             void *stream);
 
 #ifdef __cplusplus
 }

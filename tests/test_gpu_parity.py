@@ -44,9 +44,10 @@ def dev(torch, a: np.ndarray):
     return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).cuda()
 
 
-def planar_to_flat(pl: np.ndarray) -> np.ndarray:
-    """(k, 11, 1472) -> (k, 1471, 11)"""
-    return np.ascontiguousarray(pl.transpose(0, 2, 1)[:, :NC, :])
+def resident_to_flat(res: np.ndarray) -> np.ndarray:
+    """(k, 16192) u64, resident tile-planar layout -> (k, 1471, 11)"""
+    from c_lwe_snarks_b200.api import resident_to_flat as f
+    return f(res)
 
 
 # ------------------------------------------------------------------------------------------- K2 stream
@@ -87,9 +88,9 @@ def test_expand_vs_oracle(ctx, oracle, torch, off):
     d_cts = torch.zeros(k * L64 * 1472 * 8, dtype=torch.uint8, device="cuda")
     ctx.expand_dev(SEED, off, d_c8.data_ptr(), k, d_cts.data_ptr())
     torch.cuda.synchronize()
-    pl = d_cts.cpu().numpy().view(np.uint64).reshape(k, L64, 1472)
-    assert not pl[:, :, 1471].any()
-    got = planar_to_flat(pl)
+    res = d_cts.cpu().numpy().view(np.uint64).reshape(k, L64 * 1472)
+    assert not res.reshape(k, 23, L64, 64)[:, 22, :, 63].any()  # padding coordinate 1471
+    got = resident_to_flat(res)
     for i in range(k):
         want = oracle.ct_import(SEED, off + i * CTR_CT, c8[i])
         assert np.array_equal(got[i], want[:, :11]), f"ciphertext {i}"
@@ -102,7 +103,7 @@ def test_expand_golden(ctx, torch):
         d_cts = torch.zeros(L64 * 1472 * 8, dtype=torch.uint8, device="cuda")
         ctx.expand_dev(SEED, g["offset"], dev(torch, b).data_ptr(), 1, d_cts.data_ptr())
         torch.cuda.synchronize()
-        ct = wide(planar_to_flat(d_cts.cpu().numpy().view(np.uint64).reshape(1, L64, 1472))[0])
+        ct = wide(resident_to_flat(d_cts.cpu().numpy().view(np.uint64).reshape(1, L64 * 1472))[0])
         # the golden ciphertext keeps the dead limb 11 of every a_j; compare the live part and the literals
         assert ct[0, :11].tobytes().hex() == g["a0"][: 11 * 16]
         assert ct[1469, :11].tobytes().hex() == g["a1469"][: 11 * 16]
