@@ -28,7 +28,7 @@ constexpr int KS_SMEM_BYTES = 0x20000 + KS_BUF_BYTES;   // [pad/buffer A | 64 KB
 struct KsSmem {
   uint32_t tab;   // shared address of the tables (64 KB aligned)
   uint32_t buf[2];
-  uint32_t lb;    // tab | 4*lane
+  AesLut<2> lut;  // tab | 4*lane
 };
 
 __device__ __forceinline__ KsSmem ks_smem_setup(uint8_t *dyn, const uint32_t *__restrict__ t0_global) {
@@ -39,7 +39,8 @@ __device__ __forceinline__ KsSmem ks_smem_setup(uint8_t *dyn, const uint32_t *__
   if (s.tab - s0 < (uint32_t)KS_BUF_BYTES) __trap();  // dynamic smem starts within 20 KB of the window base
   s.buf[0] = s0;
   s.buf[1] = s.tab + AES_TAB_BYTES;
-  s.lb = s.tab | ((threadIdx.x & 31) << 2);
+  s.lut.lbA = s.tab | ((threadIdx.x & 31) << 2);
+  s.lut.lbB = 0;
   aes_tables_init(dyn + (s.tab - s0), t0_global, threadIdx.x, blockDim.x);
   return s;
 }
@@ -49,9 +50,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const AesState &v) {
                : "memory");
 }
 
-// keystream blocks [first, first + nblk) -> shared buffer
-__device__ __forceinline__ void ks_fill(const AesKey &key, uint64_t first, int nblk, uint32_t buf, uint32_t lb) {
-  for (int b = threadIdx.x; b < nblk; b += KS_THREADS) sts128(buf + 16u * b, aes256_ctr_block(key, first + b, lb));
+// keystream blocks [first, first + nblk) -> shared buffer (counter-mode cached AES, aes256.cuh)
+__device__ __forceinline__ void ks_fill(const AesKey &key, uint64_t first, int nblk, uint32_t buf, const AesLut<2> &lut,
+                                        AesCtrCache &cache) {
+  for (int b = threadIdx.x; b < nblk; b += KS_THREADS)
+    sts128(buf + 16u * b, aes256_ctr_block_cached<2>(lut, key, first + b, cache));
 }
 
 // the 22 live limbs of the coordinate that starts at byte `pos` of the shared buffer
@@ -88,12 +91,14 @@ k_stream_bytes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ 
                uint8_t *__restrict__ out, size_t nbytes) {
   extern __shared__ __align__(16) uint8_t dyn[];
   const KsSmem s = ks_smem_setup(dyn, t0_global);
+  AesCtrCache cache;
+  cache.window = ~0ull;
   __syncthreads();
   const uint64_t first = offset >> 4;
   const uint64_t end = offset + nbytes;
   const uint64_t nblk = ((end + 15) >> 4) - first;
   for (uint64_t b = (uint64_t)blockIdx.x * KS_THREADS + threadIdx.x; b < nblk; b += (uint64_t)gridDim.x * KS_THREADS) {
-    const AesState v = aes256_ctr_block(key, first + b, s.lb);
+    const AesState v = aes256_ctr_block_cached<2>(s.lut, key, first + b, cache);
     const uint64_t p0 = (first + b) << 4;  // stream position of this block's byte 0
     const uint32_t w[4] = {v.w0, v.w1, v.w2, v.w3};
     if (p0 >= offset && p0 + 16 <= end && (((uintptr_t)(out + (p0 - offset))) & 15) == 0) {
@@ -115,13 +120,15 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
          const uint8_t *__restrict__ c8, size_t count, uint64_t *__restrict__ cts) {
   extern __shared__ __align__(16) uint8_t dyn[];
   const KsSmem s = ks_smem_setup(dyn, t0_global);
+  AesCtrCache cache;
+  cache.window = ~0ull;
   const size_t nitems = count * KS_NTILES;
   size_t it = blockIdx.x;
   int ph = 0;
   __syncthreads();  // tables ready
   if (it < nitems) {
     const TileGeom g = tile_geom(offset + (it / KS_NTILES) * (uint64_t)CTR_CT, (int)(it % KS_NTILES));
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
   }
   __syncthreads();
   for (; it < nitems; it += gridDim.x, ph ^= 1) {
@@ -148,7 +155,7 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
     const size_t nx = it + gridDim.x;
     if (nx < nitems) {
       const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
     }
     __syncthreads();
   }
@@ -165,6 +172,8 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
            size_t d, int nchunks, uint64_t *__restrict__ partial) {
   extern __shared__ __align__(16) uint8_t dyn[];
   const KsSmem s = ks_smem_setup(dyn, t0_global);
+  AesCtrCache cache;
+  cache.window = ~0ull;
   const int tile = blockIdx.x % KS_NTILES;
   const int chunk = blockIdx.x / KS_NTILES;
 
@@ -178,7 +187,7 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
   if (m < d) {
     const size_t k = idx ? idx[m] : m;
     const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
   }
   __syncthreads();
   for (; m < d; m += nchunks, ph ^= 1) {
@@ -200,7 +209,7 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     if (nx < d) {
       const size_t kn = idx ? idx[nx] : nx;
       const TileGeom gn = tile_geom(offset + kn * (uint64_t)CTR_CT, tile);
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
     }
     __syncthreads();
   }
@@ -231,6 +240,8 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   __shared__ uint32_t red[KS_THREADS / 32][44];
   __shared__ unsigned long long cols[22];
   const KsSmem s = ks_smem_setup(dyn, t0_global);
+  AesCtrCache cache;
+  cache.window = ~0ull;
   const size_t nitems = count * KS_NTILES;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -241,7 +252,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   __syncthreads();  // tables ready
   if (it < nitems) {
     const TileGeom g = tile_geom(offset + (it / KS_NTILES) * (uint64_t)CTR_CT, 0);
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lb);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
   }
   __syncthreads();
   while (it < nitems) {
@@ -264,7 +275,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
     }
     if (nx < nitems) {
       const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lb);
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
     }
     if (tile == KS_NTILES - 1) {
       // block-reduce the per-thread sums: 16-bit halves so that warp REDUX sums cannot overflow

@@ -1,0 +1,95 @@
+// Development harness: AES-256-CTR keystream generation variants (shared-memory T-tables), blocks/s.
+//   tune_aes            -> each variant fills `nblk`-block tiles into shared memory, ITEMS tiles per CTA, 148 CTAs
+#include <cstdio>
+#include <cstdlib>
+#include "../aes256.cuh"
+using namespace mfb;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ void sts128(uint32_t addr, const AesState &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.w0), "r"(v.w1), "r"(v.w2), "r"(v.w3) : "memory");
+}
+
+// VARIANT 0: shipped (aes256_ctr_block), 1: plain on AesLut<2>, 2: cached TABS=2, 3: plain TABS=4, 4: cached TABS=4
+template <int VARIANT, int NT, int AT>
+__global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0g, int nblk,
+                                              int items, unsigned long long *digest) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(dyn);
+  const uint32_t tabA = (s0 + 0xffffu) & ~0xffffu;
+  constexpr bool four = (VARIANT >= 3);
+  const uint32_t tabB = tabA + 0x10000;
+  const uint32_t buf = s0;  // pad region below the tables
+  aes_tables_init(dyn + (tabA - s0), t0g, threadIdx.x, NT);
+  if (four) aes_tables_init_b(dyn + (tabB - s0), t0g, threadIdx.x, NT);
+  __syncthreads();
+  AesLut<four ? 4 : 2> L;
+  L.lbA = tabA | ((threadIdx.x & 31) << 2);
+  L.lbB = tabB | ((threadIdx.x & 31) << 2);
+  AesCtrCache cache;
+  cache.window = ~0ull;
+  uint32_t x = 0;
+  for (int it = 0; it < items; it++) {
+    const uint64_t first = ((uint64_t)blockIdx.x * items + it) * 8453ull + 12345;
+    if (threadIdx.x < AT)
+    for (int b = threadIdx.x; b < nblk; b += AT) {
+      AesState v;
+      if constexpr (VARIANT == 0) v = aes256_ctr_block(key, first + b, L.lbA);
+      else if constexpr (VARIANT == 1 || VARIANT == 3) v = aes256_ctr_block_plain(L, key, first + b);
+      else v = aes256_ctr_block_cached(L, key, first + b, cache);
+      sts128(buf + 16u * b, v);
+    }
+    __syncthreads();
+    // consume: fold the buffer (one word per thread per 2 KB) so the stores cannot be dropped
+    for (int w = threadIdx.x; w < nblk * 4; w += NT) x ^= lds32(buf + 4 * w) * (uint32_t)(w + 1 + it);
+    __syncthreads();
+  }
+  atomicXor(digest, (unsigned long long)x * 0x9e3779b97f4a7c15ull + blockIdx.x);
+}
+
+template <int VARIANT, int NT, int AT = NT>
+static void run(const char *name, const AesKey &key, const uint32_t *t0, int nblk, int items, unsigned long long *dig) {
+  const int smem = VARIANT >= 3 ? 0x30000 : 0x20000;
+  CK(cudaFuncSetAttribute(k_aes<VARIANT, NT, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  unsigned long long z = 0, out = 0;
+  k_aes<VARIANT, NT, AT><<<148, NT, smem>>>(key, t0, nblk, items, dig);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dig, &z, 8, cudaMemcpyHostToDevice));
+  CK(cudaEventRecord(e0));
+  k_aes<VARIANT, NT, AT><<<148, NT, smem>>>(key, t0, nblk, items, dig);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  CK(cudaMemcpy(&out, dig, 8, cudaMemcpyDeviceToHost));
+  const double blocks = 148.0 * items * nblk;
+  printf("%-26s NT=%4d AT=%4d nblk=%4d: %8.3f ms  %.3e blocks/s  (%.2f cyc/blk/SM @1.965GHz)  digest %016llx\n", name, NT, AT, nblk, ms,
+         blocks / ms * 1e3, 1.965e9 * 148 / (blocks / ms * 1e3), out);
+  fflush(stdout);
+}
+
+int main() {
+  uint8_t seed[40]; for (int i = 0; i < 40; i++) seed[i] = (uint8_t)i;
+  AesKey key; aes_host::expand(seed, &key);
+  uint32_t t0h[256]; aes_host::t0_table(t0h);
+  uint32_t *t0; unsigned long long *dig;
+  CK(cudaMalloc(&t0, 1024)); CK(cudaMemcpy(t0, t0h, 1024, cudaMemcpyHostToDevice)); CK(cudaMalloc(&dig, 8));
+  const int items = 600;
+  run<0, 512>("shipped 2-table", key, t0, 2818, items, dig);
+  run<2, 512>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 480>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 480>("ctr-cached 2-table", key, t0, 2819, items, dig);
+  run<4, 512, 480>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<2, 512, 480>("ctr-cached 2-table", key, t0, 1409, items, dig);
+  run<4, 512, 480>("ctr-cached 4-table", key, t0, 1409, items, dig);
+  run<4, 512, 480>("ctr-cached 4-table", key, t0, 1410, items, dig);
+  run<4, 512, 352>("ctr-cached 4-table", key, t0, 1409, items, dig);
+  run<2, 1024, 960>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<4, 1024, 960>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<2, 768, 704>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<4, 768, 704>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<4, 768, 704>("ctr-cached 4-table", key, t0, 1409, items, dig);
+  run<4, 1024, 704>("ctr-cached 4-table", key, t0, 1409, items, dig);
+  run<4, 640, 576>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<2, 640, 576>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  return 0;
+}
