@@ -75,6 +75,8 @@ _SIGS = {
     "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_ssp_prover_polys": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p]),
+    "mfb_ssp_eval": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_flat_to_planar_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_flat_to_resident_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
 }
@@ -240,6 +242,22 @@ class Context:
         self._ck(self.lib.mfb_decrypt(self.h, _p64(sk), _p64(cts), None if neg is None else _p8(neg), count, _p64(m),
                                       None if dot is None else _p64(dot)))
         return (m, dot) if want_dot else m
+
+    def ssp_prover_polys(self, ssp, D: int, M: int, witness_limbs, delta: int):
+        """(w, v, h) coefficient arrays (D u64 each) of the prover's polynomial step."""
+        blob, wl = _arr(ssp, np.uint8).view(np.uint64), _arr(witness_limbs, np.uint64)
+        if blob.size < D * (M + 1):
+            raise ValueError("SSP blob shorter than D*(M+1) coefficients")
+        w, v, h = (np.zeros(D, np.uint64) for _ in range(3))
+        self._ck(self.lib.mfb_ssp_prover_polys(self.h, _p64(blob), D, M, _p64(wl), wl.size, delta, _p64(w), _p64(v), _p64(h)))
+        return w, v, h
+
+    def ssp_eval(self, polys, D: int, x: int) -> np.ndarray:
+        pl = _arr(polys, np.uint64).reshape(-1)
+        npoly = pl.size // D
+        out = np.zeros(npoly, np.uint64)
+        self._ck(self.lib.mfb_ssp_eval(self.h, _p64(pl), D, npoly, x, _p64(out)))
+        return out
 
     # ---------------------------------------------------------------- device flavour (raw pointers)
     def stream_dev(self, seed, offset: int, out_ptr: int, nbytes: int, stream: int = 0):

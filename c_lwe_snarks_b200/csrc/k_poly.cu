@@ -1,0 +1,617 @@
+// F_p[x] arithmetic for the prover's polynomial step and setup's evaluations.
+//
+//   prover (snark.c:138-169):  w = delta*t + sum_{witness bit i-1} v_i,  v = w + v_0,  h = (v^2 - 1) / t
+//   setup  (snark.c:93-110):   v_i(s) for every SSP polynomial (Horner in the reference)
+//
+// p = 2^32 - 5 has 2-adicity 1 (p - 1 = 2*5*429496729), so F_p has no useful NTT.  Products are computed over the
+// integers through three 30-bit NTT primes and Garner CRT (coefficients < D * (p-1)^2 < P1*P2*P3 ~ 2^86 for D <= 2^21), then
+// reduced mod p; division is Newton inversion of the reversed divisor.  Results are canonical residues, hence
+// bit-identical to FLINT's (and to the host stand-in c_lwe_snarks_b200/host/nmod_poly.c).
+//
+// NTT: radix-2, Montgomery arithmetic.  Forward = DIF (natural in, bit-reversed out), inverse = DIT (bit-reversed in,
+// natural out), so no permutation pass is needed around the pointwise product.  Stages whose butterflies span more
+// than NTT_B elements run one stage per launch over global memory (L2-resident: 3 primes x 2^18 x 4 B = 3 MB);
+// the last log2(NTT_B) stages run in one launch in shared memory.  All three primes share a launch (grid.y).
+#include "mfb_common.cuh"
+
+namespace mfb {
+
+constexpr int NPR = 3;
+__constant__ uint32_t c_P[NPR] = {998244353u, 469762049u, 167772161u};
+__constant__ uint32_t c_PINV[NPR];  // -P^{-1} mod 2^32
+__constant__ uint32_t c_R2[NPR];    // 2^64 mod P (to Montgomery form)
+static const uint32_t h_P[NPR] = {998244353u, 469762049u, 167772161u};
+static const uint32_t h_G[NPR] = {3u, 3u, 3u};
+
+constexpr int NTT_LOG_B = 11;
+constexpr int NTT_B = 1 << NTT_LOG_B;  // elements per CTA in the shared-memory kernel
+constexpr int NTT_T = NTT_B / 2;       // threads
+
+__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t P, uint32_t pinv) {
+  const uint64_t t = (uint64_t)a * b;
+  const uint32_t m = (uint32_t)t * pinv;
+  const uint32_t r = (uint32_t)((t + (uint64_t)m * P) >> 32);  // < 2P
+  return r >= P ? r - P : r;
+}
+__device__ __forceinline__ uint32_t add_mod(uint32_t a, uint32_t b, uint32_t P) {
+  const uint32_t s = a + b;
+  return s >= P ? s - P : s;
+}
+__device__ __forceinline__ uint32_t sub_mod(uint32_t a, uint32_t b, uint32_t P) { return a >= b ? a - b : a + P - b; }
+
+// ---- host-side modular helpers (table construction) ------------------------------------------------------
+static uint32_t h_mulmod(uint32_t a, uint32_t b, uint32_t m) { return (uint32_t)((uint64_t)a * b % m); }
+static uint32_t h_powmod(uint32_t a, uint64_t e, uint32_t m) {
+  uint32_t r = 1;
+  while (e) {
+    if (e & 1) r = h_mulmod(r, a, m);
+    a = h_mulmod(a, a, m);
+    e >>= 1;
+  }
+  return r;
+}
+
+// tw[k][j] = w_k^j in Montgomery form, j < nmax/2, w_k a primitive nmax-th root of unity mod P_k (inverse table: w^-j)
+__global__ void k_twiddle_fill(uint32_t *tw, uint32_t *twi, uint32_t nmax_half, uint32_t w0, uint32_t w1, uint32_t w2,
+                               uint32_t wi0, uint32_t wi1, uint32_t wi2) {
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k], r2 = c_R2[k];
+  const uint32_t w = k == 0 ? w0 : k == 1 ? w1 : w2, wi = k == 0 ? wi0 : k == 1 ? wi1 : wi2;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nmax_half; j += gridDim.x * blockDim.x) {
+    // w^j by square-and-multiply in Montgomery form
+    uint32_t base = mont_mul(w, r2, P, pinv), basei = mont_mul(wi, r2, P, pinv);
+    uint32_t acc = mont_mul(1, r2, P, pinv), acci = acc;
+    for (uint32_t e = j; e; e >>= 1) {
+      if (e & 1) {
+        acc = mont_mul(acc, base, P, pinv);
+        acci = mont_mul(acci, basei, P, pinv);
+      }
+      base = mont_mul(base, base, P, pinv);
+      basei = mont_mul(basei, basei, P, pinv);
+    }
+    tw[(size_t)k * nmax_half + j] = acc;
+    twi[(size_t)k * nmax_half + j] = acci;
+  }
+}
+
+// one radix-2 stage over global memory.  x: [3][n].  half = butterfly span.  tw index stride = nmax / (2*half).
+template <bool INVERSE>
+__global__ void k_ntt_stage(uint32_t *x, uint32_t n, uint32_t half, const uint32_t *__restrict__ tw, uint32_t nmax_half) {
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  uint32_t *xk = x + (size_t)k * n;
+  const uint32_t *twk = tw + (size_t)k * nmax_half;
+  const uint32_t tstride = nmax_half / half;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n / 2; t += gridDim.x * blockDim.x) {
+    const uint32_t j = t & (half - 1);
+    const uint32_t i = ((t - j) << 1) + j;
+    const uint32_t a = xk[i], b = xk[i + half];
+    const uint32_t w = twk[j * tstride];
+    if (INVERSE) {  // DIT
+      const uint32_t bw = mont_mul(b, w, P, pinv);
+      xk[i] = add_mod(a, bw, P);
+      xk[i + half] = sub_mod(a, bw, P);
+    } else {  // DIF
+      xk[i] = add_mod(a, b, P);
+      xk[i + half] = mont_mul(sub_mod(a, b, P), w, P, pinv);
+    }
+  }
+}
+
+// all stages with span < NTT_B inside shared memory; one CTA per contiguous block of min(n, NTT_B) elements
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTT_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ tw,
+                                                     uint32_t nmax_half, uint32_t scale /* Montgomery n^-1, inverse only */) {
+  __shared__ uint32_t s[NTT_B];
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  uint32_t *xk = x + (size_t)k * n + (size_t)blockIdx.x * blk;
+  const uint32_t *twk = tw + (size_t)k * nmax_half;
+  for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) s[i] = xk[i];
+  __syncthreads();
+  if (!INVERSE) {
+    for (uint32_t half = blk >> 1; half >= 1; half >>= 1) {
+      const uint32_t tstride = nmax_half / half;
+      for (uint32_t t = threadIdx.x; t < blk / 2; t += NTT_T) {
+        const uint32_t j = t & (half - 1), i = ((t - j) << 1) + j;
+        const uint32_t a = s[i], b = s[i + half];
+        s[i] = add_mod(a, b, P);
+        s[i + half] = mont_mul(sub_mod(a, b, P), twk[j * tstride], P, pinv);
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) xk[i] = s[i];
+  } else {
+    for (uint32_t half = 1; half < blk; half <<= 1) {
+      const uint32_t tstride = nmax_half / half;
+      for (uint32_t t = threadIdx.x; t < blk / 2; t += NTT_T) {
+        const uint32_t j = t & (half - 1), i = ((t - j) << 1) + j;
+        const uint32_t a = s[i], bw = mont_mul(s[i + half], twk[j * tstride], P, pinv);
+        s[i] = add_mod(a, bw, P);
+        s[i + half] = sub_mod(a, bw, P);
+      }
+      __syncthreads();
+    }
+    // the 1/n scaling is folded in when this is the last kernel of the inverse transform (n <= NTT_B)
+    for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) xk[i] = scale ? mont_mul(s[i], scale, P, pinv) : s[i];
+  }
+}
+
+__global__ void k_scale(uint32_t *x, uint32_t n, uint32_t s0, uint32_t s1, uint32_t s2) {
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k], sc = k == 0 ? s0 : k == 1 ? s1 : s2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    x[(size_t)k * n + i] = mont_mul(x[(size_t)k * n + i], sc, P, pinv);
+}
+
+// lift: out[k][i] = Montgomery(in[i] mod P_k) for i < len (in: canonical residues mod p as u32), 0 for len <= i < n.
+// reverse != 0 reads in[src_len - 1 - i] (polynomial reversal).
+__global__ void k_lift(const uint32_t *__restrict__ in, uint32_t len, uint32_t src_len, int reverse, uint32_t *out, uint32_t n) {
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k], r2 = c_R2[k];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    if (i < len) {
+      v = reverse ? in[src_len - 1 - i] : in[i];
+      v = mont_mul(v % P, r2, P, pinv);
+    }
+    out[(size_t)k * n + i] = v;
+  }
+}
+
+__global__ void k_pointwise(uint32_t *a, const uint32_t *__restrict__ b, uint32_t n) {
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)k * n + i;
+    a[o] = mont_mul(a[o], b[o], P, pinv);
+  }
+}
+
+struct CrtConst {
+  uint32_t inv_p1_p2;    // P1^-1 mod P2, Montgomery form mod P2
+  uint32_t inv_p1p2_p3;  // (P1 P2)^-1 mod P3, Montgomery form mod P3
+  uint32_t p1_mod_p3;
+  uint32_t p1_mod_p, p1p2_mod_p;
+};
+constexpr uint32_t FP = P;  // 2^32 - 5
+
+// Garner: x = x1 + x2*P1 + x3*P1*P2 (the exact integer coefficient), reduced mod p.  res: [3][n] in Montgomery form.
+// out[i] for i < len; mode 0: plain; mode 1: out[i] = (2*[i==0] - x) mod p  (Newton's 2 - f*g);
+// `lo` skips the first coefficients: out[i - lo] = coefficient i (used to take the upper half of a product).
+__global__ void k_crt(const uint32_t *__restrict__ res, uint32_t n, uint32_t lo, uint32_t len, CrtConst c, int mode,
+                      uint32_t *out) {
+  const uint32_t P1 = c_P[0], P2 = c_P[1], P3 = c_P[2];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const uint32_t idx = lo + i;
+    // leave Montgomery form: mont_mul(x, 1)
+    const uint32_t x1 = mont_mul(res[idx], 1, P1, c_PINV[0]);
+    const uint32_t y2 = mont_mul(res[(size_t)n + idx], 1, P2, c_PINV[1]);
+    const uint32_t y3 = mont_mul(res[2 * (size_t)n + idx], 1, P3, c_PINV[2]);
+    const uint32_t x2 = mont_mul(sub_mod(y2, x1 % P2, P2), c.inv_p1_p2, P2, c_PINV[1]);  // (y2 - x1) / P1 mod P2
+    const uint32_t part = (uint32_t)(((uint64_t)x2 * c.p1_mod_p3 + x1 % P3) % P3);         // x1 + x2 P1 mod P3
+    const uint32_t x3 = mont_mul(sub_mod(y3, part, P3), c.inv_p1p2_p3, P3, c_PINV[2]);
+    // value mod p: three terms, each < 2^64, summed in 128-bit-free form by reducing as we go
+    uint64_t v = x1 % FP;
+    v += (uint64_t)(x2 % FP) * c.p1_mod_p % FP;
+    v += (uint64_t)(x3 % FP) * c.p1p2_mod_p % FP;
+    uint32_t r = (uint32_t)(v % FP);
+    if (mode == 1) {
+      r = r ? FP - r : 0;
+      if (idx == 0) r = (uint32_t)(((uint64_t)r + 2) % FP);
+    }
+    out[i] = r;
+  }
+}
+
+// ---- prover-specific element-wise kernels ------------------------------------------------------------------
+// w[c] = (delta * t[c] + sum_k sel[k][c]) mod p ; sel are u64 wire coefficients (reduced mod p on import, ssp.c:28-34)
+__global__ void k_ssp_accumulate(const uint64_t *__restrict__ t, uint64_t delta, const uint64_t *__restrict__ sel,
+                                 uint32_t nsel, uint32_t D, int first_batch, uint32_t *w) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
+    uint64_t acc = first_batch ? (t[c] % FP) * (delta % FP) % FP : w[c];
+    for (uint32_t k = 0; k < nsel; k++) {
+      acc += sel[(size_t)k * D + c] % FP;
+      if (acc >= ((uint64_t)1 << 63)) acc %= FP;
+    }
+    w[c] = (uint32_t)(acc % FP);
+  }
+}
+__global__ void k_add_u64poly(const uint32_t *__restrict__ a, const uint64_t *__restrict__ b, uint32_t D, uint32_t *out) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x)
+    out[c] = (uint32_t)(((uint64_t)a[c] + b[c] % FP) % FP);
+}
+__global__ void k_reduce_u64poly(const uint64_t *__restrict__ b, uint32_t D, uint32_t *out) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) out[c] = (uint32_t)(b[c] % FP);
+}
+// *len = 1 + index of the highest non-zero coefficient (0 for the zero polynomial); *len must be 0 on entry
+__global__ void k_poly_length(const uint32_t *__restrict__ a, uint32_t n, uint32_t *len) {
+  uint32_t best = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (a[i]) best = i + 1;
+  best = __reduce_max_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(len, best);
+}
+__global__ void k_sub_one(uint32_t *a) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) a[0] = a[0] ? a[0] - 1 : FP - 1;
+}
+__global__ void k_set_inv0(const uint32_t *f, uint32_t *g) {  // g[0] = f[0]^(p-2) mod p
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t base = f[0], acc = 1;
+    for (uint32_t e = FP - 2; e; e >>= 1) {
+      if (e & 1) acc = acc * base % FP;
+      base = base * base % FP;
+    }
+    g[0] = (uint32_t)acc;
+  }
+}
+// out[i] = in[len - 1 - i] for i < len, zero up to n (reverse + pad), u32 -> u32
+__global__ void k_reverse(const uint32_t *__restrict__ in, uint32_t len, uint32_t *out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i < len ? in[len - 1 - i] : 0;
+}
+__global__ void k_widen(const uint32_t *__restrict__ in, uint32_t n, uint64_t *out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// values[q] = poly_q(x) mod p for q < npoly; polys are [npoly][D] u64 wire coefficients; pw[i] = x^i mod p
+__global__ void k_powers(uint64_t x, uint32_t D, uint32_t *pw) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) {
+    uint64_t base = x % FP, acc = 1;
+    for (uint32_t e = i; e; e >>= 1) {
+      if (e & 1) acc = acc * base % FP;
+      base = base * base % FP;
+    }
+    pw[i] = (uint32_t)acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_eval(const uint64_t *__restrict__ polys, uint32_t D, const uint32_t *__restrict__ pw,
+                                              uint64_t *values) {
+  __shared__ unsigned long long part[8];
+  const uint64_t *p = polys + (size_t)blockIdx.x * D;
+  unsigned long long acc = 0;  // D * p < 2^54 for D <= 2^22
+  for (uint32_t i = threadIdx.x; i < D; i += 256) acc += (p[i] % FP) * pw[i] % FP;
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < 8; w++) s += part[w];
+    values[blockIdx.x] = s % FP;
+  }
+}
+
+// =============================================================================================== host driver
+struct PolyEngine {
+  uint32_t nmax = 0;  // twiddle tables cover transforms up to this size
+  uint32_t *tw = nullptr, *twi = nullptr;
+  uint32_t *fa = nullptr, *fb = nullptr;  // [3][nmax] work arrays
+  uint32_t *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;  // coefficient scratch (u32, nmax each)
+  uint32_t *d_len = nullptr;
+  CrtConst crt;
+  bool consts_ready = false;
+  uint64_t launches = 0;
+};
+
+static inline unsigned gridfor(uint32_t n, int threads = 256) {
+  unsigned g = (n + threads - 1) / threads;
+  return g > 1184 ? 1184 : (g ? g : 1);
+}
+
+static cudaError_t engine_consts(PolyEngine &E) {
+  if (E.consts_ready) return cudaSuccess;
+  uint32_t pinv[NPR], r2[NPR];
+  for (int k = 0; k < NPR; k++) {
+    uint32_t inv = 1;
+    for (int i = 0; i < 5; i++) inv *= 2 - h_P[k] * inv;  // P^-1 mod 2^32 (Newton)
+    pinv[k] = (uint32_t)(0u - inv);
+    r2[k] = (uint32_t)(((unsigned __int128)1 << 64) % h_P[k]);
+  }
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_PINV, pinv, sizeof(pinv))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_R2, r2, sizeof(r2))) != cudaSuccess) return e;
+  const uint64_t P1 = h_P[0], P2 = h_P[1], P3 = h_P[2];
+  auto to_mont = [](uint32_t v, uint32_t m) { return (uint32_t)(((uint64_t)v << 32) % m); };
+  E.crt.inv_p1_p2 = to_mont(h_powmod((uint32_t)(P1 % P2), P2 - 2, (uint32_t)P2), (uint32_t)P2);
+  E.crt.inv_p1p2_p3 = to_mont(h_powmod((uint32_t)(P1 * P2 % P3), P3 - 2, (uint32_t)P3), (uint32_t)P3);
+  E.crt.p1_mod_p3 = (uint32_t)(P1 % P3);
+  E.crt.p1_mod_p = (uint32_t)(P1 % FP);
+  E.crt.p1p2_mod_p = (uint32_t)((unsigned __int128)P1 * P2 % FP);
+  E.consts_ready = true;
+  return cudaSuccess;
+}
+
+static void engine_free(PolyEngine &E) {
+  cudaFree(E.tw); cudaFree(E.twi); cudaFree(E.fa); cudaFree(E.fb); cudaFree(E.t1); cudaFree(E.t2); cudaFree(E.t3);
+  cudaFree(E.d_len);
+  E = PolyEngine();
+}
+
+static cudaError_t engine_reserve(PolyEngine &E, uint32_t n, cudaStream_t st) {
+  cudaError_t e = engine_consts(E);
+  if (e != cudaSuccess) return e;
+  if (n <= E.nmax) return cudaSuccess;
+  if (n > (1u << 23)) return cudaErrorInvalidValue;  // 2-adicity of the NTT primes
+  const bool had_consts = E.consts_ready;
+  const CrtConst crt = E.crt;
+  engine_free(E);
+  E.consts_ready = had_consts;
+  E.crt = crt;
+  const size_t half = n / 2;
+  if ((e = cudaMalloc(&E.tw, NPR * half * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.twi, NPR * half * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.fa, (size_t)NPR * n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.fb, (size_t)NPR * n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.t1, (size_t)n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.t2, (size_t)n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.t3, (size_t)n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.d_len, 16)) != cudaSuccess) return e;
+  uint32_t w[NPR], wi[NPR];
+  for (int k = 0; k < NPR; k++) {
+    w[k] = h_powmod(h_G[k], (h_P[k] - 1) / n, h_P[k]);
+    wi[k] = h_powmod(w[k], h_P[k] - 2, h_P[k]);
+  }
+  dim3 g(gridfor((uint32_t)half), NPR);
+  k_twiddle_fill<<<g, 256, 0, st>>>(E.tw, E.twi, (uint32_t)half, w[0], w[1], w[2], wi[0], wi[1], wi[2]);
+  E.launches++;
+  E.nmax = n;
+  return cudaGetLastError();
+}
+
+// in-place transforms of x[3][n]
+static void ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
+  const uint32_t nh = E.nmax / 2;
+  // the table holds w_nmax^j; a size-n transform uses w_n = w_nmax^(nmax/n): fold into the stride via nmax_half/half
+  for (uint32_t half = n / 2; half >= (uint32_t)NTT_B; half >>= 1) {
+    k_ntt_stage<false><<<dim3(gridfor(n / 2), NPR), 256, 0, st>>>(x, n, half, E.tw, nh);
+    E.launches++;
+  }
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  k_ntt_local<false><<<dim3(n / blk, NPR), NTT_T, 0, st>>>(x, n, E.tw, nh, 0);
+  E.launches++;
+}
+static void ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
+  const uint32_t nh = E.nmax / 2;
+  uint32_t sc[NPR];
+  for (int k = 0; k < NPR; k++) {
+    const uint32_t ninv = h_powmod(n % h_P[k], h_P[k] - 2, h_P[k]);
+    sc[k] = (uint32_t)(((uint64_t)ninv << 32) % h_P[k]);
+  }
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  k_ntt_local<true><<<dim3(n / blk, NPR), NTT_T, 0, st>>>(x, n, E.twi, nh, 0);
+  E.launches++;
+  for (uint32_t half = NTT_B; half < n; half <<= 1) {
+    k_ntt_stage<true><<<dim3(gridfor(n / 2), NPR), 256, 0, st>>>(x, n, half, E.twi, nh);
+    E.launches++;
+  }
+  k_scale<<<dim3(gridfor(n), NPR), 256, 0, st>>>(x, n, sc[0], sc[1], sc[2]);
+  E.launches++;
+}
+
+// out[0..out_len) = coefficients [lo, lo+out_len) of a*b mod p  (mode 1: of 2 - a*b).
+// a: la coefficients (read reversed from a source of a_src_len coefficients when a_rev), b likewise.
+static cudaError_t poly_mul(PolyEngine &E, const uint32_t *a, uint32_t la, uint32_t a_src_len, int a_rev, const uint32_t *b,
+                            uint32_t lb, uint32_t b_src_len, int b_rev, uint32_t lo, uint32_t out_len, int mode, uint32_t *out,
+                            cudaStream_t st) {
+  if (la == 0 || lb == 0 || out_len == 0) return cudaSuccess;
+  uint32_t n = 1;
+  while (n < la + lb - 1) n <<= 1;
+  if (n < 2) n = 2;
+  if (n > E.nmax) return cudaErrorInvalidValue;
+  const bool square = (a == b && la == lb && a_rev == b_rev && a_src_len == b_src_len);
+  k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(a, la, a_src_len, a_rev, E.fa, n);
+  E.launches++;
+  ntt_forward(E, E.fa, n, st);
+  if (!square) {
+    k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(b, lb, b_src_len, b_rev, E.fb, n);
+    E.launches++;
+    ntt_forward(E, E.fb, n, st);
+  }
+  k_pointwise<<<dim3(gridfor(n), NPR), 256, 0, st>>>(E.fa, square ? E.fa : E.fb, n);
+  E.launches++;
+  ntt_inverse(E, E.fa, n, st);
+  k_crt<<<gridfor(out_len), 256, 0, st>>>(E.fa, n, lo, out_len, E.crt, mode, out);
+  E.launches++;
+  return cudaGetLastError();
+}
+
+// g[0..m) = f^-1 mod x^m for f of lf coefficients (f[0] != 0), Newton: g <- g * (2 - f g) mod x^2k
+static cudaError_t poly_inv_series(PolyEngine &E, const uint32_t *f, uint32_t lf, uint32_t m, uint32_t *g, cudaStream_t st) {
+  k_set_inv0<<<1, 32, 0, st>>>(f, g);
+  E.launches++;
+  for (uint32_t k = 1; k < m;) {
+    const uint32_t k2 = 2 * k < m ? 2 * k : m;
+    const uint32_t lfk = lf < k2 ? lf : k2;
+    // t1 = 2 - f*g mod x^k2   (first k coefficients are 1, 0, 0, ... by construction; all are recomputed)
+    cudaError_t e = poly_mul(E, f, lfk, lfk, 0, g, k, k, 0, 0, k2, 1, E.t1, st);
+    if (e != cudaSuccess) return e;
+    // g[k..k2) = (g * t1)[k..k2)
+    uint32_t l1 = lfk + k - 1;
+    if (l1 > k2) l1 = k2;
+    e = poly_mul(E, g, k, k, 0, E.t1, l1, l1, 0, k, k2 - k, 0, g + k, st);
+    if (e != cudaSuccess) return e;
+    k = k2;
+  }
+  return cudaGetLastError();
+}
+
+// q = a / b (Euclidean quotient): q = rev( rev(a) * rev(b)^-1 mod x^lq ), lq = la - lb + 1; writes q_out[0..out_len)
+// (zero padded / truncated).  Uses E.t2 (inverse series) and E.t3 (reversed quotient).
+static cudaError_t poly_div(PolyEngine &E, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t *q_out,
+                            uint32_t out_len, cudaStream_t st) {
+  if (lb == 0) return cudaErrorInvalidValue;
+  if (la < lb) return cudaMemsetAsync(q_out, 0, (size_t)out_len * 4, st);
+  const uint32_t lq = la - lb + 1;
+  const uint32_t lbr = lb < lq ? lb : lq;
+  // brev = first lbr coefficients of rev(b) -> E.t3 (as a plain array so that Newton can index it)
+  k_reverse<<<gridfor(lb), 256, 0, st>>>(b, lb, E.t3, lb);
+  E.launches++;
+  cudaError_t e = poly_inv_series(E, E.t3, lbr, lq, E.t2, st);
+  if (e != cudaSuccess) return e;
+  // prod = rev(a)[0..lq) * binv[0..lq) mod x^lq -> E.t3
+  e = poly_mul(E, a, lq, la, 1, E.t2, lq, lq, 0, 0, lq, 0, E.t3, st);
+  if (e != cudaSuccess) return e;
+  // q[i] = prod[lq - 1 - i]
+  k_reverse<<<gridfor(out_len), 256, 0, st>>>(E.t3, lq < out_len ? lq : lq, q_out, out_len);
+  E.launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace mfb
+
+// ================================================================================================ C-ABI part
+#include "../../include/mfb200.h"
+
+namespace mfb {
+PolyEngine *poly_engine_of(mfb_ctx *ctx);         // mfb_capi.cu
+cudaStream_t ctx_stream_of(mfb_ctx *ctx);
+int ctx_scratch(mfb_ctx *ctx, int slot, size_t bytes, void **out);
+int ctx_fail(cudaError_t e, const char *what, const char *file, int line);
+void ctx_count_launches(mfb_ctx *ctx, uint64_t n);
+int ctx_enter(mfb_ctx *ctx);
+int ctx_bad_arg(const char *msg);
+
+PolyEngine *poly_engine_new() { return new PolyEngine(); }
+void poly_engine_delete(PolyEngine *e) {
+  if (e) {
+    engine_free(*e);
+    delete e;
+  }
+}
+}  // namespace mfb
+
+using namespace mfb;
+
+#define PTRY(expr)                                                          \
+  do {                                                                      \
+    cudaError_t e_ = (expr);                                                \
+    if (e_ != cudaSuccess) return ctx_fail(e_, #expr, __FILE__, __LINE__);  \
+  } while (0)
+
+extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, const uint64_t *witness_limbs,
+                                    size_t nlimbs, uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (!ssp || !witness_limbs || !w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys: null pointer");
+  if (D < 1 || D > (1u << 21) || M < 1) return ctx_bad_arg("mfb_ssp_prover_polys: need 1 <= D <= 2^21, M >= 1");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  uint32_t n = 2;
+  while (n < 2 * D) n <<= 1;
+  PTRY(engine_reserve(E, n, st));
+
+  // selected polynomials: t, v_0, and v_i for the set witness bits (bit i-1 <-> v_i, i = 1..M-1)
+  const uint32_t Du = (uint32_t)D;
+  const size_t BATCH = 64;  // polynomials staged per accumulate launch
+  void *d_t, *d_v0, *d_sel, *d_w, *d_v, *d_h, *d_a, *d_wide;
+  if ((rc = ctx_scratch(ctx, 0, D * 8, &d_t))) return rc;
+  if ((rc = ctx_scratch(ctx, 1, D * 8, &d_v0))) return rc;
+  if ((rc = ctx_scratch(ctx, 3, BATCH * D * 8, &d_sel))) return rc;
+  if ((rc = ctx_scratch(ctx, 4, (size_t)n * 4, &d_a))) return rc;  // v^2 - 1
+  if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;
+  d_v = (uint32_t *)d_w + D;
+  d_h = (uint32_t *)d_w + 2 * D;
+  if ((rc = ctx_scratch(ctx, 6, D * 8 * 3, &d_wide))) return rc;
+  PTRY(cudaMemcpyAsync(d_t, ssp, D * 8, cudaMemcpyHostToDevice, st));
+  PTRY(cudaMemcpyAsync(d_v0, ssp + D, D * 8, cudaMemcpyHostToDevice, st));
+  size_t staged = 0;
+  int first = 1;
+  auto flush = [&]() -> cudaError_t {
+    k_ssp_accumulate<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, delta, (const uint64_t *)d_sel, (uint32_t)staged, Du,
+                                                   first, (uint32_t *)d_w);
+    E.launches++;
+    first = 0;
+    staged = 0;
+    return cudaGetLastError();
+  };
+  for (size_t i = 1; i < M; i++) {
+    if (!((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1))) continue;
+    if (staged == BATCH) {
+      // the staging buffer is reused: wait until the previous batch has been consumed
+      PTRY(flush());
+      PTRY(cudaStreamSynchronize(st));
+    }
+    PTRY(cudaMemcpyAsync((uint64_t *)d_sel + staged * D, ssp + (i + 1) * D, D * 8, cudaMemcpyHostToDevice, st));
+    staged++;
+  }
+  PTRY(flush());
+  k_add_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_w, (const uint64_t *)d_v0, Du, (uint32_t *)d_v);
+  E.launches++;
+
+  // lengths of v and t (normalised), needed on the host to size the division
+  uint32_t lens[2] = {0, 0};
+  PTRY(cudaMemsetAsync(E.d_len, 0, 16, st));
+  k_poly_length<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_v, Du, E.d_len);
+  k_reduce_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, Du, E.t1);  // t as u32 residues (E.t1 is free here)
+  k_poly_length<<<gridfor(Du), 256, 0, st>>>(E.t1, Du, E.d_len + 1);
+  E.launches += 3;
+  PTRY(cudaMemcpyAsync(lens, E.d_len, 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  const uint32_t lv = lens[0], lt = lens[1];
+  if (lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys: t(x) is the zero polynomial");
+
+  // a = v^2 - 1
+  uint32_t la;
+  if (lv == 0) {  // v = 0: a = -1
+    PTRY(cudaMemsetAsync(d_a, 0, (size_t)n * 4, st));
+    la = 1;
+  } else {
+    la = 2 * lv - 1;
+    PTRY(poly_mul(E, (const uint32_t *)d_v, lv, lv, 0, (const uint32_t *)d_v, lv, lv, 0, 0, la, 0, (uint32_t *)d_a, st));
+  }
+  k_sub_one<<<1, 32, 0, st>>>((uint32_t *)d_a);
+  E.launches++;
+  if (la == 1) {  // the constant may have become 0
+    uint32_t a0;
+    PTRY(cudaMemcpyAsync(&a0, d_a, 4, cudaMemcpyDeviceToHost, st));
+    PTRY(cudaStreamSynchronize(st));
+    if (a0 == 0) la = 0;
+  }
+  // h = a / t : t as u32 residues must survive the division (E.t1 is scratch inside it) -> keep a copy in d_sel
+  uint32_t *t32 = (uint32_t *)d_sel;
+  PTRY(cudaMemcpyAsync(t32, E.t1, (size_t)Du * 4, cudaMemcpyDeviceToDevice, st));
+  PTRY(poly_div(E, (const uint32_t *)d_a, la, t32, lt, (uint32_t *)d_h, Du, st));
+
+  // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
+  k_widen<<<gridfor(3 * Du), 256, 0, st>>>((const uint32_t *)d_w, 3 * Du, (uint64_t *)d_wide);
+  E.launches++;
+  PTRY(cudaMemcpyAsync(w_out, d_wide, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(v_out, (uint64_t *)d_wide + D, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(h_out, (uint64_t *)d_wide + 2 * D, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  ctx_count_launches(ctx, E.launches - L0);
+  return MFB_OK;
+}
+
+extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (npoly == 0) return MFB_OK;
+  if (!polys || !values) return ctx_bad_arg("mfb_ssp_eval: null pointer");
+  if (D < 1 || D > (1u << 22)) return ctx_bad_arg("mfb_ssp_eval: need 1 <= D <= 2^22");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  const size_t BATCH = (size_t)256 << 20 >> 3;  // coefficients staged per batch (256 MB)
+  size_t per = BATCH / D ? BATCH / D : 1;
+  if (per > npoly) per = npoly;
+  void *d_pw, *d_p, *d_val;
+  if ((rc = ctx_scratch(ctx, 0, D * 4, &d_pw))) return rc;
+  if ((rc = ctx_scratch(ctx, 3, per * D * 8, &d_p))) return rc;
+  if ((rc = ctx_scratch(ctx, 1, npoly * 8, &d_val))) return rc;
+  k_powers<<<gridfor((uint32_t)D), 256, 0, st>>>(x, (uint32_t)D, (uint32_t *)d_pw);
+  E.launches++;
+  for (size_t q = 0; q < npoly; q += per) {
+    const size_t cnt = npoly - q < per ? npoly - q : per;
+    PTRY(cudaMemcpyAsync(d_p, polys + q * D, cnt * D * 8, cudaMemcpyHostToDevice, st));
+    k_eval<<<(unsigned)cnt, 256, 0, st>>>((const uint64_t *)d_p, (uint32_t)D, (const uint32_t *)d_pw, (uint64_t *)d_val + q);
+    E.launches++;
+    PTRY(cudaGetLastError());
+    if (q + per < npoly) PTRY(cudaStreamSynchronize(st));  // staging buffer reuse
+  }
+  PTRY(cudaMemcpyAsync(values, d_val, npoly * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  ctx_count_launches(ctx, E.launches - L0);
+  return MFB_OK;
+}

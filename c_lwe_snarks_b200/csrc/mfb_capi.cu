@@ -52,6 +52,10 @@ cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const u
 cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, int tiled,
                                   cudaStream_t st);
 
+struct PolyEngine;  // k_poly.cu
+PolyEngine *poly_engine_new();
+void poly_engine_delete(PolyEngine *e);
+
 constexpr int MAX_CHUNKS = 256;
 constexpr int NSLOTS = 8;
 
@@ -69,6 +73,7 @@ struct mfb_ctx {
   void *slot[NSLOTS] = {};         // growable device scratch for the host flavour
   size_t slot_cap[NSLOTS] = {};
   uint64_t launches = 0;
+  mfb::PolyEngine *poly = nullptr;  // F_p[x] engine (NTT tables, work arrays), created on first use
   // optional per-kernel timing of the dominant kernel of lincomb / eval_poly calls (bench.py's roofline)
   bool profiling = false;
   int prof_n = 0;
@@ -113,6 +118,22 @@ static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
     if (!(ctx)) return set_err(MFB_EARG, "null context");      \
     MFB_CUDA_TRY(cudaSetDevice((ctx)->device));                \
   } while (0)
+
+namespace mfb {  // hooks for k_poly.cu
+PolyEngine *poly_engine_of(mfb_ctx *ctx) {
+  if (!ctx->poly) ctx->poly = poly_engine_new();
+  return ctx->poly;
+}
+cudaStream_t ctx_stream_of(mfb_ctx *ctx) { return ctx->stream; }
+int ctx_scratch(mfb_ctx *ctx, int slot, size_t bytes, void **out) { return scratch(ctx, slot, bytes, out); }
+int ctx_fail(cudaError_t e, const char *what, const char *file, int line) { return fail(e, what, file, line); }
+void ctx_count_launches(mfb_ctx *ctx, uint64_t n) { ctx->launches += n; }
+int ctx_enter(mfb_ctx *ctx) {
+  MFB_CHECK_CTX(ctx);
+  return MFB_OK;
+}
+int ctx_bad_arg(const char *msg) { return set_err(MFB_EARG, "%s", msg); }
+}  // namespace mfb
 
 extern "C" {
 
@@ -169,6 +190,7 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
   if (ctx->t0_dev) cudaFree(ctx->t0_dev);
   if (ctx->partial_ws) cudaFree(ctx->partial_ws);
   if (ctx->queue) cudaFree(ctx->queue);
+  poly_engine_delete(ctx->poly);
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;

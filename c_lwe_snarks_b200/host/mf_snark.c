@@ -103,15 +103,14 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[i] = x;
   x = vrs->alpha;
   for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[D + i] = x;
-  nmod_poly_t v_i;
-  nmod_poly_init(v_i, GAMMA_P);
-  nmod_poly_import(&v_i, &ssp[ssp_t_offset], D);
-  msg[2 * D] = (nmod_poly_evaluate_nmod(v_i, vrs->s) * vrs->beta) % GAMMA_P;
-  for (size_t i = 1; i < M; i++) {
-    nmod_poly_import(&v_i, &ssp[ssp_v_offset(i)], D);
-    msg[2 * D + i] = (nmod_poly_evaluate_nmod(v_i, vrs->s) * vrs->beta) % GAMMA_P;
-  }
-  nmod_poly_clear(v_i);
+  /* t(s) and v_i(s): the reference's M Horner passes (snark.c:97-110) as one batched device evaluation over the
+   * dense blob [t, v_0, ..., v_{M-1}] (ssp.h:6-9); v_0(s) is computed and not used, as its slot is skipped there */
+  uint64_t *vals = malloc((M + 1) * 8);
+  if (!vals) mf_die("malloc");
+  MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, M + 1, vrs->s, vals));
+  msg[2 * D] = (vals[0] * vrs->beta) % GAMMA_P;
+  for (size_t i = 1; i < M; i++) msg[2 * D + i] = (vals[i + 1] * vrs->beta) % GAMMA_P;
+  free(vals);
 
   /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order */
   uint8_t *ent = malloc(count * MFB_ENT_BYTES), *recs = malloc(count * CT_BYTES);
@@ -132,7 +131,7 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
 }
 
 /* ------------------------------------------------------------------ prover (snark.c:117-190) */
-static void lincomb_region(ct_t rop, crs_t crs, int which_as, nmod_poly_t poly) {
+static void lincomb_region(ct_t rop, crs_t crs, int which_as, const uint64_t *poly) {
   const size_t D = GAMMA_D;
   uint64_t *acc = malloc(FLAT_CT * 8);
   if (!acc) mf_die("malloc");
@@ -141,16 +140,12 @@ static void lincomb_region(ct_t rop, crs_t crs, int which_as, nmod_poly_t poly) 
   if (r && r->d == D) {
     uint32_t *co = malloc(D * 4);
     if (!co) mf_die("malloc");
-    for (size_t i = 0; i < D; i++) co[i] = (uint32_t)nmod_poly_get_coeff_ui(poly, (slong)i);
+    for (size_t i = 0; i < D; i++) co[i] = (uint32_t)poly[i];
     MF_GPU(mfb_region_lincomb(mf_gpu(), which_as ? r->as : r->s, 0, co, D, acc));
     free(co);
   } else {
-    uint64_t *co = malloc(D * 8);
-    if (!co) mf_die("malloc");
-    for (size_t i = 0; i < D; i++) co[i] = nmod_poly_get_coeff_ui(poly, (slong)i);
     MF_GPU(mfb_eval_poly(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S,
-                         (const uint8_t *)(which_as ? crs->as : crs->s), co, NULL, D, acc));
-    free(co);
+                         (const uint8_t *)(which_as ? crs->as : crs->s), poly, NULL, D, acc));
   }
   mf_ct_from_flat(rop, acc);
   free(acc);
@@ -158,17 +153,18 @@ static void lincomb_region(ct_t rop, crs_t crs, int which_as, nmod_poly_t poly) 
 
 void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   const size_t D = GAMMA_D, M = GAMMA_M;
-  nmod_poly_t t, v_i, w, h, one;
-  nmod_poly_init(t, GAMMA_P);
-  nmod_poly_init(v_i, GAMMA_P);
-  nmod_poly_init(w, GAMMA_P);
-  nmod_poly_init(h, GAMMA_P);
-  nmod_poly_init(one, GAMMA_P);
-  nmod_poly_set_coeff_ui(one, 0, 1);
-
-  nmod_poly_import(&t, &ssp[ssp_t_offset], D);
   const uint64_t delta = rand_modp();
-  nmod_poly_scalar_mul_nmod(w, t, delta);
+  if (SIZ(witness) < 0) {
+    fprintf(stderr, "mangiafuoco_b200: prover: negative witness\n");
+    abort();
+  }
+
+  /* polynomial step (snark.c:138-169) on the device: w = delta*t + sum_{w_i} v_i, v = w + v_0 (l_u = 0),
+   * h = (v^2 - 1) / t  — FLINT's scalar_mul / add / pow / div in the reference */
+  uint64_t *pw = malloc(3 * D * 8);
+  if (!pw) mf_die("malloc");
+  uint64_t *pv = pw + D, *ph = pw + 2 * D;
+  MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
 
   /* b_w = delta * CT_t + sum_{witness bit i-1} CT_v[i-1]: ciphertext k of the region at CTR_BT is t for k = 0
    * and v[k-1] after it.  The reference regenerates every a-vector to advance its stream; only the selected
@@ -184,8 +180,6 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   idx[nsel++] = 0;
   for (size_t i = 1; i < M; i++) {
     if (mpz_tstbit(witness, i - 1)) {
-      nmod_poly_import(&v_i, &ssp[ssp_v_offset(i)], D);
-      nmod_poly_add(w, w, v_i);
       co[nsel] = 1;
       idx[nsel++] = (uint32_t)i;
     }
@@ -201,27 +195,11 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   free(co);
   free(idx);
 
-  lincomb_region(pi->v_w, crs, 0, w);
-
-  /* l_u = 0: v(x) = v_0(x) + w(x) */
-  nmod_poly_import(&v_i, &ssp[ssp_v_offset(0)], D);
-  nmod_poly_add(w, w, v_i);
-  lincomb_region(pi->hat_v, crs, 1, w);
-
-  /* h = (v^2 - 1) / t */
-  nmod_poly_set(h, w);
-  nmod_poly_pow(h, h, 2);
-  nmod_poly_sub(h, h, one);
-  nmod_poly_div(h, h, t);
-
-  lincomb_region(pi->h, crs, 0, h);
-  lincomb_region(pi->hat_h, crs, 1, h);
-
-  nmod_poly_clear(h);
-  nmod_poly_clear(v_i);
-  nmod_poly_clear(w);
-  nmod_poly_clear(one);
-  nmod_poly_clear(t);
+  lincomb_region(pi->v_w, crs, 0, pw);
+  lincomb_region(pi->hat_v, crs, 1, pv);
+  lincomb_region(pi->h, crs, 0, ph);
+  lincomb_region(pi->hat_h, crs, 1, ph);
+  free(pw);
 
   /* smudging, in the reference's order: v_w twice, b_w never (snark.c:185-189) */
   ct_smudge(pi->h);

@@ -150,6 +150,19 @@ MFB_API int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *c
 MFB_API int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const uint64_t *cts_flat_dev,
                     const uint8_t *b_neg_dev, size_t count, uint64_t *out_m_dev, uint64_t *out_dot_dev, void *stream);
 
+/* ---- F_p[x] steps of prover and setup (p = 2^32 - 5) ------------------------------------------- */
+/* The prover's polynomial step (snark.c:138-169; FLINT's nmod_poly add / scalar_mul / pow / div in the reference):
+ *   w = delta*t + sum_{witness bit i-1 set} v_i,   v = w + v_0,   h = (v^2 - 1) / t   (Euclidean quotient)
+ * ssp is the dense wire blob of ssp.h:6-9 in host memory: polynomial k at ssp[k*D .. (k+1)*D) as u64 coefficients
+ * (k = 0: t, k = i+1: v_i; reduced mod p on import as nmod_poly_import does).  witness bit i-1 selects v_i, i < M.
+ * Outputs: D canonical coefficients each (h truncated to D, as eval_poly reads it).  Multiplication = 3-prime NTT
+ * + CRT on the device, division = Newton inversion; results are canonical residues, identical to FLINT's. */
+MFB_API int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, const uint64_t *witness_limbs,
+                         size_t nlimbs, uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out);
+/* values[q] = poly_q(x) mod p for npoly polynomials of D u64 coefficients each (setup's nmod_poly_evaluate_nmod
+ * calls, snark.c:97-110) */
+MFB_API int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values);
+
 /* flat [count][n][11] -> row-planar [count][11][1472] on the device (secret keys: n = 1470) */
 MFB_API int mfb_flat_to_planar_dev(mfb_ctx *ctx, const uint64_t *flat_dev, int n, size_t count, uint64_t *planar_dev,
                            void *stream);
