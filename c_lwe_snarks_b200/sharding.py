@@ -89,6 +89,14 @@ class ShardedLincomb:
             self.ops.lincomb(cts, coeffs, d_local, self.result)
             return self.result
         self.ops.lincomb(cts, coeffs, d_local, self.partial)
+        return self.exchange()
+
+    def exchange(self):
+        """Combine the ranks' canonical partial sums (already in self.partial) into self.result on every rank."""
+        p = self.plan
+        if p.world == 1:
+            self.result.copy_(self.partial)
+            return self.result
         self.ops.columns_split(self.partial, self.cols)
         self.dist.reduce_scatter_tensor(self.cols_own, self.cols, op=self.dist.ReduceOp.SUM)
         self.own_flat.zero_()
