@@ -71,6 +71,8 @@ _SIGS = {
     "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mfb_eval_poly": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u32p, C.c_size_t, _u64p]),
     "mfb_eval_poly_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_eval_poly2": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u64p, C.c_size_t, _u64p, _u64p]),
+    "mfb_eval_poly2_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "mfb_encrypt": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p]),
     "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
@@ -205,6 +207,16 @@ class Context:
         self._ck(self.lib.mfb_eval_poly(self.h, _p8(s), offset, _p8(rec), _p64(co), None if ix is None else _p32(ix),
                                         co.size, _p64(r)))
         return r
+
+    def eval_poly2(self, seed, offset: int, c8, coeffs0, coeffs1, rop0=None, rop1=None):
+        s, rec = _seed(seed), _arr(c8, np.uint8)
+        c0, c1 = _arr(coeffs0, np.uint64), _arr(coeffs1, np.uint64)
+        if c0.size != c1.size or rec.size < c0.size * CT_BYTES:
+            raise ValueError("coefficient vectors must have equal length and one record per ciphertext")
+        r0 = np.zeros((NC, L64), np.uint64) if rop0 is None else _arr(rop0, np.uint64).copy()
+        r1 = np.zeros((NC, L64), np.uint64) if rop1 is None else _arr(rop1, np.uint64).copy()
+        self._ck(self.lib.mfb_eval_poly2(self.h, _p8(s), offset, _p8(rec), _p64(c0), _p64(c1), c0.size, _p64(r0), _p64(r1)))
+        return r0, r1
 
     def lincomb(self, cts_flat, coeffs, rop=None) -> np.ndarray:
         cts, co = _arr(cts_flat, np.uint64), _arr(coeffs, np.uint32)

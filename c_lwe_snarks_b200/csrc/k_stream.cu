@@ -227,6 +227,84 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
   }
 }
 
+// ------------------------------------------------------------------------------------ fused eval_poly, two scalar vectors
+// The prover walks each CRS region twice with different scalars (v_w and h over s; hat_v and hat_h over as,
+// snark.c:157-174).  One pass with both scalar vectors halves the AES work: tiles of 245 coordinates (1470 = 6 * 245),
+// threads [0, 245) accumulate vector 0 and [245, 490) vector 1 over the SAME keystream tile.
+constexpr int KS2_TILE = 245;
+constexpr int KS2_NTILES = N / KS2_TILE;  // 6
+constexpr int KS2_TILE_BYTES = KS2_TILE * CT_BYTES;
+__device__ __forceinline__ TileGeom tile_geom2(uint64_t ct_off, int tile) {
+  const uint64_t off = ct_off + (uint64_t)tile * KS2_TILE_BYTES;
+  TileGeom g;
+  g.first = off >> 4;
+  g.delta = (uint32_t)(off & 15);
+  g.nblk = (int)((g.delta + KS2_TILE_BYTES + 15) >> 4);
+  return g;
+}
+
+__global__ void __launch_bounds__(KS_THREADS, 1)
+k_evalpoly2(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+            const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
+            size_t d, int nchunks, uint64_t *__restrict__ partial0, uint64_t *__restrict__ partial1) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  AesCtrCache cache;
+  cache.window = ~0ull;
+  const int tile = blockIdx.x % KS2_NTILES;
+  const int chunk = blockIdx.x / KS2_NTILES;
+  const int vec = threadIdx.x >= KS2_TILE ? 1 : 0;      // for threads < 2 * KS2_TILE
+  const int lc = threadIdx.x - vec * KS2_TILE;          // local coordinate
+  const bool is_mac = threadIdx.x < 2 * KS2_TILE;
+  const bool is_b = (tile == 0 && (threadIdx.x == 2 * KS2_TILE || threadIdx.x == 2 * KS2_TILE + 1));
+  const uint32_t *coeffs = (is_b ? (threadIdx.x & 1) : vec) ? coeffs1 : coeffs0;  // 490 is even: thread 491 -> vector 1
+
+  Acc704 acc;
+  acc_zero(acc);
+  size_t m = chunk;
+  int ph = 0;
+  __syncthreads();  // tables ready
+  if (m < d) {
+    const TileGeom g = tile_geom2(offset + m * (uint64_t)CTR_CT, tile);
+    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
+  }
+  __syncthreads();
+  for (; m < d; m += nchunks, ph ^= 1) {
+    if (is_mac) {
+      const TileGeom g = tile_geom2(offset + m * (uint64_t)CTR_CT, tile);
+      uint32_t a[22];
+      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * lc, a);
+      acc_mad(acc, a, coeffs[m]);
+    } else if (is_b) {
+      const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + m * CT_BYTES);
+      uint32_t a[22];
+#pragma unroll
+      for (int l = 0; l < 22; l++) a[l] = rec[l];
+      acc_mad(acc, a, coeffs[m]);
+    }
+    const size_t nx = m + nchunks;
+    if (nx < d) {
+      const TileGeom gn = tile_geom2(offset + nx * (uint64_t)CTR_CT, tile);
+      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
+    }
+    __syncthreads();
+  }
+
+  if (is_mac || is_b) {
+    const int v = is_b ? (threadIdx.x & 1) : vec;
+    uint64_t *out = (v ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
+    uint32_t r[22];
+    acc_fold(acc, r);
+    const int c = is_b ? N : tile * KS2_TILE + lc;
+#pragma unroll
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+    if (is_b) {
+#pragma unroll
+      for (int j = 0; j < L64; j++) out[(size_t)j * NCP + N + 1] = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ Regev encryption
 // One CTA per ciphertext k (grid-stride): b_k = (e_k * p + <sk, a_k> + m_k) mod 2^704, written as the
 // 92-byte wire record.  sk is planar [11][1472].  e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes)
@@ -379,6 +457,25 @@ cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint
   if (e != cudaSuccess) return e;
   k_evalpoly<<<nchunks * KS_NTILES, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, idx, d, nchunks,
                                                                      partial_ws);
+  return cudaGetLastError();
+}
+
+int evalpoly2_nchunks(size_t d, int sm_count) {
+  size_t n = sm_count / KS2_NTILES;
+  if (n < 1) n = 1;
+  if (n > d) n = d;
+  return (int)(n ? n : 1);
+}
+
+// two scalar vectors in one pass: writes nchunks partial sums to partial0 and nchunks to partial1
+cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks,
+                                      uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
+  if (d == 0 || nchunks == 0) return cudaSuccess;
+  cudaError_t e = ks_attr((const void *)k_evalpoly2);
+  if (e != cudaSuccess) return e;
+  k_evalpoly2<<<nchunks * KS2_NTILES, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, d, nchunks,
+                                                                       partial0, partial1);
   return cudaGetLastError();
 }
 

@@ -44,6 +44,10 @@ int evalpoly_nchunks(size_t d, int sm_count);
 cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
                                      const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
                                      uint64_t *partial_ws, cudaStream_t st);
+int evalpoly2_nchunks(size_t d, int sm_count);
+cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks,
+                                      uint64_t *partial0, uint64_t *partial1, cudaStream_t st);
 cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
                            const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
                            uint8_t *out_c8, int sm_count, cudaStream_t st);
@@ -301,6 +305,27 @@ int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   return MFB_OK;
 }
 
+int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                       const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, size_t d, const uint64_t *rop0_in_dev,
+                       uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || !rop0_out_dev || !rop1_out_dev || (d && (!c8_dev || !coeffs0_dev || !coeffs1_dev)))
+    return set_err(MFB_EARG, "mfb_eval_poly2_dev: null pointer");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  int nchunks = d ? evalpoly2_nchunks(d, ctx->sm_count) : 0;
+  if (2 * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / 2;
+  uint64_t *p0 = ctx->partial_ws, *p1 = ctx->partial_ws + (size_t)nchunks * PLANAR_U64;
+  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
+  MFB_CUDA_TRY(launch_evalpoly2_partials(key, ctx->t0_dev, offset, c8_dev, coeffs0_dev, coeffs1_dev, d, nchunks, p0, p1,
+                                         (cudaStream_t)stream));
+  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
+  MFB_CUDA_TRY(launch_lincomb_finish(p0, nchunks, rop0_in_dev, rop0_out_dev, nullptr, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(p1, nchunks, rop1_in_dev, rop1_out_dev, nullptr, (cudaStream_t)stream));
+  ctx->launches += d ? 3 : 2;
+  return MFB_OK;
+}
+
 int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
                     const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride, int ent_nbytes, size_t count,
                     uint8_t *out_c8_dev, void *stream) {
@@ -402,6 +427,45 @@ int mfb_eval_poly(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const u
                            (const uint64_t *)d_rop, (uint64_t *)d_rop, ctx->stream);
   if (rc == MFB_OK) {
     cudaError_t e = cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(e, "D2H", __FILE__, __LINE__);
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  free(co32);
+  return rc;
+}
+
+int mfb_eval_poly2(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
+                   const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || !rop0_flat_inout || !rop1_flat_inout || (d && (!c8 || !coeffs0 || !coeffs1)))
+    return set_err(MFB_EARG, "mfb_eval_poly2: null pointer");
+  void *d_c8, *d_co, *d_rop;
+  MFB_TRY(scratch(ctx, 0, d * CT_BYTES, &d_c8));
+  MFB_TRY(scratch(ctx, 1, 2 * d * 4, &d_co));
+  MFB_TRY(scratch(ctx, 2, 2 * MFB_FLAT_CT_U64 * 8, &d_rop));
+  uint32_t *co32 = (uint32_t *)malloc(d ? 2 * d * 4 : 8);
+  if (!co32) return set_err(MFB_ENOMEM, "out of host memory");
+  int rc = narrow_coeffs(coeffs0, d, co32);
+  if (rc == MFB_OK) rc = narrow_coeffs(coeffs1, d, co32 + d);
+  uint64_t *r0 = (uint64_t *)d_rop, *r1 = (uint64_t *)d_rop + MFB_FLAT_CT_U64;
+  if (rc == MFB_OK) {
+    cudaError_t e = cudaSuccess;
+    do {
+      if (d && (e = cudaMemcpyAsync(d_c8, c8, d * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if (d && (e = cudaMemcpyAsync(d_co, co32, 2 * d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(r0, rop0_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(r1, rop1_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
+  }
+  if (rc == MFB_OK)
+    rc = mfb_eval_poly2_dev(ctx, seed, offset, (const uint8_t *)d_c8, (const uint32_t *)d_co, (const uint32_t *)d_co + d, d,
+                            r0, r0, r1, r1, ctx->stream);
+  if (rc == MFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(rop0_flat_inout, r0, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rop1_flat_inout, r1, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(e, "D2H", __FILE__, __LINE__);
   } else {

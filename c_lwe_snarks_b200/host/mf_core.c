@@ -78,6 +78,19 @@ mfb_ctx *mf_gpu(void) {
 
 uint64_t mf_gpu_launches(void) { return g_ctx ? mfb_launch_count(g_ctx) : 0; }
 
+/* ------------------------------------------------------------------ tracing (timeit.h:4-19 analogue) */
+#include <time.h>
+double mf_now(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+void mf_trace(const char *name, double t0) {
+  static int on = -1;
+  if (on < 0) on = getenv("MF_B200_TRACE") != NULL;
+  if (on) fprintf(stderr, "%s\t%.6f\n", name, mf_now() - t0);
+}
+
 /* ------------------------------------------------------------------ conversions */
 int mf_to_flat(uint64_t out[MF_LIMBS], mpz_srcptr z) {
   const int n = abs(SIZ(z));

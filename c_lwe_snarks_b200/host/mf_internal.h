@@ -32,4 +32,9 @@ void mf_ct_to_flat(uint64_t *out, ct_t ct, const char *who); /* aborts on a nega
 void mf_ct_from_flat(ct_t ct, const uint64_t *in);
 void mf_bytes_to_mpz(mpz_ptr z, const uint8_t *bytes, size_t n);
 
+
+/* Phase timing in the reference's timeit.h format ("name\tseconds" lines on stderr) when $MF_B200_TRACE is set. */
+double mf_now(void);
+void mf_trace(const char *name, double t0);
+
 #endif

@@ -91,10 +91,13 @@ void crs_clear(crs_t crs) {
 /* ------------------------------------------------------------------ setup (snark.c:57-115) */
 void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   const size_t D = GAMMA_D, M = GAMMA_M, count = 2 * D + M;
+  double t0 = mf_now();
   vrs->alpha = rand_modp();
   vrs->beta = rand_modp();
   vrs->s = rand_modp();
   key_gen(vrs->sk);
+  mf_trace("setup.key_gen", t0);
+  t0 = mf_now();
 
   /* plaintexts in stream order (snark.h:8-12): s^i, alpha*s^i, beta*t(s), beta*v_i(s) for i = 1..M-1 */
   uint64_t *msg = malloc(count * 8);
@@ -111,14 +114,19 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   msg[2 * D] = (vals[0] * vrs->beta) % GAMMA_P;
   for (size_t i = 1; i < M; i++) msg[2 * D + i] = (vals[i + 1] * vrs->beta) % GAMMA_P;
   free(vals);
+  mf_trace("setup.plaintexts+evaluations", t0);
+  t0 = mf_now();
 
   /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order */
   uint8_t *ent = malloc(count * MFB_ENT_BYTES), *recs = malloc(count * CT_BYTES);
   uint64_t *skf = malloc(MFB_FLAT_SK_U64 * 8);
   if (!ent || !recs || !skf) mf_die("malloc");
   mf_entropy(ent, count * MFB_ENT_BYTES);
+  mf_trace("setup.entropy", t0);
+  t0 = mf_now();
   for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
   MF_GPU(mfb_encrypt(mf_gpu(), crs->seed, 0, skf, msg, ent, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+  mf_trace("setup.encrypt", t0);
   memcpy(crs->s, recs, D * CT_BYTES);
   memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);
   memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
@@ -151,6 +159,18 @@ static void lincomb_region(ct_t rop, crs_t crs, int which_as, const uint64_t *po
   free(acc);
 }
 
+static void lincomb_pair(ct_t rop0, ct_t rop1, crs_t crs, int which_as, const uint64_t *poly0, const uint64_t *poly1) {
+  uint64_t *acc = malloc(2 * FLAT_CT * 8);
+  if (!acc) mf_die("malloc");
+  mf_ct_to_flat(acc, rop0, "prover");
+  mf_ct_to_flat(acc + FLAT_CT, rop1, "prover");
+  MF_GPU(mfb_eval_poly2(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S, (const uint8_t *)(which_as ? crs->as : crs->s), poly0,
+                        poly1, GAMMA_D, acc, acc + FLAT_CT));
+  mf_ct_from_flat(rop0, acc);
+  mf_ct_from_flat(rop1, acc + FLAT_CT);
+  free(acc);
+}
+
 void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   const size_t D = GAMMA_D, M = GAMMA_M;
   const uint64_t delta = rand_modp();
@@ -164,7 +184,10 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   uint64_t *pw = malloc(3 * D * 8);
   if (!pw) mf_die("malloc");
   uint64_t *pv = pw + D, *ph = pw + 2 * D;
+  double t0 = mf_now();
   MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+  mf_trace("prover.polys", t0);
+  t0 = mf_now();
 
   /* b_w = delta * CT_t + sum_{witness bit i-1} CT_v[i-1]: ciphertext k of the region at CTR_BT is t for k = 0
    * and v[k-1] after it.  The reference regenerates every a-vector to advance its stream; only the selected
@@ -195,11 +218,23 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   free(co);
   free(idx);
 
-  lincomb_region(pi->v_w, crs, 0, pw);
-  lincomb_region(pi->hat_v, crs, 1, pv);
-  lincomb_region(pi->h, crs, 0, ph);
-  lincomb_region(pi->hat_h, crs, 1, ph);
+  mf_trace("prover.b_w", t0);
+  t0 = mf_now();
+  {
+    struct resident *r = resident_find(crs);
+    if (r && r->d == D) { /* regions resident in HBM: four lincombs at the HBM roofline */
+      lincomb_region(pi->v_w, crs, 0, pw);
+      lincomb_region(pi->hat_v, crs, 1, pv);
+      lincomb_region(pi->h, crs, 0, ph);
+      lincomb_region(pi->hat_h, crs, 1, ph);
+    } else { /* a regenerated from AES: one pass per region carrying both scalar vectors */
+      lincomb_pair(pi->v_w, pi->h, crs, 0, pw, ph);
+      lincomb_pair(pi->hat_v, pi->hat_h, crs, 1, pv, ph);
+    }
+  }
   free(pw);
+  mf_trace("prover.lincombs", t0);
+  t0 = mf_now();
 
   /* smudging, in the reference's order: v_w twice, b_w never (snark.c:185-189) */
   ct_smudge(pi->h);
@@ -207,6 +242,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   ct_smudge(pi->hat_v);
   ct_smudge(pi->v_w);
   ct_smudge(pi->v_w);
+  mf_trace("prover.smudge", t0);
 }
 
 /* ------------------------------------------------------------------ verifier (snark.c:192-250) */

@@ -129,6 +129,15 @@ MFB_API int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t off
                       const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
                       uint64_t *rop_out_dev, void *stream);
 
+/* Two scalar vectors over the SAME ciphertexts in one pass (half the AES work of two mfb_eval_poly calls):
+ * rop0 += sum coeffs0[m] * CT_m, rop1 += sum coeffs1[m] * CT_m.  The prover pairs (v_w, h) over the s region and
+ * (hat_v, hat_h) over the as region (snark.c:157-174). */
+MFB_API int mfb_eval_poly2(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
+                   const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
+MFB_API int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                       const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, size_t d, const uint64_t *rop0_in_dev,
+                       uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, void *stream);
+
 /* ---- K3+K5: Regev encryption -------------------------------------------------------------- */
 /* out_c8[k] = ct_export(regev_encrypt2(rng at offset + k*MFB_CTR_CT, sk, msg[k], e_k)) for k < count
  * (lwe.c:78-97, 115-119): b = (e*p + <sk, a> + m) mod 2^704.  e_k is the little-endian integer of

@@ -196,6 +196,19 @@ def test_lincomb_resident_vs_fused_and_oracle(ctx, oracle, torch):
     assert np.array_equal(wide(d_rop.cpu().numpy().view(np.uint64).reshape(NC, L64)), want)
 
 
+@pytest.mark.parametrize("d,off", [(1, 0), (7, 3 * CTR_CT + 8), (60, 11), (333, 2**36 + 5 * CTR_CT)])
+def test_eval_poly2_vs_oracle(ctx, oracle, d, off):
+    """two scalar vectors in one pass == two eval_poly calls == the oracle (prover pairs v_w/h and hat_v/hat_h)"""
+    c8 = xof_records(f"ev2-c8-{d}", d)
+    h0, h1 = xof_scalars(f"ev2-h0-{d}", d), xof_scalars(f"ev2-h1-{d}", d)
+    h1[0] = 0
+    rop0 = xof(f"ev2-rop-{d}", NC * 88).view("<u8").reshape(NC, L64)
+    got0, got1 = ctx.eval_poly2(SEED, off, c8, h0, h1, rop0=rop0)
+    assert np.array_equal(wide(got0), oracle.eval_poly(SEED, off, c8, h0, rop=wide(rop0)))
+    assert np.array_equal(wide(got1), oracle.eval_poly(SEED, off, c8, h1))
+    assert np.array_equal(got1, ctx.eval_poly(SEED, off, c8, h1))
+
+
 def test_region(ctx, oracle):
     d, off = 64, 9 * CTR_CT
     c8, h = xof_records("reg-c8", d), xof_scalars("reg-h", d)
