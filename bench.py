@@ -142,7 +142,7 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cores = max(1, min(cores, 64))
+    cores = max(1, min(cores, 256))
     steps, warm = args.steps, args.warmup
     # ~2 ms per ciphertext-MAC per core; keep the whole run near two minutes
     per_core = max(16, min(2048, int(120.0 / (steps + warm) / 2.1e-3)))
@@ -166,8 +166,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts, n=1470, logq=736 "
-                                   f"(eff. 704); CPU sample {total} ciphertexts per step",
+            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts per GPU, n=1470, logq=736 "
+                                   f"(eff. 704), p=2^32-5",
+                       "reference_path": "eval_poly of the unmodified reference (oracle/_ref): AES-CTR regeneration + GMP MAC",
                        "sample_ciphertexts_per_step": total},
             "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
                              "sample": f"{total} ciphertexts per step ({per_core} per core x {cores} processes over disjoint "

@@ -105,6 +105,36 @@ class Snark:
         """Flip one bit of the proof (limb 0 of h's b coordinate)."""
         self.proof.h[N].d[0] ^= 1 << 40
 
+    # persistence (mf_io.c)
+    def save_crs(self, path: str):
+        if self.lib.mf_crs_write(str(path).encode(), C.byref(self.crs)) != 0:
+            raise OSError(f"mf_crs_write({path}) failed")
+
+    def load_crs(self, path: str):
+        if not self._crs_live:
+            self.lib.crs_init(C.byref(self.crs))
+            self._crs_live = True
+        if self.lib.mf_crs_read(str(path).encode(), C.byref(self.crs)) != 0:
+            raise OSError(f"mf_crs_read({path}) failed (wrong instance size or truncated file)")
+
+    def save_proof(self, path: str):
+        if self.lib.mf_proof_write(str(path).encode(), C.byref(self.proof)) != 0:
+            raise OSError(f"mf_proof_write({path}) failed")
+
+    def load_proof(self, path: str):
+        if not self._proof_live:
+            self.lib.proof_init(C.byref(self.proof))
+            self._proof_live = True
+        if self.lib.mf_proof_read(str(path).encode(), C.byref(self.proof)) != 0:
+            raise OSError(f"mf_proof_read({path}) failed")
+
+    def crs_records(self):
+        """(seed, s, as, t, v) of the live CRS as numpy copies."""
+        D, M = self.D, self.M
+        grab = lambda p, n: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).copy()  # noqa: E731
+        return (bytes(self.crs.seed), grab(self.crs.s, 92 * D), grab(self.crs.as_, 92 * D), grab(self.crs.t, 92),
+                grab(self.crs.v, 92 * (M - 1)))
+
     def gpu_launches(self) -> int:
         return int(self.lib.mf_gpu_launches())
 

@@ -233,6 +233,13 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi);
  * regeneration of the a-vectors is then paid once instead of per proof.  mf_crs_release frees them. */
 void mf_crs_make_resident(crs_t crs);
 void mf_crs_release(crs_t crs);
+/* Persistence (the reference only sketches a "crs.mfuoco" mmap, benchmark_snark.c:23-24): the CRS file is a 24-byte
+ * header (magic, D, M) + seed + the 92-byte records in stream order s, as, t, v; a proof file holds the five
+ * ciphertexts as 88-byte magnitudes plus the sign of each b.  Return 0, or -1 with errno set. */
+int mf_crs_write(const char *path, crs_t crs);
+int mf_crs_read(const char *path, crs_t crs);
+int mf_proof_write(const char *path, proof_t pi);
+int mf_proof_read(const char *path, proof_t pi);
 /* number of GPU kernels launched by the library so far */
 uint64_t mf_gpu_launches(void);
 

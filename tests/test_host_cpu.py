@@ -80,3 +80,62 @@ def test_python_binding_argument_checks():
         _seed(b"short")
     import c_lwe_snarks_b200 as m
     assert m.ALGO_BYTES_PER_MAC == 1471 * 88 and m.PLANAR_U64 * 8 == 129536 and m.CTR_CT == 135240 and m.P == P
+
+
+def test_crs_file_roundtrip(tmp_path):
+    """mf_crs_write / mf_crs_read: header + seed + records in stream order (s, as, t, v); size mismatch is refused."""
+    import ctypes as C
+
+    from c_lwe_snarks_b200.snark import Snark
+    D, M = 32, 16
+    a = Snark(D, M)
+    a.lib.crs_init(C.byref(a.crs))
+    a._crs_live = True
+    for ptr, n, label in ((a.crs.s, 92 * D, "s"), (a.crs.as_, 92 * D, "as"), (a.crs.t, 92, "t"), (a.crs.v, 92 * (M - 1), "v")):
+        C.memmove(ptr, xof("crs-" + label, n).tobytes(), n)
+    path = tmp_path / "crs.mfuoco"
+    a.save_crs(path)
+    raw = path.read_bytes()
+    seed, s_, as_, t_, v_ = a.crs_records()
+    assert raw[:8] == b"MFUOCO1\0" and int.from_bytes(raw[8:16], "little") == D and int.from_bytes(raw[16:24], "little") == M
+    assert raw[24:64] == seed and raw[64:] == s_.tobytes() + as_.tobytes() + t_.tobytes() + v_.tobytes()
+    b = Snark(D, M)
+    b.load_crs(path)
+    assert b.crs_records()[0] == seed and all(np.array_equal(x, y) for x, y in zip(a.crs_records()[1:], b.crs_records()[1:]))
+    c = Snark(2 * D, M)
+    with pytest.raises(OSError):
+        c.load_crs(path)
+    a.lib.mf_set_instance(D, M)
+    for sn in (a, b, c):
+        sn.lib.mf_set_instance(sn.D, sn.M)
+        sn.close()
+
+
+def test_proof_file_roundtrip(tmp_path):
+    import ctypes as C
+
+    from c_lwe_snarks_b200.snark import N, Snark
+    sn = Snark(32, 16)
+    sn.lib.proof_init(C.byref(sn.proof))
+    sn._proof_live = True
+    imp = getattr(sn.gmp, "__gmpz_import")
+    imp.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p]
+    neg = getattr(sn.gmp, "__gmpz_neg")
+    cmp_ = getattr(sn.gmp, "__gmpz_cmp")
+    elems = [sn.proof.h, sn.proof.hat_h, sn.proof.hat_v, sn.proof.v_w, sn.proof.b_w]
+    for k, el in enumerate(elems):
+        data = xof(f"proof-{k}", (N + 1) * 88)
+        for i in range(0, N + 1, 97):
+            imp(C.byref(el[i]), 88, -1, 1, -1, 0, data[i * 88:(i + 1) * 88].ctypes.data)
+        imp(C.byref(el[N]), 88, -1, 1, -1, 0, data[N * 88:].ctypes.data)
+    neg(C.byref(elems[3][N]), C.byref(elems[3][N]))  # a negative b, as ct_smudge can leave it
+    path = tmp_path / "proof.bin"
+    sn.save_proof(path)
+    other = Snark(32, 16)
+    other.load_proof(path)
+    for a, b in zip(elems, [other.proof.h, other.proof.hat_h, other.proof.hat_v, other.proof.v_w, other.proof.b_w]):
+        for i in list(range(0, N + 1, 97)) + [1, N]:
+            assert cmp_(C.byref(a[i]), C.byref(b[i])) == 0
+    assert other.proof.v_w[N].size < 0
+    sn.close()
+    other.close()
