@@ -110,7 +110,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
-def ref_lib(d_hint: int = 256):
+def ref_lib():
+    """The compiled reference (oracle/_ref/libmfref_d256_m64.so); eval_poly does not depend on the instance size."""
     from oracle.loader import Reference
     return Reference(256, 64)
 

@@ -126,7 +126,6 @@ void mpz_add_dotp(mpz_t rop, mpz_t a[], mpz_t b[], size_t len) {
   }
   uint64_t *ct = calloc(FLAT_CT, 8), *sk = calloc(MFB_FLAT_SK_U64, 8);
   if (!ct || !sk) mf_die("malloc");
-  int neg = 0;
   for (size_t i = 0; i < len; i++) {
     /* (-x)(-y) = xy; a single negative factor flips the product: fold signs into the a side mod 2^704 */
     int na = mf_to_flat(ct + i * MF_LIMBS, a[i]), nb = mf_to_flat(sk + i * MF_LIMBS, b[i]);
@@ -136,10 +135,8 @@ void mpz_add_dotp(mpz_t rop, mpz_t a[], mpz_t b[], size_t len) {
         x[l] = ~x[l] + carry;
         carry = carry && x[l] == 0;
       }
-      neg = 1;
     }
   }
-  (void)neg;
   uint64_t m_unused, dot[MF_LIMBS];
   MF_GPU(mfb_decrypt(mf_gpu(), sk, ct, NULL, 1, &m_unused, dot));
   mpz_t d;

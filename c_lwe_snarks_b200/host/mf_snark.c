@@ -65,8 +65,18 @@ void mf_crs_make_resident(crs_t crs) {
   if (!r) mf_die("malloc");
   r->owner = crs;
   r->d = GAMMA_D;
-  MF_GPU(mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s));
-  MF_GPU(mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as));
+  /* 2 x D x 129 536 B of HBM; when that does not fit (D = 2^20 needs 272 GB on one GPU) the regions simply stay
+   * non-resident and prover() keeps regenerating a from AES in-kernel — slower, same result */
+  int rc = mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s);
+  if (rc == MFB_OK) rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
+  if (rc != MFB_OK) {
+    if (rc != MFB_ENOMEM) mf_die("mfb_region_create");
+    fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident: %s; the CRS stays non-resident\n", mfb_last_error());
+    mfb_region_destroy(mf_gpu(), r->s);
+    mfb_region_destroy(mf_gpu(), r->as);
+    free(r);
+    return;
+  }
   r->next = g_resident;
   g_resident = r;
 }
