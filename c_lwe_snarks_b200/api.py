@@ -63,6 +63,8 @@ _SIGS = {
     "mfb_stream_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp]),
     "mfb_expand_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, C.c_size_t, _vp, _vp]),
     "mfb_lincomb_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_lincomb2_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
+    "mfb_region_lincomb2": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
     "mfb_lincomb": (C.c_int, [_vp, _u64p, _u32p, C.c_size_t, _u64p]),
     "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_region_destroy": (None, [_vp, _vp]),
@@ -78,6 +80,9 @@ _SIGS = {
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_ssp_prover_polys": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p]),
+    "mfb_ssp_create": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
+    "mfb_ssp_destroy": (None, [_vp, _vp]),
+    "mfb_ssp_prover_polys_resident": (C.c_int, [_vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p]),
     "mfb_ssp_eval": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_flat_to_planar_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_flat_to_resident_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
@@ -140,9 +145,38 @@ class Region:
         self.ctx._ck(self.ctx.lib.mfb_region_lincomb(self.ctx.h, self.handle, first, _p32(co), co.size, _p64(r)))
         return r
 
+    def lincomb2(self, coeffs0, coeffs1, first: int = 0, rop0=None, rop1=None):
+        c0, c1 = _arr(coeffs0, np.uint32), _arr(coeffs1, np.uint32)
+        if c0.size != c1.size:
+            raise ValueError("coefficient vectors must have equal length")
+        r0 = np.zeros((NC, L64), np.uint64) if rop0 is None else _arr(rop0, np.uint64).copy()
+        r1 = np.zeros((NC, L64), np.uint64) if rop1 is None else _arr(rop1, np.uint64).copy()
+        self.ctx._ck(self.ctx.lib.mfb_region_lincomb2(self.ctx.h, self.handle, first, _p32(c0), _p32(c1), c0.size, _p64(r0),
+                                                      _p64(r1)))
+        return r0, r1
+
     def close(self):
         if self.handle:
             self.ctx.lib.mfb_region_destroy(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class ResidentSsp:
+    """An SSP blob kept on the device (with the cached Newton inverse of rev(t))."""
+
+    def __init__(self, ctx: "Context", handle, D: int, M: int):
+        self.ctx, self.handle, self.D, self.M = ctx, handle, D, M
+
+    def prover_polys(self, witness_limbs, delta: int):
+        wl = _arr(witness_limbs, np.uint64)
+        w, v, h = (np.zeros(self.D, np.uint64) for _ in range(3))
+        self.ctx._ck(self.ctx.lib.mfb_ssp_prover_polys_resident(self.ctx.h, self.handle, _p64(wl), wl.size, delta, _p64(w),
+                                                                _p64(v), _p64(h)))
+        return w, v, h
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.mfb_ssp_destroy(self.ctx.h, self.handle)
             self.handle = None
 
 
@@ -263,6 +297,14 @@ class Context:
         w, v, h = (np.zeros(D, np.uint64) for _ in range(3))
         self._ck(self.lib.mfb_ssp_prover_polys(self.h, _p64(blob), D, M, _p64(wl), wl.size, delta, _p64(w), _p64(v), _p64(h)))
         return w, v, h
+
+    def ssp_resident(self, ssp, D: int, M: int) -> "ResidentSsp":
+        blob = _arr(ssp, np.uint8).view(np.uint64)
+        if blob.size < D * (M + 1):
+            raise ValueError("SSP blob shorter than D*(M+1) coefficients")
+        h = _vp()
+        self._ck(self.lib.mfb_ssp_create(self.h, _p64(blob), D, M, C.byref(h)))
+        return ResidentSsp(self, h, D, M)
 
     def ssp_eval(self, polys, D: int, x: int) -> np.ndarray:
         pl = _arr(polys, np.uint64).reshape(-1)

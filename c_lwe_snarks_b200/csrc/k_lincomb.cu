@@ -54,9 +54,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // grid (23 tiles, nslots).  queue[tile * LC_CTR_STRIDE] = next chunk of that tile (zero on entry; reset by finish).
 // partial[slot] is row-planar: limb row j, coordinate c at j*1472 + c.
+// NVEC scalar vectors share one pass over the ciphertexts (coeffs[v], partial + v * partial_stride): the prover pairs
+// (v_w, h) over the s region and (hat_v, hat_h) over the as region, halving its HBM traffic.
+template <int NVEC>
 __global__ void __launch_bounds__(LC_TILE)
-k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs, size_t d, uint32_t chunk_len,
-          unsigned int *__restrict__ queue, uint64_t *__restrict__ partial) {
+k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
+          size_t d, uint32_t chunk_len, unsigned int *__restrict__ queue, uint64_t *__restrict__ partial,
+          size_t partial_stride) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * LC_STAGES];  // [0, S): full (tx), [S, 2S): empty (2 warps)
   __shared__ uint32_t meta_first[LC_STAGES];             // first ciphertext of the stage (d < 2^32 per GPU)
@@ -104,8 +108,9 @@ k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs,
   if (threadIdx.x == 0)
     for (int s = 0; s < LC_STAGES; s++) issue(s);
 
-  Acc704 acc;
-  acc_zero(acc);
+  Acc704 acc[NVEC];
+#pragma unroll
+  for (int v = 0; v < NVEC; v++) acc_zero(acc[v]);
   for (uint32_t it = 0;; it++) {
     const int s = (int)(it % LC_STAGES);
     const uint32_t ph = (it / LC_STAGES) & 1;
@@ -122,7 +127,8 @@ k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs,
         a[2 * j] = (uint32_t)v;
         a[2 * j + 1] = (uint32_t)(v >> 32);
       }
-      acc_mad(acc, a, __ldg(coeffs + first + g));
+      acc_mad(acc[0], a, __ldg(coeffs0 + first + g));
+      if constexpr (NVEC == 2) acc_mad(acc[1], a, __ldg(coeffs1 + first + g));
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bbase + 8 * (LC_STAGES + s));  // this warp is done with slot s
@@ -132,11 +138,14 @@ k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs,
     }
   }
 
-  uint32_t r[22];
-  acc_fold(acc, r);
-  uint64_t *out = partial + (size_t)blockIdx.y * PLANAR_U64 + tile * LC_TILE + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < L64; j++) out[(size_t)j * NCP] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+  for (int v = 0; v < NVEC; v++) {
+    uint32_t r[22];
+    acc_fold(acc[v], r);
+    uint64_t *out = partial + v * partial_stride + (size_t)blockIdx.y * PLANAR_U64 + tile * LC_TILE + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+  }
 }
 
 // rop[c] = (rop_in[c] + sum_k partial[k][c]) mod 2^704.  rop is "flat": [1471][11] u64, coordinate-major.
@@ -239,33 +248,45 @@ __global__ void k_columns_carry(const uint64_t *__restrict__ cols, int c0, int n
 
 // ---------------------------------------------------------------------------------------------
 // number of CTA slots per tile such that every CTA of the grid is resident at once
-int lincomb_nslots(size_t d, int sm_count) {
+template <int NVEC>
+static int nslots_for(size_t d, int sm_count) {
   static int occ = 0;
   if (!occ) {
-    cudaFuncSetAttribute(k_lincomb, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb, LC_TILE, LC_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 8;
+    cudaFuncSetAttribute(k_lincomb<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb<NVEC>, LC_TILE, LC_SMEM_BYTES) != cudaSuccess || occ < 1)
+      occ = 6;
   }
   size_t n = (size_t)sm_count * occ / RT_NTILES;
   const size_t chunks = (d + 3) / 4;
   if (n > chunks) n = chunks;
   return (int)(n ? n : 1);
 }
+int lincomb_nslots(size_t d, int sm_count, int nvec) {
+  return nvec == 2 ? nslots_for<2>(d, sm_count) : nslots_for<1>(d, sm_count);
+}
 
 typedef void (*mark_fn)(void *, int, cudaStream_t);
-// launches the main kernel only; *nslots_inout returns the number of partial sums written
-cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
-                                    unsigned int *queue, int *nslots_inout, cudaStream_t st, mark_fn mark,
-                                    void *mark_arg) {
+// launches the main kernel only; *nslots_inout returns the number of partial sums written per vector.
+// coeffs1 == nullptr: one scalar vector; else two (partials of vector 1 start at partial_ws + nslots * PLANAR_U64).
+cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
+                                    uint64_t *partial_ws, unsigned int *queue, int *nslots_inout, cudaStream_t st,
+                                    mark_fn mark, void *mark_arg) {
   int nslots = d ? *nslots_inout : 0;
   if (nslots > 0) {
     if (d >> 32) return cudaErrorInvalidValue;  // stage metadata holds 32-bit ciphertext indices
-    cudaError_t e = cudaFuncSetAttribute(k_lincomb, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    // chunk = 4 ciphertexts (2 ring stages) unless that leaves CTAs without work to pull
-    const uint32_t chunk_len = 4;
+    const uint32_t chunk_len = 4;  // ciphertexts per queue entry = one full ring (2 stages x 2 blocks)
     dim3 grid(RT_NTILES, nslots);
-    if (mark) mark(mark_arg, 0, st);
-    k_lincomb<<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs, d, chunk_len, queue, partial_ws);
+    cudaError_t e;
+    if (coeffs1) {
+      if ((e = cudaFuncSetAttribute(k_lincomb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES)) != cudaSuccess) return e;
+      if (mark) mark(mark_arg, 0, st);
+      k_lincomb<2><<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs0, coeffs1, d, chunk_len, queue, partial_ws,
+                                                          (size_t)nslots * PLANAR_U64);
+    } else {
+      if ((e = cudaFuncSetAttribute(k_lincomb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES)) != cudaSuccess) return e;
+      if (mark) mark(mark_arg, 0, st);
+      k_lincomb<1><<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs0, nullptr, d, chunk_len, queue, partial_ws, 0);
+    }
     if (mark) mark(mark_arg, 1, st);
   }
   *nslots_inout = nslots;

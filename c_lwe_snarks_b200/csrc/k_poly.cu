@@ -218,6 +218,17 @@ __global__ void k_ssp_accumulate(const uint64_t *__restrict__ t, uint64_t delta,
     w[c] = (uint32_t)(acc % FP);
   }
 }
+// resident SSP (u32 residues, polynomial k at blob[k*D .. (k+1)*D)): w = delta*t + sum of the selected polynomials, v = w + v_0
+__global__ void k_ssp_accumulate_res(const uint32_t *__restrict__ blob, uint32_t D, const uint32_t *__restrict__ sel,
+                                     uint32_t nsel, uint64_t delta, uint32_t *w, uint32_t *v) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
+    uint64_t acc = (uint64_t)blob[c] * (delta % FP) % FP;
+    for (uint32_t k = 0; k < nsel; k++) acc += blob[(size_t)sel[k] * D + c];  // nsel < 2^31 terms below 2^32
+    const uint32_t wc = (uint32_t)(acc % FP);
+    w[c] = wc;
+    v[c] = (uint32_t)(((uint64_t)wc + blob[(size_t)D + c]) % FP);
+  }
+}
 __global__ void k_add_u64poly(const uint32_t *__restrict__ a, const uint64_t *__restrict__ b, uint32_t D, uint32_t *out) {
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x)
     out[c] = (uint32_t)(((uint64_t)a[c] + b[c] % FP) % FP);
@@ -435,6 +446,24 @@ static cudaError_t poly_inv_series(PolyEngine &E, const uint32_t *f, uint32_t lf
   return cudaGetLastError();
 }
 
+// q_out[0..out_len) = rev( rev(a)[0..lq) * binv[0..lq) mod x^lq ) for binv = rev(b)^-1 mod x^(>= lq); uses E.t3
+static cudaError_t poly_quot_from_inverse(PolyEngine &E, const uint32_t *a, uint32_t la, uint32_t lq, const uint32_t *binv,
+                                          uint32_t *q_out, uint32_t out_len, cudaStream_t st) {
+  cudaError_t e = poly_mul(E, a, lq, la, 1, binv, lq, lq, 0, 0, lq, 0, E.t3, st);
+  if (e != cudaSuccess) return e;
+  k_reverse<<<gridfor(out_len), 256, 0, st>>>(E.t3, lq, q_out, out_len);
+  E.launches++;
+  return cudaGetLastError();
+}
+
+// binv[0..prec) = rev(b)^-1 mod x^prec (Newton); uses E.t1, E.t3
+static cudaError_t poly_rev_inverse(PolyEngine &E, const uint32_t *b, uint32_t lb, uint32_t prec, uint32_t *binv,
+                                    cudaStream_t st) {
+  k_reverse<<<gridfor(lb), 256, 0, st>>>(b, lb, E.t3, lb);
+  E.launches++;
+  return poly_inv_series(E, E.t3, lb < prec ? lb : prec, prec, binv, st);
+}
+
 // q = a / b (Euclidean quotient): q = rev( rev(a) * rev(b)^-1 mod x^lq ), lq = la - lb + 1; writes q_out[0..out_len)
 // (zero padded / truncated).  Uses E.t2 (inverse series) and E.t3 (reversed quotient).
 static cudaError_t poly_div(PolyEngine &E, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t *q_out,
@@ -442,19 +471,9 @@ static cudaError_t poly_div(PolyEngine &E, const uint32_t *a, uint32_t la, const
   if (lb == 0) return cudaErrorInvalidValue;
   if (la < lb) return cudaMemsetAsync(q_out, 0, (size_t)out_len * 4, st);
   const uint32_t lq = la - lb + 1;
-  const uint32_t lbr = lb < lq ? lb : lq;
-  // brev = first lbr coefficients of rev(b) -> E.t3 (as a plain array so that Newton can index it)
-  k_reverse<<<gridfor(lb), 256, 0, st>>>(b, lb, E.t3, lb);
-  E.launches++;
-  cudaError_t e = poly_inv_series(E, E.t3, lbr, lq, E.t2, st);
+  cudaError_t e = poly_rev_inverse(E, b, lb, lq, E.t2, st);
   if (e != cudaSuccess) return e;
-  // prod = rev(a)[0..lq) * binv[0..lq) mod x^lq -> E.t3
-  e = poly_mul(E, a, lq, la, 1, E.t2, lq, lq, 0, 0, lq, 0, E.t3, st);
-  if (e != cudaSuccess) return e;
-  // q[i] = prod[lq - 1 - i]
-  k_reverse<<<gridfor(out_len), 256, 0, st>>>(E.t3, lq < out_len ? lq : lq, q_out, out_len);
-  E.launches++;
-  return cudaGetLastError();
+  return poly_quot_from_inverse(E, a, la, lq, E.t2, q_out, out_len, st);
 }
 
 }  // namespace mfb
@@ -488,6 +507,87 @@ using namespace mfb;
     if (e_ != cudaSuccess) return ctx_fail(e_, #expr, __FILE__, __LINE__);  \
   } while (0)
 
+// A dense SSP blob kept on the device as u32 residues, with the Newton inverse of rev(t) cached: it depends on the
+// instance only, so every proof after the first divides with one multiplication.
+struct mfb_ssp {
+  uint32_t *blob = nullptr;  // [(M + 1)][D]: t, v_0, ..., v_{M-1}
+  size_t D = 0, M = 0;
+  uint32_t lt = 0;           // normalised length of t
+  uint32_t *binv = nullptr;  // rev(t)^-1 mod x^binv_len
+  uint32_t binv_len = 0, binv_cap = 0;
+};
+
+// v (D residues, device) and t (lt residues, stable device pointer) -> h = (v^2 - 1) / t truncated to D, then w | v | h
+// back to the host as u64.  d_w, d_v, d_h are consecutive D-element u32 arrays.
+static int polys_tail(mfb_ctx *ctx, PolyEngine &E, cudaStream_t st, uint32_t Du, uint32_t n, uint32_t *d_w, uint32_t *d_a,
+                      uint64_t *d_wide, const uint32_t *t32, uint32_t lt, mfb_ssp *cache, uint64_t *w_out, uint64_t *v_out,
+                      uint64_t *h_out) {
+  uint32_t *d_v = d_w + Du, *d_h = d_w + 2 * Du;
+  uint32_t lv = 0;
+  PTRY(cudaMemsetAsync(E.d_len, 0, 16, st));
+  k_poly_length<<<gridfor(Du), 256, 0, st>>>(d_v, Du, E.d_len);
+  E.launches++;
+  PTRY(cudaMemcpyAsync(&lv, E.d_len, 4, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+
+  // a = v^2 - 1
+  uint32_t la;
+  if (lv == 0) {  // v = 0: a = -1
+    PTRY(cudaMemsetAsync(d_a, 0, (size_t)n * 4, st));
+    la = 1;
+  } else {
+    la = 2 * lv - 1;
+    PTRY(poly_mul(E, d_v, lv, lv, 0, d_v, lv, lv, 0, 0, la, 0, d_a, st));
+  }
+  k_sub_one<<<1, 32, 0, st>>>(d_a);
+  E.launches++;
+  if (la == 1) {  // the constant may have become 0
+    uint32_t a0;
+    PTRY(cudaMemcpyAsync(&a0, d_a, 4, cudaMemcpyDeviceToHost, st));
+    PTRY(cudaStreamSynchronize(st));
+    if (a0 == 0) la = 0;
+  }
+  // h = a / t.  When t has (much) lower degree than D the quotient is longer than D and the transforms of the
+  // Newton iteration / of the final product need up to 2*lq points: grow the engine for this call if necessary.
+  if (la >= lt) {
+    const uint64_t lq64 = (uint64_t)la - lt + 1;
+    uint64_t need = 2 * lq64 > lq64 + lq64 / 2 + lt + 8 ? 2 * lq64 : lq64 + lq64 / 2 + lt + 8;
+    uint32_t nn = n;
+    while (nn < need) nn <<= 1;
+    PTRY(engine_reserve(E, nn, st));
+  }
+  if (la < lt) {
+    PTRY(cudaMemsetAsync(d_h, 0, (size_t)Du * 4, st));
+  } else if (cache) {
+    const uint32_t lq = la - lt + 1;
+    if (cache->binv_len < lq) {  // (re)build the cached inverse to the precision this quotient needs
+      if (cache->binv_cap < lq) {
+        if (cache->binv) PTRY(cudaFree(cache->binv));
+        cache->binv = nullptr;
+        cache->binv_cap = cache->binv_len = 0;
+        const uint32_t cap = lq > Du ? lq : Du;
+        PTRY(cudaMalloc(&cache->binv, (size_t)cap * 4));
+        cache->binv_cap = cap;
+      }
+      const uint32_t prec = cache->binv_cap;
+      PTRY(poly_rev_inverse(E, t32, lt, prec, cache->binv, st));
+      cache->binv_len = prec;
+    }
+    PTRY(poly_quot_from_inverse(E, d_a, la, lq, cache->binv, d_h, Du, st));
+  } else {
+    PTRY(poly_div(E, d_a, la, t32, lt, d_h, Du, st));
+  }
+  // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
+  k_widen<<<gridfor(3 * Du), 256, 0, st>>>(d_w, 3 * Du, d_wide);
+  E.launches++;
+  PTRY(cudaMemcpyAsync(w_out, d_wide, (size_t)Du * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(v_out, d_wide + Du, (size_t)Du * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(h_out, d_wide + 2 * (size_t)Du, (size_t)Du * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  (void)ctx;
+  return MFB_OK;
+}
+
 extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, const uint64_t *witness_limbs,
                                     size_t nlimbs, uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
   int rc = ctx_enter(ctx);
@@ -504,15 +604,14 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
   // selected polynomials: t, v_0, and v_i for the set witness bits (bit i-1 <-> v_i, i = 1..M-1)
   const uint32_t Du = (uint32_t)D;
   const size_t BATCH = 64;  // polynomials staged per accumulate launch
-  void *d_t, *d_v0, *d_sel, *d_w, *d_v, *d_h, *d_a, *d_wide;
+  void *d_t, *d_v0, *d_sel, *d_w, *d_a, *d_wide;
   if ((rc = ctx_scratch(ctx, 0, D * 8, &d_t))) return rc;
   if ((rc = ctx_scratch(ctx, 1, D * 8, &d_v0))) return rc;
   if ((rc = ctx_scratch(ctx, 3, BATCH * D * 8, &d_sel))) return rc;
   if ((rc = ctx_scratch(ctx, 4, (size_t)n * 4, &d_a))) return rc;  // v^2 - 1
-  if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;
-  d_v = (uint32_t *)d_w + D;
-  d_h = (uint32_t *)d_w + 2 * D;
+  if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;      // w | v | h
   if ((rc = ctx_scratch(ctx, 6, D * 8 * 3, &d_wide))) return rc;
+  uint32_t *d_v = (uint32_t *)d_w + D;
   PTRY(cudaMemcpyAsync(d_t, ssp, D * 8, cudaMemcpyHostToDevice, st));
   PTRY(cudaMemcpyAsync(d_v0, ssp + D, D * 8, cudaMemcpyHostToDevice, st));
   size_t staged = 0;
@@ -536,52 +635,116 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
     staged++;
   }
   PTRY(flush());
-  k_add_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_w, (const uint64_t *)d_v0, Du, (uint32_t *)d_v);
+  k_add_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_w, (const uint64_t *)d_v0, Du, d_v);
   E.launches++;
 
-  // lengths of v and t (normalised), needed on the host to size the division
-  uint32_t lens[2] = {0, 0};
-  PTRY(cudaMemsetAsync(E.d_len, 0, 16, st));
-  k_poly_length<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_v, Du, E.d_len);
-  k_reduce_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, Du, E.t1);  // t as u32 residues (E.t1 is free here)
-  k_poly_length<<<gridfor(Du), 256, 0, st>>>(E.t1, Du, E.d_len + 1);
-  E.launches += 3;
-  PTRY(cudaMemcpyAsync(lens, E.d_len, 8, cudaMemcpyDeviceToHost, st));
-  PTRY(cudaStreamSynchronize(st));
-  const uint32_t lv = lens[0], lt = lens[1];
-  if (lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys: t(x) is the zero polynomial");
-
-  // a = v^2 - 1
-  uint32_t la;
-  if (lv == 0) {  // v = 0: a = -1
-    PTRY(cudaMemsetAsync(d_a, 0, (size_t)n * 4, st));
-    la = 1;
-  } else {
-    la = 2 * lv - 1;
-    PTRY(poly_mul(E, (const uint32_t *)d_v, lv, lv, 0, (const uint32_t *)d_v, lv, lv, 0, 0, la, 0, (uint32_t *)d_a, st));
-  }
-  k_sub_one<<<1, 32, 0, st>>>((uint32_t *)d_a);
-  E.launches++;
-  if (la == 1) {  // the constant may have become 0
-    uint32_t a0;
-    PTRY(cudaMemcpyAsync(&a0, d_a, 4, cudaMemcpyDeviceToHost, st));
-    PTRY(cudaStreamSynchronize(st));
-    if (a0 == 0) la = 0;
-  }
-  // h = a / t : t as u32 residues must survive the division (E.t1 is scratch inside it) -> keep a copy in d_sel
+  // t as u32 residues in a buffer that survives the division (the staging area is free again), and its length
   uint32_t *t32 = (uint32_t *)d_sel;
-  PTRY(cudaMemcpyAsync(t32, E.t1, (size_t)Du * 4, cudaMemcpyDeviceToDevice, st));
-  PTRY(poly_div(E, (const uint32_t *)d_a, la, t32, lt, (uint32_t *)d_h, Du, st));
-
-  // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
-  k_widen<<<gridfor(3 * Du), 256, 0, st>>>((const uint32_t *)d_w, 3 * Du, (uint64_t *)d_wide);
-  E.launches++;
-  PTRY(cudaMemcpyAsync(w_out, d_wide, D * 8, cudaMemcpyDeviceToHost, st));
-  PTRY(cudaMemcpyAsync(v_out, (uint64_t *)d_wide + D, D * 8, cudaMemcpyDeviceToHost, st));
-  PTRY(cudaMemcpyAsync(h_out, (uint64_t *)d_wide + 2 * D, D * 8, cudaMemcpyDeviceToHost, st));
+  uint32_t lt = 0;
+  PTRY(cudaStreamSynchronize(st));  // the last accumulate launch still reads d_sel
+  k_reduce_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, Du, t32);
+  PTRY(cudaMemsetAsync(E.d_len, 0, 16, st));
+  k_poly_length<<<gridfor(Du), 256, 0, st>>>(t32, Du, E.d_len);
+  E.launches += 2;
+  PTRY(cudaMemcpyAsync(&lt, E.d_len, 4, cudaMemcpyDeviceToHost, st));
   PTRY(cudaStreamSynchronize(st));
+  if (lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys: t(x) is the zero polynomial");
+  rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, t32, lt, nullptr, w_out, v_out, h_out);
   ctx_count_launches(ctx, E.launches - L0);
+  return rc;
+}
+
+extern "C" int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, mfb_ssp **out) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (!ssp || !out) return ctx_bad_arg("mfb_ssp_create: null pointer");
+  *out = nullptr;
+  if (D < 1 || D > (1u << 21) || M < 1) return ctx_bad_arg("mfb_ssp_create: need 1 <= D <= 2^21, M >= 1");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  uint32_t n = 2;
+  while (n < 2 * D) n <<= 1;
+  PTRY(engine_reserve(E, n, st));
+  mfb_ssp *h = new mfb_ssp();
+  h->D = D;
+  h->M = M;
+  const size_t total = (M + 1) * D;
+  cudaError_t e = cudaMalloc(&h->blob, total * 4);
+  if (e != cudaSuccess) {
+    delete h;
+    return ctx_fail(e, "cudaMalloc of the resident SSP", __FILE__, __LINE__);
+  }
+  const size_t STAGE = (size_t)32 << 20;  // u64 coefficients per upload batch (256 MB)
+  void *d_stage;
+  rc = ctx_scratch(ctx, 3, (total < STAGE ? total : STAGE) * 8, &d_stage);
+  for (size_t o = 0; rc == MFB_OK && o < total; o += STAGE) {
+    const size_t cnt = total - o < STAGE ? total - o : STAGE;
+    if ((e = cudaMemcpyAsync(d_stage, ssp + o, cnt * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    k_reduce_u64poly<<<gridfor((uint32_t)cnt), 256, 0, st>>>((const uint64_t *)d_stage, (uint32_t)cnt, h->blob + o);
+    E.launches++;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+  }
+  if (rc == MFB_OK && e == cudaSuccess) {
+    e = cudaMemsetAsync(E.d_len, 0, 16, st);
+    k_poly_length<<<gridfor((uint32_t)D), 256, 0, st>>>(h->blob, (uint32_t)D, E.d_len);
+    E.launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h->lt, E.d_len, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  ctx_count_launches(ctx, E.launches - L0);
+  if (rc != MFB_OK || e != cudaSuccess) {
+    cudaFree(h->blob);
+    delete h;
+    return rc != MFB_OK ? rc : ctx_fail(e, "resident SSP upload", __FILE__, __LINE__);
+  }
+  *out = h;
   return MFB_OK;
+}
+
+extern "C" void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h) {
+  if (!h) return;
+  if (ctx) ctx_enter(ctx);
+  cudaFree(h->blob);
+  cudaFree(h->binv);
+  delete h;
+}
+
+extern "C" int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                             uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (!h || !witness_limbs || !w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
+  if (h->lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys_resident: t(x) is the zero polynomial");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  const size_t D = h->D, M = h->M;
+  const uint32_t Du = (uint32_t)D;
+  uint32_t n = 2;
+  while (n < 2 * D) n <<= 1;
+  PTRY(engine_reserve(E, n, st));
+  void *d_idx, *d_w, *d_a, *d_wide;
+  if ((rc = ctx_scratch(ctx, 0, M * 4, &d_idx))) return rc;
+  if ((rc = ctx_scratch(ctx, 4, (size_t)n * 4, &d_a))) return rc;
+  if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;
+  if ((rc = ctx_scratch(ctx, 6, D * 8 * 3, &d_wide))) return rc;
+  uint32_t *sel = (uint32_t *)malloc(M * 4);
+  if (!sel) return ctx_bad_arg("out of host memory");
+  uint32_t nsel = 0;
+  for (size_t i = 1; i < M; i++)
+    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) sel[nsel++] = (uint32_t)(i + 1);
+  cudaError_t e = nsel ? cudaMemcpyAsync(d_idx, sel, (size_t)nsel * 4, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // sel is about to be freed
+  free(sel);
+  PTRY(e);
+  k_ssp_accumulate_res<<<gridfor(Du), 256, 0, st>>>(h->blob, Du, (const uint32_t *)d_idx, nsel, delta, (uint32_t *)d_w,
+                                                     (uint32_t *)d_w + D);
+  E.launches++;
+  PTRY(cudaGetLastError());
+  rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, h->blob, h->lt, h, w_out, v_out, h_out);
+  ctx_count_launches(ctx, E.launches - L0);
+  return rc;
 }
 
 extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values) {

@@ -26,11 +26,11 @@ int fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 // kernels / launchers (k_*.cu)
-int lincomb_nslots(size_t d, int sm_count);
+int lincomb_nslots(size_t d, int sm_count, int nvec);
 typedef void (*mark_fn)(void *, int, cudaStream_t);
-cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs, size_t d, uint64_t *partial_ws,
-                                    unsigned int *queue, int *nslots_inout, cudaStream_t st, mark_fn mark,
-                                    void *mark_arg);
+cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
+                                    uint64_t *partial_ws, unsigned int *queue, int *nslots_inout, cudaStream_t st,
+                                    mark_fn mark, void *mark_arg);
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   unsigned int *queue, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
@@ -260,12 +260,31 @@ int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeff
                     const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream) {
   MFB_CHECK_CTX(ctx);
   if (!rop_out_dev || (d && (!cts_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_lincomb_dev: null pointer");
-  int nslots = lincomb_nslots(d, ctx->sm_count);
+  int nslots = lincomb_nslots(d, ctx->sm_count, 1);
   if (nslots > MAX_CHUNKS) nslots = MAX_CHUNKS;
-  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, d, ctx->partial_ws, ctx->queue, &nslots, (cudaStream_t)stream,
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
+                                       (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
   MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nslots, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
+int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
+                     size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
+                     uint64_t *rop1_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!rop0_out_dev || !rop1_out_dev || (d && (!cts_dev || !coeffs0_dev || !coeffs1_dev)))
+    return set_err(MFB_EARG, "mfb_lincomb2_dev: null pointer");
+  int nslots = lincomb_nslots(d, ctx->sm_count, 2);
+  if (2 * nslots > MAX_CHUNKS) nslots = MAX_CHUNKS / 2;
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs0_dev, coeffs1_dev, d, ctx->partial_ws, ctx->queue, &nslots,
+                                       (cudaStream_t)stream,
+                                       [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nslots, rop0_in_dev, rop0_out_dev, nullptr, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws + (size_t)nslots * PLANAR_U64, nslots, rop1_in_dev, rop1_out_dev,
+                                     ctx->queue, (cudaStream_t)stream));
+  ctx->launches += d ? 3 : 2;
   return MFB_OK;
 }
 
@@ -549,6 +568,30 @@ int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, const ui
   MFB_TRY(mfb_lincomb_dev(ctx, r->cts + first * PLANAR_U64, (const uint32_t *)d_co, d, (const uint64_t *)d_rop,
                           (uint64_t *)d_rop, ctx->stream));
   MFB_CUDA_TRY(cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs0, const uint32_t *coeffs1,
+                        size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!r || !rop0_flat_inout || !rop1_flat_inout || (d && (!coeffs0 || !coeffs1)))
+    return set_err(MFB_EARG, "mfb_region_lincomb2: null pointer");
+  if (first > r->count || d > r->count - first) return set_err(MFB_EARG, "mfb_region_lincomb2: range exceeds the region");
+  void *d_co, *d_rop;
+  MFB_TRY(scratch(ctx, 1, 2 * d * 4, &d_co));
+  MFB_TRY(scratch(ctx, 2, 2 * MFB_FLAT_CT_U64 * 8, &d_rop));
+  uint32_t *c0 = (uint32_t *)d_co, *c1 = (uint32_t *)d_co + d;
+  uint64_t *r0 = (uint64_t *)d_rop, *r1 = (uint64_t *)d_rop + MFB_FLAT_CT_U64;
+  if (d) {
+    MFB_CUDA_TRY(cudaMemcpyAsync(c0, coeffs0, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MFB_CUDA_TRY(cudaMemcpyAsync(c1, coeffs1, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MFB_CUDA_TRY(cudaMemcpyAsync(r0, rop0_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(r1, rop1_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_lincomb2_dev(ctx, r->cts + first * PLANAR_U64, c0, c1, d, r0, r0, r1, r1, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(rop0_flat_inout, r0, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(rop1_flat_inout, r1, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MFB_OK;
 }

@@ -81,6 +81,52 @@ void mf_crs_make_resident(crs_t crs) {
   g_resident = r;
 }
 
+/* ------------------------------------------------------------------ resident SSP blobs (addition) */
+struct resident_ssp {
+  const uint8_t *owner;
+  mfb_ssp *h;
+  size_t d, m;
+  struct resident_ssp *next;
+};
+static struct resident_ssp *g_resident_ssp = NULL;
+
+void mf_ssp_release(ssp_t ssp) {
+  struct resident_ssp **pp = &g_resident_ssp;
+  while (*pp) {
+    struct resident_ssp *r = *pp;
+    if (r->owner == ssp) {
+      mfb_ssp_destroy(mf_gpu(), r->h);
+      *pp = r->next;
+      free(r);
+    } else {
+      pp = &r->next;
+    }
+  }
+}
+
+void mf_ssp_make_resident(ssp_t ssp) {
+  mf_ssp_release(ssp);
+  struct resident_ssp *r = calloc(1, sizeof(*r));
+  if (!r) mf_die("malloc");
+  r->owner = ssp;
+  r->d = GAMMA_D;
+  r->m = GAMMA_M;
+  const int rc = mfb_ssp_create(mf_gpu(), (const uint64_t *)ssp, r->d, r->m, &r->h);
+  if (rc != MFB_OK) {
+    fprintf(stderr, "mangiafuoco_b200: mf_ssp_make_resident: %s; the SSP stays on the host\n", mfb_last_error());
+    free(r);
+    return;
+  }
+  r->next = g_resident_ssp;
+  g_resident_ssp = r;
+}
+
+static mfb_ssp *resident_ssp_find(ssp_t ssp) {
+  for (struct resident_ssp *r = g_resident_ssp; r; r = r->next)
+    if (r->owner == ssp && r->d == GAMMA_D && r->m == GAMMA_M) return r->h;
+  return NULL;
+}
+
 void crs_init(crs_t crs) { /* snark.c:35-48 */
   mf_entropy(crs->seed, sizeof(rseed_t));
   crs->s = malloc(CT_BYTES * GAMMA_D);
@@ -149,24 +195,22 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
 }
 
 /* ------------------------------------------------------------------ prover (snark.c:117-190) */
-static void lincomb_region(ct_t rop, crs_t crs, int which_as, const uint64_t *poly) {
+static void lincomb_pair_resident(ct_t rop0, ct_t rop1, mfb_region *reg, const uint64_t *poly0, const uint64_t *poly1) {
   const size_t D = GAMMA_D;
-  uint64_t *acc = malloc(FLAT_CT * 8);
-  if (!acc) mf_die("malloc");
-  mf_ct_to_flat(acc, rop, "prover"); /* eval_poly adds into rop (0 after proof_init) */
-  struct resident *r = resident_find(crs);
-  if (r && r->d == D) {
-    uint32_t *co = malloc(D * 4);
-    if (!co) mf_die("malloc");
-    for (size_t i = 0; i < D; i++) co[i] = (uint32_t)poly[i];
-    MF_GPU(mfb_region_lincomb(mf_gpu(), which_as ? r->as : r->s, 0, co, D, acc));
-    free(co);
-  } else {
-    MF_GPU(mfb_eval_poly(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S,
-                         (const uint8_t *)(which_as ? crs->as : crs->s), poly, NULL, D, acc));
+  uint64_t *acc = malloc(2 * FLAT_CT * 8);
+  uint32_t *co = malloc(2 * D * 4);
+  if (!acc || !co) mf_die("malloc");
+  mf_ct_to_flat(acc, rop0, "prover");
+  mf_ct_to_flat(acc + FLAT_CT, rop1, "prover");
+  for (size_t i = 0; i < D; i++) {
+    co[i] = (uint32_t)poly0[i];
+    co[D + i] = (uint32_t)poly1[i];
   }
-  mf_ct_from_flat(rop, acc);
+  MF_GPU(mfb_region_lincomb2(mf_gpu(), reg, 0, co, co + D, D, acc, acc + FLAT_CT));
+  mf_ct_from_flat(rop0, acc);
+  mf_ct_from_flat(rop1, acc + FLAT_CT);
   free(acc);
+  free(co);
 }
 
 static void lincomb_pair(ct_t rop0, ct_t rop1, crs_t crs, int which_as, const uint64_t *poly0, const uint64_t *poly1) {
@@ -195,7 +239,11 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   if (!pw) mf_die("malloc");
   uint64_t *pv = pw + D, *ph = pw + 2 * D;
   double t0 = mf_now();
-  MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+  mfb_ssp *rssp = resident_ssp_find(ssp);
+  if (rssp)
+    MF_GPU(mfb_ssp_prover_polys_resident(mf_gpu(), rssp, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+  else
+    MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
   mf_trace("prover.polys", t0);
   t0 = mf_now();
 
@@ -232,11 +280,9 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   t0 = mf_now();
   {
     struct resident *r = resident_find(crs);
-    if (r && r->d == D) { /* regions resident in HBM: four lincombs at the HBM roofline */
-      lincomb_region(pi->v_w, crs, 0, pw);
-      lincomb_region(pi->hat_v, crs, 1, pv);
-      lincomb_region(pi->h, crs, 0, ph);
-      lincomb_region(pi->hat_h, crs, 1, ph);
+    if (r && r->d == D) { /* regions resident in HBM: one pass per region at the HBM roofline, two scalar vectors each */
+      lincomb_pair_resident(pi->v_w, pi->h, r->s, pw, ph);
+      lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, pv, ph);
     } else { /* a regenerated from AES: one pass per region carrying both scalar vectors */
       lincomb_pair(pi->v_w, pi->h, crs, 0, pw, ph);
       lincomb_pair(pi->hat_v, pi->hat_h, crs, 1, pv, ph);

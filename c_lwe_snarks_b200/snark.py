@@ -85,7 +85,10 @@ class Snark:
         return time.perf_counter() - t0
 
     def make_resident(self):
+        """Keep the CRS regions s / as (expanded) and the SSP blob (with the cached inverse of rev(t)) in HBM."""
         self.lib.mf_crs_make_resident(C.byref(self.crs))
+        self.lib.mf_ssp_make_resident(self._ssp_ptr())
+        self._ssp_resident = True
 
     def prove(self) -> float:
         if self._proof_live:
@@ -139,6 +142,9 @@ class Snark:
         return int(self.lib.mf_gpu_launches())
 
     def close(self):
+        if getattr(self, "_ssp_resident", False):
+            self.lib.mf_ssp_release(self._ssp_ptr())
+            self._ssp_resident = False
         if self._proof_live:
             self.lib.proof_clear(C.byref(self.proof))
             self._proof_live = False

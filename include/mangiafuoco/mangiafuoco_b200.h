@@ -233,6 +233,11 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi);
  * regeneration of the a-vectors is then paid once instead of per proof.  mf_crs_release frees them. */
 void mf_crs_make_resident(crs_t crs);
 void mf_crs_release(crs_t crs);
+/* The same for the SSP instance: the dense blob is uploaded once (as u32 residues) and the Newton inverse that the
+ * prover's division h = (v^2 - 1)/t needs is cached with it; prover() then only ships the witness.  The blob must not
+ * change while it is resident (mf_ssp_release before modifying or freeing it). */
+void mf_ssp_make_resident(ssp_t ssp);
+void mf_ssp_release(ssp_t ssp);
 /* Persistence (the reference only sketches a "crs.mfuoco" mmap, benchmark_snark.c:23-24): the CRS file is a 24-byte
  * header (magic, D, M) + seed + the 92-byte records in stream order s, as, t, v; a proof file holds the five
  * ciphertexts as 88-byte magnitudes plus the sign of each b.  Return 0, or -1 with errno set. */

@@ -98,6 +98,10 @@ MFB_API int mfb_expand_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
  * NULL (zero) or equal to rop_out.  One call at a time per context (it owns the partial-sum workspace). */
 MFB_API int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
                     const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
+/* two scalar vectors in one pass over the same resident ciphertexts (half the HBM traffic of two calls) */
+MFB_API int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
+                     size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
+                     uint64_t *rop1_out_dev, void *stream);
 /* host flavour over flat host ciphertexts (d small: ct_add / ct_mul_ui / ct_addmul_ui on ct_t objects) */
 MFB_API int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, size_t d, uint64_t *rop_flat_inout);
 
@@ -109,6 +113,9 @@ MFB_API void mfb_region_destroy(mfb_ctx *ctx, mfb_region *r);
 /* rop += sum_i coeffs[i] * region[first + i], i < d; coeffs/rop in host memory */
 MFB_API int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs, size_t d,
                        uint64_t *rop_flat_inout);
+
+MFB_API int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs0,
+                        const uint32_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
 
 /* ---- multi-GPU exchange helpers (one process per GPU; the collective itself is NCCL) ------ */
 /* cols_dev[1472][22] u64 <- the 32-bit limbs of flat_dev, widened, so that an elementwise integer sum over
@@ -168,6 +175,13 @@ MFB_API int mfb_decrypt_dev(mfb_ctx *ctx, const uint64_t *sk_planar_dev, const u
  * + CRT on the device, division = Newton inversion; results are canonical residues, identical to FLINT's. */
 MFB_API int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, const uint64_t *witness_limbs,
                          size_t nlimbs, uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out);
+/* The same with the SSP blob kept on the device (u32 residues, (M+1)*D*4 bytes) and rev(t)^-1 cached in the handle:
+ * after the first proof the division is one multiplication and nothing but the witness crosses PCIe. */
+typedef struct mfb_ssp mfb_ssp;
+MFB_API int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, mfb_ssp **out);
+MFB_API void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h);
+MFB_API int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                  uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out);
 /* values[q] = poly_q(x) mod p for npoly polynomials of D u64 coefficients each (setup's nmod_poly_evaluate_nmod
  * calls, snark.c:97-110) */
 MFB_API int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values);

@@ -479,8 +479,10 @@ void ref_prover_resident(const uint8_t *ssp, const uint8_t seed[40], const uint8
   mpz_from_limbs(w, witness_limbs, (int)witness_nlimbs);
   crs_from_wire(crs, seed, crs_s, crs_as, crs_v, crs_tb);
   mf_crs_make_resident(crs);
+  mf_ssp_make_resident((ssp_t)ssp);
   proof_init(pi);
   prover(pi, crs, (ssp_t)ssp, w);
+  mf_ssp_release((ssp_t)ssp);
   mf_crs_release(crs);
   const size_t stride = REF_NC * REF_LIMBS;
   ct_to_flat(proof_flat + 0 * stride, siz ? siz + 0 * REF_NC : NULL, pi->h);

@@ -221,6 +221,21 @@ def test_region(ctx, oracle):
         reg.close()
 
 
+def test_region_two_vectors(ctx, oracle):
+    d, off = 300, 4 * CTR_CT
+    c8 = xof_records("reg2-c8", d)
+    h0, h1 = xof_scalars("reg2-h0", d), xof_scalars("reg2-h1", d)
+    reg = ctx.region(SEED, off, c8)
+    try:
+        rop1 = xof("reg2-rop", NC * 88).view("<u8").reshape(NC, L64)
+        r0, r1 = reg.lincomb2(h0, h1, rop1=rop1)
+        assert np.array_equal(wide(r0), oracle.eval_poly(SEED, off, c8, h0))
+        assert np.array_equal(wide(r1), oracle.eval_poly(SEED, off, c8, h1, rop=wide(rop1)))
+        assert np.array_equal(reg.lincomb(h0), r0)  # the queues were re-armed
+    finally:
+        reg.close()
+
+
 def test_ct_ops_golden(ctx, oracle):
     # ct_mul_ui / ct_add / ct_addmul_ui (lwe.c:131-157) as lincombs over host ciphertexts
     d, c8, h, _ = golden_eval_inputs()

@@ -138,6 +138,34 @@ def test_prover_polys_2_16(ctx):
     assert len(trim(r)) < len(trim([int(c) for c in t]))
 
 
+def test_low_degree_t_on_a_fresh_context():
+    """lq ~ 2D needs transforms of up to 4D points: the engine must grow by itself (a fresh context starts small)."""
+    import c_lwe_snarks_b200 as m
+    c = m.Context(0)
+    try:
+        test_prover_polys_general_division(c, 3000, 4, 7)
+        test_prover_polys_general_division(c, 512, 4, 100)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("D,M,t_len", [(64, 16, 64), (1000, 8, 1000), (1000, 8, 40), (4096, 4, 4096)])
+def test_resident_ssp_matches_host_blob_path(ctx, D, M, t_len):
+    """mfb_ssp_create + mfb_ssp_prover_polys_resident (cached inverse) == mfb_ssp_prover_polys, for several witnesses."""
+    blob, wl, bits, t, v = make_ssp(D, M, f"poly-res-{D}-{t_len}", exact=(t_len == D), t_len=t_len)
+    res = ctx.ssp_resident(blob.view(np.uint8), D, M)
+    try:
+        for k, delta in enumerate([1, 0x9E3779B9 % P, P - 1]):
+            wit = wl.copy()
+            wit[0] ^= np.uint64(0x5555 * k)
+            a = ctx.ssp_prover_polys(blob.view(np.uint8), D, M, wit, delta)
+            b = res.prover_polys(wit, delta)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+    finally:
+        res.close()
+
+
 @pytest.mark.parametrize("D,npoly", [(1, 3), (64, 17), (1000, 5), (65536, 66)])
 def test_ssp_eval(ctx, D, npoly):
     raw = xof(f"eval-{D}-{npoly}", 8 * D * npoly).view("<u8").copy()
