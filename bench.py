@@ -273,6 +273,22 @@ def run_gpu_arm(args):
     ms = float(t_all.item())
     result = d_rop.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64).copy()
 
+    # ---- informational: the two-scalar-vector pass the prover uses over a resident region (k_lincomb<2>)
+    d_r0 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
+    d_r1 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
+    d_h1 = torch.roll(d_h, 1)
+    for _ in range(3):
+        ctx.lincomb2_dev(d_cts.data_ptr(), d_h.data_ptr(), d_h1.data_ptr(), D, None, d_r0.data_ptr(), None, d_r1.data_ptr(), st)
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        ctx.lincomb2_dev(d_cts.data_ptr(), d_h.data_ptr(), d_h1.data_ptr(), D, None, d_r0.data_ptr(), None, d_r1.data_ptr(), st)
+    e3.record()
+    torch.cuda.synchronize()
+    pair_ms = e2.elapsed_time(e3) / steps
+    pair_ok = bool(np.array_equal(d_r0.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64), result)) if world == 1 else None
+
     # ---- e2e: host buffers through mfb_eval_poly (fused AES regeneration), every rank its own range
     e2e_steps = max(2, min(steps, 5))
     pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
@@ -383,6 +399,9 @@ def run_gpu_arm(args):
                              "d2h_bytes_per_step": NC * 88, "ms_per_step": 1e3 * res_s / steps, "steps": steps,
                              "path": "mfb_region_lincomb (host scalars -> host result; the CRS region was expanded into HBM "
                                      "once by mfb_region_create, as mf_crs_make_resident does for prover())"},
+            "two_vector_pass": {"ms_per_pass": pair_ms, "mac_per_s": 2 * D / (pair_ms * 1e-3), "matches_single": pair_ok,
+                                "note": "k_lincomb<2>: two scalar vectors over the same resident ciphertexts in one pass "
+                                        "(the prover pairs v_w/h and hat_v/hat_h); per-GPU, no exchange"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -323,6 +323,11 @@ class Context:
     def lincomb_dev(self, cts_ptr: int, coeffs_ptr: int, d: int, rop_in_ptr, rop_out_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_lincomb_dev(self.h, cts_ptr, coeffs_ptr, d, rop_in_ptr, rop_out_ptr, stream))
 
+    def lincomb2_dev(self, cts_ptr: int, coeffs0_ptr: int, coeffs1_ptr: int, d: int, rop0_in, rop0_out: int, rop1_in,
+                     rop1_out: int, stream: int = 0):
+        self._ck(self.lib.mfb_lincomb2_dev(self.h, cts_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in, rop0_out, rop1_in, rop1_out,
+                                           stream))
+
     def eval_poly_dev(self, seed, offset: int, c8_ptr: int, coeffs_ptr: int, idx_ptr, d: int, rop_in_ptr,
                       rop_out_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_eval_poly_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, coeffs_ptr, idx_ptr, d, rop_in_ptr,

@@ -305,13 +305,10 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
 bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi) {
   const size_t D = GAMMA_D;
   const uint64_t p = GAMMA_P;
-  nmod_poly_t pp;
-  nmod_poly_init(pp, GAMMA_P);
-  nmod_poly_import(&pp, &ssp[ssp_t_offset], D);
-  const uint64_t t_s = nmod_poly_evaluate_nmod(pp, vrs->s);
-  nmod_poly_import(&pp, &ssp[ssp_v_offset(0)], D);
-  const uint64_t v0_s = nmod_poly_evaluate_nmod(pp, vrs->s);
-  nmod_poly_clear(pp);
+  /* t(s) and v_0(s): the first two polynomials of the blob, one batched device evaluation (snark.c:197-201,214-215) */
+  uint64_t ts_v0s[2];
+  MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, 2, vrs->s, ts_v0s));
+  const uint64_t t_s = ts_v0s[0], v0_s = ts_v0s[1];
 
   /* one batch: decrypt h, hat_h, hat_v, v_w, b_w; the dot product of b_w is also the test-error input */
   mpz_t *elems[5] = {pi->h, pi->hat_h, pi->hat_v, pi->v_w, pi->b_w};
