@@ -65,6 +65,7 @@ _SIGS = {
     "mfb_lincomb_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_lincomb2_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "mfb_region_lincomb2": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
+    "mfb_lincomb_generic_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp, _vp]),
     "mfb_lincomb": (C.c_int, [_vp, _u64p, _u32p, C.c_size_t, _u64p]),
     "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_region_destroy": (None, [_vp, _vp]),
@@ -327,6 +328,9 @@ class Context:
                      rop1_out: int, stream: int = 0):
         self._ck(self.lib.mfb_lincomb2_dev(self.h, cts_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in, rop0_out, rop1_in, rop1_out,
                                            stream))
+
+    def lincomb_generic_dev(self, limbs64: int, ncoords: int, cts_ptr: int, coeffs_ptr: int, d: int, out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_lincomb_generic_dev(self.h, limbs64, ncoords, cts_ptr, coeffs_ptr, d, out_ptr, stream))
 
     def eval_poly_dev(self, seed, offset: int, c8_ptr: int, coeffs_ptr: int, idx_ptr, d: int, rop_in_ptr,
                       rop_out_ptr: int, stream: int = 0):

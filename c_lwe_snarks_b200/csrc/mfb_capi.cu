@@ -56,6 +56,9 @@ cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const u
 cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, int tiled,
                                   cudaStream_t st);
 
+cudaError_t launch_lincomb_generic(int limbs64, const uint64_t *cts, const uint32_t *coeffs, size_t d, int ntiles, uint64_t *out,
+                                   uint64_t *partial_ws, size_t partial_cap_u64, unsigned int *queue, int sm_count,
+                                   cudaStream_t st);
 struct PolyEngine;  // k_poly.cu
 PolyEngine *poly_engine_new();
 void poly_engine_delete(PolyEngine *e);
@@ -285,6 +288,20 @@ int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coef
   MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws + (size_t)nslots * PLANAR_U64, nslots, rop1_in_dev, rop1_out_dev,
                                      ctx->queue, (cudaStream_t)stream));
   ctx->launches += d ? 3 : 2;
+  return MFB_OK;
+}
+
+int mfb_lincomb_generic_dev(mfb_ctx *ctx, int limbs64, int ncoords, const uint64_t *cts_dev, const uint32_t *coeffs_dev,
+                            size_t d, uint64_t *out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!cts_dev || !coeffs_dev || !out_dev || d == 0 || (d >> 32)) return set_err(MFB_EARG, "mfb_lincomb_generic_dev: bad argument");
+  if (ncoords < 1 || ncoords > 2048) return set_err(MFB_EARG, "mfb_lincomb_generic_dev: 1 <= ncoords <= 2048");
+  const int ntiles = (ncoords + 63) / 64;
+  cudaError_t e = launch_lincomb_generic(limbs64, cts_dev, coeffs_dev, d, ntiles, out_dev, ctx->partial_ws,
+                                         (size_t)MAX_CHUNKS * PLANAR_U64, ctx->queue, ctx->sm_count, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return set_err(MFB_EARG, "mfb_lincomb_generic_dev: limbs64 must be one of 4,6,8,10,11,12,13,14,16");
+  MFB_CUDA_TRY(e);
+  ctx->launches += 2;
   return MFB_OK;
 }
 

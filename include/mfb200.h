@@ -117,6 +117,14 @@ MFB_API int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, 
 MFB_API int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs0,
                         const uint32_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
 
+/* Other LWE parameter points (BASELINE configs[4]); the reference implements only (1470, 736), so this entry point
+ * has no reference counterpart: out = sum_i coeffs[i] * cts[i] mod 2^(64*limbs64), coordinate-wise, for ciphertexts
+ * of ncoords coordinates (= n + 1) in the tile-planar layout with limbs64 rows per tile:
+ * u64 index (ct i, row j, coordinate c) = i*T*64*L + (c/64)*64*L + j*64 + c%64, T = ceil(ncoords/64), L = limbs64.
+ * out has the shape of one ciphertext.  limbs64 in {4,6,8,10,11,12,13,14,16}. */
+MFB_API int mfb_lincomb_generic_dev(mfb_ctx *ctx, int limbs64, int ncoords, const uint64_t *cts_dev, const uint32_t *coeffs_dev,
+                            size_t d, uint64_t *out_dev, void *stream);
+
 /* ---- multi-GPU exchange helpers (one process per GPU; the collective itself is NCCL) ------ */
 /* cols_dev[1472][22] u64 <- the 32-bit limbs of flat_dev, widened, so that an elementwise integer sum over
  * ranks is exact; carry: flat_out[c] = (flat_in[c] + sum_l cols[c - c0][l] << 32l) mod 2^704 for the
