@@ -126,6 +126,23 @@ def cpu_baseline_single(sample: int):
                       f"per ciphertext: ct_import (AES regen) {t_imp * 1e6:.0f} us, ct_addmul_ui (GMP) {t_mac * 1e6:.1f} us"}
 
 
+def config1_reference():
+    """BASELINE configs[0]: the reference's benchmark_snark (setup / prover / verifier seconds, benchmark_snark.c:56-82) at
+    the default LWE parameters on a ~2^10-constraint random SSP (D = 1024, M = 64), single-threaded CPU, and the same
+    three calls through the drop-in on the GPU."""
+    from oracle.loader import Reference
+    try:
+        ref = Reference(1024, 64)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+    s_ref, p_ref, v_ref, ok = ref.benchmark_snark()
+    ours = snark_latency(10, 64)
+    return {"D": 1024, "M": 64, "reference_cpu_ms": {"setup": 1e3 * s_ref, "prove": 1e3 * p_ref, "verify": 1e3 * v_ref, "accept": ok,
+                                                       "cores": 1},
+            "b200_ms": {"setup": ours["setup_ms"], "prove": ours["prove_ms"], "prove_resident": ours["prove_resident_ms"],
+                        "verify": ours["verify_ms"], "accept": ours["accept"]}}
+
+
 def _ref_worker(args):
     first, count, reps = args
     ref = ref_lib()
@@ -409,6 +426,7 @@ def run_gpu_arm(args):
             line["snark"] = snark_latency(args.log2d, 64)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
+            line["config1_reference_cpu"] = config1_reference()
         emit(line)
     if world > 1:
         dist.destroy_process_group()

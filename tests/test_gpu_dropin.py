@@ -108,6 +108,26 @@ def test_full_snark_beside_compiled_reference(dropin, reference):
     assert reference.verifier(b["ssp"], b["crs"], a["proof"]) and dropin.verifier(a["ssp"], a["crs"], b["proof"])
 
 
+def test_full_snark_config1_beside_compiled_reference(dropin):
+    """BASELINE configs[0]: default LWE parameters, ~2^10-constraint SSP (D = 1024, M = 64), reference CPU path beside ours."""
+    from oracle.loader import Reference
+    try:
+        ref = Reference(1024, 64)
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"compiled reference for D=1024 unavailable: {e}")
+    D, M = 1024, 64
+    dropin.set_instance(D, M)
+    ent = xof("snark-entropy-d1024-m64", snark_entropy_len(D, M))
+    a = run_snark(dropin, D, M, ent)
+    b = run_snark(ref, D, M, ent)
+    assert a["used"] == b["used"] == ent.size
+    for key in ("seed", "s", "as_", "t", "sk"):
+        assert np.array_equal(a["crs"][key], b["crs"][key]), key
+    assert np.array_equal(a["crs"]["v"][: M - 1], b["crs"]["v"][: M - 1])
+    assert np.array_equal(a["proof"], b["proof"]) and np.array_equal(a["siz"] < 0, b["siz"] < 0)
+    assert a["ok"] and b["ok"] and not a["ok_bad"] and not b["ok_bad"]
+
+
 def test_lwe_api_beside_compiled_reference(dropin, reference):
     """ct_import / eval_poly / ct_mul_ui / ct_add / ct_addmul_ui / encrypt / decrypt / dotp / smudge / urandomb / modq."""
     dropin.set_instance(256, 64)
