@@ -166,136 +166,119 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
 // Work item m of the list: ciphertext index idx[m] (or m), scalar coeffs[m]; CTA (tile, chunk) walks
 // m = chunk, chunk + nchunks, ...  The b coordinate (1470) is handled by thread KS_TILE of the tile-0 CTAs,
 // straight from the wire records.
+//
+// Pipeline: THREE keystream buffers and two mbarriers per buffer (full: every warp has stored its blocks; empty:
+// every warp has read its coordinates) instead of a CTA-wide __syncthreads per item.  A tile is 2818 blocks for 512
+// threads — 5.5 per thread — and the assignment rotates by half a CTA every item, so that each warp gets 5 and 6
+// blocks alternately; with the AES of item t+2 running while item t is consumed, a warp that is ahead keeps
+// working instead of waiting for the slowest warp of every item (that wait cost 6/5.5 of the time).
+constexpr int KS_NBUF = 3;
+constexpr int KS3_SMEM_BYTES = 0x20000 + 2 * KS_BUF_BYTES;  // [pad: buffer 0 | 64 KB tables | buffers 1, 2]
+
+__device__ __forceinline__ void ksb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ksb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ksb_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// blocks [first, first + nblk) -> buffer; thread -> block assignment rotated by `rot` (a multiple of 32)
+__device__ __forceinline__ void ks_fill_rot(const AesKey &key, uint64_t first, int nblk, uint32_t buf, const AesLut<2> &lut,
+                                            AesCtrCache &cache, int rot) {
+  for (int b = (threadIdx.x + rot) & (KS_THREADS - 1); b < nblk; b += KS_THREADS)
+    sts128(buf + 16u * b, aes256_ctr_block_cached<2>(lut, key, first + b, cache));
+}
+
+template <int NVEC>
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
-           const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs, const uint32_t *__restrict__ idx,
-           size_t d, int nchunks, uint64_t *__restrict__ partial) {
+           const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
+           const uint32_t *__restrict__ idx, size_t d, int nchunks, uint64_t *__restrict__ partial0,
+           uint64_t *__restrict__ partial1) {
+  // NVEC = 1: tiles of 490 coordinates, thread t < 490 owns coordinate t.
+  // NVEC = 2: tiles of 245 coordinates, threads [0,245) accumulate vector 0 and [245,490) vector 1 from the same tile.
+  constexpr int TILE = KS_TILE / NVEC;
+  constexpr int NTILES = N / TILE;
+  constexpr int TILE_BYTES = TILE * CT_BYTES;
   extern __shared__ __align__(16) uint8_t dyn[];
-  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  __shared__ __align__(8) uint64_t bars[2 * KS_NBUF];
+  KsSmem s = ks_smem_setup(dyn, t0_global);
+  auto buf_of = [&](int b) { return b == 0 ? s.buf[0] : s.buf[1] + (uint32_t)(b - 1) * (uint32_t)KS_BUF_BYTES; };
+  const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(bars);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2 * KS_NBUF; b++) ksb_init(bbase + 8 * b, KS_THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   AesCtrCache cache;
   cache.window = ~0ull;
-  const int tile = blockIdx.x % KS_NTILES;
-  const int chunk = blockIdx.x / KS_NTILES;
+  const int tile = blockIdx.x % NTILES;
+  const int chunk = blockIdx.x / NTILES;
+  const int lane = threadIdx.x & 31;
+  const int vec = (NVEC == 2 && threadIdx.x >= TILE) ? 1 : 0;
+  const int lc = threadIdx.x - vec * TILE;
+  const bool is_mac = threadIdx.x < NVEC * TILE;
+  const bool is_b = tile == 0 && threadIdx.x >= NVEC * TILE && threadIdx.x < NVEC * TILE + NVEC;
+  const int my_vec = is_b ? (int)(threadIdx.x - NVEC * TILE) : vec;
+  const uint32_t *coeffs = my_vec ? coeffs1 : coeffs0;
+
+  auto geom = [&](size_t m) {
+    const size_t k = idx ? idx[m] : m;
+    const uint64_t off = offset + k * (uint64_t)CTR_CT + (uint64_t)tile * TILE_BYTES;
+    TileGeom g;
+    g.first = off >> 4;
+    g.delta = (uint32_t)(off & 15);
+    g.nblk = (int)((g.delta + TILE_BYTES + 15) >> 4);
+    return g;
+  };
+  const size_t nitems = d > (size_t)chunk ? (d - chunk + nchunks - 1) / nchunks : 0;  // items chunk, chunk+nchunks, ...
+  auto fill = [&](size_t t) {  // item t of this CTA -> buffer t % 3
+    const int b = (int)(t % KS_NBUF);
+    if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
+    const TileGeom g = geom(chunk + t * nchunks);
+    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+    __syncwarp();
+    if (lane == 0) ksb_arrive(bbase + 8 * b);
+  };
 
   Acc704 acc;
   acc_zero(acc);
-  const bool is_b = (tile == 0 && threadIdx.x == KS_TILE);
-
-  size_t m = chunk;
-  int ph = 0;
-  __syncthreads();  // tables ready
-  if (m < d) {
-    const size_t k = idx ? idx[m] : m;
-    const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
-  }
-  __syncthreads();
-  for (; m < d; m += nchunks, ph ^= 1) {
-    const size_t k = idx ? idx[m] : m;
-    const uint32_t h = coeffs[m];
-    if (threadIdx.x < KS_TILE) {
-      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+  __syncthreads();  // tables and barriers ready
+  if (nitems > 0) fill(0);
+  if (nitems > 1) fill(1);
+  for (size_t t = 0; t < nitems; t++) {
+    const int b = (int)(t % KS_NBUF);
+    const size_t m = chunk + t * nchunks;
+    ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));  // every warp has stored its blocks of item t
+    if (is_mac) {
+      const TileGeom g = geom(m);
       uint32_t a[22];
-      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
-      acc_mad(acc, a, h);
+      ks_read_coord(buf_of(b), g.delta + CT_BYTES * lc, a);
+      acc_mad(acc, a, coeffs[m]);
     } else if (is_b) {
+      const size_t k = idx ? idx[m] : m;
       const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + k * CT_BYTES);  // 92 % 4 == 0
       uint32_t a[22];
 #pragma unroll
       for (int l = 0; l < 22; l++) a[l] = rec[l];
-      acc_mad(acc, a, h);
-    }
-    const size_t nx = m + nchunks;
-    if (nx < d) {
-      const size_t kn = idx ? idx[nx] : nx;
-      const TileGeom gn = tile_geom(offset + kn * (uint64_t)CTR_CT, tile);
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
-    }
-    __syncthreads();
-  }
-
-  uint64_t *out = partial + (size_t)chunk * PLANAR_U64;
-  if (threadIdx.x < KS_TILE || is_b) {
-    uint32_t r[22];
-    acc_fold(acc, r);
-    const int c = is_b ? N : tile * KS_TILE + threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
-  } else if (tile == 0 && threadIdx.x == KS_TILE + 1) {
-#pragma unroll
-    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + N + 1] = 0;
-  }
-}
-
-// ------------------------------------------------------------------------------------ fused eval_poly, two scalar vectors
-// The prover walks each CRS region twice with different scalars (v_w and h over s; hat_v and hat_h over as,
-// snark.c:157-174).  One pass with both scalar vectors halves the AES work: tiles of 245 coordinates (1470 = 6 * 245),
-// threads [0, 245) accumulate vector 0 and [245, 490) vector 1 over the SAME keystream tile.
-constexpr int KS2_TILE = 245;
-constexpr int KS2_NTILES = N / KS2_TILE;  // 6
-constexpr int KS2_TILE_BYTES = KS2_TILE * CT_BYTES;
-__device__ __forceinline__ TileGeom tile_geom2(uint64_t ct_off, int tile) {
-  const uint64_t off = ct_off + (uint64_t)tile * KS2_TILE_BYTES;
-  TileGeom g;
-  g.first = off >> 4;
-  g.delta = (uint32_t)(off & 15);
-  g.nblk = (int)((g.delta + KS2_TILE_BYTES + 15) >> 4);
-  return g;
-}
-
-__global__ void __launch_bounds__(KS_THREADS, 1)
-k_evalpoly2(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
-            const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
-            size_t d, int nchunks, uint64_t *__restrict__ partial0, uint64_t *__restrict__ partial1) {
-  extern __shared__ __align__(16) uint8_t dyn[];
-  const KsSmem s = ks_smem_setup(dyn, t0_global);
-  AesCtrCache cache;
-  cache.window = ~0ull;
-  const int tile = blockIdx.x % KS2_NTILES;
-  const int chunk = blockIdx.x / KS2_NTILES;
-  const int vec = threadIdx.x >= KS2_TILE ? 1 : 0;      // for threads < 2 * KS2_TILE
-  const int lc = threadIdx.x - vec * KS2_TILE;          // local coordinate
-  const bool is_mac = threadIdx.x < 2 * KS2_TILE;
-  const bool is_b = (tile == 0 && (threadIdx.x == 2 * KS2_TILE || threadIdx.x == 2 * KS2_TILE + 1));
-  const uint32_t *coeffs = (is_b ? (threadIdx.x & 1) : vec) ? coeffs1 : coeffs0;  // 490 is even: thread 491 -> vector 1
-
-  Acc704 acc;
-  acc_zero(acc);
-  size_t m = chunk;
-  int ph = 0;
-  __syncthreads();  // tables ready
-  if (m < d) {
-    const TileGeom g = tile_geom2(offset + m * (uint64_t)CTR_CT, tile);
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
-  }
-  __syncthreads();
-  for (; m < d; m += nchunks, ph ^= 1) {
-    if (is_mac) {
-      const TileGeom g = tile_geom2(offset + m * (uint64_t)CTR_CT, tile);
-      uint32_t a[22];
-      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * lc, a);
-      acc_mad(acc, a, coeffs[m]);
-    } else if (is_b) {
-      const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + m * CT_BYTES);
-      uint32_t a[22];
-#pragma unroll
-      for (int l = 0; l < 22; l++) a[l] = rec[l];
       acc_mad(acc, a, coeffs[m]);
     }
-    const size_t nx = m + nchunks;
-    if (nx < d) {
-      const TileGeom gn = tile_geom2(offset + nx * (uint64_t)CTR_CT, tile);
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
-    }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
+    if (t + 2 < nitems) fill(t + 2);
   }
 
   if (is_mac || is_b) {
-    const int v = is_b ? (threadIdx.x & 1) : vec;
-    uint64_t *out = (v ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
+    uint64_t *out = (my_vec ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
     uint32_t r[22];
     acc_fold(acc, r);
-    const int c = is_b ? N : tile * KS2_TILE + lc;
+    const int c = is_b ? N : tile * TILE + lc;
 #pragma unroll
     for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
     if (is_b) {
@@ -453,15 +436,15 @@ cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint
                                      const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
                                      uint64_t *partial_ws, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
-  cudaError_t e = ks_attr((const void *)k_evalpoly);
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly<<<nchunks * KS_NTILES, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, idx, d, nchunks,
-                                                                     partial_ws);
+  k_evalpoly<1><<<nchunks * KS_NTILES, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, nullptr, idx, d, nchunks,
+                                                                         partial_ws, nullptr);
   return cudaGetLastError();
 }
 
 int evalpoly2_nchunks(size_t d, int sm_count) {
-  size_t n = sm_count / KS2_NTILES;
+  size_t n = sm_count / (2 * KS_NTILES);
   if (n < 1) n = 1;
   if (n > d) n = d;
   return (int)(n ? n : 1);
@@ -472,10 +455,10 @@ cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uin
                                       const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks,
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
-  cudaError_t e = ks_attr((const void *)k_evalpoly2);
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly2<<<nchunks * KS2_NTILES, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, d, nchunks,
-                                                                       partial0, partial1);
+  k_evalpoly<2><<<nchunks * 2 * KS_NTILES, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, nullptr, d,
+                                                                             nchunks, partial0, partial1);
   return cudaGetLastError();
 }
 
