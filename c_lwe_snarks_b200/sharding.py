@@ -63,6 +63,11 @@ class DeviceOps:
     def columns_split(self, flat, cols):
         self.ctx.columns_split_dev(flat.data_ptr(), cols.data_ptr(), self._st())
 
+    def encrypt(self, seed, sk_planar, msg, ent, first, count, out):
+        """out[count*92] <- records of ciphertexts [first, first+count) (msg / ent are this rank's slices)."""
+        self.ctx.encrypt_dev(seed, first * 135240, sk_planar.data_ptr(), msg.data_ptr(), ent.data_ptr(), 70, 69, count,
+                             out.data_ptr(), self._st())
+
     def columns_carry(self, cols_own, first_coord, ncoord, out_own_flat):
         # the kernel indexes its output by absolute coordinate: bias the pointer so that it lands in the slice
         self.ctx.columns_carry_dev(cols_own.data_ptr(), first_coord, ncoord, None,
@@ -103,3 +108,32 @@ class ShardedLincomb:
         self.ops.columns_carry(self.cols_own, p.first_coord, p.coords_per_rank, self.own_flat)
         self.dist.all_gather_into_tensor(self.result, self.own_flat)
         return self.result
+
+
+class ShardedSetup:
+    """CRS generation (setup's 2D + M Regev encryptions, snark.c:75-110) sharded by ciphertext index: rank r encrypts
+    the contiguous range ShardPlan.ct_range(count) with the stream positioned at first * 135240 and its slice of the
+    messages / entropy; outputs are disjoint 92-byte records, so the only communication is the gather of the records.
+    `encrypt(first, count) -> uint8 tensor (count * 92)` is the kernel call (DeviceOps.encrypt or a test double)."""
+
+    def __init__(self, plan: ShardPlan, dist, new_u8):
+        self.plan, self.dist, self.new_u8 = plan, dist, new_u8
+
+    def run(self, total: int, encrypt):
+        p = self.plan
+        first, count = p.ct_range(total)
+        mine = encrypt(first, count)
+        if p.world == 1:
+            return mine
+        # ranges differ by at most one ciphertext: pad to the longest, gather, cut the padding
+        longest = (total + p.world - 1) // p.world
+        buf = self.new_u8(longest * 92)
+        buf[: count * 92] = mine
+        out = self.new_u8(p.world * longest * 92)
+        self.dist.all_gather_into_tensor(out, buf)
+        parts = []
+        for r in range(p.world):
+            _, c = ShardPlan(p.world, r).ct_range(total)
+            parts.append(out[r * longest * 92: r * longest * 92 + c * 92])
+        import torch
+        return torch.cat(parts)

@@ -71,6 +71,53 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _setup_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from conftest import SEED, xof, xof_scalars
+    from c_lwe_snarks_b200.sharding import ShardedSetup, ShardPlan
+    from oracle.loader import Oracle
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        total = 7
+        orc = Oracle()
+        sk = orc.key_gen(xof("shard-sk", N * 92))
+        msg, ent = xof_scalars("shard-msg", total), xof("shard-ent", total * 70)
+
+        def encrypt(first, count):  # stand-in for DeviceOps.encrypt: the oracle on this rank's slice
+            recs = orc.encrypt(SEED, first * CTR_CT, sk, msg[first:first + count], ent[first * 70:(first + count) * 70])
+            return torch.from_numpy(recs.reshape(-1).copy())
+
+        out = ShardedSetup(ShardPlan(world, rank), dist, lambda n: torch.zeros(n, dtype=torch.uint8)).run(total, encrypt)
+        q.put((rank, out.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_setup_matches_single_process_oracle(oracle):
+    import torch.multiprocessing as mp
+
+    from conftest import SEED, xof, xof_scalars
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_setup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    sk = oracle.key_gen(xof("shard-sk", N * 92))
+    want = oracle.encrypt(SEED, 0, sk, xof_scalars("shard-msg", 7), xof("shard-ent", 7 * 70)).reshape(-1)
+    for _, got in out:
+        assert np.array_equal(got, want)
+
+
 def test_shard_plan():
     from c_lwe_snarks_b200.sharding import ShardPlan
     for world in (1, 2, 4, 8):
