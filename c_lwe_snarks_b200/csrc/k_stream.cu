@@ -300,6 +300,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   extern __shared__ __align__(16) uint8_t dyn[];
   __shared__ uint32_t red[KS_THREADS / 32][44];
   __shared__ unsigned long long cols[22];
+  __shared__ uint32_t elimb[22], blimb[23];
   const KsSmem s = ks_smem_setup(dyn, t0_global);
   AesCtrCache cache;
   cache.window = ~0ull;
@@ -321,22 +322,35 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
     const int tile = (int)(it % KS_NTILES);
     // next item of this CTA: next tile of the same ciphertext, else tile 0 of ciphertext k + gridDim.x
     const size_t nx = (tile + 1 < KS_NTILES) ? it + 1 : (k + gridDim.x) * KS_NTILES;
-    if (threadIdx.x < KS_TILE) {
-      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
-      uint32_t a[22], b[22];
-      ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
-      const int c = tile * KS_TILE + threadIdx.x;
+    // The 253-product MAC runs on the FMA pipe, the AES on the ALU + LSU pipes: the lower half of the warps does
+    // MAC(t) then AES(t+1), the upper half the other way round, so the two kinds of work overlap on the SM.
+    auto mac = [&]() {
+      if (threadIdx.x < KS_TILE) {
+        const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+        uint32_t a[22], b[22];
+        ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
+        const int c = tile * KS_TILE + threadIdx.x;
 #pragma unroll
-      for (int j = 0; j < L64; j++) {
-        const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
-        b[2 * j] = (uint32_t)v;
-        b[2 * j + 1] = (uint32_t)(v >> 32);
+        for (int j = 0; j < L64; j++) {
+          const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
+          b[2 * j] = (uint32_t)v;
+          b[2 * j + 1] = (uint32_t)(v >> 32);
+        }
+        acc_mul(acc, a, b);
       }
-      acc_mul(acc, a, b);
-    }
-    if (nx < nitems) {
-      const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
-      ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
+    };
+    auto aes_next = [&]() {
+      if (nx < nitems) {
+        const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
+        ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
+      }
+    };
+    if (warp < KS_THREADS / 64) {
+      mac();
+      aes_next();
+    } else {
+      aes_next();
+      mac();
     }
     if (tile == KS_NTILES - 1) {
       // block-reduce the per-thread sums: 16-bit halves so that warp REDUX sums cannot overflow
@@ -360,35 +374,35 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
           hi += red[w][2 * threadIdx.x + 1];
         }
         cols[threadIdx.x] = lo + (hi << 16);
+        // noise limb l of e (little-endian bytes 4l..4l+3), fetched by 22 threads in parallel: the serial carry
+        // chain below then touches shared memory only
+        const uint8_t *e8 = ent + k * (size_t)ent_stride;
+        uint32_t el = 0;
+        for (int i = 0; i < 4; i++) {
+          const int byte = 4 * (int)threadIdx.x + i;
+          if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
+        }
+        elimb[threadIdx.x] = el;
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         // b = sum_l cols[l] << 32l  +  e * p  +  m      (mod 2^704)
-        const uint8_t *e8 = ent + k * (size_t)ent_stride;
         const uint64_t mm = msg[k];
         uint64_t carry = 0;  // < 2^34 throughout
-        uint8_t *rec = out_c8 + k * CT_BYTES;
         for (int l = 0; l < 22; l++) {
-          uint32_t el = 0;
-          for (int i = 0; i < 4; i++) {
-            const int byte = 4 * l + i;
-            if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
-          }
           uint64_t t = cols[l] + carry;  // < 2^44
           if (l == 0) t += mm & 0xffffffffu;
           if (l == 1) t += mm >> 32;
-          const uint64_t prod = (uint64_t)el * P;
+          const uint64_t prod = (uint64_t)elimb[l] * P;
           const uint64_t sum = t + prod;
           const uint64_t c_out = sum < prod ? 1 : 0;
           carry = (sum >> 32) + (c_out << 32);
-          const uint32_t limb = (uint32_t)sum;
-          rec[4 * l + 0] = (uint8_t)limb;
-          rec[4 * l + 1] = (uint8_t)(limb >> 8);
-          rec[4 * l + 2] = (uint8_t)(limb >> 16);
-          rec[4 * l + 3] = (uint8_t)(limb >> 24);
+          blimb[l] = (uint32_t)sum;
         }
-        rec[88] = rec[89] = rec[90] = rec[91] = 0;
+        blimb[22] = 0;  // bytes 88..91 of the record
       }
+      __syncthreads();
+      if (threadIdx.x < 23) reinterpret_cast<uint32_t *>(out_c8 + k * CT_BYTES)[threadIdx.x] = blimb[threadIdx.x];  // 92 % 4 == 0
     }
     __syncthreads();
     it = nx;

@@ -110,6 +110,49 @@ class ShardedLincomb:
         return self.result
 
 
+class PipelinedShardedLincomb:
+    """Back-to-back sharded lincombs (the prover runs several per proof) with the exchange of call i overlapped with the
+    lincomb kernel of call i+1: the lincomb runs on the caller's stream, the exchange chain (columns_split,
+    reduce-scatter, columns_carry, all-gather) on a side stream, two sets of exchange buffers alternate.
+    Results land in self.results[i % 2]; call drain() before reading the last ones."""
+
+    def __init__(self, plan: ShardPlan, ops, dist, new_i64, torch):
+        self.torch = torch
+        self.lanes = [ShardedLincomb(plan, ops, dist, new_i64) for _ in range(2)]
+        self.results = [lane.result for lane in self.lanes]
+        self.side = torch.cuda.Stream()
+        self.done = [None, None]   # event: exchange of the call that last used lane k has finished
+        self.calls = 0
+
+    def submit(self, cts, coeffs, d_local):
+        t = self.torch
+        k = self.calls % 2
+        lane = self.lanes[k]
+        main = t.cuda.current_stream()
+        if self.done[k] is not None:
+            main.wait_event(self.done[k])          # lane.partial is about to be overwritten
+        if lane.plan.world == 1:
+            lane.ops.lincomb(cts, coeffs, d_local, lane.result)
+        else:
+            lane.ops.lincomb(cts, coeffs, d_local, lane.partial)
+            ready = t.cuda.Event()
+            ready.record(main)
+            self.side.wait_event(ready)
+            with t.cuda.stream(self.side):
+                lane.exchange()
+                ev = t.cuda.Event()
+                ev.record(self.side)
+            self.done[k] = ev
+        self.calls += 1
+        return self.results[k]
+
+    def drain(self):
+        main = self.torch.cuda.current_stream()
+        for ev in self.done:
+            if ev is not None:
+                main.wait_event(ev)
+
+
 class ShardedSetup:
     """CRS generation (setup's 2D + M Regev encryptions, snark.c:75-110) sharded by ciphertext index: rank r encrypts
     the contiguous range ShardPlan.ct_range(count) with the stream positioned at first * 135240 and its slice of the
