@@ -190,24 +190,48 @@ struct AesCtrCache {
   uint32_t q0, q1, q2, q3;  // round-2 columns: contributions of the constant round-1 columns 0 and 3 (+ round key)
 };
 
-template <int TABS>
+// FM: bit K set = the address of a byte-K lookup is computed on the FMA pipe (idle otherwise) instead of by the
+// ALU-pipe PRMT: byte = mul.hi(w * 2^(8*(3-K)), 2^8), address = byte * 2^8 + lanebase.  The multipliers are run-time
+// values (m8, m16, m24 come from kernel parameters) so that ptxas keeps IMADs and does not strength-reduce to shifts.
+template <int TABS, int FM = 0>
 struct AesLut {
   uint32_t lbA, lbB;
+  uint32_t m8, m16, m24;
+  template <int K> __device__ __forceinline__ uint32_t addr(uint32_t w, uint32_t lb) const {
+    if constexpr ((FM >> K) & 1) {
+      uint32_t b, a;
+      if constexpr (K == 3) {
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(b) : "r"(w), "r"(m8));
+      } else {
+        uint32_t t;
+        const uint32_t mm = K == 2 ? m8 : K == 1 ? m16 : m24;
+        asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(mm));
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(b) : "r"(t), "r"(m8));
+      }
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(b), "r"(m8), "r"(lb));
+      return a;
+    } else {
+      return aes_addr<K>(w, lb);
+    }
+  }
   // Tn[byte K of w]
-  template <int K> __device__ __forceinline__ uint32_t t0(uint32_t w) const { return lds32(aes_addr<K>(w, lbA)); }
-  template <int K> __device__ __forceinline__ uint32_t t2(uint32_t w) const { return lds32_t2(aes_addr<K>(w, lbA)); }
+  template <int K> __device__ __forceinline__ uint32_t t0(uint32_t w) const { return lds32(addr<K>(w, lbA)); }
+  template <int K> __device__ __forceinline__ uint32_t t2(uint32_t w) const { return lds32_t2(addr<K>(w, lbA)); }
   template <int K> __device__ __forceinline__ uint32_t t1(uint32_t w) const {
-    if constexpr (TABS == 4) return lds32(aes_addr<K>(w, lbB));
-    else return rotl8(lds32(aes_addr<K>(w, lbA)));
+    if constexpr (TABS == 4) return lds32(addr<K>(w, lbB));
+    else return rotl8(lds32(addr<K>(w, lbA)));
   }
   template <int K> __device__ __forceinline__ uint32_t t3(uint32_t w) const {
-    if constexpr (TABS == 4) return lds32_t2(aes_addr<K>(w, lbB));
-    else return rotl8(lds32_t2(aes_addr<K>(w, lbA)));
+    if constexpr (TABS == 4) return lds32_t2(addr<K>(w, lbB));
+    else return rotl8(lds32_t2(addr<K>(w, lbA)));
   }
+  // raw loads (no rotation) from region A, for the formulations that rotate after XOR-combining
+  template <int K> __device__ __forceinline__ uint32_t a0(uint32_t w) const { return lds32(addr<K>(w, lbA)); }
+  template <int K> __device__ __forceinline__ uint32_t a2(uint32_t w) const { return lds32_t2(addr<K>(w, lbA)); }
 };
 
-template <int TABS>
-__device__ __forceinline__ void aes_round(const AesLut<TABS> &L, uint32_t &s0, uint32_t &s1, uint32_t &s2, uint32_t &s3,
+template <int TABS, int FM>
+__device__ __forceinline__ void aes_round(const AesLut<TABS, FM> &L, uint32_t &s0, uint32_t &s1, uint32_t &s2, uint32_t &s3,
                                           uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
   if constexpr (TABS == 4) {
     const uint32_t a0 = L.template t0<0>(s0), a1 = L.template t1<1>(s1), a2 = L.template t2<2>(s2), a3 = L.template t3<3>(s3);
@@ -219,14 +243,14 @@ __device__ __forceinline__ void aes_round(const AesLut<TABS> &L, uint32_t &s0, u
     s2 = c0 ^ c1 ^ c2 ^ c3 ^ k2;
     s3 = d0 ^ d1 ^ d2 ^ d3 ^ k3;
   } else {
-    const uint32_t a0 = lds32(aes_addr<0>(s0, L.lbA)), a1 = lds32(aes_addr<1>(s1, L.lbA));
-    const uint32_t a2 = lds32_t2(aes_addr<2>(s2, L.lbA)), a3 = lds32_t2(aes_addr<3>(s3, L.lbA));
-    const uint32_t b0 = lds32(aes_addr<0>(s1, L.lbA)), b1 = lds32(aes_addr<1>(s2, L.lbA));
-    const uint32_t b2 = lds32_t2(aes_addr<2>(s3, L.lbA)), b3 = lds32_t2(aes_addr<3>(s0, L.lbA));
-    const uint32_t c0 = lds32(aes_addr<0>(s2, L.lbA)), c1 = lds32(aes_addr<1>(s3, L.lbA));
-    const uint32_t c2 = lds32_t2(aes_addr<2>(s0, L.lbA)), c3 = lds32_t2(aes_addr<3>(s1, L.lbA));
-    const uint32_t d0 = lds32(aes_addr<0>(s3, L.lbA)), d1 = lds32(aes_addr<1>(s0, L.lbA));
-    const uint32_t d2 = lds32_t2(aes_addr<2>(s1, L.lbA)), d3 = lds32_t2(aes_addr<3>(s2, L.lbA));
+    const uint32_t a0 = L.template a0<0>(s0), a1 = L.template a0<1>(s1);
+    const uint32_t a2 = L.template a2<2>(s2), a3 = L.template a2<3>(s3);
+    const uint32_t b0 = L.template a0<0>(s1), b1 = L.template a0<1>(s2);
+    const uint32_t b2 = L.template a2<2>(s3), b3 = L.template a2<3>(s0);
+    const uint32_t c0 = L.template a0<0>(s2), c1 = L.template a0<1>(s3);
+    const uint32_t c2 = L.template a2<2>(s0), c3 = L.template a2<3>(s1);
+    const uint32_t d0 = L.template a0<0>(s3), d1 = L.template a0<1>(s0);
+    const uint32_t d2 = L.template a2<2>(s1), d3 = L.template a2<3>(s2);
     s0 = a0 ^ a2 ^ k0 ^ rotl8(a1 ^ a3);
     s1 = b0 ^ b2 ^ k1 ^ rotl8(b1 ^ b3);
     s2 = c0 ^ c2 ^ k2 ^ rotl8(c1 ^ c3);
@@ -234,18 +258,18 @@ __device__ __forceinline__ void aes_round(const AesLut<TABS> &L, uint32_t &s0, u
   }
 }
 
-template <int TABS>
-__device__ __forceinline__ AesState aes_last_round(const AesLut<TABS> &L, const AesKey &k, uint32_t s0, uint32_t s1,
+template <int TABS, int FM>
+__device__ __forceinline__ AesState aes_last_round(const AesLut<TABS, FM> &L, const AesKey &k, uint32_t s0, uint32_t s1,
                                                    uint32_t s2, uint32_t s3) {
   // S sits in byte 0 and 3 of T2 (= S,3S,2S,S) and in byte 1 and 2 of T0 (= 2S,S,S,3S): already in position
-  const uint32_t a0 = lds32_t2(aes_addr<0>(s0, L.lbA)), a1 = lds32(aes_addr<1>(s1, L.lbA));
-  const uint32_t a2 = lds32(aes_addr<2>(s2, L.lbA)), a3 = lds32_t2(aes_addr<3>(s3, L.lbA));
-  const uint32_t b0 = lds32_t2(aes_addr<0>(s1, L.lbA)), b1 = lds32(aes_addr<1>(s2, L.lbA));
-  const uint32_t b2 = lds32(aes_addr<2>(s3, L.lbA)), b3 = lds32_t2(aes_addr<3>(s0, L.lbA));
-  const uint32_t c0 = lds32_t2(aes_addr<0>(s2, L.lbA)), c1 = lds32(aes_addr<1>(s3, L.lbA));
-  const uint32_t c2 = lds32(aes_addr<2>(s0, L.lbA)), c3 = lds32_t2(aes_addr<3>(s1, L.lbA));
-  const uint32_t d0 = lds32_t2(aes_addr<0>(s3, L.lbA)), d1 = lds32(aes_addr<1>(s0, L.lbA));
-  const uint32_t d2 = lds32(aes_addr<2>(s1, L.lbA)), d3 = lds32_t2(aes_addr<3>(s2, L.lbA));
+  const uint32_t a0 = L.template a2<0>(s0), a1 = L.template a0<1>(s1);
+  const uint32_t a2 = L.template a0<2>(s2), a3 = L.template a2<3>(s3);
+  const uint32_t b0 = L.template a2<0>(s1), b1 = L.template a0<1>(s2);
+  const uint32_t b2 = L.template a0<2>(s3), b3 = L.template a2<3>(s0);
+  const uint32_t c0 = L.template a2<0>(s2), c1 = L.template a0<1>(s3);
+  const uint32_t c2 = L.template a0<2>(s0), c3 = L.template a2<3>(s1);
+  const uint32_t d0 = L.template a2<0>(s3), d1 = L.template a0<1>(s0);
+  const uint32_t d2 = L.template a0<2>(s1), d3 = L.template a2<3>(s2);
   AesState o;
   o.w0 = ((a0 & 0x000000ffu) | (a1 & 0x0000ff00u) | (a2 & 0x00ff0000u) | (a3 & 0xff000000u)) ^ k.rk[56];
   o.w1 = ((b0 & 0x000000ffu) | (b1 & 0x0000ff00u) | (b2 & 0x00ff0000u) | (b3 & 0xff000000u)) ^ k.rk[57];
@@ -254,8 +278,8 @@ __device__ __forceinline__ AesState aes_last_round(const AesLut<TABS> &L, const 
   return o;
 }
 
-template <int TABS>
-__device__ __forceinline__ void aes_ctr_cache_fill(const AesLut<TABS> &L, const AesKey &k, uint64_t ctr, AesCtrCache &c) {
+template <int TABS, int FM>
+__device__ __forceinline__ void aes_ctr_cache_fill(const AesLut<TABS, FM> &L, const AesKey &k, uint64_t ctr, AesCtrCache &c) {
   const uint32_t s0 = k.nonce[0] ^ k.rk[0], s1 = k.nonce[1] ^ k.rk[1];
   const uint32_t s2 = (uint32_t)ctr ^ k.rk[2], s3 = (uint32_t)(ctr >> 32) ^ k.rk[3];
   // round 1: columns 0 and 3 are constant in the window (they see counter bytes 2 and 3 only)
@@ -272,10 +296,10 @@ __device__ __forceinline__ void aes_ctr_cache_fill(const AesLut<TABS> &L, const 
 }
 
 // One AES-256 encryption of (nonce || LE64(ctr)) with the counter-mode cache.
-template <int TABS>
-__device__ __forceinline__ AesState aes256_ctr_block_cached(const AesLut<TABS> &L, const AesKey &k, uint64_t ctr,
+template <int TABS, int FM>
+__device__ __forceinline__ AesState aes256_ctr_block_cached(const AesLut<TABS, FM> &L, const AesKey &k, uint64_t ctr,
                                                             AesCtrCache &c) {
-  if ((ctr >> 16) != c.window) aes_ctr_cache_fill<TABS>(L, k, ctr, c);
+  if ((ctr >> 16) != c.window) aes_ctr_cache_fill<TABS, FM>(L, k, ctr, c);
   const uint32_t s2 = (uint32_t)ctr ^ k.rk[2];
   // round 1, columns 1 and 2
   const uint32_t r1 = c.k1p ^ L.template t1<1>(s2);
@@ -287,18 +311,18 @@ __device__ __forceinline__ AesState aes256_ctr_block_cached(const AesLut<TABS> &
   uint32_t s3 = c.q3 ^ L.template t2<2>(r1) ^ L.template t3<3>(r2);
   uint32_t s2v = t2v;
 #pragma unroll
-  for (int r = 3; r < 14; r++) aes_round<TABS>(L, s0, s1, s2v, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
-  return aes_last_round<TABS>(L, k, s0, s1, s2v, s3);
+  for (int r = 3; r < 14; r++) aes_round<TABS, FM>(L, s0, s1, s2v, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
+  return aes_last_round<TABS, FM>(L, k, s0, s1, s2v, s3);
 }
 
 // Plain variant (no cache) on the same table abstraction.
-template <int TABS>
-__device__ __forceinline__ AesState aes256_ctr_block_plain(const AesLut<TABS> &L, const AesKey &k, uint64_t ctr) {
+template <int TABS, int FM>
+__device__ __forceinline__ AesState aes256_ctr_block_plain(const AesLut<TABS, FM> &L, const AesKey &k, uint64_t ctr) {
   uint32_t s0 = k.nonce[0] ^ k.rk[0], s1 = k.nonce[1] ^ k.rk[1];
   uint32_t s2 = (uint32_t)ctr ^ k.rk[2], s3 = (uint32_t)(ctr >> 32) ^ k.rk[3];
 #pragma unroll
-  for (int r = 1; r < 14; r++) aes_round<TABS>(L, s0, s1, s2, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
-  return aes_last_round<TABS>(L, k, s0, s1, s2, s3);
+  for (int r = 1; r < 14; r++) aes_round<TABS, FM>(L, s0, s1, s2, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
+  return aes_last_round<TABS, FM>(L, k, s0, s1, s2, s3);
 }
 
 // Fill region B (T1 | T3, 64 KB) for TABS = 4 from the global T0 table.

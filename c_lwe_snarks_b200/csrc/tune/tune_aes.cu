@@ -11,9 +11,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, const AesState &v) {
 }
 
 // VARIANT 0: shipped (aes256_ctr_block), 1: plain on AesLut<2>, 2: cached TABS=2, 3: plain TABS=4, 4: cached TABS=4
-template <int VARIANT, int NT, int AT>
+template <int VARIANT, int NT, int AT, int FM = 0>
 __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0g, int nblk,
-                                              int items, unsigned long long *digest) {
+                                              int items, unsigned long long *digest, uint32_t m8, uint32_t m16, uint32_t m24) {
   extern __shared__ __align__(16) uint8_t dyn[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(dyn);
   const uint32_t tabA = (s0 + 0xffffu) & ~0xffffu;
@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   aes_tables_init(dyn + (tabA - s0), t0g, threadIdx.x, NT);
   if (four) aes_tables_init_b(dyn + (tabB - s0), t0g, threadIdx.x, NT);
   __syncthreads();
-  AesLut<four ? 4 : 2> L;
+  AesLut<four ? 4 : 2, FM> L;
   L.lbA = tabA | ((threadIdx.x & 31) << 2);
   L.lbB = tabB | ((threadIdx.x & 31) << 2);
+  L.m8 = m8; L.m16 = m16; L.m24 = m24;
   AesCtrCache cache;
   cache.window = ~0ull;
   uint32_t x = 0;
@@ -47,22 +48,22 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   atomicXor(digest, (unsigned long long)x * 0x9e3779b97f4a7c15ull + blockIdx.x);
 }
 
-template <int VARIANT, int NT, int AT = NT>
+template <int VARIANT, int NT, int AT = NT, int FM = 0>
 static void run(const char *name, const AesKey &key, const uint32_t *t0, int nblk, int items, unsigned long long *dig) {
   const int smem = VARIANT >= 3 ? 0x30000 : 0x20000;
-  CK(cudaFuncSetAttribute(k_aes<VARIANT, NT, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_aes<VARIANT, NT, AT, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   unsigned long long z = 0, out = 0;
-  k_aes<VARIANT, NT, AT><<<148, NT, smem>>>(key, t0, nblk, items, dig);
+  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(dig, &z, 8, cudaMemcpyHostToDevice));
   CK(cudaEventRecord(e0));
-  k_aes<VARIANT, NT, AT><<<148, NT, smem>>>(key, t0, nblk, items, dig);
+  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   CK(cudaMemcpy(&out, dig, 8, cudaMemcpyDeviceToHost));
   const double blocks = 148.0 * items * nblk;
-  printf("%-26s NT=%4d AT=%4d nblk=%4d: %8.3f ms  %.3e blocks/s  (%.2f cyc/blk/SM @1.965GHz)  digest %016llx\n", name, NT, AT, nblk, ms,
+  printf("%-26s FM=%2d NT=%4d AT=%4d nblk=%4d: %8.3f ms  %.3e blocks/s  (%.2f cyc/blk/SM @1.965GHz)  digest %016llx\n", name, FM, NT, AT, nblk, ms,
          blocks / ms * 1e3, 1.965e9 * 148 / (blocks / ms * 1e3), out);
   fflush(stdout);
 }
@@ -76,20 +77,16 @@ int main() {
   const int items = 600;
   run<0, 512>("shipped 2-table", key, t0, 2818, items, dig);
   run<2, 512>("ctr-cached 2-table", key, t0, 2818, items, dig);
-  run<2, 512, 480>("ctr-cached 2-table", key, t0, 2818, items, dig);
-  run<2, 512, 480>("ctr-cached 2-table", key, t0, 2819, items, dig);
-  run<4, 512, 480>("ctr-cached 4-table", key, t0, 2818, items, dig);
-  run<2, 512, 480>("ctr-cached 2-table", key, t0, 1409, items, dig);
-  run<4, 512, 480>("ctr-cached 4-table", key, t0, 1409, items, dig);
-  run<4, 512, 480>("ctr-cached 4-table", key, t0, 1410, items, dig);
-  run<4, 512, 352>("ctr-cached 4-table", key, t0, 1409, items, dig);
-  run<2, 1024, 960>("ctr-cached 2-table", key, t0, 2818, items, dig);
-  run<4, 1024, 960>("ctr-cached 4-table", key, t0, 2818, items, dig);
-  run<2, 768, 704>("ctr-cached 2-table", key, t0, 2818, items, dig);
-  run<4, 768, 704>("ctr-cached 4-table", key, t0, 2818, items, dig);
-  run<4, 768, 704>("ctr-cached 4-table", key, t0, 1409, items, dig);
-  run<4, 1024, 704>("ctr-cached 4-table", key, t0, 1409, items, dig);
-  run<4, 640, 576>("ctr-cached 4-table", key, t0, 2818, items, dig);
-  run<2, 640, 576>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x8>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0xC>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0xE>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0xF>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x9>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x5>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<4, 512>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<4, 512, 512, 0x8>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<4, 512, 512, 0xC>("ctr-cached 4-table", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x8>("ctr-cached 2-table", key, t0, 1409, items, dig);
+  run<2, 512, 512, 0xC>("ctr-cached 2-table", key, t0, 1409, items, dig);
   return 0;
 }
