@@ -181,6 +181,18 @@ def test_reference_test_programs_against_the_dropin(name):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_reference_benchmark_snark_against_the_dropin():
+    """benchmark_snark.c of the reference, unmodified (debug instance): prints setup/prover/verifier seconds in its own
+    format and exits 0 iff the verifier accepts (benchmark_snark.c:94-96)."""
+    exe = ROOT / "oracle" / "_ref" / "dropin_benchmark_snark_debug"
+    if not exe.exists():
+        pytest.skip("built only where the reference sources are present (oracle/Makefile dropin-tests)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    names = [line.split("\t")[0] for line in r.stdout.splitlines() if "\t" in line]
+    assert names == ["setup", "prover", "verifier"]
+
+
 def test_python_snark_binding_roundtrip():
     """c_lwe_snarks_b200.snark.Snark (ctypes over the drop-in's own structs) with OS entropy: accept, then reject."""
     from c_lwe_snarks_b200.snark import Snark
