@@ -12,6 +12,8 @@
 // natural out), so no permutation pass is needed around the pointwise product.  Stages whose butterflies span more
 // than NTT_B elements run one stage per launch over global memory (L2-resident: 3 primes x 2^18 x 4 B = 3 MB);
 // the last log2(NTT_B) stages run in one launch in shared memory.  All three primes share a launch (grid.y).
+#include <vector>
+
 #include "mfb_common.cuh"
 
 namespace mfb {
@@ -489,6 +491,8 @@ int ctx_fail(cudaError_t e, const char *what, const char *file, int line);
 void ctx_count_launches(mfb_ctx *ctx, uint64_t n);
 int ctx_enter(mfb_ctx *ctx);
 int ctx_bad_arg(const char *msg);
+int ctx_h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces, cudaStream_t st);
+int ctx_h2d(mfb_ctx *ctx, void *dst_dev, const void *src, size_t bytes, cudaStream_t st);
 
 PolyEngine *poly_engine_new() { return new PolyEngine(); }
 void poly_engine_delete(PolyEngine *e) {
@@ -603,7 +607,10 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
 
   // selected polynomials: t, v_0, and v_i for the set witness bits (bit i-1 <-> v_i, i = 1..M-1)
   const uint32_t Du = (uint32_t)D;
-  const size_t BATCH = 64;  // polynomials staged per accumulate launch
+  // polynomials staged per accumulate launch: up to 256 MB of wire coefficients
+  size_t BATCH = ((size_t)256 << 20) / (D * 8);
+  if (BATCH < 1) BATCH = 1;
+  if (BATCH > M) BATCH = M;
   void *d_t, *d_v0, *d_sel, *d_w, *d_a, *d_wide;
   if ((rc = ctx_scratch(ctx, 0, D * 8, &d_t))) return rc;
   if ((rc = ctx_scratch(ctx, 1, D * 8, &d_v0))) return rc;
@@ -614,27 +621,22 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
   uint32_t *d_v = (uint32_t *)d_w + D;
   PTRY(cudaMemcpyAsync(d_t, ssp, D * 8, cudaMemcpyHostToDevice, st));
   PTRY(cudaMemcpyAsync(d_v0, ssp + D, D * 8, cudaMemcpyHostToDevice, st));
-  size_t staged = 0;
+  std::vector<const void *> pieces;
+  for (size_t i = 1; i < M; i++)
+    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) pieces.push_back(ssp + (i + 1) * D);
   int first = 1;
-  auto flush = [&]() -> cudaError_t {
-    k_ssp_accumulate<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, delta, (const uint64_t *)d_sel, (uint32_t)staged, Du,
-                                                   first, (uint32_t *)d_w);
+  size_t done = 0;
+  do {
+    const size_t cnt = pieces.size() - done < BATCH ? pieces.size() - done : BATCH;
+    if (done) PTRY(cudaStreamSynchronize(st));  // the staging area is reused: the previous accumulate must have read it
+    if (cnt && (rc = ctx_h2d_pieces(ctx, d_sel, pieces.data() + done, D * 8, cnt, st))) return rc;
+    k_ssp_accumulate<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, delta, (const uint64_t *)d_sel, (uint32_t)cnt, Du, first,
+                                                   (uint32_t *)d_w);
     E.launches++;
+    PTRY(cudaGetLastError());
     first = 0;
-    staged = 0;
-    return cudaGetLastError();
-  };
-  for (size_t i = 1; i < M; i++) {
-    if (!((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1))) continue;
-    if (staged == BATCH) {
-      // the staging buffer is reused: wait until the previous batch has been consumed
-      PTRY(flush());
-      PTRY(cudaStreamSynchronize(st));
-    }
-    PTRY(cudaMemcpyAsync((uint64_t *)d_sel + staged * D, ssp + (i + 1) * D, D * 8, cudaMemcpyHostToDevice, st));
-    staged++;
-  }
-  PTRY(flush());
+    done += cnt;
+  } while (done < pieces.size());
   k_add_u64poly<<<gridfor(Du), 256, 0, st>>>((const uint32_t *)d_w, (const uint64_t *)d_v0, Du, d_v);
   E.launches++;
 
@@ -680,7 +682,7 @@ extern "C" int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_
   rc = ctx_scratch(ctx, 3, (total < STAGE ? total : STAGE) * 8, &d_stage);
   for (size_t o = 0; rc == MFB_OK && o < total; o += STAGE) {
     const size_t cnt = total - o < STAGE ? total - o : STAGE;
-    if ((e = cudaMemcpyAsync(d_stage, ssp + o, cnt * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((rc = ctx_h2d(ctx, d_stage, ssp + o, cnt * 8, st)) != MFB_OK) break;
     k_reduce_u64poly<<<gridfor((uint32_t)cnt), 256, 0, st>>>((const uint64_t *)d_stage, (uint32_t)cnt, h->blob + o);
     E.launches++;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
@@ -767,7 +769,7 @@ extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_
   E.launches++;
   for (size_t q = 0; q < npoly; q += per) {
     const size_t cnt = npoly - q < per ? npoly - q : per;
-    PTRY(cudaMemcpyAsync(d_p, polys + q * D, cnt * D * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = ctx_h2d(ctx, d_p, polys + q * D, cnt * D * 8, st)) != MFB_OK) return rc;
     k_eval<<<(unsigned)cnt, 256, 0, st>>>((const uint64_t *)d_p, (uint32_t)D, (const uint32_t *)d_pw, (uint64_t *)d_val + q);
     E.launches++;
     PTRY(cudaGetLastError());

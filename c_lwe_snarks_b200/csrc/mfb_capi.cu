@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "../../include/mfb200.h"
 #include "aes256.cuh"
@@ -81,6 +83,10 @@ struct mfb_ctx {
   size_t slot_cap[NSLOTS] = {};
   uint64_t launches = 0;
   mfb::PolyEngine *poly = nullptr;  // F_p[x] engine (NTT tables, work arrays), created on first use
+  // pinned bounce buffers for large host->device transfers from pageable memory (SSP blobs are GBs)
+  uint8_t *bounce[2] = {nullptr, nullptr};
+  cudaEvent_t bounce_free[2] = {nullptr, nullptr};
+  bool bounce_used[2] = {false, false};  // an H2D from this buffer has been queued at some point
   // optional per-kernel timing of the dominant kernel of lincomb / eval_poly calls (bench.py's roofline)
   bool profiling = false;
   int prof_n = 0;
@@ -126,7 +132,75 @@ static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
     MFB_CUDA_TRY(cudaSetDevice((ctx)->device));                \
   } while (0)
 
+// Host -> device copy of `npieces` equally sized pieces (src[i], piece_bytes each) into one contiguous device range.
+// Pageable sources make cudaMemcpyAsync stage through a small driver buffer at 4-5 GB/s; here the pieces are packed
+// into two 64 MB pinned bounce buffers by a few host threads while the previous buffer is in flight on the DMA engine.
+static const size_t BOUNCE_BYTES = (size_t)64 << 20;
+static int h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces,
+                      cudaStream_t st) {
+  if (npieces == 0 || piece_bytes == 0) return MFB_OK;
+  for (int k = 0; k < 2; k++) {
+    if (!ctx->bounce[k]) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->bounce[k], BOUNCE_BYTES, cudaHostAllocDefault));
+    if (!ctx->bounce_free[k]) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->bounce_free[k], cudaEventDisableTiming));
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned nthreads = hw >= 16 ? 8 : hw >= 4 ? 4 : 1;
+  uint8_t *dst = (uint8_t *)dst_dev;
+  size_t piece = 0, in_piece = 0;  // cursor over the logical concatenation
+  int k = 0;
+  while (piece < npieces) {
+    if (ctx->bounce_used[k]) MFB_CUDA_TRY(cudaEventSynchronize(ctx->bounce_free[k]));  // also across calls
+    // plan this chunk: a list of (source pointer, bytes, offset in the bounce buffer)
+    struct Seg { const uint8_t *p; size_t n, off; };
+    std::vector<Seg> segs;
+    size_t fill = 0;
+    while (piece < npieces && fill < BOUNCE_BYTES) {
+      size_t n = piece_bytes - in_piece;
+      if (n > BOUNCE_BYTES - fill) n = BOUNCE_BYTES - fill;
+      // cut long segments so that the copy threads get even shares
+      const size_t cut = (size_t)4 << 20;
+      for (size_t o = 0; o < n; o += cut)
+        segs.push_back({(const uint8_t *)src[piece] + in_piece + o, n - o < cut ? n - o : cut, fill + o});
+      fill += n;
+      in_piece += n;
+      if (in_piece == piece_bytes) {
+        piece++;
+        in_piece = 0;
+      }
+    }
+    uint8_t *bb = ctx->bounce[k];
+    auto work = [&](unsigned t) {
+      for (size_t i = t; i < segs.size(); i += nthreads) memcpy(bb + segs[i].off, segs[i].p, segs[i].n);
+    };
+    if (nthreads == 1 || segs.size() < 2) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+      work(0);
+      for (auto &th : pool) th.join();
+    }
+    MFB_CUDA_TRY(cudaMemcpyAsync(dst, bb, fill, cudaMemcpyHostToDevice, st));
+    MFB_CUDA_TRY(cudaEventRecord(ctx->bounce_free[k], st));
+    ctx->bounce_used[k] = true;
+    dst += fill;
+    k ^= 1;
+  }
+  return MFB_OK;
+}
+
 namespace mfb {  // hooks for k_poly.cu
+int ctx_h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces, cudaStream_t st) {
+  return h2d_pieces(ctx, dst_dev, src, piece_bytes, npieces, st);
+}
+int ctx_h2d(mfb_ctx *ctx, void *dst_dev, const void *src, size_t bytes, cudaStream_t st) {
+  if (bytes < ((size_t)8 << 20)) {  // small: the driver's own staging is fine
+    MFB_CUDA_TRY(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
+    return MFB_OK;
+  }
+  const void *one[1] = {src};
+  return h2d_pieces(ctx, dst_dev, one, bytes, 1, st);
+}
 PolyEngine *poly_engine_of(mfb_ctx *ctx) {
   if (!ctx->poly) ctx->poly = poly_engine_new();
   return ctx->poly;
@@ -198,6 +272,10 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
   if (ctx->partial_ws) cudaFree(ctx->partial_ws);
   if (ctx->queue) cudaFree(ctx->queue);
   poly_engine_delete(ctx->poly);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->bounce[k]) cudaFreeHost(ctx->bounce[k]);
+    if (ctx->bounce_free[k]) cudaEventDestroy(ctx->bounce_free[k]);
+  }
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;
