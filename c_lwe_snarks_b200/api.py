@@ -77,6 +77,8 @@ _SIGS = {
     "mfb_eval_poly2": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u64p, C.c_size_t, _u64p, _u64p]),
     "mfb_eval_poly2_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "mfb_encrypt": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p]),
+    "mfb_encrypt_cb": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
+                                C.c_int, C.c_size_t, _u8p]),
     "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
@@ -278,6 +280,27 @@ class Context:
         out = np.zeros((m.size, CT_BYTES), np.uint8)
         self._ck(self.lib.mfb_encrypt(self.h, _p8(s), offset, _p64(sk), _p64(m), _p8(e), ent_stride, ent_nbytes,
                                       m.size, _p8(out)))
+        return out
+
+    def encrypt_cb(self, seed, offset: int, sk_flat, msg, draw, ent_stride: int = ENT_BYTES,
+                   ent_nbytes: int = ENT_BYTES - 1) -> np.ndarray:
+        """encrypt() with the entropy drawn through ``draw(nbytes) -> bytes`` piece by piece, in order, while the
+        device encrypts the previous piece (mfb_encrypt_cb; what setup() uses)."""
+        s, sk, m = _seed(seed), _arr(sk_flat, np.uint64), _arr(msg, np.uint64)
+        if sk.size != FLAT_SK_U64:
+            raise ValueError("sk_flat must be (1470, 11) uint64")
+        out = np.zeros((m.size, CT_BYTES), np.uint8)
+        fn_t = _SIGS["mfb_encrypt_cb"][1][5]
+
+        def _draw(_user, dst, nbytes):
+            data = bytes(draw(nbytes))
+            if len(data) != nbytes:
+                raise ValueError("entropy callback returned the wrong number of bytes")
+            C.memmove(dst, data, nbytes)
+
+        cb = fn_t(_draw)
+        self._ck(self.lib.mfb_encrypt_cb(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes, m.size,
+                                         _p8(out)))
         return out
 
     def decrypt(self, sk_flat, cts_flat, b_neg=None, want_dot: bool = False):

@@ -243,7 +243,10 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     const int b = (int)(t % KS_NBUF);
     if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
     const TileGeom g = geom(chunk + t * nchunks);
-    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+    // NVEC = 1: 2818 blocks = 5.5 per thread, rotate by half a CTA (5, 6, 5, 6, ...); NVEC = 2: 1409 blocks = 2.75
+    // per thread, rotate by a quarter (3, 3, 3, 2, ...): every warp averages the same work over a few items
+    const int rot = NVEC == 1 ? (int)((t & 1) * (KS_THREADS / 2)) : (int)((t & 3) * (KS_THREADS / 4));
+    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, rot);
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * b);
   };
@@ -290,124 +293,141 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
 }
 
 // ------------------------------------------------------------------------------------ Regev encryption
-// One CTA per ciphertext k (grid-stride): b_k = (e_k * p + <sk, a_k> + m_k) mod 2^704, written as the
-// 92-byte wire record.  sk is planar [11][1472].  e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes)
-// (69 noise bytes of errdist_uniform lwe.c:60-63; the sign byte that follows is consumed by the host
-// protocol and never used, lwe.c:86-87).
+// b_k = (e_k * p + <sk, a_k> + m_k) mod 2^704, written as the 92-byte wire record.  sk is row-planar [11][1472].
+// e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes) (69 noise bytes of errdist_uniform lwe.c:60-63;
+// the sign byte that follows is consumed by the host protocol and never used, lwe.c:86-87).
+//
+// A CTA takes whole ciphertexts k = blockIdx.x, blockIdx.x + gridDim.x, ...; its work items are their 3 coordinate
+// tiles in order, on the same three-buffer mbarrier pipeline as k_evalpoly (no CTA-wide barrier in steady state):
+//   item t:  wait full[t % 3] -> thread c < 490: acc += a_c * sk_c (253 limb products on the FMA pipe, idle during AES)
+//            -> release the buffer -> AES of item t + 2 (ALU + LSU pipes).
+// After a ciphertext's third tile every warp reduces its threads' sums (REDUX on 16-bit halves, no overflow), adds
+// them to per-ciphertext columns in shared memory with 32-bit atomics and counts itself in; the LAST warp to arrive
+// adds e*p + m, propagates the carries (one uniform 22-step chain) and writes the record while the others are already
+// generating the next ciphertext's keystream.
+constexpr int KS_NWARPS = KS_THREADS / 32;
+
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
           const uint64_t *__restrict__ sk, const uint64_t *__restrict__ msg, const uint8_t *__restrict__ ent,
           int ent_stride, int ent_nbytes, size_t count, uint8_t *__restrict__ out_c8) {
   extern __shared__ __align__(16) uint8_t dyn[];
-  __shared__ uint32_t red[KS_THREADS / 32][44];
-  __shared__ unsigned long long cols[22];
-  __shared__ uint32_t elimb[22], blimb[23];
-  const KsSmem s = ks_smem_setup(dyn, t0_global);
+  __shared__ __align__(8) uint64_t bars[2 * KS_NBUF];
+  __shared__ uint32_t cols[2][2 * L32];  // [ciphertext parity][limb l: low-half sum, high-half sum]
+  __shared__ uint32_t arrived[2];
+  KsSmem s = ks_smem_setup(dyn, t0_global);
+  auto buf_of = [&](int b) { return b == 0 ? s.buf[0] : s.buf[1] + (uint32_t)(b - 1) * (uint32_t)KS_BUF_BYTES; };
+  const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(bars);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2 * KS_NBUF; b++) ksb_init(bbase + 8 * b, KS_NWARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    arrived[0] = arrived[1] = 0;
+  }
+  if (threadIdx.x < 4 * L32) cols[threadIdx.x / (2 * L32)][threadIdx.x % (2 * L32)] = 0;
   AesCtrCache cache;
   cache.window = ~0ull;
-  const size_t nitems = count * KS_NTILES;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool is_mac = threadIdx.x < KS_TILE;
+  const size_t nct = count > blockIdx.x ? (count - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const size_t nitems = nct * KS_NTILES;
+  auto ct_of = [&](size_t t) { return (size_t)blockIdx.x + (t / KS_NTILES) * gridDim.x; };
+  auto fill = [&](size_t t) {  // item t of this CTA -> buffer t % 3
+    const int b = (int)(t % KS_NBUF);
+    if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
+    const TileGeom g = tile_geom(offset + ct_of(t) * (uint64_t)CTR_CT, (int)(t % KS_NTILES));
+    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+    __syncwarp();
+    if (lane == 0) ksb_arrive(bbase + 8 * b);
+  };
 
   Acc704 acc;
   acc_zero(acc);
-  size_t it = (size_t)blockIdx.x * KS_NTILES;  // a CTA takes whole ciphertexts: items 3k, 3k+1, 3k+2
-  int ph = 0;
-  __syncthreads();  // tables ready
-  if (it < nitems) {
-    const TileGeom g = tile_geom(offset + (it / KS_NTILES) * (uint64_t)CTR_CT, 0);
-    ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
-  }
-  __syncthreads();
-  while (it < nitems) {
-    const size_t k = it / KS_NTILES;
-    const int tile = (int)(it % KS_NTILES);
-    // next item of this CTA: next tile of the same ciphertext, else tile 0 of ciphertext k + gridDim.x
-    const size_t nx = (tile + 1 < KS_NTILES) ? it + 1 : (k + gridDim.x) * KS_NTILES;
-    // The 253-product MAC runs on the FMA pipe, the AES on the ALU + LSU pipes: the lower half of the warps does
-    // MAC(t) then AES(t+1), the upper half the other way round, so the two kinds of work overlap on the SM.
-    auto mac = [&]() {
-      if (threadIdx.x < KS_TILE) {
-        const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
-        uint32_t a[22], b[22];
-        ks_read_coord((ph ? s.buf[1] : s.buf[0]), g.delta + CT_BYTES * threadIdx.x, a);
-        const int c = tile * KS_TILE + threadIdx.x;
+  __syncthreads();  // tables, barriers, columns ready
+  if (nitems > 0) fill(0);
+  if (nitems > 1) fill(1);
+  for (size_t t = 0; t < nitems; t++) {
+    const int b = (int)(t % KS_NBUF);
+    const int tile = (int)(t % KS_NTILES);
+    const size_t k = ct_of(t);
+    ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));  // every warp has stored its blocks of item t
+    if (is_mac) {
+      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+      uint32_t a[22], w[22];
+      ks_read_coord(buf_of(b), g.delta + CT_BYTES * threadIdx.x, a);
+      const int c = tile * KS_TILE + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < L64; j++) {
-          const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
-          b[2 * j] = (uint32_t)v;
-          b[2 * j + 1] = (uint32_t)(v >> 32);
-        }
-        acc_mul(acc, a, b);
+      for (int j = 0; j < L64; j++) {
+        const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
+        w[2 * j] = (uint32_t)v;
+        w[2 * j + 1] = (uint32_t)(v >> 32);
       }
-    };
-    auto aes_next = [&]() {
-      if (nx < nitems) {
-        const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
-        ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
-      }
-    };
-    if (warp < KS_THREADS / 64) {
-      mac();
-      aes_next();
-    } else {
-      aes_next();
-      mac();
+      acc_mul(acc, a, w);
     }
+    __syncwarp();
+    if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
+
     if (tile == KS_NTILES - 1) {
-      // block-reduce the per-thread sums: 16-bit halves so that warp REDUX sums cannot overflow
+      const int slot = (int)((t / KS_NTILES) & 1);
       uint32_t r[22];
       acc_fold(acc, r);
       acc_zero(acc);
+      uint32_t mylo = 0, myhi = 0;
 #pragma unroll
       for (int l = 0; l < 22; l++) {
         const uint32_t lo = __reduce_add_sync(0xffffffffu, r[l] & 0xffffu);
         const uint32_t hi = __reduce_add_sync(0xffffffffu, r[l] >> 16);
-        if (lane == 0) {
-          red[warp][2 * l] = lo;
-          red[warp][2 * l + 1] = hi;
+        if (lane == l) {
+          mylo = lo;
+          myhi = hi;
         }
       }
-      __syncthreads();
-      if (threadIdx.x < 22) {
-        unsigned long long lo = 0, hi = 0;
-        for (int w = 0; w < KS_THREADS / 32; w++) {
-          lo += red[w][2 * threadIdx.x];
-          hi += red[w][2 * threadIdx.x + 1];
-        }
-        cols[threadIdx.x] = lo + (hi << 16);
-        // noise limb l of e (little-endian bytes 4l..4l+3), fetched by 22 threads in parallel: the serial carry
-        // chain below then touches shared memory only
-        const uint8_t *e8 = ent + k * (size_t)ent_stride;
+      if (lane < L32) {
+        atomicAdd(&cols[slot][2 * lane], mylo);  // < 512 * 2^16: no overflow
+        atomicAdd(&cols[slot][2 * lane + 1], myhi);
+      }
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        prev = atomicAdd(&arrived[slot], 1u);
+      }
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == KS_NWARPS - 1) {  // this warp is the last one: all column sums are in
+        __threadfence_block();
+        unsigned long long col = 0;
         uint32_t el = 0;
-        for (int i = 0; i < 4; i++) {
-          const int byte = 4 * (int)threadIdx.x + i;
-          if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
+        if (lane < L32) {
+          volatile uint32_t *cv = cols[slot];
+          col = (unsigned long long)cv[2 * lane] + ((unsigned long long)cv[2 * lane + 1] << 16);
+          cv[2 * lane] = 0;  // re-armed for the ciphertext after the next
+          cv[2 * lane + 1] = 0;
+          const uint8_t *e8 = ent + k * (size_t)ent_stride;
+          for (int i = 0; i < 4; i++) {
+            const int byte = 4 * lane + i;
+            if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
+          }
         }
-        elimb[threadIdx.x] = el;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        // b = sum_l cols[l] << 32l  +  e * p  +  m      (mod 2^704)
+        if (lane == 0) *(volatile uint32_t *)&arrived[slot] = 0;
+        // b = sum_l col_l << 32l  +  e * p  +  m      (mod 2^704), the same 22-step chain in every lane
         const uint64_t mm = msg[k];
         uint64_t carry = 0;  // < 2^34 throughout
-        for (int l = 0; l < 22; l++) {
-          uint64_t t = cols[l] + carry;  // < 2^44
-          if (l == 0) t += mm & 0xffffffffu;
-          if (l == 1) t += mm >> 32;
-          const uint64_t prod = (uint64_t)elimb[l] * P;
-          const uint64_t sum = t + prod;
+        uint32_t myb = 0;
+#pragma unroll
+        for (int l = 0; l < L32; l++) {
+          uint64_t tt = __shfl_sync(0xffffffffu, col, l) + carry;  // < 2^44
+          if (l == 0) tt += mm & 0xffffffffu;
+          if (l == 1) tt += mm >> 32;
+          const uint64_t prod = (uint64_t)__shfl_sync(0xffffffffu, el, l) * P;
+          const uint64_t sum = tt + prod;
           const uint64_t c_out = sum < prod ? 1 : 0;
           carry = (sum >> 32) + (c_out << 32);
-          blimb[l] = (uint32_t)sum;
+          if (lane == l) myb = (uint32_t)sum;
         }
-        blimb[22] = 0;  // bytes 88..91 of the record
+        // lanes 0..21: the 88 live bytes; lane 22: bytes 88..91 of the record (zero)
+        if (lane <= L32) reinterpret_cast<uint32_t *>(out_c8 + k * CT_BYTES)[lane] = myb;  // 92 % 4 == 0
       }
-      __syncthreads();
-      if (threadIdx.x < 23) reinterpret_cast<uint32_t *>(out_c8 + k * CT_BYTES)[threadIdx.x] = blimb[threadIdx.x];  // 92 % 4 == 0
     }
-    __syncthreads();
-    it = nx;
-    ph ^= 1;
+    if (t + 2 < nitems) fill(t + 2);
   }
 }
 
@@ -481,10 +501,10 @@ cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offse
                            const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
                            uint8_t *out_c8, int sm_count, cudaStream_t st) {
   if (count == 0) return cudaSuccess;
-  cudaError_t e = ks_attr((const void *)k_encrypt);
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
-  k_encrypt<<<(unsigned)grid, KS_THREADS, KS_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
+  k_encrypt<<<(unsigned)grid, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
                                                                count, out_c8);
   return cudaGetLastError();
 }

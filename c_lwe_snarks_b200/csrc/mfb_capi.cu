@@ -87,6 +87,10 @@ struct mfb_ctx {
   uint8_t *bounce[2] = {nullptr, nullptr};
   cudaEvent_t bounce_free[2] = {nullptr, nullptr};
   bool bounce_used[2] = {false, false};  // an H2D from this buffer has been queued at some point
+  // pinned entropy staging of mfb_encrypt_cb (two pieces in flight)
+  uint8_t *ent_pin[2] = {nullptr, nullptr};
+  size_t ent_pin_cap = 0;
+  cudaEvent_t ent_free[2] = {nullptr, nullptr};
   // optional per-kernel timing of the dominant kernel of lincomb / eval_poly calls (bench.py's roofline)
   bool profiling = false;
   int prof_n = 0;
@@ -275,6 +279,8 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
   for (int k = 0; k < 2; k++) {
     if (ctx->bounce[k]) cudaFreeHost(ctx->bounce[k]);
     if (ctx->bounce_free[k]) cudaEventDestroy(ctx->bounce_free[k]);
+    if (ctx->ent_pin[k]) cudaFreeHost(ctx->ent_pin[k]);
+    if (ctx->ent_free[k]) cudaEventDestroy(ctx->ent_free[k]);
   }
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
@@ -713,6 +719,66 @@ int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uin
   MFB_CUDA_TRY(cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MFB_OK;
+}
+
+int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+  MFB_CHECK_CTX(ctx);
+  if (count == 0) return MFB_OK;
+  if (!seed || !sk_flat || !msg || !draw || !out_c8) return set_err(MFB_EARG, "mfb_encrypt_cb: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
+    return set_err(MFB_EARG, "mfb_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
+  // pieces: a short first one so that the device starts early, then ~110 ciphertexts per SM and launch
+  const size_t piece = (size_t)ctx->sm_count * 110, first_piece = (size_t)ctx->sm_count * 16;
+  const size_t cap = piece * (size_t)ent_stride;
+  if (ctx->ent_pin_cap < cap) {
+    for (int k = 0; k < 2; k++) {
+      if (ctx->ent_pin[k]) MFB_CUDA_TRY(cudaFreeHost(ctx->ent_pin[k]));
+      ctx->ent_pin[k] = nullptr;
+    }
+    ctx->ent_pin_cap = 0;
+    for (int k = 0; k < 2; k++) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->ent_pin[k], cap, cudaHostAllocDefault));
+    ctx->ent_pin_cap = cap;
+  }
+  for (int k = 0; k < 2; k++)
+    if (!ctx->ent_free[k]) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ent_free[k], cudaEventDisableTiming));
+  void *d_skf, *d_skp, *d_msg, *d_ent, *d_out;
+  MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
+  MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
+  MFB_TRY(scratch(ctx, 1, count * 8, &d_msg));
+  MFB_TRY(scratch(ctx, 3, count * (size_t)ent_stride, &d_ent));
+  MFB_TRY(scratch(ctx, 5, count * CT_BYTES, &d_out));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_msg, msg, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_skf, N, 1, (uint64_t *)d_skp, ctx->stream));
+  int rc = MFB_OK;
+  bool used[2] = {false, false};
+  int k = 0;
+  for (size_t done = 0; done < count && rc == MFB_OK; k ^= 1) {
+    size_t cnt = done == 0 ? first_piece : piece;
+    if (cnt > count - done) cnt = count - done;
+    const size_t nb = cnt * (size_t)ent_stride;
+    if (used[k]) MFB_CUDA_TRY(cudaEventSynchronize(ctx->ent_free[k]));  // the H2D that last read this buffer is done
+    draw(user, ctx->ent_pin[k], nb);
+    uint8_t *d_e = (uint8_t *)d_ent + done * (size_t)ent_stride;
+    MFB_CUDA_TRY(cudaMemcpyAsync(d_e, ctx->ent_pin[k], nb, cudaMemcpyHostToDevice, ctx->stream));
+    MFB_CUDA_TRY(cudaEventRecord(ctx->ent_free[k], ctx->stream));
+    used[k] = true;
+    rc = mfb_encrypt_dev(ctx, seed, offset + done * (uint64_t)CTR_CT, (const uint64_t *)d_skp, (const uint64_t *)d_msg + done,
+                         d_e, ent_stride, ent_nbytes, cnt, (uint8_t *)d_out + done * CT_BYTES, ctx->stream);
+    done += cnt;
+  }
+  if (rc == MFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = mfb::fail(e, "mfb_encrypt_cb: copy back", __FILE__, __LINE__);
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  // the noise is secret: do not leave it in the staging buffers (device scratch is overwritten by later calls)
+  for (int j = 0; j < 2; j++) memset(ctx->ent_pin[j], 0, ctx->ent_pin_cap);
+  cudaMemsetAsync(d_ent, 0, count * (size_t)ent_stride, ctx->stream);
+  return rc;
 }
 
 int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,

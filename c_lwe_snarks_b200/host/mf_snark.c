@@ -145,6 +145,11 @@ void crs_clear(crs_t crs) {
 }
 
 /* ------------------------------------------------------------------ setup (snark.c:57-115) */
+static void draw_entropy(void *user, uint8_t *dst, size_t nbytes) {
+  (void)user;
+  mf_entropy(dst, nbytes);
+}
+
 void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   const size_t D = GAMMA_D, M = GAMMA_M, count = 2 * D + M;
   double t0 = mf_now();
@@ -173,22 +178,19 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   mf_trace("setup.plaintexts+evaluations", t0);
   t0 = mf_now();
 
-  /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order */
-  uint8_t *ent = malloc(count * MFB_ENT_BYTES), *recs = malloc(count * CT_BYTES);
+  /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order.
+   * The draws go through mfb_encrypt_cb's callback piece by piece — same bytes, same order — so that getrandom(2)
+   * for the next piece runs while the device encrypts the previous one. */
+  uint8_t *recs = malloc(count * CT_BYTES);
   uint64_t *skf = malloc(MFB_FLAT_SK_U64 * 8);
-  if (!ent || !recs || !skf) mf_die("malloc");
-  mf_entropy(ent, count * MFB_ENT_BYTES);
-  mf_trace("setup.entropy", t0);
-  t0 = mf_now();
+  if (!recs || !skf) mf_die("malloc");
   for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
-  MF_GPU(mfb_encrypt(mf_gpu(), crs->seed, 0, skf, msg, ent, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
-  mf_trace("setup.encrypt", t0);
+  MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+  mf_trace("setup.entropy+encrypt", t0);
   memcpy(crs->s, recs, D * CT_BYTES);
   memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);
   memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
   memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
-  memset(ent, 0, count * MFB_ENT_BYTES);
-  free(ent);
   free(recs);
   free(skf);
   free(msg);

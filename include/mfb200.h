@@ -161,6 +161,14 @@ MFB_API int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t of
  * lwe.c:86-87) or an explicit noise value for a custom chi (stride = nbytes <= 88). */
 MFB_API int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                 const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
+/* The same with the entropy DRAWN THROUGH A CALLBACK (the shape of the reference's own injection point, the `chi`
+ * argument of regev_encrypt2, lwe.c:78): `draw(user, dst, nbytes)` is called from the calling thread for consecutive
+ * pieces of the count*ent_stride entropy bytes, in order, exactly once each — so a getrandom-backed callback consumes
+ * the OS entropy in the reference's order (per encryption: 69 noise bytes, then 1 sign byte) — while the device
+ * encrypts the previous piece: setup()'s 2D+M draws (tens of ms of getrandom) hide behind the kernel. */
+typedef void (*mfb_entropy_fn)(void *user, uint8_t *dst, size_t nbytes);
+MFB_API int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
 MFB_API int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
                     const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride, int ent_nbytes, size_t count,
                     uint8_t *out_c8_dev, void *stream);

@@ -332,3 +332,26 @@ def test_decrypt_after_smudge_signs(ctx, oracle):
     got = ctx.decrypt(sk[:, :11], np.stack([out[:, :11], out2[:, :11], small[:, :11]]), b_neg=[True, False, False])
     assert [int(v) for v in got] == [oracle.decrypt(sk, out, True), oracle.decrypt(sk, out2, False),
                                      oracle.decrypt(sk, small, False)]
+
+
+@pytest.mark.parametrize("cnt", [1, 5, 148 * 16, 148 * 16 + 1, 148 * 126 + 77, 40000])
+def test_encrypt_cb_equals_encrypt(ctx, oracle, cnt):
+    """mfb_encrypt_cb (entropy drawn piece by piece through a callback while the device works; setup() uses it) gives
+    the records of mfb_encrypt on the same entropy, draws every byte exactly once and in order."""
+    sk = oracle.key_gen(xof("sk-cb", N * CT_BYTES))
+    m = xof_scalars(f"m-cb-{cnt}", cnt)
+    ent = xof(f"ent-cb-{cnt}", cnt * 70)
+    pos, calls = [0], []
+
+    def draw(n):
+        out = ent[pos[0]: pos[0] + n].tobytes()
+        calls.append(n)
+        pos[0] += n
+        return out
+
+    got = ctx.encrypt_cb(SEED, 7 * CTR_CT + 3, sk[:, :11], m, draw)
+    assert pos[0] == cnt * 70 and all(n % 70 == 0 and n > 0 for n in calls)
+    assert np.array_equal(got, ctx.encrypt(SEED, 7 * CTR_CT + 3, sk[:, :11], m, ent))
+    k = cnt - 1
+    want = oracle.encrypt(SEED, 7 * CTR_CT + 3 + k * CTR_CT, sk, m[k:k + 1], ent[70 * k: 70 * k + 70])
+    assert np.array_equal(got[k], want[0])
