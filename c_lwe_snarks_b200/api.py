@@ -70,6 +70,16 @@ _SIGS = {
     "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_region_destroy": (None, [_vp, _vp]),
     "mfb_region_lincomb": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, C.c_size_t, _u64p]),
+    "mfb_peer_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), _u8p]),
+    "mfb_peer_base": (_vp, [_vp]),
+    "mfb_peer_connect": (C.c_int, [_vp, _vp, _u8p]),
+    "mfb_peer_connect_local": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "mfb_peer_set_timeout": (C.c_int, [_vp, C.c_double]),
+    "mfb_peer_status": (C.c_int, [_vp, _vp]),
+    "mfb_peer_disconnect": (C.c_int, [_vp, _vp]),
+    "mfb_peer_destroy": (None, [_vp, _vp]),
+    "mfb_lincomb_peer_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_eval_poly_peer_dev": (C.c_int, [_vp, _vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mfb_eval_poly": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u32p, C.c_size_t, _u64p]),
@@ -162,6 +172,61 @@ class Region:
         if self.handle:
             self.ctx.lib.mfb_region_destroy(self.ctx.h, self.handle)
             self.handle = None
+
+
+PEER_HANDLE_BYTES = 64
+
+
+class PeerGroup:
+    """This rank's end of a peer-memory exchange group (mfb_peer_*): a symmetric buffer the other ranks map over
+    NVLink; lincomb_dev / eval_poly_dev run the sharded lincomb with the exchange fused into the finish kernel."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        h = _vp()
+        handle = np.zeros(PEER_HANDLE_BYTES, np.uint8)
+        ctx._ck(ctx.lib.mfb_peer_create(ctx.h, world, rank, C.byref(h), _p8(handle)))
+        self.handle_, self.ipc_handle = h, handle
+
+    @property
+    def base(self) -> int:
+        return int(self.ctx.lib.mfb_peer_base(self.handle_))
+
+    def connect(self, handles):
+        """handles: world x 64 bytes, rank order (every rank's ``ipc_handle``)."""
+        hs = _arr(handles, np.uint8).reshape(-1)
+        if hs.size != self.world * PEER_HANDLE_BYTES:
+            raise ValueError("need one 64-byte handle per rank")
+        self.ctx._ck(self.ctx.lib.mfb_peer_connect(self.ctx.h, self.handle_, _p8(hs)))
+
+    def connect_local(self, bases):
+        """Same-process group: bases[r] = PeerGroup.base of rank r."""
+        arr = (_vp * self.world)(*[int(b) for b in bases])
+        self.ctx._ck(self.ctx.lib.mfb_peer_connect_local(self.ctx.h, self.handle_, arr))
+
+    def set_timeout(self, seconds: float):
+        self.ctx._ck(self.ctx.lib.mfb_peer_set_timeout(self.handle_, float(seconds)))
+
+    def check(self):
+        self.ctx._ck(self.ctx.lib.mfb_peer_status(self.ctx.h, self.handle_))
+
+    def lincomb_dev(self, cts_ptr: int, coeffs_ptr: int, d: int, rop_in_ptr, rop_out_ptr: int, stream: int = 0):
+        self.ctx._ck(self.ctx.lib.mfb_lincomb_peer_dev(self.ctx.h, self.handle_, cts_ptr, coeffs_ptr, d, rop_in_ptr, rop_out_ptr,
+                                                       stream))
+
+    def eval_poly_dev(self, seed, offset: int, c8_ptr: int, coeffs_ptr: int, idx_ptr, d: int, rop_in_ptr, rop_out_ptr: int,
+                      stream: int = 0):
+        self.ctx._ck(self.ctx.lib.mfb_eval_poly_peer_dev(self.ctx.h, self.handle_, _p8(_seed(seed)), offset, c8_ptr, coeffs_ptr,
+                                                         idx_ptr, d, rop_in_ptr, rop_out_ptr, stream))
+
+    def disconnect(self):
+        if self.handle_:
+            self.ctx._ck(self.ctx.lib.mfb_peer_disconnect(self.ctx.h, self.handle_))
+
+    def close(self):
+        if self.handle_:
+            self.ctx.lib.mfb_peer_destroy(self.ctx.h, self.handle_)
+            self.handle_ = None
 
 
 class ResidentSsp:
@@ -312,6 +377,9 @@ class Context:
         self._ck(self.lib.mfb_decrypt(self.h, _p64(sk), _p64(cts), None if neg is None else _p8(neg), count, _p64(m),
                                       None if dot is None else _p64(dot)))
         return (m, dot) if want_dot else m
+
+    def peer_group(self, world: int, rank: int) -> PeerGroup:
+        return PeerGroup(self, world, rank)
 
     def ssp_prover_polys(self, ssp, D: int, M: int, witness_limbs, delta: int):
         """(w, v, h) coefficient arrays (D u64 each) of the prover's polynomial step."""

@@ -152,14 +152,11 @@ k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs0
 // CTA = 64 coordinates x FIN_SLICES slices of the partial index: each thread adds every FIN_SLICES-th partial
 // (loads of successive partials are independent, so several are in flight), the slices meet in shared memory.
 constexpr int FIN_SLICES = 8;
-__global__ void __launch_bounds__(64 * FIN_SLICES)
-k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                 unsigned int *queue) {
-  __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
-  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;  // one CTA per tile: re-arm its chunk queue
-  const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
-  uint32_t r[22];
+
+// Sum of the row-planar partials for coordinate c; the result is in r for the slice-0 threads.  Contains two
+// __syncthreads (the second protects `sm` for reuse by the caller).
+__device__ __forceinline__ void fin_sum_partials(const uint64_t *__restrict__ partial, int nparts,
+                                                 uint32_t (*sm)[22][64], int c, int cl, int slice, uint32_t (&r)[22]) {
 #pragma unroll
   for (int j = 0; j < 22; j++) r[j] = 0;
 #pragma unroll 2
@@ -178,23 +175,149 @@ k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_
     for (int j = 0; j < 22; j++) sm[slice - 1][j][cl] = r[j];
   }
   __syncthreads();
-  if (slice == 0 && c < NC) {
+  if (slice == 0) {
     for (int s2 = 0; s2 < FIN_SLICES - 1; s2++) {
       uint32_t b[22];
 #pragma unroll
       for (int j = 0; j < 22; j++) b[j] = sm[s2][j][cl];
       add704(r, b);
     }
-    if (rop_in) {
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void fin_add_flat(uint32_t (&r)[22], const uint64_t *flat, int c) {
+  uint32_t b[22];
+#pragma unroll
+  for (int j = 0; j < L64; j++) {
+    const uint64_t v = flat[(size_t)c * L64 + j];
+    b[2 * j] = (uint32_t)v;
+    b[2 * j + 1] = (uint32_t)(v >> 32);
+  }
+  add704(r, b);
+}
+
+__global__ void __launch_bounds__(64 * FIN_SLICES)
+k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                 unsigned int *queue) {
+  __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
+  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;  // one CTA per tile: re-arm its chunk queue
+  const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  uint32_t r[22];
+  fin_sum_partials(partial, nparts, sm, c, cl, slice, r);
+  if (slice == 0 && c < NC) {
+    if (rop_in) fin_add_flat(r, rop_in, c);
+#pragma unroll
+    for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+  }
+}
+
+// --- multi-GPU: the finish step FUSED with the exchange over NVLink peer memory -----------------
+// Every rank owns a "symmetric" buffer that its peers map (CUDA IPC between processes, plain peer access inside
+// one); mfb_common.cuh: PEER_*.  For the call with sequence number `epoch` (parity q = epoch & 1), CTA `tile`
+//   1. adds this rank's row-planar partials for its 64 coordinates (as k_lincomb_finish does);
+//   2. PUSHES the 5632-byte flat tile into slot [q][rank] of EVERY rank's buffer (coalesced 16-byte stores that
+//      travel over NVLink / NVSwitch; its own copy is a local store), fences at system scope and then releases
+//      flag [q][rank][tile] = epoch in every rank's buffer;
+//   3. waits until the flags [q][s][tile] of its OWN buffer carry `epoch` for every source rank s (acquire loads
+//      of local memory, written remotely), and
+//   4. adds the `world` tiles now sitting in local HBM/L2 (exact mod 2^704: the order does not matter), adds the
+//      incoming rop and writes the result — every rank ends with the full sum, with one NVLink store latency
+//      on the critical path instead of the four launches of split -> reduce-scatter -> carry -> all-gather.
+// Two parities suffice: a rank can only push call e+2 after it has seen every peer's flags of call e+1, which a
+// peer raises in the kernel that follows (in stream order) its own reads of call e.
+struct PeerTable {
+  uint8_t *base[PEER_MAX];
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(64 * FIN_SLICES)
+k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                      unsigned int *queue, const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch,
+                      uint64_t timeout_ns, int *status) {
+  __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
+  __shared__ __align__(16) uint64_t stage[RT_TILE * L64];  // the flat tile: [64][11] u64
+  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;
+  const int tile = blockIdx.x;
+  const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = tile * 64 + cl;
+  const uint32_t q = epoch & 1u;
+  uint32_t r[22];
+  fin_sum_partials(partial, nparts, sm, c, cl, slice, r);
+  if (slice == 0) {
+#pragma unroll
+    for (int j = 0; j < L64; j++) stage[cl * L64 + j] = c < NC ? ((uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32) : 0;
+  }
+  __syncthreads();
+  // 2. push: 352 threads x one uint4 per destination rank
+  constexpr int TILE_FLAT_BYTES = RT_TILE * L64 * 8;  // 5632
+  if (threadIdx.x < TILE_FLAT_BYTES / 16) {
+    const uint4 v = reinterpret_cast<const uint4 *>(stage)[threadIdx.x];
+    for (int i = 0; i < world; i++) {
+      const int p = (rank + 1 + i) % world;  // remote destinations first, the local copy last
+      uint8_t *dst = peers.base[p] + peer_slot_offset(q, world, rank) + (size_t)tile * TILE_FLAT_BYTES + 16 * threadIdx.x;
+      *reinterpret_cast<uint4 *>(dst) = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world)
+    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, tile)), epoch);
+  // 3. wait for every source rank's tile
+  if ((int)threadIdx.x < world) {
+    const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, tile));
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_sys_u32(f) != epoch) {
+      if (globaltimer_ns() - t0 > timeout_ns) {  // a peer never arrived: report instead of hanging the GPU
+        *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+  // 4. add the world tiles (L2 loads: the lines were written by remote stores, never cached in this SM's L1)
+#pragma unroll
+  for (int j = 0; j < 22; j++) r[j] = 0;
+  for (int src = slice; src < world; src += FIN_SLICES) {
+    const uint64_t *t = reinterpret_cast<const uint64_t *>(peers.base[rank] + peer_slot_offset(q, world, src)) + (size_t)c * L64;
+    uint32_t b[22];
+#pragma unroll
+    for (int j = 0; j < L64; j++) {
+      const uint64_t v = __ldcg(t + j);
+      b[2 * j] = (uint32_t)v;
+      b[2 * j + 1] = (uint32_t)(v >> 32);
+    }
+    add704(r, b);
+  }
+  if (slice > 0) {
+#pragma unroll
+    for (int j = 0; j < 22; j++) sm[slice - 1][j][cl] = r[j];
+  }
+  __syncthreads();
+  if (slice == 0 && c < NC) {
+    const int nsl = world < FIN_SLICES ? world : FIN_SLICES;
+    for (int s2 = 0; s2 < nsl - 1; s2++) {
       uint32_t b[22];
 #pragma unroll
-      for (int j = 0; j < L64; j++) {
-        const uint64_t v = rop_in[(size_t)c * L64 + j];
-        b[2 * j] = (uint32_t)v;
-        b[2 * j + 1] = (uint32_t)(v >> 32);
-      }
+      for (int j = 0; j < 22; j++) b[j] = sm[s2][j][cl];
       add704(r, b);
     }
+    if (rop_in) fin_add_flat(r, rop_in, c);
 #pragma unroll
     for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
   }
@@ -296,6 +419,16 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   unsigned int *queue, cudaStream_t st) {
   k_lincomb_finish<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                                       unsigned int *queue, uint8_t *const *bases, int world, int rank, uint32_t epoch,
+                                       uint64_t timeout_ns, int *status, cudaStream_t st) {
+  PeerTable t = {};
+  for (int i = 0; i < world; i++) t.base[i] = bases[i];
+  k_lincomb_finish_peer<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue, t, world, rank, epoch,
+                                                               timeout_ns, status);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,9 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
                                     mark_fn mark, void *mark_arg);
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   unsigned int *queue, cudaStream_t st);
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
+                                       unsigned int *queue, uint8_t *const *bases, int world, int rank, uint32_t epoch,
+                                       uint64_t timeout_ns, int *status, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
 cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
                                  cudaStream_t st);
@@ -357,6 +360,173 @@ int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeff
   return MFB_OK;
 }
 
+/* ---- peer-memory exchange groups ---------------------------------------------------------- */
+}  // extern "C"
+struct mfb_peer_group {
+  int world = 1, rank = 0, device = 0;
+  uint8_t *own = nullptr;          // this rank's symmetric buffer (cudaMalloc, exported through CUDA IPC)
+  uint8_t *base[PEER_MAX] = {};    // every rank's buffer as mapped into this process
+  bool opened[PEER_MAX] = {};      // mapped with cudaIpcOpenMemHandle (to be closed)
+  bool connected = false;
+  uint32_t epoch = 0;              // sequence number of the last *_peer_dev call
+  int *status = nullptr;           // pinned + mapped: the kernel writes 1 + (missing rank) on a timeout
+  uint64_t timeout_ns = 20000000000ull;
+};
+extern "C" {
+
+int mfb_peer_create(mfb_ctx *ctx, int world, int rank, mfb_peer_group **out, uint8_t handle_out[MFB_PEER_HANDLE_BYTES]) {
+  MFB_CHECK_CTX(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == MFB_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  static_assert(PEER_MAX == MFB_PEER_MAX, "peer table size");
+  if (!out || !handle_out) return set_err(MFB_EARG, "mfb_peer_create: null pointer");
+  if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
+    return set_err(MFB_EARG, "mfb_peer_create: need 1 <= world <= %d and 0 <= rank < world", PEER_MAX);
+  mfb_peer_group *g = new (std::nothrow) mfb_peer_group();
+  if (!g) return set_err(MFB_ENOMEM, "mfb_peer_create: out of host memory");
+  g->world = world;
+  g->rank = rank;
+  g->device = ctx->device;
+  const size_t bytes = peer_buffer_bytes(world);
+  cudaError_t e = cudaMalloc((void **)&g->own, bytes);
+  if (e == cudaSuccess) e = cudaMemset(g->own, 0, bytes);
+  if (e == cudaSuccess) e = cudaHostAlloc((void **)&g->status, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *g->status = 0;
+    e = cudaDeviceSynchronize();  // the zeroed flags are in memory before any peer can learn the handle
+  }
+  memset(handle_out, 0, MFB_PEER_HANDLE_BYTES);
+  if (e == cudaSuccess && world > 1) {
+    cudaIpcMemHandle_t h;
+    // not fatal: a same-process group (mfb_peer_connect_local) needs no IPC handle
+    if (cudaIpcGetMemHandle(&h, g->own) == cudaSuccess) memcpy(handle_out, &h, sizeof(h));
+    else cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    if (g->own) cudaFree(g->own);
+    if (g->status) cudaFreeHost(g->status);
+    delete g;
+    return mfb::fail(e, "mfb_peer_create", __FILE__, __LINE__);
+  }
+  g->base[rank] = g->own;
+  if (world == 1) g->connected = true;
+  *out = g;
+  return MFB_OK;
+}
+
+void *mfb_peer_base(mfb_peer_group *g) { return g ? g->own : nullptr; }
+
+int mfb_peer_connect(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t *handles) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !handles) return set_err(MFB_EARG, "mfb_peer_connect: null pointer");
+  if (g->connected) return set_err(MFB_EARG, "mfb_peer_connect: already connected");
+  for (int p = 0; p < g->world; p++) {
+    if (p == g->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)p * MFB_PEER_HANDLE_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int k = 0; k < p; k++)
+        if (g->opened[k]) {
+          cudaIpcCloseMemHandle(g->base[k]);
+          g->opened[k] = false;
+          g->base[k] = nullptr;
+        }
+      return mfb::fail(e, "cudaIpcOpenMemHandle (peer exchange buffer)", __FILE__, __LINE__);
+    }
+    g->base[p] = (uint8_t *)ptr;
+    g->opened[p] = true;
+  }
+  g->connected = true;
+  return MFB_OK;
+}
+
+int mfb_peer_connect_local(mfb_ctx *ctx, mfb_peer_group *g, void *const *bases) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !bases) return set_err(MFB_EARG, "mfb_peer_connect_local: null pointer");
+  if (g->connected) return set_err(MFB_EARG, "mfb_peer_connect_local: already connected");
+  for (int p = 0; p < g->world; p++) {
+    if (!bases[p]) return set_err(MFB_EARG, "mfb_peer_connect_local: null base for rank %d", p);
+    if (p == g->rank) continue;
+    cudaPointerAttributes at;
+    MFB_CUDA_TRY(cudaPointerGetAttributes(&at, bases[p]));
+    if (at.type != cudaMemoryTypeDevice) return set_err(MFB_EARG, "mfb_peer_connect_local: rank %d's base is not device memory", p);
+    if (at.device != g->device) {
+      int can = 0;
+      MFB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, g->device, at.device));
+      if (!can) return set_err(MFB_EARG, "mfb_peer_connect_local: device %d cannot access device %d", g->device, at.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else MFB_CUDA_TRY(e);
+    }
+    g->base[p] = (uint8_t *)bases[p];
+  }
+  g->connected = true;
+  return MFB_OK;
+}
+
+int mfb_peer_set_timeout(mfb_peer_group *g, double seconds) {
+  if (!g || !(seconds > 0) || seconds > 3600) return set_err(MFB_EARG, "mfb_peer_set_timeout: 0 < seconds <= 3600");
+  g->timeout_ns = (uint64_t)(seconds * 1e9);
+  return MFB_OK;
+}
+
+int mfb_peer_status(mfb_ctx *ctx, mfb_peer_group *g) {
+  MFB_CHECK_CTX(ctx);
+  if (!g) return set_err(MFB_EARG, "mfb_peer_status: null group");
+  const int st = *(volatile int *)g->status;
+  if (st) return set_err(MFB_EPEER, "peer exchange: rank %d never delivered its partial sum to rank %d (timeout)", st - 1, g->rank);
+  return MFB_OK;
+}
+
+int mfb_peer_disconnect(mfb_ctx *ctx, mfb_peer_group *g) {
+  MFB_CHECK_CTX(ctx);
+  if (!g) return MFB_OK;
+  MFB_CUDA_TRY(cudaDeviceSynchronize());
+  for (int p = 0; p < g->world; p++) {
+    if (g->opened[p]) MFB_CUDA_TRY(cudaIpcCloseMemHandle(g->base[p]));
+    g->opened[p] = false;
+    if (p != g->rank) g->base[p] = nullptr;
+  }
+  g->connected = g->world == 1;
+  return MFB_OK;
+}
+
+void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g) {
+  if (!g) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < g->world; p++)
+    if (g->opened[p]) cudaIpcCloseMemHandle(g->base[p]);
+  if (g->own) cudaFree(g->own);
+  if (g->status) cudaFreeHost(g->status);
+  delete g;
+}
+
+static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, int nparts, const uint64_t *rop_in_dev, uint64_t *rop_out_dev,
+                       unsigned int *queue, cudaStream_t st) {
+  g->epoch += 1;
+  if (g->epoch == 0) g->epoch = 2;  // wrapped: keep the parity sequence, never use 0 (the flags' initial value)
+  MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, nparts, rop_in_dev, rop_out_dev, queue, g->base, g->world, g->rank,
+                                          g->epoch, g->timeout_ns, g->status, st));
+  return MFB_OK;
+}
+
+int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
+                         const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_lincomb_peer_dev: the peer group is not connected");
+  if (!rop_out_dev || (d && (!cts_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_lincomb_peer_dev: null pointer");
+  int nslots = lincomb_nslots(d, ctx->sm_count, 1);
+  if (nslots > MAX_CHUNKS) nslots = MAX_CHUNKS;
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
+                                       (cudaStream_t)stream,
+                                       [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
+  MFB_TRY(peer_finish(ctx, g, nslots, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
+  ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
 int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
                      size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
                      uint64_t *rop1_out_dev, void *stream) {
@@ -421,6 +591,25 @@ int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
                                         ctx->partial_ws, (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
   MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
+  ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
+int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                           const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
+                           uint64_t *rop_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_eval_poly_peer_dev: the peer group is not connected");
+  if (!seed || !rop_out_dev || (d && (!c8_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_eval_poly_peer_dev: null pointer");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
+  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
+  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
+  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
+                                        ctx->partial_ws, (cudaStream_t)stream));
+  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
+  MFB_TRY(peer_finish(ctx, g, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }

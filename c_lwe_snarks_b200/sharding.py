@@ -14,6 +14,11 @@ NCCL SUM exact.  The messages are 259 KB in / 129 KB out: latency-bound, so NCCL
 
 The kernels are reached through an `ops` object (DeviceOps = the CUDA path); the collectives through
 torch.distributed.  The CPU test-suite drives the same code with gloo and a stand-in `ops`.
+
+PeerShardedLincomb is the same step with the exchange FUSED into the finish kernel over NVLink peer memory
+(include/mfb200.h, mfb_peer_*): every rank's finish kernel pushes its partial into all ranks' symmetric buffers,
+waits for the others' and adds them — two kernel launches per sharded lincomb, as on one GPU, and no collective
+call on the data path.  torch.distributed is only used once, to hand the 64-byte CUDA IPC handles around.
 """
 from __future__ import annotations
 
@@ -108,6 +113,61 @@ class ShardedLincomb:
         self.ops.columns_carry(self.cols_own, p.first_coord, p.coords_per_rank, self.own_flat)
         self.dist.all_gather_into_tensor(self.result, self.own_flat)
         return self.result
+
+
+def gather_peer_handles(plan: ShardPlan, dist, my_handle: bytes, new_u8) -> bytes:
+    """Every rank's 64-byte IPC handle, concatenated in rank order (one all-gather; also a barrier: a handle is only
+    published after its buffer has been zeroed)."""
+    import torch
+    mine = new_u8(64)
+    mine.copy_(torch.frombuffer(bytearray(my_handle), dtype=torch.uint8))
+    if plan.world == 1:
+        return bytes(mine.cpu().numpy().tobytes())
+    out = new_u8(64 * plan.world)
+    dist.all_gather_into_tensor(out, mine)
+    return bytes(out.cpu().numpy().tobytes())
+
+
+class PeerShardedLincomb:
+    """Sharded lincomb with the exchange fused into the finish kernel over peer memory.  `group` is this rank's
+    api.PeerGroup (or a test double with ipc_handle / connect / lincomb_dev / eval_poly_dev / check / disconnect /
+    close).  Results alternate between two buffers so that call i+1 can start while the host still reads result i."""
+
+    def __init__(self, plan: ShardPlan, group, dist, new_i64, new_u8, stream_of=lambda: 0):
+        self.plan, self.group, self.dist, self.stream_of = plan, group, dist, stream_of
+        handles = gather_peer_handles(plan, dist, bytes(group.ipc_handle), new_u8)
+        if plan.world > 1:
+            group.connect(handles)
+        self.results = [new_i64(NCP * L64), new_i64(NCP * L64)]
+        self.calls = 0
+
+    def step(self, cts, coeffs, d_local, rop_in=None):
+        """result <- rop_in + sum over ALL ranks' ciphertexts, on every rank; flat [1472][11] (1471 is padding)."""
+        out = self.results[self.calls % 2]
+        self.calls += 1
+        self.group.lincomb_dev(cts.data_ptr(), coeffs.data_ptr(), d_local, None if rop_in is None else rop_in.data_ptr(),
+                               out.data_ptr(), self.stream_of())
+        return out
+
+    def step_fused(self, seed, offset, c8, coeffs, d_local, rop_in=None):
+        """the same with the rank's a-vectors regenerated by AES in-kernel (nothing resident)"""
+        out = self.results[self.calls % 2]
+        self.calls += 1
+        self.group.eval_poly_dev(seed, offset, c8.data_ptr(), coeffs.data_ptr(), None, d_local,
+                                 None if rop_in is None else rop_in.data_ptr(), out.data_ptr(), self.stream_of())
+        return out
+
+    def check(self):
+        """raises if a peer never arrived (call after synchronising the stream)"""
+        self.group.check()
+
+    def close(self):
+        if self.plan.world > 1:
+            self.dist.barrier()  # nobody is still inside an exchange
+        self.group.disconnect()
+        if self.plan.world > 1:
+            self.dist.barrier()  # every rank has unmapped its peers' buffers: they can be freed
+        self.group.close()
 
 
 class PipelinedShardedLincomb:

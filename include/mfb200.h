@@ -133,6 +133,38 @@ MFB_API int mfb_columns_split_dev(mfb_ctx *ctx, const uint64_t *flat_dev, uint64
 MFB_API int mfb_columns_carry_dev(mfb_ctx *ctx, const uint64_t *cols_dev, int c0, int ncoord, const uint64_t *flat_in_dev,
                           uint64_t *flat_out_dev, void *stream);
 
+/* ---- multi-GPU: sharded lincomb with the exchange FUSED into the finish kernel over peer memory ----------
+ * No reference counterpart (the reference is single-threaded); SURVEY.md §8e.  The prover's sum over ciphertext
+ * indices is sharded across GPUs; every rank owns a symmetric exchange buffer that the others map over NVLink
+ * (CUDA IPC between processes: mfb_peer_connect; plain peer access inside one process: mfb_peer_connect_local).
+ * mfb_lincomb_peer_dev = mfb_lincomb_dev over this rank's ciphertexts, except that the finish kernel pushes the
+ * rank's partial sum into every rank's buffer, waits for the other ranks' and adds them: rop_out on EVERY rank =
+ * (rop_in + sum over all ranks and their ciphertexts) mod 2^704, bit-identical to the single-GPU result, in the
+ * same two kernel launches as the single-GPU call.  Like any collective, every rank of the group must make the
+ * same sequence of *_peer_dev calls (one stream per group).  A rank that waits longer than the group's timeout
+ * (default 20 s) gives up; mfb_peer_status then returns MFB_EPEER.
+ *   create      allocates the buffer, returns the 64-byte CUDA IPC handle to hand to the other ranks
+ *   connect     handles = world x 64 bytes in rank order (e.g. gathered with torch.distributed)
+ *   disconnect  unmaps the peers' buffers; call on every rank (and synchronise the ranks) BEFORE any destroy */
+#define MFB_EPEER (-5) /* a peer rank did not arrive in time */
+#define MFB_PEER_HANDLE_BYTES 64
+#define MFB_PEER_MAX 16
+typedef struct mfb_peer_group mfb_peer_group;
+MFB_API int mfb_peer_create(mfb_ctx *ctx, int world, int rank, mfb_peer_group **out, uint8_t handle_out[MFB_PEER_HANDLE_BYTES]);
+MFB_API void *mfb_peer_base(mfb_peer_group *g);
+MFB_API int mfb_peer_connect(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t *handles);
+MFB_API int mfb_peer_connect_local(mfb_ctx *ctx, mfb_peer_group *g, void *const *bases);
+MFB_API int mfb_peer_set_timeout(mfb_peer_group *g, double seconds);
+MFB_API int mfb_peer_status(mfb_ctx *ctx, mfb_peer_group *g);
+MFB_API int mfb_peer_disconnect(mfb_ctx *ctx, mfb_peer_group *g);
+MFB_API void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g);
+MFB_API int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
+                         const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
+/* the same for the fused AES + MAC path (mfb_eval_poly_dev over this rank's ciphertexts) */
+MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
+                           const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
+                           uint64_t *rop_out_dev, void *stream);
+
 /* ---- K2+K1 fused: eval_poly with a regenerated in-kernel ----------------------------------- */
 /* rop += sum_{m<d} coeffs[m] * CT_{k(m)},  k(m) = idx ? idx[m] : m, where CT_k = ct_import(stream at
  * offset + k*MFB_CTR_CT, c8[k]).  Exactly eval_poly (lwe.c:176-186) with the rng positioned at `offset`;

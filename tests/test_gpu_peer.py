@@ -1,0 +1,227 @@
+"""The peer-memory exchange (mfb_peer_*, k_lincomb_finish_peer): the sharded lincomb whose finish kernel pushes its
+partial sum into every rank's symmetric buffer over NVLink, waits for the others' and adds them.
+
+One GPU is enough to exercise the whole protocol: `world` ranks = `world` contexts in this process, each with its
+own stream, connected with mfb_peer_connect_local; their finish kernels run concurrently and really wait for each
+other's flags.  With two or more GPUs the same test runs with one rank per device (true peer access), and the
+multi-process test drives the CUDA-IPC path under torch.distributed/NCCL beside the NCCL exchange.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import SEED, xof_records, xof_scalars
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+N, NC, NCP, L64, CT_BYTES, CTR_CT = 1470, 1471, 1472, 11, 92, 92 * 1470
+
+
+def _flat(t):
+    return t.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64)
+
+
+def _run_local_world(world, d_total, calls, devices, fused=False):
+    import torch
+
+    import c_lwe_snarks_b200 as m
+    from c_lwe_snarks_b200.sharding import ShardPlan
+
+    c8, h = xof_records(f"peer-c8-{d_total}", d_total), xof_scalars(f"peer-h-{d_total}", d_total)
+    ranks = []
+    for r in range(world):
+        dev = devices[r % len(devices)]
+        torch.cuda.set_device(dev)
+        ctx = m.Context(dev)
+        first, cnt = ShardPlan(world, r).ct_range(d_total)
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.device(dev):
+            d_c8 = torch.from_numpy(c8[first:first + cnt].reshape(-1).copy()).cuda()
+            d_h = torch.from_numpy(h[first:first + cnt].astype(np.uint32).view(np.int32)).cuda()
+            d_cts = torch.zeros(max(cnt, 1) * NCP * L64, dtype=torch.int64, device="cuda")
+            ctx.expand_dev(SEED, first * CTR_CT, d_c8.data_ptr(), cnt, d_cts.data_ptr(), 0)
+            out = [torch.zeros(NCP * L64, dtype=torch.int64, device="cuda") for _ in range(2)]
+            torch.cuda.synchronize()
+        g = ctx.peer_group(world, r)
+        g.set_timeout(5.0)
+        ranks.append(dict(ctx=ctx, g=g, st=st, first=first, cnt=cnt, c8=d_c8, h=d_h, cts=d_cts, out=out, dev=dev))
+    bases = [rk["g"].base for rk in ranks]
+    if world > 1:
+        for rk in ranks:
+            torch.cuda.set_device(rk["dev"])
+            rk["g"].connect_local(bases)
+    # reference: one context over all the ciphertexts
+    torch.cuda.set_device(devices[0])
+    want1 = ranks[0]["ctx"].eval_poly(SEED, 0, c8, h)
+    results = []
+    try:
+        for i in range(calls):
+            # call i accumulates into the result of call i-1: rop_in is exercised and every call has a new answer
+            for rk in ranks:
+                torch.cuda.set_device(rk["dev"])
+                prev = rk["out"][(i + 1) % 2] if i else None
+                if fused:
+                    rk["g"].eval_poly_dev(SEED, rk["first"] * CTR_CT, rk["c8"].data_ptr(), rk["h"].data_ptr(), None, rk["cnt"],
+                                          None if prev is None else prev.data_ptr(), rk["out"][i % 2].data_ptr(),
+                                          rk["st"].cuda_stream)
+                else:
+                    rk["g"].lincomb_dev(rk["cts"].data_ptr(), rk["h"].data_ptr(), rk["cnt"],
+                                        None if prev is None else prev.data_ptr(), rk["out"][i % 2].data_ptr(),
+                                        rk["st"].cuda_stream)
+        for rk in ranks:
+            torch.cuda.set_device(rk["dev"])
+            rk["st"].synchronize()
+            rk["g"].check()
+            results.append(_flat(rk["out"][(calls - 1) % 2]))
+    finally:
+        for rk in ranks:
+            torch.cuda.set_device(rk["dev"])
+            rk["g"].disconnect()
+        for rk in ranks:
+            torch.cuda.set_device(rk["dev"])
+            rk["g"].close()
+            rk["ctx"].close()
+        torch.cuda.set_device(devices[0])
+    # expected: calls x the single-context sum, mod 2^704
+    mask = (1 << 704) - 1
+    want = np.zeros((NC, L64), np.uint64)
+    for c in range(NC):
+        v = int.from_bytes(want1[c].tobytes(), "little") * calls & mask
+        want[c] = np.frombuffer(v.to_bytes(88, "little"), "<u8")
+    return results, want
+
+
+@pytest.mark.parametrize("world,d_total,calls", [(1, 37, 3), (2, 13, 1), (2, 300, 6), (3, 50, 5), (8, 1000, 7)])
+def test_peer_exchange_ranks_in_one_process(world, d_total, calls):
+    results, want = _run_local_world(world, d_total, calls, devices=[0])
+    for r, got in enumerate(results):
+        assert np.array_equal(got, want), f"rank {r}"
+
+
+def test_peer_exchange_fused_eval_poly():
+    results, want = _run_local_world(4, 64, 3, devices=[0], fused=True)
+    for got in results:
+        assert np.array_equal(got, want)
+
+
+def test_peer_exchange_empty_rank():
+    # fewer ciphertexts than ranks: some ranks contribute a zero partial (d = 0) and still take part
+    results, want = _run_local_world(4, 2, 2, devices=[0])
+    for got in results:
+        assert np.array_equal(got, want)
+
+
+def test_peer_timeout_is_reported_not_hung():
+    """a rank whose peer never calls gives up after the timeout and mfb_peer_status says who was missing"""
+    import torch
+
+    import c_lwe_snarks_b200 as m
+    ctx0, ctx1 = m.Context(0), m.Context(0)
+    g0, g1 = ctx0.peer_group(2, 0), ctx1.peer_group(2, 1)
+    try:
+        g0.set_timeout(0.2)
+        bases = [g0.base, g1.base]
+        g0.connect_local(bases)
+        g1.connect_local(bases)
+        out = torch.zeros(NCP * L64, dtype=torch.int64, device="cuda")
+        g0.lincomb_dev(0, 0, 0, None, out.data_ptr(), 0)  # rank 1 never calls
+        torch.cuda.synchronize()
+        with pytest.raises(m.api.MfbError, match="rank 1 never delivered"):
+            g0.check()
+    finally:
+        g0.disconnect()
+        g1.disconnect()
+        g0.close()
+        g1.close()
+        ctx0.close()
+        ctx1.close()
+
+
+def test_peer_exchange_one_rank_per_gpu_same_process():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    world = min(n, 8)
+    results, want = _run_local_world(world, 500, 5, devices=list(range(world)))
+    for r, got in enumerate(results):
+        assert np.array_equal(got, want), f"rank {r}"
+
+
+def _ipc_worker(rank, world, port, d_per_rank, calls, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import c_lwe_snarks_b200 as m
+    from c_lwe_snarks_b200.sharding import DeviceOps, PeerShardedLincomb, ShardedLincomb, ShardPlan
+    from conftest import SEED as S, xof_records as xr, xof_scalars as xs
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ctx = m.Context(rank)
+    plan = ShardPlan(world, rank)
+    d_total = world * d_per_rank
+    c8, h = xr(f"ipc-c8-{d_total}", d_total), xs(f"ipc-h-{d_total}", d_total)
+    first, cnt = plan.ct_range(d_total)
+    d_c8 = torch.from_numpy(c8[first:first + cnt].reshape(-1).copy()).cuda()
+    d_h = torch.from_numpy(h[first:first + cnt].astype(np.uint32).view(np.int32)).cuda()
+    d_cts = torch.zeros(cnt * NCP * L64, dtype=torch.int64, device="cuda")
+    ctx.expand_dev(S, first * CTR_CT, d_c8.data_ptr(), cnt, d_cts.data_ptr(), 0)
+    new_i64 = lambda n: torch.zeros(n, dtype=torch.int64, device="cuda")  # noqa: E731
+    new_u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda")  # noqa: E731
+    group = ctx.peer_group(world, rank)
+    group.set_timeout(10.0)
+    peer = PeerShardedLincomb(plan, group, dist, new_i64, new_u8)
+    nccl = ShardedLincomb(plan, DeviceOps(ctx, torch), dist, new_i64)
+    ok = True
+    for i in range(calls):
+        a = peer.step(d_cts, d_h, cnt)
+        b = nccl.step(d_cts, d_h, cnt)
+        torch.cuda.synchronize()
+        peer.check()
+        ok = ok and bool(torch.equal(a[: NC * L64], b[: NC * L64]))
+    f = peer.step_fused(S, first * CTR_CT, d_c8, d_h, cnt)
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(f[: NC * L64], b[: NC * L64]))
+    res = a[: NC * L64].cpu().numpy().view(np.uint64).reshape(NC, L64).copy()
+    peer.close()
+    ctx.close()
+    dist.destroy_process_group()
+    q.put((rank, ok, res))
+
+
+def test_peer_exchange_cuda_ipc_beside_nccl():
+    """one process per GPU (torch.distributed, NCCL for the handle gather): the IPC peer exchange equals the NCCL
+    reduce-scatter / all-gather exchange and a single-GPU eval_poly over all ciphertexts."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    import c_lwe_snarks_b200 as m
+    world, d_per_rank, calls = min(n, 8), 200, 4
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_ipc_worker, args=(r, world, port, d_per_rank, calls, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    d_total = world * d_per_rank
+    c8, h = xof_records(f"ipc-c8-{d_total}", d_total), xof_scalars(f"ipc-h-{d_total}", d_total)
+    ctx = m.Context(0)
+    want = ctx.eval_poly(SEED, 0, c8, h)
+    ctx.close()
+    for rank, ok, res in got:
+        assert ok, f"rank {rank}: peer exchange != NCCL exchange"
+        assert np.array_equal(res, want), f"rank {rank}"
