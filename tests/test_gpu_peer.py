@@ -29,7 +29,10 @@ def _run_local_world(world, d_total, calls, devices, fused=False):
     import torch
 
     import c_lwe_snarks_b200 as m
-    from c_lwe_snarks_b200.sharding import ShardPlan
+
+    def ct_range(r):  # ShardPlan.ct_range without its "world divides 1472" rule (that one is the NCCL exchange's)
+        base, extra = divmod(d_total, world)
+        return r * base + min(r, extra), base + (1 if r < extra else 0)
 
     c8, h = xof_records(f"peer-c8-{d_total}", d_total), xof_scalars(f"peer-h-{d_total}", d_total)
     ranks = []
@@ -37,7 +40,7 @@ def _run_local_world(world, d_total, calls, devices, fused=False):
         dev = devices[r % len(devices)]
         torch.cuda.set_device(dev)
         ctx = m.Context(dev)
-        first, cnt = ShardPlan(world, r).ct_range(d_total)
+        first, cnt = ct_range(r)
         st = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
             d_c8 = torch.from_numpy(c8[first:first + cnt].reshape(-1).copy()).cuda()
