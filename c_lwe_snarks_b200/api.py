@@ -428,6 +428,11 @@ class Context:
         self._ck(self.lib.mfb_eval_poly_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, coeffs_ptr, idx_ptr, d, rop_in_ptr,
                                             rop_out_ptr, stream))
 
+    def eval_poly2_dev(self, seed, offset: int, c8_ptr: int, coeffs0_ptr: int, coeffs1_ptr: int, d: int, rop0_in, rop0_out: int,
+                       rop1_in, rop1_out: int, stream: int = 0):
+        self._ck(self.lib.mfb_eval_poly2_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in,
+                                             rop0_out, rop1_in, rop1_out, stream))
+
     def columns_split_dev(self, flat_ptr: int, cols_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_columns_split_dev(self.h, flat_ptr, cols_ptr, stream))
 

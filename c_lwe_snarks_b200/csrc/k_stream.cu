@@ -123,8 +123,12 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
   const KsSmem s = ks_smem_setup(dyn, t0_global);
   AesCtrCache cache;
   cache.window = ~0ull;
-  const size_t nitems = count * KS_NTILES;
-  size_t it = blockIdx.x;
+  // a CTA takes a CONTIGUOUS range of the (ciphertext, tile) items: consecutive items are consecutive in the
+  // stream, so the counter-mode cache (one refill per 65536-block window) is refilled every ~23 items only
+  const size_t total = count * KS_NTILES;
+  const size_t per = total / gridDim.x, rem = total % gridDim.x;
+  size_t it = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+  const size_t nitems = it + per + (blockIdx.x < rem ? 1 : 0);  // end of this CTA's range
   int ph = 0;
   __syncthreads();  // tables ready
   if (it < nitems) {
@@ -132,7 +136,7 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
     ks_fill(key, g.first, g.nblk, s.buf[0], s.lut, cache);
   }
   __syncthreads();
-  for (; it < nitems; it += gridDim.x, ph ^= 1) {
+  for (; it < nitems; it += 1, ph ^= 1) {
     const size_t k = it / KS_NTILES;
     const int tile = (int)(it % KS_NTILES);
     const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
@@ -153,7 +157,7 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
       dst[resident_index(N, j)] = v;
       dst[resident_index(N + 1, j)] = 0;
     }
-    const size_t nx = it + gridDim.x;
+    const size_t nx = it + 1;
     if (nx < nitems) {
       const TileGeom gn = tile_geom(offset + (nx / KS_NTILES) * (uint64_t)CTR_CT, (int)(nx % KS_NTILES));
       ks_fill(key, gn.first, gn.nblk, (ph ? s.buf[0] : s.buf[1]), s.lut, cache);
@@ -164,15 +168,20 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
 
 // ------------------------------------------------------------------------------------ fused eval_poly
 // partial[chunk] (planar, canonical) = sum over this CTA's ciphertexts of coeff * CT, for the CTA's tile.
-// Work item m of the list: ciphertext index idx[m] (or m), scalar coeffs[m]; CTA (tile, chunk) walks
-// m = chunk, chunk + nchunks, ...  The b coordinate (1470) is handled by thread KS_TILE of the tile-0 CTAs,
-// straight from the wire records.
+// Work item m of the list: ciphertext index idx[m] (or m), scalar coeffs[m].  The grid is `ncta` CTAs (one per SM);
+// CTA b works on tile b % NTILES as chunk b / NTILES of that tile, so the first ncta % NTILES tiles have one chunk
+// more than the others; a tile's chunks split [0, d) into CONTIGUOUS, balanced ranges (consecutive ciphertexts are
+// 8452.5 blocks apart: the counter-mode cache is refilled every ~8 items instead of every item).  The b coordinate
+// (1470) is handled by thread KS_TILE of the tile-0 CTAs, straight from the wire records.
 //
 // Pipeline: THREE keystream buffers and two mbarriers per buffer (full: every warp has stored its blocks; empty:
 // every warp has read its coordinates) instead of a CTA-wide __syncthreads per item.  A tile is 2818 blocks for 512
 // threads — 5.5 per thread — and the assignment rotates by half a CTA every item, so that each warp gets 5 and 6
 // blocks alternately; with the AES of item t+2 running while item t is consumed, a warp that is ahead keeps
 // working instead of waiting for the slowest warp of every item (that wait cost 6/5.5 of the time).
+// The warps are STAGGERED: half of the warps (two per scheduler) consume item t and then generate item t+2, the others
+// generate item t+2 first and consume item t afterwards, so that at any time half of the warps are in the MAC phase (FMA pipe: IMAD.WIDE
+// carry chains) while the other half is in the AES phase (ALU + LSU pipes) instead of all of them queueing on one.
 constexpr int KS_NBUF = 3;
 constexpr int KS3_SMEM_BYTES = 0x20000 + 2 * KS_BUF_BYTES;  // [pad: buffer 0 | 64 KB tables | buffers 1, 2]
 
@@ -201,7 +210,7 @@ template <int NVEC>
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
            const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
-           const uint32_t *__restrict__ idx, size_t d, int nchunks, uint64_t *__restrict__ partial0,
+           const uint32_t *__restrict__ idx, size_t d, int nparts, uint64_t *__restrict__ partial0,
            uint64_t *__restrict__ partial1) {
   // NVEC = 1: tiles of 490 coordinates, thread t < 490 owns coordinate t.
   // NVEC = 2: tiles of 245 coordinates, threads [0,245) accumulate vector 0 and [245,490) vector 1 from the same tile.
@@ -238,11 +247,15 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     g.nblk = (int)((g.delta + TILE_BYTES + 15) >> 4);
     return g;
   };
-  const size_t nitems = d > (size_t)chunk ? (d - chunk + nchunks - 1) / nchunks : 0;  // items chunk, chunk+nchunks, ...
+  // this tile's chunks: tiles below gridDim.x % NTILES have one more; chunk c takes a balanced contiguous range
+  const int nch = (int)(gridDim.x / NTILES) + (tile < (int)(gridDim.x % NTILES) ? 1 : 0);
+  const size_t per = d / nch, rem = d % nch;
+  const size_t m0 = (size_t)chunk * per + ((size_t)chunk < rem ? (size_t)chunk : rem);
+  const size_t nitems = per + ((size_t)chunk < rem ? 1 : 0);
   auto fill = [&](size_t t) {  // item t of this CTA -> buffer t % 3
     const int b = (int)(t % KS_NBUF);
     if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
-    const TileGeom g = geom(chunk + t * nchunks);
+    const TileGeom g = geom(m0 + t);
     // NVEC = 1: 2818 blocks = 5.5 per thread, rotate by half a CTA (5, 6, 5, 6, ...); NVEC = 2: 1409 blocks = 2.75
     // per thread, rotate by a quarter (3, 3, 3, 2, ...): every warp averages the same work over a few items
     const int rot = NVEC == 1 ? (int)((t & 1) * (KS_THREADS / 2)) : (int)((t & 3) * (KS_THREADS / 4));
@@ -254,11 +267,14 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
   Acc704 acc;
   acc_zero(acc);
   __syncthreads();  // tables and barriers ready
+  // warp w runs on scheduler w % 4: warps 4-7 and 12-15 are the late ones, so every scheduler has two of each kind
+  const bool late = (threadIdx.x >> 7) & 1;  // late warps: AES of item t+2 before the MAC of item t
   if (nitems > 0) fill(0);
   if (nitems > 1) fill(1);
   for (size_t t = 0; t < nitems; t++) {
     const int b = (int)(t % KS_NBUF);
-    const size_t m = chunk + t * nchunks;
+    const size_t m = m0 + t;
+    if (late && t + 2 < nitems) fill(t + 2);
     ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));  // every warp has stored its blocks of item t
     if (is_mac) {
       const TileGeom g = geom(m);
@@ -275,10 +291,21 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     }
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
-    if (t + 2 < nitems) fill(t + 2);
+    if (!late && t + 2 < nitems) fill(t + 2);
   }
 
   if (is_mac || is_b) {
+    // the finish kernel adds `nparts` partials for every coordinate: a tile with one chunk fewer zeroes the last slot
+    if (chunk == nch - 1 && nch < nparts) {
+      uint64_t *z = (my_vec ? partial1 : partial0) + (size_t)nch * PLANAR_U64;
+      const int c = is_b ? N : tile * TILE + lc;
+#pragma unroll
+      for (int j = 0; j < L64; j++) z[(size_t)j * NCP + c] = 0;
+      if (is_b) {
+#pragma unroll
+        for (int j = 0; j < L64; j++) z[(size_t)j * NCP + N + 1] = 0;
+      }
+    }
     uint64_t *out = (my_vec ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
     uint32_t r[22];
     acc_fold(acc, r);
@@ -297,7 +324,7 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
 // e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes) (69 noise bytes of errdist_uniform lwe.c:60-63;
 // the sign byte that follows is consumed by the host protocol and never used, lwe.c:86-87).
 //
-// A CTA takes whole ciphertexts k = blockIdx.x, blockIdx.x + gridDim.x, ...; its work items are their 3 coordinate
+// A CTA takes a contiguous range of whole ciphertexts; its work items are their 3 coordinate
 // tiles in order, on the same three-buffer mbarrier pipeline as k_evalpoly (no CTA-wide barrier in steady state):
 //   item t:  wait full[t % 3] -> thread c < 490: acc += a_c * sk_c (253 limb products on the FMA pipe, idle during AES)
 //            -> release the buffer -> AES of item t + 2 (ALU + LSU pipes).
@@ -328,9 +355,12 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   cache.window = ~0ull;
   const int lane = threadIdx.x & 31;
   const bool is_mac = threadIdx.x < KS_TILE;
-  const size_t nct = count > blockIdx.x ? (count - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // contiguous, balanced range of ciphertexts per CTA (keeps the counter-mode cache warm across items)
+  const size_t per = count / gridDim.x, rem = count % gridDim.x;
+  const size_t k0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+  const size_t nct = per + (blockIdx.x < rem ? 1 : 0);
   const size_t nitems = nct * KS_NTILES;
-  auto ct_of = [&](size_t t) { return (size_t)blockIdx.x + (t / KS_NTILES) * gridDim.x; };
+  auto ct_of = [&](size_t t) { return k0 + t / KS_NTILES; };
   auto fill = [&](size_t t) {  // item t of this CTA -> buffer t % 3
     const int b = (int)(t % KS_NBUF);
     if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
@@ -343,12 +373,16 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   Acc704 acc;
   acc_zero(acc);
   __syncthreads();  // tables, barriers, columns ready
+  // staggered like k_evalpoly: early warps MAC item t then AES item t+2, late warps the other way round — here the MAC
+  // is 253 limb products per coordinate, a fifth of the kernel's issue slots, and it must not queue up behind itself
+  const bool late = (threadIdx.x >> 7) & 1;  // warps 4-7, 12-15: two early and two late warps per scheduler
   if (nitems > 0) fill(0);
   if (nitems > 1) fill(1);
   for (size_t t = 0; t < nitems; t++) {
     const int b = (int)(t % KS_NBUF);
     const int tile = (int)(t % KS_NTILES);
     const size_t k = ct_of(t);
+    if (late && t + 2 < nitems) fill(t + 2);
     ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));  // every warp has stored its blocks of item t
     if (is_mac) {
       const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
@@ -427,7 +461,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
         if (lane <= L32) reinterpret_cast<uint32_t *>(out_c8 + k * CT_BYTES)[lane] = myb;  // 92 % 4 == 0
       }
     }
-    if (t + 2 < nitems) fill(t + 2);
+    if (!late && t + 2 < nitems) fill(t + 2);
   }
 }
 
@@ -459,41 +493,56 @@ cudaError_t launch_expand(const AesKey &key, const uint32_t *t0, uint64_t offset
   return cudaGetLastError();
 }
 
+// CTAs of the fused eval_poly grid: one per SM, at most one per (tile, ciphertext); *nparts = partial sums per coordinate
+static int evalpoly_plan(size_t d, int sm_count, int ntiles, int max_parts, int *nparts) {
+  size_t ncta = (size_t)sm_count;
+  if (ncta > (size_t)ntiles * d) ncta = (size_t)ntiles * d;
+  if (ncta > (size_t)ntiles * max_parts) ncta = (size_t)ntiles * max_parts;
+  if (ncta < (size_t)ntiles) ncta = ntiles;
+  *nparts = (int)((ncta + ntiles - 1) / ntiles);
+  return (int)ncta;
+}
+constexpr int EVALPOLY_MAX_PARTS = 128;  // mfb_capi.cu: MAX_CHUNKS = 256 row-planar slots, two vectors
+
 int evalpoly_nchunks(size_t d, int sm_count) {
-  size_t n = sm_count / KS_NTILES;
-  if (n < 1) n = 1;
-  if (n > d) n = d;
-  return (int)(n ? n : 1);
+  int nparts;
+  evalpoly_plan(d, sm_count, KS_NTILES, EVALPOLY_MAX_PARTS, &nparts);
+  return nparts;
 }
 
-// writes `nchunks` canonical planar partial sums to partial_ws
+// writes `nchunks` (= evalpoly_nchunks) canonical planar partial sums to partial_ws
 cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
+                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks, int sm_count,
                                      uint64_t *partial_ws, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
+  int nparts;
+  const int ncta = evalpoly_plan(d, sm_count, KS_NTILES, nchunks, &nparts);
+  if (nparts != nchunks) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly<1><<<nchunks * KS_NTILES, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, nullptr, idx, d, nchunks,
-                                                                         partial_ws, nullptr);
+  k_evalpoly<1><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, nullptr, idx, d, nparts, partial_ws,
+                                                            nullptr);
   return cudaGetLastError();
 }
 
 int evalpoly2_nchunks(size_t d, int sm_count) {
-  size_t n = sm_count / (2 * KS_NTILES);
-  if (n < 1) n = 1;
-  if (n > d) n = d;
-  return (int)(n ? n : 1);
+  int nparts;
+  evalpoly_plan(d, sm_count, 2 * KS_NTILES, EVALPOLY_MAX_PARTS, &nparts);
+  return nparts;
 }
 
 // two scalar vectors in one pass: writes nchunks partial sums to partial0 and nchunks to partial1
 cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks,
+                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks, int sm_count,
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
+  int nparts;
+  const int ncta = evalpoly_plan(d, sm_count, 2 * KS_NTILES, nchunks, &nparts);
+  if (nparts != nchunks) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly<2><<<nchunks * 2 * KS_NTILES, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, nullptr, d,
-                                                                             nchunks, partial0, partial1);
+  k_evalpoly<2><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, nullptr, d, nparts, partial0,
+                                                            partial1);
   return cudaGetLastError();
 }
 

@@ -47,11 +47,11 @@ cudaError_t launch_expand(const AesKey &key, const uint32_t *t0, uint64_t offset
                           uint64_t *cts, int sm_count, cudaStream_t st);
 int evalpoly_nchunks(size_t d, int sm_count);
 cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks,
+                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks, int sm_count,
                                      uint64_t *partial_ws, cudaStream_t st);
 int evalpoly2_nchunks(size_t d, int sm_count);
 cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks,
+                                      const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks, int sm_count,
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st);
 cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
                            const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
@@ -587,7 +587,7 @@ int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
   if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
   if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
+  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks, ctx->sm_count,
                                         ctx->partial_ws, (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
   MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
@@ -606,7 +606,7 @@ int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[4
   int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
   if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
   if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks,
+  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks, ctx->sm_count,
                                         ctx->partial_ws, (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
   MFB_TRY(peer_finish(ctx, g, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
@@ -626,7 +626,7 @@ int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, co
   if (2 * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / 2;
   uint64_t *p0 = ctx->partial_ws, *p1 = ctx->partial_ws + (size_t)nchunks * PLANAR_U64;
   if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly2_partials(key, ctx->t0_dev, offset, c8_dev, coeffs0_dev, coeffs1_dev, d, nchunks, p0, p1,
+  MFB_CUDA_TRY(launch_evalpoly2_partials(key, ctx->t0_dev, offset, c8_dev, coeffs0_dev, coeffs1_dev, d, nchunks, ctx->sm_count, p0, p1,
                                          (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
   MFB_CUDA_TRY(launch_lincomb_finish(p0, nchunks, rop0_in_dev, rop0_out_dev, nullptr, (cudaStream_t)stream));

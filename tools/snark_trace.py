@@ -1,13 +1,23 @@
-import sys; sys.path.insert(0, '.')
-from c_lwe_snarks_b200.snark import Snark
-import time
-sn = Snark(1 << 16, 64)
+"""Phase timings of setup / prover / verifier through the drop-in C layer (MF_B200_TRACE=1 prints the phases).
+Usage: MF_B200_TRACE=1 python tools/snark_trace.py [log2d] [M]"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from c_lwe_snarks_b200.snark import Snark  # noqa: E402
+
+log2d = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+sn = Snark(1 << log2d, M)
 sn.random_ssp()
+print("setup (cold)", sn.setup(), file=sys.stderr)
 print("setup", sn.setup(), file=sys.stderr)
-print("prove", sn.prove(), file=sys.stderr)
+print("setup", sn.setup(), file=sys.stderr)
+print("prove (cold)", sn.prove(), file=sys.stderr)
 print("prove", sn.prove(), file=sys.stderr)
 sn.make_resident()
+print("prove_res (cold)", sn.prove(), file=sys.stderr)
 print("prove_res", sn.prove(), file=sys.stderr)
-print("prove_res", sn.prove(), file=sys.stderr)
+print("verify", sn.verify(), file=sys.stderr)
 print("verify", sn.verify(), file=sys.stderr)
 sn.close()
