@@ -19,8 +19,10 @@ over D = 2^16 Regev ciphertexts per GPU (n = 1470, log q = 736 / effective 704),
   cpu_baseline  the compiled reference (oracle/_ref, unmodified lwe.c/entropy.c/aes.c) on one host core, over a
             bounded prefix of the same ciphertexts.
   N > 1     weak scaling: every rank holds its own 2^16 ciphertexts (global D = N * 2^16); a step adds the
-            exchange of SURVEY §8e: widen partial sums to u64 columns, NCCL reduce-scatter, carry-propagate +
-            truncate on the owner, all-gather.
+            exchange of SURVEY §8e.  --exchange p2p (default): fused into the finish kernel over NVLink peer memory
+            (k_lincomb_finish_peer: push the partial to every rank, per-tile flags, local sum).  --exchange nccl:
+            widen partial sums to u64 columns, NCCL reduce-scatter, carry-propagate + truncate on the owner,
+            all-gather (also what runs if CUDA IPC is not available on the box).
 
 `--impl reference` times the reference's own CPU eval_poly with every host core (one process per core over disjoint
 ciphertext ranges positioned with rng_seek, partials folded with ct_add), each step a bounded sample.
@@ -262,14 +264,40 @@ def run_gpu_arm(args):
 
     # the timed steps are independent eval_polys (a proof runs several): for N > 1 the exchange of step i overlaps
     # the lincomb kernel of step i+1 (side stream, alternating exchange buffers)
-    pipe = PipelinedShardedLincomb(plan, DeviceOps(ctx, torch), dist,
-                                   lambda n: torch.zeros(n, dtype=torch.int64, device="cuda"), torch) if world > 1 else None
+    new_i64 = lambda n: torch.zeros(n, dtype=torch.int64, device="cuda")  # noqa: E731
+    new_u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda")  # noqa: E731
+    pipe = peer = None
+    exchange = "none"
+    if world > 1 and args.exchange == "p2p":
+        # the exchange fused into the finish kernel over peer memory; every rank must agree on the outcome of the
+        # IPC hand-shake, so a rank that cannot map its peers makes ALL ranks take the NCCL exchange
+        from c_lwe_snarks_b200.sharding import PeerShardedLincomb
+        ok, why = 1, ""
+        try:
+            group = ctx.peer_group(world, rank)
+            peer = PeerShardedLincomb(plan, group, dist, new_i64, new_u8, lambda: torch.cuda.current_stream().cuda_stream)
+        except Exception as e:  # noqa: BLE001
+            ok, why, peer = 0, str(e), None
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if why:
+                print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({why}); using the NCCL exchange", file=sys.stderr)
+            peer = None
+        else:
+            exchange = ("fused into the finish kernel over NVLink peer memory (CUDA IPC): push to every rank's symmetric "
+                        "buffer, per-tile flags, local sum; no collective call on the data path")
+    if world > 1 and peer is None:
+        pipe = PipelinedShardedLincomb(plan, DeviceOps(ctx, torch), dist, new_i64, torch)
+        exchange = ("u64-column reduce-scatter + carry + all-gather (NCCL) on a side stream, overlapped with the next "
+                    "step's lincomb kernel")
 
     def step():
+        if peer is not None:
+            return peer.step(d_cts, d_h, D)
         if pipe is None:
-            sl.step(d_cts, d_h, D)
-        else:
-            pipe.submit(d_cts, d_h, D)
+            return sl.step(d_cts, d_h, D)
+        return pipe.submit(d_cts, d_h, D)
 
     def barrier():
         if world > 1:
@@ -294,6 +322,9 @@ def run_gpu_arm(args):
     ms = e0.elapsed_time(e1)
     if pipe is not None:
         d_rop = pipe.results[(pipe.calls - 1) % 2]
+    if peer is not None:
+        peer.check()
+        d_rop = peer.results[(peer.calls - 1) % 2]
     k_ms, k_n = ctx.profile_end()
     launches = ctx.launches - l0  # our kernels only (NCCL's and torch's zero_ are not counted)
     t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -340,8 +371,11 @@ def run_gpu_arm(args):
             # the same exchange as the resident path, result back to pinned host memory
             d_c8_e.copy_(p_c8, non_blocking=True)
             d_h_e.copy_(p_h32, non_blocking=True)
-            ctx.eval_poly_dev(SEED, stream_off, d_c8_e.data_ptr(), d_h_e.data_ptr(), None, D, None, sl.partial.data_ptr(), st)
-            res = sl.exchange()
+            if peer is not None:
+                res = peer.step_fused(SEED, stream_off, d_c8_e, d_h_e, D)
+            else:
+                ctx.eval_poly_dev(SEED, stream_off, d_c8_e.data_ptr(), d_h_e.data_ptr(), None, D, None, sl.partial.data_ptr(), st)
+                res = sl.exchange()
             p_rop.copy_(res[: NC * L64], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -370,7 +404,7 @@ def run_gpu_arm(args):
             ctx._ck(ctx.lib.mfb_region_lincomb(ctx.h, reg.handle, 0, m.api._p32(co32), D, m.api._p64(np_rop)))
         else:
             d_co_r.copy_(p_co32, non_blocking=True)
-            res = sl.step(d_cts, d_co_r, D)
+            res = peer.step(d_cts, d_co_r, D) if peer is not None else sl.step(d_cts, d_co_r, D)
             p_rop.copy_(res[: NC * L64], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -415,8 +449,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts per GPU resident in HBM "
                                    f"({D * PLANAR_BYTES / 1e9:.2f} GB planar), n=1470, logq=736 (eff. 704), p=2^32-5",
                        "ciphertexts_per_gpu": D, "l2": "inputs (8.49 GB per step) exceed the 126 MB L2; no flush needed",
-                       "exchange": "none" if world == 1 else "u64-column reduce-scatter + carry + all-gather (NCCL) on a side "
-                                                              "stream, overlapped with the next step's lincomb kernel",
+                       "exchange": exchange,
                        "parity_check": check},
             "roofline": {"bound": "hbm", "kernel": "k_lincomb", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -441,6 +474,9 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
             line["config1_reference_cpu"] = config1_reference()
         emit(line)
+    if peer is not None:
+        peer.check()
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
@@ -470,6 +506,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=6000, help="ciphertexts timed by the 1-core cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-snark", action="store_true", help="skip the full setup/prove/verify latency leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = exchange fused into the finish kernel over NVLink peer memory (CUDA IPC); "
+                         "nccl = u64-column reduce-scatter + carry + all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
