@@ -266,35 +266,37 @@ def run_gpu_arm(args):
     # the lincomb kernel of step i+1 (side stream, alternating exchange buffers)
     new_i64 = lambda n: torch.zeros(n, dtype=torch.int64, device="cuda")  # noqa: E731
     new_u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda")  # noqa: E731
-    pipe = peer = None
+    pipe = peer = ppipe = None
     exchange = "none"
     if world > 1 and args.exchange == "p2p":
         # the exchange fused into the finish kernel over peer memory; every rank must agree on the outcome of the
         # IPC hand-shake, so a rank that cannot map its peers makes ALL ranks take the NCCL exchange
-        from c_lwe_snarks_b200.sharding import PeerShardedLincomb
+        from c_lwe_snarks_b200.sharding import PipelinedPeerShardedLincomb
         ok, why = 1, ""
         try:
             group = ctx.peer_group(world, rank)
-            peer = PeerShardedLincomb(plan, group, dist, new_i64, new_u8, lambda: torch.cuda.current_stream().cuda_stream)
+            ppipe = PipelinedPeerShardedLincomb(plan, group, dist, new_i64, new_u8, torch)
+            peer = ppipe.inner
         except Exception as e:  # noqa: BLE001
-            ok, why, peer = 0, str(e), None
+            ok, why, peer, ppipe = 0, str(e), None, None
         flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             if why:
                 print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({why}); using the NCCL exchange", file=sys.stderr)
-            peer = None
+            peer = ppipe = None
         else:
-            exchange = ("fused into the finish kernel over NVLink peer memory (CUDA IPC): push to every rank's symmetric "
-                        "buffer, per-tile flags, local sum; no collective call on the data path")
+            exchange = ("over NVLink peer memory (CUDA IPC), no collective call on the data path: the finish kernel pushes "
+                        "the partial sum into every rank's symmetric buffer (per-tile flags); a 23-CTA kernel on a side "
+                        "stream adds the ranks' tiles next to the following step's lincomb kernel and acknowledges")
     if world > 1 and peer is None:
         pipe = PipelinedShardedLincomb(plan, DeviceOps(ctx, torch), dist, new_i64, torch)
         exchange = ("u64-column reduce-scatter + carry + all-gather (NCCL) on a side stream, overlapped with the next "
                     "step's lincomb kernel")
 
     def step():
-        if peer is not None:
-            return peer.step(d_cts, d_h, D)
+        if ppipe is not None:
+            return ppipe.submit(d_cts, d_h, D)
         if pipe is None:
             return sl.step(d_cts, d_h, D)
         return pipe.submit(d_cts, d_h, D)
@@ -317,14 +319,16 @@ def run_gpu_arm(args):
         step()
     if pipe is not None:
         pipe.drain()
+    if ppipe is not None:
+        ppipe.drain()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     if pipe is not None:
         d_rop = pipe.results[(pipe.calls - 1) % 2]
-    if peer is not None:
-        peer.check()
-        d_rop = peer.results[(peer.calls - 1) % 2]
+    if ppipe is not None:
+        ppipe.check()
+        d_rop = ppipe.results[(ppipe.calls - 1) % 2]
     k_ms, k_n = ctx.profile_end()
     launches = ctx.launches - l0  # our kernels only (NCCL's and torch's zero_ are not counted)
     t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")

@@ -170,6 +170,49 @@ class PeerShardedLincomb:
         self.group.close()
 
 
+class PipelinedPeerShardedLincomb:
+    """Back-to-back sharded lincombs over peer memory: the lincomb kernel and the pushing finish kernel run on the
+    caller's stream and never wait for a peer; the small sum kernel of call i runs on a side stream, next to the
+    lincomb kernel of call i+1.  Results land in self.results[i % 2]; call drain() before reading the last ones."""
+
+    def __init__(self, plan: ShardPlan, group, dist, new_i64, new_u8, torch):
+        self.torch = torch
+        self.inner = PeerShardedLincomb(plan, group, dist, new_i64, new_u8, lambda: torch.cuda.current_stream().cuda_stream)
+        self.group, self.results = group, self.inner.results
+        self.side = torch.cuda.Stream()
+        self.done = [None, None]
+        self.calls = 0
+
+    def submit(self, cts, coeffs, d_local):
+        t = self.torch
+        k = self.calls % 2
+        main = t.cuda.current_stream()
+        self.group.push_dev(cts.data_ptr(), coeffs.data_ptr(), d_local, main.cuda_stream)
+        pushed = t.cuda.Event()
+        pushed.record(main)
+        self.side.wait_event(pushed)
+        if self.done[k] is not None:
+            self.side.wait_event(self.done[k])  # (same stream: keeps the order explicit)
+        self.group.sum_dev(None, self.results[k].data_ptr(), self.side.cuda_stream)
+        ev = t.cuda.Event()
+        ev.record(self.side)
+        self.done[k] = ev
+        self.calls += 1
+        return self.results[k]
+
+    def drain(self):
+        main = self.torch.cuda.current_stream()
+        for ev in self.done:
+            if ev is not None:
+                main.wait_event(ev)
+
+    def check(self):
+        self.inner.check()
+
+    def close(self):
+        self.inner.close()
+
+
 class PipelinedShardedLincomb:
     """Back-to-back sharded lincombs (the prover runs several per proof) with the exchange of call i overlapped with the
     lincomb kernel of call i+1: the lincomb runs on the caller's stream, the exchange chain (columns_split,

@@ -160,6 +160,13 @@ MFB_API int mfb_peer_disconnect(mfb_ctx *ctx, mfb_peer_group *g);
 MFB_API void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g);
 MFB_API int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
                          const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
+/* The exchange in two halves, for back-to-back lincombs: push = the lincomb kernel + a finish kernel that pushes the
+ * partial sum to every rank and returns without waiting for anybody; sum = a small kernel (co-resident with the next
+ * lincomb kernel, so put it on a side stream after an event) that waits for all ranks' tiles of that call, adds them
+ * and acknowledges.  Calls are matched in order; at most two pushes may be ahead of their sums. */
+MFB_API int mfb_lincomb_peer_push_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev,
+                              size_t d, void *stream);
+MFB_API int mfb_peer_sum_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
 /* the same for the fused AES + MAC path (mfb_eval_poly_dev over this rank's ciphertexts) */
 MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                            const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,

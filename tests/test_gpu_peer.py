@@ -25,7 +25,7 @@ def _flat(t):
     return t.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64)
 
 
-def _run_local_world(world, d_total, calls, devices, fused=False):
+def _run_local_world(world, d_total, calls, devices, fused=False, split=False):
     import torch
 
     import c_lwe_snarks_b200 as m
@@ -51,7 +51,8 @@ def _run_local_world(world, d_total, calls, devices, fused=False):
             torch.cuda.synchronize()
         g = ctx.peer_group(world, r)
         g.set_timeout(5.0)
-        ranks.append(dict(ctx=ctx, g=g, st=st, first=first, cnt=cnt, c8=d_c8, h=d_h, cts=d_cts, out=out, dev=dev))
+        st2 = torch.cuda.Stream(device=dev)
+        ranks.append(dict(ctx=ctx, g=g, st=st, st2=st2, first=first, cnt=cnt, c8=d_c8, h=d_h, cts=d_cts, out=out, dev=dev))
     bases = [rk["g"].base for rk in ranks]
     if world > 1:
         for rk in ranks:
@@ -67,7 +68,13 @@ def _run_local_world(world, d_total, calls, devices, fused=False):
             for rk in ranks:
                 torch.cuda.set_device(rk["dev"])
                 prev = rk["out"][(i + 1) % 2] if i else None
-                if fused:
+                if split:  # push on the main stream, sum on the side stream (PipelinedPeerShardedLincomb's schedule)
+                    rk["g"].push_dev(rk["cts"].data_ptr(), rk["h"].data_ptr(), rk["cnt"], rk["st"].cuda_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(rk["st"])
+                    rk["st2"].wait_event(ev)
+                    rk["g"].sum_dev(None if prev is None else prev.data_ptr(), rk["out"][i % 2].data_ptr(), rk["st2"].cuda_stream)
+                elif fused:
                     rk["g"].eval_poly_dev(SEED, rk["first"] * CTR_CT, rk["c8"].data_ptr(), rk["h"].data_ptr(), None, rk["cnt"],
                                           None if prev is None else prev.data_ptr(), rk["out"][i % 2].data_ptr(),
                                           rk["st"].cuda_stream)
@@ -78,6 +85,7 @@ def _run_local_world(world, d_total, calls, devices, fused=False):
         for rk in ranks:
             torch.cuda.set_device(rk["dev"])
             rk["st"].synchronize()
+            rk["st2"].synchronize()
             rk["g"].check()
             results.append(_flat(rk["out"][(calls - 1) % 2]))
     finally:
@@ -109,6 +117,13 @@ def test_peer_exchange_fused_eval_poly():
     results, want = _run_local_world(4, 64, 3, devices=[0], fused=True)
     for got in results:
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("world,d_total,calls", [(1, 20, 3), (2, 300, 9), (4, 100, 6), (8, 64, 5)])
+def test_peer_exchange_split_push_and_sum(world, d_total, calls):
+    results, want = _run_local_world(world, d_total, calls, devices=[0], split=True)
+    for r, got in enumerate(results):
+        assert np.array_equal(got, want), f"rank {r}"
 
 
 def test_peer_exchange_empty_rank():
@@ -193,6 +208,17 @@ def _ipc_worker(rank, world, port, d_per_rank, calls, q):
     f = peer.step_fused(S, first * CTR_CT, d_c8, d_h, cnt)
     torch.cuda.synchronize()
     ok = ok and bool(torch.equal(f[: NC * L64], b[: NC * L64]))
+    # the split schedule on the same group: push on the main stream, sum on a side stream, several calls in flight
+    from c_lwe_snarks_b200.sharding import PipelinedPeerShardedLincomb
+    pipe = PipelinedPeerShardedLincomb.__new__(PipelinedPeerShardedLincomb)
+    pipe.torch, pipe.inner, pipe.group, pipe.results = torch, peer, group, peer.results
+    pipe.side, pipe.done, pipe.calls = torch.cuda.Stream(), [None, None], 0
+    for i in range(5):
+        p_res = pipe.submit(d_cts, d_h, cnt)
+    pipe.drain()
+    torch.cuda.synchronize()
+    peer.check()
+    ok = ok and bool(torch.equal(p_res[: NC * L64], b[: NC * L64]))
     res = a[: NC * L64].cpu().numpy().view(np.uint64).reshape(NC, L64).copy()
     peer.close()
     ctx.close()
