@@ -275,7 +275,7 @@ def run_gpu_arm(args):
         ok, why = 1, ""
         try:
             group = ctx.peer_group(world, rank)
-            ppipe = PipelinedPeerShardedLincomb(plan, group, dist, new_i64, new_u8, torch)
+            ppipe = PipelinedPeerShardedLincomb(plan, ctx, group, dist, new_i64, new_u8, torch)
             peer = ppipe.inner
         except Exception as e:  # noqa: BLE001
             ok, why, peer, ppipe = 0, str(e), None, None
@@ -286,9 +286,9 @@ def run_gpu_arm(args):
                 print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({why}); using the NCCL exchange", file=sys.stderr)
             peer = ppipe = None
         else:
-            exchange = ("over NVLink peer memory (CUDA IPC), no collective call on the data path: the finish kernel pushes "
-                        "the partial sum into every rank's symmetric buffer (per-tile flags); a 23-CTA kernel on a side "
-                        "stream adds the ranks' tiles next to the following step's lincomb kernel and acknowledges")
+            exchange = ("over NVLink peer memory (CUDA IPC), no collective call on the data path: ONE 23-CTA kernel per step "
+                        "on a side stream pushes the rank's partial sum into every rank's symmetric buffer, waits on per-tile "
+                        "flags and adds the ranks' tiles, next to the following step's lincomb kernel")
     if world > 1 and peer is None:
         pipe = PipelinedShardedLincomb(plan, DeviceOps(ctx, torch), dist, new_i64, torch)
         exchange = ("u64-column reduce-scatter + carry + all-gather (NCCL) on a side stream, overlapped with the next "

@@ -79,8 +79,7 @@ _SIGS = {
     "mfb_peer_disconnect": (C.c_int, [_vp, _vp]),
     "mfb_peer_destroy": (None, [_vp, _vp]),
     "mfb_lincomb_peer_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
-    "mfb_lincomb_peer_push_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
-    "mfb_peer_sum_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mfb_peer_allreduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mfb_eval_poly_peer_dev": (C.c_int, [_vp, _vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
@@ -216,11 +215,8 @@ class PeerGroup:
         self.ctx._ck(self.ctx.lib.mfb_lincomb_peer_dev(self.ctx.h, self.handle_, cts_ptr, coeffs_ptr, d, rop_in_ptr, rop_out_ptr,
                                                        stream))
 
-    def push_dev(self, cts_ptr: int, coeffs_ptr: int, d: int, stream: int = 0):
-        self.ctx._ck(self.ctx.lib.mfb_lincomb_peer_push_dev(self.ctx.h, self.handle_, cts_ptr, coeffs_ptr, d, stream))
-
-    def sum_dev(self, rop_in_ptr, rop_out_ptr: int, stream: int = 0):
-        self.ctx._ck(self.ctx.lib.mfb_peer_sum_dev(self.ctx.h, self.handle_, rop_in_ptr, rop_out_ptr, stream))
+    def allreduce_dev(self, partial_flat_ptr: int, rop_in_ptr, rop_out_ptr: int, stream: int = 0):
+        self.ctx._ck(self.ctx.lib.mfb_peer_allreduce_dev(self.ctx.h, self.handle_, partial_flat_ptr, rop_in_ptr, rop_out_ptr, stream))
 
     def eval_poly_dev(self, seed, offset: int, c8_ptr: int, coeffs_ptr: int, idx_ptr, d: int, rop_in_ptr, rop_out_ptr: int,
                       stream: int = 0):

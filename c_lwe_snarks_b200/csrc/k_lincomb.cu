@@ -271,11 +271,6 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const ui
 #pragma unroll
     for (int j = 0; j < L64; j++) stage[cl * L64 + j] = c < NC ? ((uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32) : 0;
   }
-  // (calls of the split variant may be mixed in: honour its acknowledgements — see k_lincomb_finish_push)
-  if (epoch > 2 && (int)threadIdx.x < world) {
-    const uint32_t *a = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_ack_offset(q, world, (int)threadIdx.x, tile));
-    if (!peer_wait_u32(a, epoch - 2, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
-  }
   __syncthreads();
   // 2. push: 352 threads x one uint4 per destination rank
   constexpr int TILE_FLAT_BYTES = RT_TILE * L64 * 8;  // 5632
@@ -329,62 +324,36 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const ui
 #pragma unroll
     for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
   }
-  // the tiles have been consumed (their values went through shared memory before the barrier above)
-  if ((int)threadIdx.x < world)
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_ack_offset(q, world, rank, tile)), epoch);
 }
 
-// The same exchange split in two kernels for back-to-back lincombs: k_lincomb_finish_push (steps 1-2) stays on the
-// stream of the lincomb kernels and never waits for a peer in steady state; k_peer_sum (steps 3-4; 64 threads per tile,
-// no shared memory, so it co-resides with the next k_lincomb) runs on a side stream.  Without the wait inside one
-// kernel nothing would stop a fast rank from overwriting slot parity q two calls later, so the reader acknowledges:
-// after its loads, k_peer_sum releases ack[q][reader][tile] = epoch in every source rank's buffer, and the push of
-// call epoch first checks the acks of call epoch - 2 (long since there, unless a peer is two calls behind).
-__global__ void __launch_bounds__(64 * FIN_SLICES)
-k_lincomb_finish_push(const uint64_t *__restrict__ partial, int nparts, unsigned int *queue,
-                      const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, uint64_t timeout_ns,
-                      int *status) {
-  __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
-  __shared__ __align__(16) uint64_t stage[RT_TILE * L64];
-  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;
+// The exchange alone (mfb_peer_allreduce_dev): this rank's contribution is already a flat ciphertext.  64 threads per
+// tile and no shared memory, so that the kernel is co-resident with a running k_lincomb (which fills the SMs' shared
+// memory): on a side stream it overlaps the NEXT lincomb kernel completely.
+__global__ void __launch_bounds__(RT_TILE)
+k_peer_allreduce(const uint64_t *__restrict__ flat_partial, const uint64_t *rop_in, uint64_t *rop_out,
+                 const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status) {
   const int tile = blockIdx.x;
-  const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int c = tile * 64 + cl;
+  const int c = tile * RT_TILE + threadIdx.x;
   const uint32_t q = epoch & 1u;
-  uint32_t r[22];
-  fin_sum_partials(partial, nparts, sm, c, cl, slice, r);
-  if (slice == 0) {
-#pragma unroll
-    for (int j = 0; j < L64; j++) stage[cl * L64 + j] = c < NC ? ((uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32) : 0;
-  }
-  // every reader is done with this slot's previous content (call epoch - 2)
-  if (epoch > 2 && (int)threadIdx.x < world) {
-    const uint32_t *a = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_ack_offset(q, world, (int)threadIdx.x, tile));
-    if (!peer_wait_u32(a, epoch - 2, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
-  }
-  __syncthreads();
-  constexpr int TILE_FLAT_BYTES = RT_TILE * L64 * 8;
-  if (threadIdx.x < TILE_FLAT_BYTES / 16) {
-    const uint4 v = reinterpret_cast<const uint4 *>(stage)[threadIdx.x];
-    for (int i = 0; i < world; i++) {
-      const int p = (rank + 1 + i) % world;
-      uint8_t *dst = peers.base[p] + peer_slot_offset(q, world, rank) + (size_t)tile * TILE_FLAT_BYTES + 16 * threadIdx.x;
-      *reinterpret_cast<uint4 *>(dst) = v;
+  constexpr int TILE_FLAT_U64 = RT_TILE * L64;  // 704 u64 = 352 x 16 bytes
+  // push: the tile as 16-byte pieces (the flat input ends at coordinate 1470: the padding coordinate is sent as zeros)
+  for (int i = threadIdx.x; i < TILE_FLAT_U64 / 2; i += RT_TILE) {
+    const size_t e = (size_t)tile * TILE_FLAT_U64 + 2 * (size_t)i;
+    uint4 v;
+    const uint64_t lo = e < (size_t)NC * L64 ? flat_partial[e] : 0, hi = e + 1 < (size_t)NC * L64 ? flat_partial[e + 1] : 0;
+    v.x = (uint32_t)lo;
+    v.y = (uint32_t)(lo >> 32);
+    v.z = (uint32_t)hi;
+    v.w = (uint32_t)(hi >> 32);
+    for (int k = 0; k < world; k++) {
+      const int p = (rank + 1 + k) % world;
+      *reinterpret_cast<uint4 *>(peers.base[p] + peer_slot_offset(q, world, rank) + e * 8) = v;
     }
   }
   __threadfence_system();
   __syncthreads();
-  if ((int)threadIdx.x < world)
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, tile)), epoch);
-}
-
-__global__ void __launch_bounds__(RT_TILE)
-k_peer_sum(const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, const uint64_t *rop_in,
-           uint64_t *rop_out, uint64_t timeout_ns, int *status) {
-  const int tile = blockIdx.x;
-  const int c = tile * RT_TILE + threadIdx.x;
-  const uint32_t q = epoch & 1u;
   if ((int)threadIdx.x < world) {
+    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, tile)), epoch);
     const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, tile));
     if (!peer_wait_u32(f, epoch, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
   }
@@ -408,9 +377,6 @@ k_peer_sum(const __grid_constant__ PeerTable peers, int world, int rank, uint32_
 #pragma unroll
     for (int j = 0; j < L64; j++) rop_out[(size_t)c * L64 + j] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
   }
-  __syncthreads();  // every thread's loads of the tiles have been consumed
-  if ((int)threadIdx.x < world)
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_ack_offset(q, world, rank, tile)), epoch);
 }
 
 // --- multi-GPU exchange helpers --------------------------------------------------
@@ -512,28 +478,16 @@ cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                       unsigned int *queue, uint8_t *const *bases, int world, int rank, uint32_t epoch,
-                                       uint64_t timeout_ns, int *status, cudaStream_t st) {
-  PeerTable t = {};
-  for (int i = 0; i < world; i++) t.base[i] = bases[i];
-  k_lincomb_finish_peer<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue, t, world, rank, epoch,
-                                                               timeout_ns, status);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_lincomb_finish_push(const uint64_t *partial_ws, int nparts, unsigned int *queue, uint8_t *const *bases,
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *flat_partial,
+                                       const uint64_t *rop_in, uint64_t *rop_out, unsigned int *queue, uint8_t *const *bases,
                                        int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st) {
   PeerTable t = {};
   for (int i = 0; i < world; i++) t.base[i] = bases[i];
-  k_lincomb_finish_push<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, queue, t, world, rank, epoch, timeout_ns, status);
-  return cudaGetLastError();
-}
-cudaError_t launch_peer_sum(uint8_t *const *bases, int world, int rank, uint32_t epoch, const uint64_t *rop_in, uint64_t *rop_out,
-                            uint64_t timeout_ns, int *status, cudaStream_t st) {
-  PeerTable t = {};
-  for (int i = 0; i < world; i++) t.base[i] = bases[i];
-  k_peer_sum<<<RT_NTILES, RT_TILE, 0, st>>>(t, world, rank, epoch, rop_in, rop_out, timeout_ns, status);
+  if (flat_partial)
+    k_peer_allreduce<<<RT_NTILES, RT_TILE, 0, st>>>(flat_partial, rop_in, rop_out, t, world, rank, epoch, timeout_ns, status);
+  else
+    k_lincomb_finish_peer<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue, t, world, rank, epoch,
+                                                                 timeout_ns, status);
   return cudaGetLastError();
 }
 

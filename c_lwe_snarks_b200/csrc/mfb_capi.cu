@@ -35,13 +35,9 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
                                     mark_fn mark, void *mark_arg);
 cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
                                   unsigned int *queue, cudaStream_t st);
-cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                       unsigned int *queue, uint8_t *const *bases, int world, int rank, uint32_t epoch,
-                                       uint64_t timeout_ns, int *status, cudaStream_t st);
-cudaError_t launch_lincomb_finish_push(const uint64_t *partial_ws, int nparts, unsigned int *queue, uint8_t *const *bases,
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *flat_partial,
+                                       const uint64_t *rop_in, uint64_t *rop_out, unsigned int *queue, uint8_t *const *bases,
                                        int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st);
-cudaError_t launch_peer_sum(uint8_t *const *bases, int world, int rank, uint32_t epoch, const uint64_t *rop_in, uint64_t *rop_out,
-                            uint64_t timeout_ns, int *status, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
 cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
                                  cudaStream_t st);
@@ -372,8 +368,7 @@ struct mfb_peer_group {
   uint8_t *base[PEER_MAX] = {};    // every rank's buffer as mapped into this process
   bool opened[PEER_MAX] = {};      // mapped with cudaIpcOpenMemHandle (to be closed)
   bool connected = false;
-  uint32_t epoch = 0;              // sequence number of the last call that pushed (fused or split)
-  uint32_t sum_epoch = 0;          // sequence number of the last call that summed
+  uint32_t epoch = 0;              // sequence number of the last exchange
   int *status = nullptr;           // pinned + mapped: the kernel writes 1 + (missing rank) on a timeout
   uint64_t timeout_ns = 20000000000ull;
 };
@@ -508,14 +503,12 @@ void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g) {
   delete g;
 }
 
-static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, int nparts, const uint64_t *rop_in_dev, uint64_t *rop_out_dev,
-                       unsigned int *queue, cudaStream_t st) {
-  if (g->sum_epoch != g->epoch) return set_err(MFB_EARG, "peer exchange: a pushed call has not been summed yet (mfb_peer_sum_dev)");
+static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, int nparts, const uint64_t *flat_partial_dev, const uint64_t *rop_in_dev,
+                       uint64_t *rop_out_dev, unsigned int *queue, cudaStream_t st) {
   if (g->epoch == 0xffffffffu) return set_err(MFB_EARG, "peer exchange: 2^32 calls on one group; create a new one");
   g->epoch += 1;
-  g->sum_epoch = g->epoch;
-  MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, nparts, rop_in_dev, rop_out_dev, queue, g->base, g->world, g->rank,
-                                          g->epoch, g->timeout_ns, g->status, st));
+  MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, nparts, flat_partial_dev, rop_in_dev, rop_out_dev, queue, g->base,
+                                          g->world, g->rank, g->epoch, g->timeout_ns, g->status, st));
   return MFB_OK;
 }
 
@@ -529,38 +522,17 @@ int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_de
   MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
                                        (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  MFB_TRY(peer_finish(ctx, g, nslots, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
+  MFB_TRY(peer_finish(ctx, g, nslots, nullptr, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }
 
-int mfb_lincomb_peer_push_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
-                              void *stream) {
+int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, const uint64_t *rop_in_dev,
+                           uint64_t *rop_out_dev, void *stream) {
   MFB_CHECK_CTX(ctx);
-  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_lincomb_peer_push_dev: the peer group is not connected");
-  if (d && (!cts_dev || !coeffs_dev)) return set_err(MFB_EARG, "mfb_lincomb_peer_push_dev: null pointer");
-  if (g->epoch - g->sum_epoch >= 2) return set_err(MFB_EARG, "mfb_lincomb_peer_push_dev: two pushed calls are waiting for mfb_peer_sum_dev");
-  if (g->epoch == 0xffffffffu) return set_err(MFB_EARG, "peer exchange: 2^32 calls on one group; create a new one");
-  int nslots = lincomb_nslots(d, ctx->sm_count, 1);
-  if (nslots > MAX_CHUNKS) nslots = MAX_CHUNKS;
-  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
-                                       (cudaStream_t)stream,
-                                       [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  g->epoch += 1;
-  MFB_CUDA_TRY(launch_lincomb_finish_push(ctx->partial_ws, nslots, ctx->queue, g->base, g->world, g->rank, g->epoch, g->timeout_ns,
-                                          g->status, (cudaStream_t)stream));
-  ctx->launches += d ? 2 : 1;
-  return MFB_OK;
-}
-
-int mfb_peer_sum_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream) {
-  MFB_CHECK_CTX(ctx);
-  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_sum_dev: the peer group is not connected");
-  if (!rop_out_dev) return set_err(MFB_EARG, "mfb_peer_sum_dev: null pointer");
-  if (g->sum_epoch == g->epoch) return set_err(MFB_EARG, "mfb_peer_sum_dev: no pushed call is waiting");
-  g->sum_epoch += 1;
-  MFB_CUDA_TRY(launch_peer_sum(g->base, g->world, g->rank, g->sum_epoch, rop_in_dev, rop_out_dev, g->timeout_ns, g->status,
-                               (cudaStream_t)stream));
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: the peer group is not connected");
+  if (!partial_flat_dev || !rop_out_dev) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: null pointer");
+  MFB_TRY(peer_finish(ctx, g, 0, partial_flat_dev, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
   ctx->launches += 1;
   return MFB_OK;
 }
@@ -647,7 +619,7 @@ int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[4
   MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks, ctx->sm_count,
                                         ctx->partial_ws, (cudaStream_t)stream));
   if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
-  MFB_TRY(peer_finish(ctx, g, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
+  MFB_TRY(peer_finish(ctx, g, nchunks, nullptr, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }

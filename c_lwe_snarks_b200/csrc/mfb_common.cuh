@@ -45,13 +45,8 @@ __host__ __device__ __forceinline__ size_t peer_slot_offset(uint32_t q, int worl
 __host__ __device__ __forceinline__ size_t peer_flag_offset(uint32_t q, int world, int src, int tile) {
   return (size_t)2 * world * PEER_SLOT_BYTES + (((size_t)q * world + src) * RT_NTILES + tile) * 4;
 }
-// acknowledgements of the split (pipelined) variant: reader rank r has consumed tile `tile` of call parity q
-__host__ __device__ __forceinline__ size_t peer_ack_offset(uint32_t q, int world, int reader, int tile) {
-  return (size_t)2 * world * PEER_SLOT_BYTES + (size_t)2 * world * RT_NTILES * 4 +
-         (((size_t)q * world + reader) * RT_NTILES + tile) * 4;
-}
 __host__ __device__ __forceinline__ size_t peer_buffer_bytes(int world) {
-  return (size_t)2 * world * PEER_SLOT_BYTES + (size_t)4 * world * RT_NTILES * 4;
+  return (size_t)2 * world * PEER_SLOT_BYTES + (size_t)2 * world * RT_NTILES * 4;
 }
 
 // ---------------------------------------------------------------------------------------------

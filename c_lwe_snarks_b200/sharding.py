@@ -171,29 +171,31 @@ class PeerShardedLincomb:
 
 
 class PipelinedPeerShardedLincomb:
-    """Back-to-back sharded lincombs over peer memory: the lincomb kernel and the pushing finish kernel run on the
-    caller's stream and never wait for a peer; the small sum kernel of call i runs on a side stream, next to the
+    """Back-to-back sharded lincombs over peer memory: the plain lincomb (k_lincomb + k_lincomb_finish) runs on the
+    caller's stream into one of two partial buffers; the exchange of call i — ONE 23-CTA kernel that pushes the partial
+    to every rank, waits for the others' and adds them (mfb_peer_allreduce_dev) — runs on a side stream next to the
     lincomb kernel of call i+1.  Results land in self.results[i % 2]; call drain() before reading the last ones."""
 
-    def __init__(self, plan: ShardPlan, group, dist, new_i64, new_u8, torch):
-        self.torch = torch
+    def __init__(self, plan: ShardPlan, ctx, group, dist, new_i64, new_u8, torch):
+        self.torch, self.ctx = torch, ctx
         self.inner = PeerShardedLincomb(plan, group, dist, new_i64, new_u8, lambda: torch.cuda.current_stream().cuda_stream)
         self.group, self.results = group, self.inner.results
+        self.partials = [new_i64(NCP * L64), new_i64(NCP * L64)]
         self.side = torch.cuda.Stream()
-        self.done = [None, None]
+        self.done = [None, None]   # event: the exchange that last read partials[k] / wrote results[k] has finished
         self.calls = 0
 
     def submit(self, cts, coeffs, d_local):
         t = self.torch
         k = self.calls % 2
         main = t.cuda.current_stream()
-        self.group.push_dev(cts.data_ptr(), coeffs.data_ptr(), d_local, main.cuda_stream)
-        pushed = t.cuda.Event()
-        pushed.record(main)
-        self.side.wait_event(pushed)
         if self.done[k] is not None:
-            self.side.wait_event(self.done[k])  # (same stream: keeps the order explicit)
-        self.group.sum_dev(None, self.results[k].data_ptr(), self.side.cuda_stream)
+            main.wait_event(self.done[k])          # partials[k] is about to be overwritten
+        self.ctx.lincomb_dev(cts.data_ptr(), coeffs.data_ptr(), d_local, None, self.partials[k].data_ptr(), main.cuda_stream)
+        ready = t.cuda.Event()
+        ready.record(main)
+        self.side.wait_event(ready)
+        self.group.allreduce_dev(self.partials[k].data_ptr(), None, self.results[k].data_ptr(), self.side.cuda_stream)
         ev = t.cuda.Event()
         ev.record(self.side)
         self.done[k] = ev

@@ -160,13 +160,12 @@ MFB_API int mfb_peer_disconnect(mfb_ctx *ctx, mfb_peer_group *g);
 MFB_API void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g);
 MFB_API int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev, size_t d,
                          const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
-/* The exchange in two halves, for back-to-back lincombs: push = the lincomb kernel + a finish kernel that pushes the
- * partial sum to every rank and returns without waiting for anybody; sum = a small kernel (co-resident with the next
- * lincomb kernel, so put it on a side stream after an event) that waits for all ranks' tiles of that call, adds them
- * and acknowledges.  Calls are matched in order; at most two pushes may be ahead of their sums. */
-MFB_API int mfb_lincomb_peer_push_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_dev, const uint32_t *coeffs_dev,
-                              size_t d, void *stream);
-MFB_API int mfb_peer_sum_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in_dev, uint64_t *rop_out_dev, void *stream);
+/* The exchange alone: rop_out on every rank = (rop_in + sum over ranks of partial_flat) mod 2^704 for one flat
+ * ciphertext per rank — one 23-CTA kernel (push, flags, wait, add).  For back-to-back lincombs run mfb_lincomb_dev on
+ * the main stream and this on a side stream: it is co-resident with the next lincomb kernel, so the exchange costs
+ * the main stream nothing (sharding.PipelinedPeerShardedLincomb). */
+MFB_API int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, const uint64_t *rop_in_dev,
+                           uint64_t *rop_out_dev, void *stream);
 /* the same for the fused AES + MAC path (mfb_eval_poly_dev over this rank's ciphertexts) */
 MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                            const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
