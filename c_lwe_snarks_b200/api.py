@@ -81,6 +81,16 @@ _SIGS = {
     "mfb_lincomb_peer_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_peer_allreduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mfb_eval_poly_peer_dev": (C.c_int, [_vp, _vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "mfb_ctx_device": (C.c_int, [_vp]),
+    "mfb_region_cts": (_vp, [_vp]),
+    "mfb_region_count": (C.c_size_t, [_vp]),
+    "mfb_set_create": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "mfb_set_destroy": (None, [_vp]),
+    "mfb_set_size": (C.c_int, [_vp]),
+    "mfb_set_last_error": (C.c_char_p, []),
+    "mfb_set_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
+    "mfb_set_region_destroy": (None, [_vp, _vp]),
+    "mfb_set_region_lincomb2": (C.c_int, [_vp, _vp, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
     "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mfb_eval_poly": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u32p, C.c_size_t, _u64p]),
@@ -233,6 +243,67 @@ class PeerGroup:
             self.handle_ = None
 
 
+class DeviceSet:
+    """Several GPUs driven by this thread (mfb_set_*): the primary context plus one member per entry of `devices`."""
+
+    def __init__(self, ctx: "Context", devices):
+        self.ctx = ctx
+        devs = (C.c_int * len(devices))(*devices)
+        h = _vp()
+        rc = ctx.lib.mfb_set_create(ctx.h, devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise MfbError(f"mfb_set_create failed ({rc}): {ctx.lib.mfb_set_last_error().decode()}")
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MfbError(f"mfb_set call failed ({rc}): {self.ctx.lib.mfb_set_last_error().decode()}")
+
+    @property
+    def size(self) -> int:
+        return int(self.ctx.lib.mfb_set_size(self.h))
+
+    def region(self, seed, offset: int, c8) -> "SetRegion":
+        s, rec = _seed(seed), _arr(c8, np.uint8)
+        count = rec.size // CT_BYTES
+        h = _vp()
+        self._ck(self.ctx.lib.mfb_set_region_create(self.h, _p8(s), offset, _p8(rec), count, C.byref(h)))
+        return SetRegion(self, h, count)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.mfb_set_destroy(self.h)
+            self.h = None
+
+
+class SetRegion:
+    """A CRS region sharded by ciphertext index over the members of a DeviceSet."""
+
+    def __init__(self, dset: DeviceSet, handle, count: int):
+        self.dset, self.handle, self.count = dset, handle, count
+
+    def lincomb(self, coeffs, rop=None) -> np.ndarray:
+        co = _arr(coeffs, np.uint32)
+        r = np.zeros((NC, L64), np.uint64) if rop is None else _arr(rop, np.uint64).copy()
+        self.dset._ck(self.dset.ctx.lib.mfb_set_region_lincomb2(self.dset.h, self.handle, _p32(co), None, co.size, _p64(r), None))
+        return r
+
+    def lincomb2(self, coeffs0, coeffs1, rop0=None, rop1=None):
+        c0, c1 = _arr(coeffs0, np.uint32), _arr(coeffs1, np.uint32)
+        if c0.size != c1.size:
+            raise ValueError("coefficient vectors must have equal length")
+        r0 = np.zeros((NC, L64), np.uint64) if rop0 is None else _arr(rop0, np.uint64).copy()
+        r1 = np.zeros((NC, L64), np.uint64) if rop1 is None else _arr(rop1, np.uint64).copy()
+        self.dset._ck(self.dset.ctx.lib.mfb_set_region_lincomb2(self.dset.h, self.handle, _p32(c0), _p32(c1), c0.size, _p64(r0),
+                                                               _p64(r1)))
+        return r0, r1
+
+    def close(self):
+        if self.handle:
+            self.dset.ctx.lib.mfb_set_region_destroy(self.dset.h, self.handle)
+            self.handle = None
+
+
 class ResidentSsp:
     """An SSP blob kept on the device (with the cached Newton inverse of rev(t))."""
 
@@ -381,6 +452,10 @@ class Context:
         self._ck(self.lib.mfb_decrypt(self.h, _p64(sk), _p64(cts), None if neg is None else _p8(neg), count, _p64(m),
                                       None if dot is None else _p64(dot)))
         return (m, dot) if want_dot else m
+
+    def device_set(self, devices) -> DeviceSet:
+        """this context + one member per entry of `devices` (entries may repeat / equal this context's device)"""
+        return DeviceSet(self, list(devices))
 
     def peer_group(self, world: int, rank: int) -> PeerGroup:
         return PeerGroup(self, world, rank)

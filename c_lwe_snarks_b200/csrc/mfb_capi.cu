@@ -290,6 +290,7 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
   delete ctx;
 }
 
+int mfb_ctx_device(mfb_ctx *ctx) { return ctx ? ctx->device : -1; }
 int mfb_device_sm_count(mfb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t mfb_launch_count(mfb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int mfb_sync(mfb_ctx *ctx) {
@@ -847,6 +848,9 @@ int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   *out = r;
   return MFB_OK;
 }
+
+const void *mfb_region_cts(const mfb_region *r) { return r ? r->cts : nullptr; }
+size_t mfb_region_count(const mfb_region *r) { return r ? r->count : 0; }
 
 void mfb_region_destroy(mfb_ctx *ctx, mfb_region *r) {
   if (!r) return;

@@ -1,0 +1,253 @@
+// Device sets: several B200s driven by ONE host thread (the reference is a single-threaded C program, so this is the
+// shape in which its prover() can use a whole NVSwitch box without becoming a multi-process job).
+//
+// A set is a primary context plus one context per further device, joined in a peer-memory exchange group
+// (same-process peer access, mfb_peer_connect_local).  A set region is a CRS region sharded by ciphertext index
+// (SURVEY.md §8e): member i holds a contiguous range resident in its HBM.  A lincomb over the region runs
+// k_lincomb<2> on every member over its range (launches are asynchronous, the members work in parallel) and then
+// one k_peer_allreduce per scalar vector; the result is read from the primary.  Built on the public C-ABI only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mfb200.h"
+
+namespace {
+
+struct Member {
+  mfb_ctx *ctx = nullptr;
+  bool owned = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  mfb_peer_group *group = nullptr;
+  // device scratch of the lincomb: coefficients, the member's flat partial sums, the reduced results
+  uint32_t *co = nullptr;
+  size_t co_cap = 0;
+  uint64_t *part = nullptr;  // 2 x flat
+  uint64_t *res = nullptr;   // 2 x flat
+};
+
+thread_local char g_set_err[256] = "";
+int set_fail(int code, const char *msg) {
+  snprintf(g_set_err, sizeof(g_set_err), "%s", msg);
+  return code;
+}
+
+}  // namespace
+
+struct mfb_set {
+  std::vector<Member> m;
+};
+
+struct mfb_set_region {
+  std::vector<mfb_region *> shard;   // one per member (null when its range is empty)
+  std::vector<size_t> first, count;  // ciphertext range of every member
+  size_t total = 0;
+};
+
+#define SET_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != MFB_OK) return _r; \
+  } while (0)
+#define SET_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      snprintf(g_set_err, sizeof(g_set_err), "%s -> %s", #expr, cudaGetErrorString(_e));      \
+      return MFB_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+extern "C" {
+
+MFB_API const char *mfb_set_last_error(void) { return g_set_err[0] ? g_set_err : mfb_last_error(); }
+
+MFB_API void mfb_set_destroy(mfb_set *s) {
+  if (!s) return;
+  for (auto &mb : s->m) {
+    if (!mb.ctx) continue;
+    cudaSetDevice(mb.device);
+    cudaDeviceSynchronize();
+  }
+  for (auto &mb : s->m)
+    if (mb.ctx && mb.group) mfb_peer_disconnect(mb.ctx, mb.group);
+  for (auto &mb : s->m) {
+    if (!mb.ctx) continue;
+    cudaSetDevice(mb.device);
+    if (mb.group) mfb_peer_destroy(mb.ctx, mb.group);
+    if (mb.co) cudaFree(mb.co);
+    if (mb.part) cudaFree(mb.part);
+    if (mb.res) cudaFree(mb.res);
+    if (mb.stream) cudaStreamDestroy(mb.stream);
+    if (mb.owned) mfb_ctx_destroy(mb.ctx);
+  }
+  if (!s->m.empty()) cudaSetDevice(s->m[0].device);
+  delete s;
+}
+
+// primary: an existing context (stays owned by the caller) = member 0; devices[0..ndev): one further member each
+// (a device may repeat, and may be the primary's: the members then share that GPU — how the tests run on one GPU).
+MFB_API int mfb_set_create(mfb_ctx *primary, const int *devices, int ndev, mfb_set **out) {
+  g_set_err[0] = 0;
+  if (!primary || !out || (ndev && !devices) || ndev < 0 || ndev + 1 > MFB_PEER_MAX)
+    return set_fail(MFB_EARG, "mfb_set_create: bad argument (at most 16 members)");
+  *out = nullptr;
+  mfb_set *s = new (std::nothrow) mfb_set();
+  if (!s) return set_fail(MFB_ENOMEM, "out of host memory");
+  const int world = ndev + 1;
+  s->m.resize(world);
+  int rc = MFB_OK;
+  for (int i = 0; i < world && rc == MFB_OK; i++) {
+    Member &mb = s->m[i];
+    mb.device = i == 0 ? mfb_ctx_device(primary) : devices[i - 1];
+    if (i == 0) {
+      mb.ctx = primary;
+    } else {
+      rc = mfb_ctx_create(&mb.ctx, mb.device);
+      mb.owned = rc == MFB_OK;
+    }
+    if (rc != MFB_OK) break;
+    cudaError_t e = cudaSetDevice(mb.device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&mb.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.part, 2 * MFB_PLANAR_U64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.res, 2 * MFB_PLANAR_U64 * 8);
+    if (e != cudaSuccess) {
+      snprintf(g_set_err, sizeof(g_set_err), "mfb_set_create: device %d: %s", mb.device, cudaGetErrorString(e));
+      rc = MFB_ECUDA;
+      break;
+    }
+    uint8_t handle[MFB_PEER_HANDLE_BYTES];
+    rc = mfb_peer_create(mb.ctx, world, i, &mb.group, handle);
+  }
+  if (rc == MFB_OK && world > 1) {
+    void *bases[MFB_PEER_MAX];
+    for (int i = 0; i < world; i++) bases[i] = mfb_peer_base(s->m[i].group);
+    for (int i = 0; i < world && rc == MFB_OK; i++) rc = mfb_peer_connect_local(s->m[i].ctx, s->m[i].group, bases);
+  }
+  if (rc != MFB_OK) {
+    char keep[256];
+    snprintf(keep, sizeof(keep), "%s", mfb_set_last_error());
+    mfb_set_destroy(s);
+    snprintf(g_set_err, sizeof(g_set_err), "%s", keep);
+    return rc;
+  }
+  cudaSetDevice(s->m[0].device);
+  *out = s;
+  return MFB_OK;
+}
+
+MFB_API int mfb_set_size(const mfb_set *s) { return s ? (int)s->m.size() : 0; }
+
+MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r) {
+  if (!r) return;
+  if (s)
+    for (size_t i = 0; i < r->shard.size() && i < s->m.size(); i++)
+      if (r->shard[i]) mfb_region_destroy(s->m[i].ctx, r->shard[i]);
+  if (s && !s->m.empty()) cudaSetDevice(s->m[0].device);
+  delete r;
+}
+
+// The region of `count` ciphertexts at stream offset `offset` (records c8), sharded contiguously over the members.
+MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                                  mfb_set_region **out) {
+  g_set_err[0] = 0;
+  if (!s || !seed || !out || (count && !c8)) return set_fail(MFB_EARG, "mfb_set_region_create: null pointer");
+  *out = nullptr;
+  mfb_set_region *r = new (std::nothrow) mfb_set_region();
+  if (!r) return set_fail(MFB_ENOMEM, "out of host memory");
+  const size_t world = s->m.size();
+  r->shard.assign(world, nullptr);
+  r->first.assign(world, 0);
+  r->count.assign(world, 0);
+  r->total = count;
+  const size_t base = count / world, extra = count % world;
+  int rc = MFB_OK;
+  for (size_t i = 0; i < world && rc == MFB_OK; i++) {
+    r->first[i] = i * base + (i < extra ? i : extra);
+    r->count[i] = base + (i < extra ? 1 : 0);
+    // (mfb_region_create expands synchronously: the members' AES expansions run one after the other; making a
+    // region resident is a one-off cost next to the proofs that reuse it)
+    rc = mfb_region_create(s->m[i].ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
+                           r->count[i], &r->shard[i]);
+  }
+  if (rc != MFB_OK) {
+    char keep[256];
+    snprintf(keep, sizeof(keep), "%s", mfb_set_last_error());
+    mfb_set_region_destroy(s, r);
+    snprintf(g_set_err, sizeof(g_set_err), "%s", keep);
+    return rc;
+  }
+  cudaSetDevice(s->m[0].device);
+  *out = r;
+  return MFB_OK;
+}
+
+// rop0 += sum coeffs0[i] * CT_i, rop1 += sum coeffs1[i] * CT_i over the WHOLE region (d = its ciphertext count);
+// coeffs1 / rop1 may both be NULL for a single scalar vector.  Host buffers in, host buffers out, synchronous.
+MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1,
+                                    size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
+  g_set_err[0] = 0;
+  if (!s || !r || !rop0_flat_inout || (d && !coeffs0) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
+    return set_fail(MFB_EARG, "mfb_set_region_lincomb2: null pointer");
+  if (d != r->total) return set_fail(MFB_EARG, "mfb_set_region_lincomb2: d must be the region's ciphertext count");
+  const size_t world = s->m.size();
+  const int nvec = coeffs1 ? 2 : 1;
+  const size_t FLAT = MFB_FLAT_CT_U64;
+  // 1. every member: coefficients to the device, lincomb over its shard into its flat partial(s)
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    const size_t cnt = r->count[i], first = r->first[i];
+    if (mb.co_cap < 2 * cnt + 4) {
+      if (mb.co) SET_CUDA(cudaFree(mb.co));
+      mb.co = nullptr;
+      mb.co_cap = 0;
+      SET_CUDA(cudaMalloc((void **)&mb.co, (2 * cnt + 4) * 4));
+      mb.co_cap = 2 * cnt + 4;
+    }
+    uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
+    if (cnt) {
+      SET_CUDA(cudaMemcpyAsync(c0, coeffs0 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, coeffs1 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+    }
+    if (i == 0) {  // the incoming accumulators join the sum on the primary
+      SET_CUDA(cudaMemcpyAsync(mb.res, rop0_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
+      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(mb.res + MFB_PLANAR_U64, rop1_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
+    }
+    const uint64_t *cts = (const uint64_t *)mfb_region_cts(r->shard[i]);
+    if (nvec == 2)
+      SET_TRY(mfb_lincomb2_dev(mb.ctx, cts, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + MFB_PLANAR_U64, mb.stream));
+    else
+      SET_TRY(mfb_lincomb_dev(mb.ctx, cts, c0, cnt, nullptr, mb.part, mb.stream));
+  }
+  // 2. every member: one all-reduce kernel per vector (push to all members, wait, add); only the primary's result
+  //    (which also adds the incoming accumulator) is read back
+  for (int v = 0; v < nvec; v++)
+    for (size_t i = 0; i < world; i++) {
+      Member &mb = s->m[i];
+      SET_CUDA(cudaSetDevice(mb.device));
+      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
+      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
+    }
+  Member &p = s->m[0];
+  SET_CUDA(cudaSetDevice(p.device));
+  SET_CUDA(cudaMemcpyAsync(rop0_flat_inout, p.res, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  if (nvec == 2) SET_CUDA(cudaMemcpyAsync(rop1_flat_inout, p.res + MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  int rc = MFB_OK;
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_CUDA(cudaStreamSynchronize(mb.stream));
+    const int st = mfb_peer_status(mb.ctx, mb.group);
+    if (st != MFB_OK) rc = st;
+  }
+  SET_CUDA(cudaSetDevice(p.device));
+  return rc;
+}
+
+}  // extern "C"

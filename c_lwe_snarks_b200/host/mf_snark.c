@@ -32,11 +32,49 @@ void proof_clear(proof_t pi) {
 /* ------------------------------------------------------------------ resident CRS regions (addition) */
 struct resident {
   struct crs *owner;
-  mfb_region *s, *as;
+  mfb_region *s, *as;          /* one GPU */
+  mfb_set_region *ms, *mas;    /* sharded over the device set */
   size_t d;
   struct resident *next;
 };
 static struct resident *g_resident = NULL;
+
+/* device set (mf_set_devices): created on first use, lives as long as the process */
+static int g_ndev = 0, g_spread = 1;
+static mfb_set *g_set = NULL;
+
+void mf_set_devices(int n, int spread) {
+  if (g_set) {
+    if (g_resident) {
+      fprintf(stderr, "mangiafuoco_b200: mf_set_devices: release the resident CRS regions first\n");
+      abort();
+    }
+    mfb_set_destroy(g_set);
+    g_set = NULL;
+  }
+  g_ndev = n < 1 ? 1 : n;
+  g_spread = spread;
+}
+
+static mfb_set *device_set(void) {
+  if (g_ndev == 0) {
+    const char *e = getenv("MF_B200_DEVICES");
+    g_ndev = e ? atoi(e) : 1;
+    if (g_ndev < 1) g_ndev = 1;
+  }
+  if (g_ndev == 1) return NULL;
+  if (!g_set) {
+    int devs[MFB_PEER_MAX];
+    if (g_ndev > MFB_PEER_MAX) g_ndev = MFB_PEER_MAX;
+    const int base = mfb_ctx_device(mf_gpu());
+    for (int i = 1; i < g_ndev; i++) devs[i - 1] = g_spread ? base + i : base;
+    if (mfb_set_create(mf_gpu(), devs, g_ndev - 1, &g_set) != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_create(%d devices) failed: %s\n", g_ndev, mfb_set_last_error());
+      abort();
+    }
+  }
+  return g_set;
+}
 
 static struct resident *resident_find(struct crs *crs) {
   for (struct resident *r = g_resident; r; r = r->next)
@@ -51,6 +89,8 @@ void mf_crs_release(crs_t crs) {
     if (r->owner == crs) {
       mfb_region_destroy(mf_gpu(), r->s);
       mfb_region_destroy(mf_gpu(), r->as);
+      mfb_set_region_destroy(g_set, r->ms);
+      mfb_set_region_destroy(g_set, r->mas);
       *pp = r->next;
       free(r);
     } else {
@@ -67,6 +107,22 @@ void mf_crs_make_resident(crs_t crs) {
   r->d = GAMMA_D;
   /* 2 x D x 129 536 B of HBM; when that does not fit (D = 2^20 needs 272 GB on one GPU) the regions simply stay
    * non-resident and prover() keeps regenerating a from AES in-kernel — slower, same result */
+  mfb_set *set = device_set();
+  if (set) { /* sharded by ciphertext index over the set's GPUs */
+    int rc = mfb_set_region_create(set, crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->ms);
+    if (rc == MFB_OK) rc = mfb_set_region_create(set, crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->mas);
+    if (rc != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident over %d devices: %s; the CRS stays non-resident\n",
+              mfb_set_size(set), mfb_set_last_error());
+      mfb_set_region_destroy(set, r->ms);
+      mfb_set_region_destroy(set, r->mas);
+      free(r);
+      return;
+    }
+    r->next = g_resident;
+    g_resident = r;
+    return;
+  }
   int rc = mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s);
   if (rc == MFB_OK) rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
   if (rc != MFB_OK) {
@@ -197,7 +253,8 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
 }
 
 /* ------------------------------------------------------------------ prover (snark.c:117-190) */
-static void lincomb_pair_resident(ct_t rop0, ct_t rop1, mfb_region *reg, const uint64_t *poly0, const uint64_t *poly1) {
+static void lincomb_pair_resident(ct_t rop0, ct_t rop1, mfb_region *reg, mfb_set_region *mreg, const uint64_t *poly0,
+                                  const uint64_t *poly1) {
   const size_t D = GAMMA_D;
   uint64_t *acc = malloc(2 * FLAT_CT * 8);
   uint32_t *co = malloc(2 * D * 4);
@@ -208,7 +265,14 @@ static void lincomb_pair_resident(ct_t rop0, ct_t rop1, mfb_region *reg, const u
     co[i] = (uint32_t)poly0[i];
     co[D + i] = (uint32_t)poly1[i];
   }
-  MF_GPU(mfb_region_lincomb2(mf_gpu(), reg, 0, co, co + D, D, acc, acc + FLAT_CT));
+  if (mreg) {
+    if (mfb_set_region_lincomb2(g_set, mreg, co, co + D, D, acc, acc + FLAT_CT) != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_region_lincomb2 failed: %s\n", mfb_set_last_error());
+      abort();
+    }
+  } else {
+    MF_GPU(mfb_region_lincomb2(mf_gpu(), reg, 0, co, co + D, D, acc, acc + FLAT_CT));
+  }
   mf_ct_from_flat(rop0, acc);
   mf_ct_from_flat(rop1, acc + FLAT_CT);
   free(acc);
@@ -283,8 +347,8 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   {
     struct resident *r = resident_find(crs);
     if (r && r->d == D) { /* regions resident in HBM: one pass per region at the HBM roofline, two scalar vectors each */
-      lincomb_pair_resident(pi->v_w, pi->h, r->s, pw, ph);
-      lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, pv, ph);
+      lincomb_pair_resident(pi->v_w, pi->h, r->s, r->ms, pw, ph);
+      lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, r->mas, pv, ph);
     } else { /* a regenerated from AES: one pass per region carrying both scalar vectors */
       lincomb_pair(pi->v_w, pi->h, crs, 0, pw, ph);
       lincomb_pair(pi->hat_v, pi->hat_h, crs, 1, pv, ph);

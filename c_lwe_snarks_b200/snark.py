@@ -84,6 +84,10 @@ class Snark:
         self._vrs_live = True
         return time.perf_counter() - t0
 
+    def set_devices(self, n: int, spread: bool = True):
+        """Shard the resident CRS regions over n GPUs driven by this thread (mf_set_devices); call before make_resident."""
+        self.lib.mf_set_devices(int(n), 1 if spread else 0)
+
     def make_resident(self):
         """Keep the CRS regions s / as (expanded) and the SSP blob (with the cached inverse of rev(t)) in HBM."""
         self.lib.mf_crs_make_resident(C.byref(self.crs))

@@ -233,6 +233,13 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi);
  * regeneration of the a-vectors is then paid once instead of per proof.  mf_crs_release frees them. */
 void mf_crs_make_resident(crs_t crs);
 void mf_crs_release(crs_t crs);
+/* Number of GPUs the resident regions are sharded over (by ciphertext index), all driven by the calling thread:
+ * n devices starting at the library's device (mf_set_device / $MF_B200_DEVICE), default $MF_B200_DEVICES or 1.
+ * With n > 1 mf_crs_make_resident spreads the two regions over the GPUs' HBM (D = 2^20 needs 2 x 136 GB) and
+ * prover() runs every lincomb on all of them at once, combining the partial sums over NVLink peer memory; results
+ * are bit-identical.  Call before mf_crs_make_resident.  `spread` = 0 puts all members on the library's device
+ * (testing on a one-GPU box). */
+void mf_set_devices(int n, int spread);
 /* The same for the SSP instance: the dense blob is uploaded once (as u32 residues) and the Newton inverse that the
  * prover's division h = (v^2 - 1)/t needs is cached with it; prover() then only ships the witness.  The blob must not
  * change while it is resident (mf_ssp_release before modifying or freeing it). */

@@ -70,6 +70,7 @@ MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
 MFB_API void mfb_ctx_destroy(mfb_ctx *ctx);
 MFB_API const char *mfb_last_error(void);
 MFB_API int mfb_device_sm_count(mfb_ctx *ctx);
+MFB_API int mfb_ctx_device(mfb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 MFB_API uint64_t mfb_launch_count(mfb_ctx *ctx);
 MFB_API int mfb_sync(mfb_ctx *ctx);
@@ -116,6 +117,10 @@ MFB_API int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, 
 
 MFB_API int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs0,
                         const uint32_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
+/* device pointer of the region's resident ciphertext array (for the _dev entry points) */
+MFB_API const void *mfb_region_cts(const mfb_region *r);
+MFB_API size_t mfb_region_count(const mfb_region *r);
+
 
 /* Other LWE parameter points (BASELINE configs[4]); the reference implements only (1470, 736), so this entry point
  * has no reference counterpart: out = sum_i coeffs[i] * cts[i] mod 2^(64*limbs64), coordinate-wise, for ciphertexts
@@ -170,6 +175,25 @@ MFB_API int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64
 MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                            const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
                            uint64_t *rop_out_dev, void *stream);
+
+/* ---- device sets: several GPUs driven by ONE host thread ----------------------------------------------------
+ * The shape in which the reference's single-threaded prover() (snark.c:117-190) uses a whole NVSwitch box: a set is
+ * the primary context plus one context per further device, joined in a same-process peer exchange group; a set
+ * region is a CRS region sharded by ciphertext index over the members' HBM (D = 2^20: 2 x 136 GB over 8 GPUs).
+ * mfb_set_region_lincomb2 = mfb_region_lincomb2 over the sharded region: every member runs the two-vector lincomb
+ * kernel over its shard, one peer all-reduce kernel per vector combines them; host buffers in and out.
+ * devices[] may repeat and may include the primary's device (members then share a GPU). */
+typedef struct mfb_set mfb_set;
+typedef struct mfb_set_region mfb_set_region;
+MFB_API int mfb_set_create(mfb_ctx *primary, const int *devices, int ndev, mfb_set **out);
+MFB_API void mfb_set_destroy(mfb_set *s);
+MFB_API int mfb_set_size(const mfb_set *s);
+MFB_API const char *mfb_set_last_error(void);
+MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                          mfb_set_region **out);
+MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r);
+MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
+                            uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
 
 /* ---- K2+K1 fused: eval_poly with a regenerated in-kernel ----------------------------------- */
 /* rop += sum_{m<d} coeffs[m] * CT_{k(m)},  k(m) = idx ? idx[m] : m, where CT_k = ct_import(stream at

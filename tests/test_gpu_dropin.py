@@ -90,6 +90,28 @@ def test_prover_with_resident_crs_is_identical(dropin):
         assert sha(proof[k]) == g["proof_sha"][k]
 
 
+@pytest.mark.parametrize("n", [2, 3])
+def test_prover_with_crs_sharded_over_a_device_set_is_identical(dropin, n):
+    """mf_set_devices(n): the resident regions are sharded by ciphertext index over n members (here all on GPU 0, or one
+    per GPU when the box has them) and every lincomb is combined over peer memory: the proof does not change."""
+    import torch
+    g = GOLD["snark_d64_m16"]
+    D, M = g["D"], g["M"]
+    dropin.set_instance(D, M)
+    spread = 1 if torch.cuda.device_count() >= n else 0
+    dropin.lib.mf_set_devices(n, spread)
+    try:
+        dropin.set_entropy(xof("snark-entropy-d64-m16", g["entropy_bytes"]))
+        ssp, wit = dropin.random_ssp()
+        crs = dropin.setup(ssp)
+        proof, _ = dropin.prover_resident(ssp, crs, wit)
+        dropin.clear_entropy()
+    finally:
+        dropin.lib.mf_set_devices(1, 1)
+    for k in range(5):
+        assert sha(proof[k]) == g["proof_sha"][k]
+
+
 def test_full_snark_beside_compiled_reference(dropin, reference):
     D, M = reference.D, reference.M  # 256, 64
     dropin.set_instance(D, M)

@@ -263,3 +263,65 @@ def test_peer_exchange_cuda_ipc_beside_nccl():
     for rank, ok, res in got:
         assert ok, f"rank {rank}: peer exchange != NCCL exchange"
         assert np.array_equal(res, want), f"rank {rank}"
+
+
+# ------------------------------------------------------------------------------------------- device sets
+@pytest.mark.parametrize("nmembers,d", [(1, 50), (2, 101), (3, 64), (4, 1000), (4, 3)])
+def test_device_set_region_lincomb_on_one_gpu(nmembers, d, oracle):
+    """mfb_set_*: a region sharded over the members of a device set (here all on GPU 0) gives the single-context result,
+    for one and two scalar vectors, accumulating into rop, call after call."""
+    import c_lwe_snarks_b200 as m
+    off = 5 * CTR_CT + 8
+    c8 = xof_records(f"set-c8-{d}", d)
+    h0, h1 = xof_scalars(f"set-h0-{d}", d), xof_scalars(f"set-h1-{d}", d)
+    rop = xof_records("set-rop", NC)[:, :88].copy().view("<u8").reshape(NC, L64)
+    ctx = m.Context(0)
+    dset = ctx.device_set([0] * (nmembers - 1))
+    try:
+        assert dset.size == nmembers
+        reg = dset.region(SEED, off, c8)
+        try:
+            want0 = ctx.eval_poly(SEED, off, c8, h0, rop=rop)
+            want1 = ctx.eval_poly(SEED, off, c8, h1)
+            for _ in range(3):  # epochs advance: both slot parities are reused
+                r0, r1 = reg.lincomb2(h0, h1, rop0=rop)
+                assert np.array_equal(r0, want0) and np.array_equal(r1, want1)
+                assert np.array_equal(reg.lincomb(h1), want1)
+        finally:
+            reg.close()
+    finally:
+        dset.close()
+        ctx.close()
+    small = min(d, 40)
+    w = oracle.eval_poly(SEED, off, c8[:small], h1[:small])
+    ctx = m.Context(0)
+    try:
+        assert np.array_equal(ctx.eval_poly(SEED, off, c8[:small], h1[:small]), w[:, :11])
+    finally:
+        ctx.close()
+
+
+def test_device_set_over_all_gpus():
+    import torch
+
+    import c_lwe_snarks_b200 as m
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    d, off = 4000, 2 * CTR_CT
+    c8 = xof_records("setN-c8", d)
+    h0, h1 = xof_scalars("setN-h0", d), xof_scalars("setN-h1", d)
+    ctx = m.Context(0)
+    dset = ctx.device_set(list(range(1, min(n, 8))))
+    try:
+        reg = dset.region(SEED, off, c8)
+        try:
+            for _ in range(3):
+                r0, r1 = reg.lincomb2(h0, h1)
+                assert np.array_equal(r0, ctx.eval_poly(SEED, off, c8, h0))
+                assert np.array_equal(r1, ctx.eval_poly(SEED, off, c8, h1))
+        finally:
+            reg.close()
+    finally:
+        dset.close()
+        ctx.close()
