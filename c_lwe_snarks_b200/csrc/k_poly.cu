@@ -581,6 +581,11 @@ static int polys_tail(mfb_ctx *ctx, PolyEngine &E, cudaStream_t st, uint32_t Du,
   } else {
     PTRY(poly_div(E, d_a, la, t32, lt, d_h, Du, st));
   }
+  if (!w_out) {  // device-resident pipeline (mfb_prove_resident): w | v | h stay on the device as u32 residues
+    PTRY(cudaStreamSynchronize(st));
+    (void)ctx;
+    return MFB_OK;
+  }
   // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
   k_widen<<<gridfor(3 * Du), 256, 0, st>>>(d_w, 3 * Du, d_wide);
   E.launches++;
@@ -712,11 +717,11 @@ extern "C" void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h) {
   delete h;
 }
 
-extern "C" int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
-                                             uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
+static int polys_resident_impl(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta,
+                               uint64_t *w_out, uint64_t *v_out, uint64_t *h_out, const uint32_t **wvh_dev) {
   int rc = ctx_enter(ctx);
   if (rc) return rc;
-  if (!h || !witness_limbs || !w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
+  if (!h || !witness_limbs) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
   if (h->lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys_resident: t(x) is the zero polynomial");
   PolyEngine &E = *poly_engine_of(ctx);
   cudaStream_t st = ctx_stream_of(ctx);
@@ -746,8 +751,25 @@ extern "C" int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uin
   PTRY(cudaGetLastError());
   rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, h->blob, h->lt, h, w_out, v_out, h_out);
   ctx_count_launches(ctx, E.launches - L0);
+  if (wvh_dev) *wvh_dev = (const uint32_t *)d_w;
   return rc;
 }
+
+extern "C" int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                             uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
+  if (!w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
+  return polys_resident_impl(ctx, h, witness_limbs, nlimbs, delta, w_out, v_out, h_out, nullptr);
+}
+
+// The same, results left ON THE DEVICE: *wvh_dev = three consecutive arrays of D u32 residues (w, v, h) in the context's
+// scratch, valid until the next polynomial / encrypt / decrypt call on this context.  The stream is idle on return.
+extern "C" int mfb_ssp_prover_polys_resident_dev(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                                 uint64_t delta, const uint32_t **wvh_dev) {
+  if (!wvh_dev) return ctx_bad_arg("mfb_ssp_prover_polys_resident_dev: null pointer");
+  return polys_resident_impl(ctx, h, witness_limbs, nlimbs, delta, nullptr, nullptr, nullptr, wvh_dev);
+}
+
+extern "C" size_t mfb_ssp_degree_bound(const mfb_ssp *h) { return h ? h->D : 0; }
 
 extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values) {
   int rc = ctx_enter(ctx);

@@ -900,6 +900,32 @@ int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const u
   return MFB_OK;
 }
 
+int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
+                       const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                       uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+  MFB_CHECK_CTX(ctx);
+  if (!ssp || !reg_s || !reg_as || !witness_limbs || !v_w_flat_inout || !h_flat_inout || !hat_v_flat_inout || !hat_h_flat_inout)
+    return set_err(MFB_EARG, "mfb_prove_resident: null pointer");
+  const size_t D = mfb_ssp_degree_bound(ssp);
+  if (reg_s->count != D || reg_as->count != D) return set_err(MFB_EARG, "mfb_prove_resident: the regions must hold D ciphertexts");
+  const uint32_t *wvh = nullptr;
+  MFB_TRY(mfb_ssp_prover_polys_resident_dev(ctx, ssp, witness_limbs, nlimbs, delta, &wvh));
+  const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
+  void *d_rop;
+  MFB_TRY(scratch(ctx, 2, 4 * MFB_FLAT_CT_U64 * 8, &d_rop));
+  uint64_t *r = (uint64_t *)d_rop;
+  uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
+  for (int k = 0; k < 4; k++)
+    MFB_CUDA_TRY(cudaMemcpyAsync(r + k * MFB_FLAT_CT_U64, host[k], MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + MFB_FLAT_CT_U64, r + MFB_FLAT_CT_U64, ctx->stream));
+  MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * MFB_FLAT_CT_U64, r + 2 * MFB_FLAT_CT_U64,
+                           r + 3 * MFB_FLAT_CT_U64, r + 3 * MFB_FLAT_CT_U64, ctx->stream));
+  for (int k = 0; k < 4; k++)
+    MFB_CUDA_TRY(cudaMemcpyAsync(host[k], r + k * MFB_FLAT_CT_U64, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
 int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                 const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
   MFB_CHECK_CTX(ctx);

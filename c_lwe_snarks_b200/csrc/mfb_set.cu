@@ -27,8 +27,8 @@ struct Member {
   // device scratch of the lincomb: coefficients, the member's flat partial sums, the reduced results
   uint32_t *co = nullptr;
   size_t co_cap = 0;
-  uint64_t *part = nullptr;  // 2 x flat
-  uint64_t *res = nullptr;   // 2 x flat
+  uint64_t *part = nullptr;  // 4 x flat
+  uint64_t *res = nullptr;   // 4 x flat
 };
 
 thread_local char g_set_err[256] = "";
@@ -114,8 +114,8 @@ MFB_API int mfb_set_create(mfb_ctx *primary, const int *devices, int ndev, mfb_s
     if (rc != MFB_OK) break;
     cudaError_t e = cudaSetDevice(mb.device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&mb.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.part, 2 * MFB_PLANAR_U64 * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.res, 2 * MFB_PLANAR_U64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.part, 4 * MFB_PLANAR_U64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.res, 4 * MFB_PLANAR_U64 * 8);
     if (e != cudaSuccess) {
       snprintf(g_set_err, sizeof(g_set_err), "mfb_set_create: device %d: %s", mb.device, cudaGetErrorString(e));
       rc = MFB_ECUDA;
@@ -238,6 +238,71 @@ MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const u
   SET_CUDA(cudaSetDevice(p.device));
   SET_CUDA(cudaMemcpyAsync(rop0_flat_inout, p.res, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
   if (nvec == 2) SET_CUDA(cudaMemcpyAsync(rop1_flat_inout, p.res + MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  int rc = MFB_OK;
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_CUDA(cudaStreamSynchronize(mb.stream));
+    const int st = mfb_peer_status(mb.ctx, mb.group);
+    if (st != MFB_OK) rc = st;
+  }
+  SET_CUDA(cudaSetDevice(p.device));
+  return rc;
+}
+
+// mfb_prove_resident over sharded regions (see mfb200.h)
+MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras,
+                                   const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                                   uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+  g_set_err[0] = 0;
+  if (!s || !ssp || !rs || !ras || !witness_limbs || !v_w_flat_inout || !h_flat_inout || !hat_v_flat_inout || !hat_h_flat_inout)
+    return set_fail(MFB_EARG, "mfb_set_prove_resident: null pointer");
+  const size_t D = mfb_ssp_degree_bound(ssp), world = s->m.size(), FLAT = MFB_FLAT_CT_U64;
+  if (rs->total != D || ras->total != D) return set_fail(MFB_EARG, "mfb_set_prove_resident: the regions must hold D ciphertexts");
+  for (size_t i = 0; i < world; i++)
+    if (rs->first[i] != ras->first[i] || rs->count[i] != ras->count[i])
+      return set_fail(MFB_EARG, "mfb_set_prove_resident: the two regions are sharded differently");
+  Member &p = s->m[0];
+  SET_CUDA(cudaSetDevice(p.device));
+  const uint32_t *wvh = nullptr;
+  SET_TRY(mfb_ssp_prover_polys_resident_dev(p.ctx, ssp, witness_limbs, nlimbs, delta, &wvh));  // stream idle on return
+  uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
+  for (int k = 0; k < 4; k++)
+    SET_CUDA(cudaMemcpyAsync(p.res + (size_t)k * MFB_PLANAR_U64, host[k], FLAT * 8, cudaMemcpyHostToDevice, p.stream));
+  // every member: its slices of w, v, h over NVLink, then both two-vector passes over its shards
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    const size_t cnt = rs->count[i], first = rs->first[i];
+    if (mb.co_cap < 3 * cnt + 4) {
+      if (mb.co) SET_CUDA(cudaFree(mb.co));
+      mb.co = nullptr;
+      mb.co_cap = 0;
+      SET_CUDA(cudaMalloc((void **)&mb.co, (3 * cnt + 4) * 4));
+      mb.co_cap = 3 * cnt + 4;
+    }
+    uint32_t *cw = mb.co, *cv = mb.co + cnt, *ch = mb.co + 2 * cnt;
+    if (cnt) {
+      SET_CUDA(cudaMemcpyPeerAsync(cw, mb.device, wvh + first, p.device, cnt * 4, mb.stream));
+      SET_CUDA(cudaMemcpyPeerAsync(cv, mb.device, wvh + D + first, p.device, cnt * 4, mb.stream));
+      SET_CUDA(cudaMemcpyPeerAsync(ch, mb.device, wvh + 2 * D + first, p.device, cnt * 4, mb.stream));
+    }
+    uint64_t *pt = mb.part;
+    SET_TRY(mfb_lincomb2_dev(mb.ctx, (const uint64_t *)mfb_region_cts(rs->shard[i]), cw, ch, cnt, nullptr, pt, nullptr,
+                             pt + MFB_PLANAR_U64, mb.stream));
+    SET_TRY(mfb_lincomb2_dev(mb.ctx, (const uint64_t *)mfb_region_cts(ras->shard[i]), cv, ch, cnt, nullptr, pt + 2 * MFB_PLANAR_U64,
+                             nullptr, pt + 3 * MFB_PLANAR_U64, mb.stream));
+  }
+  for (int v = 0; v < 4; v++)
+    for (size_t i = 0; i < world; i++) {
+      Member &mb = s->m[i];
+      SET_CUDA(cudaSetDevice(mb.device));
+      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
+      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
+    }
+  SET_CUDA(cudaSetDevice(p.device));
+  for (int k = 0; k < 4; k++)
+    SET_CUDA(cudaMemcpyAsync(host[k], p.res + (size_t)k * MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
   int rc = MFB_OK;
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];

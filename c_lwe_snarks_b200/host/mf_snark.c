@@ -299,17 +299,25 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     abort();
   }
 
-  /* polynomial step (snark.c:138-169) on the device: w = delta*t + sum_{w_i} v_i, v = w + v_0 (l_u = 0),
-   * h = (v^2 - 1) / t  — FLINT's scalar_mul / add / pow / div in the reference */
-  uint64_t *pw = malloc(3 * D * 8);
-  if (!pw) mf_die("malloc");
-  uint64_t *pv = pw + D, *ph = pw + 2 * D;
   double t0 = mf_now();
   mfb_ssp *rssp = resident_ssp_find(ssp);
-  if (rssp)
-    MF_GPU(mfb_ssp_prover_polys_resident(mf_gpu(), rssp, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
-  else
-    MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+  struct resident *res = resident_find(crs);
+  const int all_resident = rssp && res && res->d == D;
+
+  /* polynomial step (snark.c:138-169) on the device: w = delta*t + sum_{w_i} v_i, v = w + v_0 (l_u = 0),
+   * h = (v^2 - 1) / t  — FLINT's scalar_mul / add / pow / div in the reference.  With the SSP and both CRS regions
+   * resident the coefficients never leave the device(s): see the fused pipeline below. */
+  uint64_t *pw = NULL, *pv = NULL, *ph = NULL;
+  if (!all_resident) {
+    pw = malloc(3 * D * 8);
+    if (!pw) mf_die("malloc");
+    pv = pw + D;
+    ph = pw + 2 * D;
+    if (rssp)
+      MF_GPU(mfb_ssp_prover_polys_resident(mf_gpu(), rssp, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+    else
+      MF_GPU(mfb_ssp_prover_polys(mf_gpu(), (const uint64_t *)ssp, D, M, PTR(witness), (size_t)SIZ(witness), delta, pw, pv, ph));
+  }
   mf_trace("prover.polys", t0);
   t0 = mf_now();
 
@@ -344,8 +352,33 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
 
   mf_trace("prover.b_w", t0);
   t0 = mf_now();
-  {
-    struct resident *r = resident_find(crs);
+  if (all_resident) {
+    /* SSP and regions resident: ONE device pipeline — polynomial step, then both two-vector passes with the
+     * coefficients read where they were computed (sharded regions: every GPU fetches its slices over NVLink);
+     * only the witness bits and the four accumulators cross PCIe */
+    uint64_t *acc = malloc(4 * FLAT_CT * 8);
+    if (!acc) mf_die("malloc");
+    mf_ct_to_flat(acc, pi->v_w, "prover");
+    mf_ct_to_flat(acc + FLAT_CT, pi->h, "prover");
+    mf_ct_to_flat(acc + 2 * FLAT_CT, pi->hat_v, "prover");
+    mf_ct_to_flat(acc + 3 * FLAT_CT, pi->hat_h, "prover");
+    if (res->ms) {
+      if (mfb_set_prove_resident(g_set, rssp, res->ms, res->mas, PTR(witness), (size_t)SIZ(witness), delta, acc, acc + FLAT_CT,
+                                 acc + 2 * FLAT_CT, acc + 3 * FLAT_CT) != MFB_OK) {
+        fprintf(stderr, "mangiafuoco_b200: mfb_set_prove_resident failed: %s\n", mfb_set_last_error());
+        abort();
+      }
+    } else {
+      MF_GPU(mfb_prove_resident(mf_gpu(), rssp, res->s, res->as, PTR(witness), (size_t)SIZ(witness), delta, acc, acc + FLAT_CT,
+                                acc + 2 * FLAT_CT, acc + 3 * FLAT_CT));
+    }
+    mf_ct_from_flat(pi->v_w, acc);
+    mf_ct_from_flat(pi->h, acc + FLAT_CT);
+    mf_ct_from_flat(pi->hat_v, acc + 2 * FLAT_CT);
+    mf_ct_from_flat(pi->hat_h, acc + 3 * FLAT_CT);
+    free(acc);
+  } else {
+    struct resident *r = res;
     if (r && r->d == D) { /* regions resident in HBM: one pass per region at the HBM roofline, two scalar vectors each */
       lincomb_pair_resident(pi->v_w, pi->h, r->s, r->ms, pw, ph);
       lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, r->mas, pv, ph);

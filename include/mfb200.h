@@ -64,6 +64,7 @@ extern "C" {
 #endif
 
 typedef struct mfb_ctx mfb_ctx;
+typedef struct mfb_ssp mfb_ssp;       /* an SSP blob kept on the device (mfb_ssp_create) */
 
 /* ---- context ------------------------------------------------------------------------------ */
 MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
@@ -194,6 +195,11 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
 MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r);
 MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
                             uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
+/* mfb_prove_resident over sharded regions: the polynomial step runs on the primary, the members fetch their slices of
+ * w, v, h over NVLink, run both two-vector passes over their shards, and four peer all-reduce kernels combine them. */
+MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *reg_s, const mfb_set_region *reg_as,
+                           const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                           uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout);
 
 /* ---- K2+K1 fused: eval_poly with a regenerated in-kernel ----------------------------------- */
 /* rop += sum_{m<d} coeffs[m] * CT_{k(m)},  k(m) = idx ? idx[m] : m, where CT_k = ct_import(stream at
@@ -255,11 +261,22 @@ MFB_API int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D, si
                          size_t nlimbs, uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out);
 /* The same with the SSP blob kept on the device (u32 residues, (M+1)*D*4 bytes) and rev(t)^-1 cached in the handle:
  * after the first proof the division is one multiplication and nothing but the witness crosses PCIe. */
-typedef struct mfb_ssp mfb_ssp;
 MFB_API int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_t M, mfb_ssp **out);
 MFB_API void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h);
 MFB_API int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
                                   uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out);
+/* The same with the results left on the device: *wvh_dev = three consecutive arrays of D uint32 residues (w, v, h),
+ * valid until the next polynomial / encrypt / decrypt call on this context. */
+MFB_API int mfb_ssp_prover_polys_resident_dev(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                      uint64_t delta, const uint32_t **wvh_dev);
+MFB_API size_t mfb_ssp_degree_bound(const mfb_ssp *h);
+/* The prover's main pipeline with everything resident (snark.c:138-174) in ONE call, nothing but the witness bits and
+ * the four accumulators crossing PCIe: polynomial step on the device, then
+ *   (v_w, h) += sum (w_i, h_i) * CT_i over the s region,   (hat_v, hat_h) += sum (v_i, h_i) * CT_i over the as region
+ * as two two-vector passes; regions of D = the SSP's degree bound ciphertexts.  Flat accumulators in and out. */
+MFB_API int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
+                       const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                       uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout);
 /* values[q] = poly_q(x) mod p for npoly polynomials of D u64 coefficients each (setup's nmod_poly_evaluate_nmod
  * calls, snark.c:97-110) */
 MFB_API int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values);
