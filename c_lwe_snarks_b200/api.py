@@ -111,6 +111,7 @@ _SIGS = {
     "mfb_ssp_degree_bound": (C.c_size_t, [_vp]),
     "mfb_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "mfb_set_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
+    "mfb_ssp_eval_resident": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_ssp_eval": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_flat_to_planar_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_flat_to_resident_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
@@ -320,6 +321,11 @@ class ResidentSsp:
         self.ctx._ck(self.ctx.lib.mfb_ssp_prover_polys_resident(self.ctx.h, self.handle, _p64(wl), wl.size, delta, _p64(w),
                                                                 _p64(v), _p64(h)))
         return w, v, h
+
+    def eval(self, first: int, npoly: int, x: int) -> np.ndarray:
+        out = np.zeros(npoly, np.uint64)
+        self.ctx._ck(self.ctx.lib.mfb_ssp_eval_resident(self.ctx.h, self.handle, first, npoly, x, _p64(out)))
+        return out
 
     def close(self):
         if self.handle:

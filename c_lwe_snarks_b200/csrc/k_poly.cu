@@ -294,6 +294,23 @@ __global__ void __launch_bounds__(256) k_eval(const uint64_t *__restrict__ polys
   }
 }
 
+// the same over the u32 residues of a resident SSP blob
+__global__ void __launch_bounds__(256) k_eval32(const uint32_t *__restrict__ polys, uint32_t D, const uint32_t *__restrict__ pw,
+                                                uint64_t *values) {
+  __shared__ unsigned long long part[8];
+  const uint32_t *p = polys + (size_t)blockIdx.x * D;
+  unsigned long long acc = 0;
+  for (uint32_t i = threadIdx.x; i < D; i += 256) acc += (unsigned long long)p[i] * pw[i] % FP;
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < 8; w++) s += part[w];
+    values[blockIdx.x] = s % FP;
+  }
+}
+
 // =============================================================================================== host driver
 struct PolyEngine {
   uint32_t nmax = 0;  // twiddle tables cover transforms up to this size
@@ -797,6 +814,31 @@ extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_
     PTRY(cudaGetLastError());
     if (q + per < npoly) PTRY(cudaStreamSynchronize(st));  // staging buffer reuse
   }
+  PTRY(cudaMemcpyAsync(values, d_val, npoly * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  ctx_count_launches(ctx, E.launches - L0);
+  return MFB_OK;
+}
+
+// values[q] = poly_{first+q}(x) for the polynomials first .. first+npoly of a RESIDENT blob ([t, v_0, ..., v_{M-1}]):
+// the verifier's t(s), v_0(s) (snark.c:197-201, 214-215) without shipping 16 D bytes per proof check.
+extern "C" int mfb_ssp_eval_resident(mfb_ctx *ctx, const mfb_ssp *h, size_t first, size_t npoly, uint64_t x, uint64_t *values) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (npoly == 0) return MFB_OK;
+  if (!h || !values) return ctx_bad_arg("mfb_ssp_eval_resident: null pointer");
+  if (first > h->M + 1 || npoly > h->M + 1 - first) return ctx_bad_arg("mfb_ssp_eval_resident: polynomial range exceeds the blob");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  const size_t D = h->D;
+  void *d_pw, *d_val;
+  if ((rc = ctx_scratch(ctx, 0, D * 4, &d_pw))) return rc;
+  if ((rc = ctx_scratch(ctx, 1, npoly * 8, &d_val))) return rc;
+  k_powers<<<gridfor((uint32_t)D), 256, 0, st>>>(x, (uint32_t)D, (uint32_t *)d_pw);
+  k_eval32<<<(unsigned)npoly, 256, 0, st>>>(h->blob + first * D, (uint32_t)D, (const uint32_t *)d_pw, (uint64_t *)d_val);
+  E.launches += 2;
+  PTRY(cudaGetLastError());
   PTRY(cudaMemcpyAsync(values, d_val, npoly * 8, cudaMemcpyDeviceToHost, st));
   PTRY(cudaStreamSynchronize(st));
   ctx_count_launches(ctx, E.launches - L0);

@@ -227,7 +227,11 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
    * dense blob [t, v_0, ..., v_{M-1}] (ssp.h:6-9); v_0(s) is computed and not used, as its slot is skipped there */
   uint64_t *vals = malloc((M + 1) * 8);
   if (!vals) mf_die("malloc");
-  MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, M + 1, vrs->s, vals));
+  mfb_ssp *rssp = resident_ssp_find(ssp);
+  if (rssp)
+    MF_GPU(mfb_ssp_eval_resident(mf_gpu(), rssp, 0, M + 1, vrs->s, vals));
+  else
+    MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, M + 1, vrs->s, vals));
   msg[2 * D] = (vals[0] * vrs->beta) % GAMMA_P;
   for (size_t i = 1; i < M; i++) msg[2 * D + i] = (vals[i + 1] * vrs->beta) % GAMMA_P;
   free(vals);
@@ -388,7 +392,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     }
   }
   free(pw);
-  mf_trace("prover.lincombs", t0);
+  mf_trace(all_resident ? "prover.polys+lincombs (device pipeline)" : "prover.lincombs", t0);
   t0 = mf_now();
 
   /* smudging, in the reference's order: v_w twice, b_w never (snark.c:185-189) */
@@ -406,7 +410,11 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi) {
   const uint64_t p = GAMMA_P;
   /* t(s) and v_0(s): the first two polynomials of the blob, one batched device evaluation (snark.c:197-201,214-215) */
   uint64_t ts_v0s[2];
-  MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, 2, vrs->s, ts_v0s));
+  mfb_ssp *rssp = resident_ssp_find(ssp);
+  if (rssp)
+    MF_GPU(mfb_ssp_eval_resident(mf_gpu(), rssp, 0, 2, vrs->s, ts_v0s));
+  else
+    MF_GPU(mfb_ssp_eval(mf_gpu(), (const uint64_t *)ssp, D, 2, vrs->s, ts_v0s));
   const uint64_t t_s = ts_v0s[0], v0_s = ts_v0s[1];
 
   /* one batch: decrypt h, hat_h, hat_v, v_w, b_w; the dot product of b_w is also the test-error input */

@@ -270,6 +270,9 @@ MFB_API int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64
 MFB_API int mfb_ssp_prover_polys_resident_dev(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
                                       uint64_t delta, const uint32_t **wvh_dev);
 MFB_API size_t mfb_ssp_degree_bound(const mfb_ssp *h);
+/* values[q] = poly_{first+q}(x) mod p over a resident blob [t, v_0, ..., v_{M-1}] (polynomial 0 = t): setup's and the
+ * verifier's evaluations (snark.c:97-110, 197-201, 214-215) without shipping the coefficients again. */
+MFB_API int mfb_ssp_eval_resident(mfb_ctx *ctx, const mfb_ssp *h, size_t first, size_t npoly, uint64_t x, uint64_t *values);
 /* The prover's main pipeline with everything resident (snark.c:138-174) in ONE call, nothing but the witness bits and
  * the four accumulators crossing PCIe: polynomial step on the device, then
  *   (v_w, h) += sum (w_i, h_i) * CT_i over the s region,   (hat_v, hat_h) += sum (v_i, h_i) * CT_i over the as region

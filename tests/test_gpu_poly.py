@@ -177,3 +177,37 @@ def test_ssp_eval(ctx, D, npoly):
         for c in raw[q * D:(q + 1) * D][::-1]:
             acc = (acc * x + int(c) % P) % P
         assert int(got[q]) == acc
+
+
+@pytest.mark.parametrize("D,M", [(64, 16), (1000, 8), (65536, 64)])
+def test_ssp_eval_resident_equals_host_blob_eval(ctx, D, M):
+    """mfb_ssp_eval_resident (the verifier's / setup's evaluations from the resident blob) == mfb_ssp_eval"""
+    blob, *_ = make_ssp(D, M, f"poly-evres-{D}", exact=False)
+    blob[:5] = np.uint64(2**64 - 1)  # unreduced wire coefficients
+    x = 0xDEADBEEF % P
+    want = ctx.ssp_eval(blob, D, x)  # all M + 1 polynomials
+    res = ctx.ssp_resident(blob.view(np.uint8), D, M)
+    try:
+        assert np.array_equal(res.eval(0, M + 1, x), want)
+        assert np.array_equal(res.eval(0, 2, x), want[:2])          # the verifier's call: t(s), v_0(s)
+        assert np.array_equal(res.eval(3, M - 2, x), want[3:M + 1])
+    finally:
+        res.close()
+
+
+def test_prover_polys_2_20_identity_at_random_points(ctx):
+    """D = 2^20 (BASELINE configs[3]): v = w + v_0 and v^2 - 1 = h*t + r with deg r < deg t, checked by evaluating both
+    sides at random points — with delta = 1 the instance is exact (r = 0), so v(x)^2 - 1 == h(x) t(x) mod p."""
+    D, M = 1 << 20, 8
+    blob, wl, bits, t, v = make_ssp(D, M, "poly-2-20")
+    w, vv, h = ctx.ssp_prover_polys(blob.view(np.uint8), D, M, wl, 1)
+    polys = np.stack([w, vv, h, t, v[0]]).astype(np.uint64)
+    for x in (2, 0x7FFFFFFF, 0xFFFFFFFA):
+        ws, vs, hs, ts, v0s = (int(e) for e in ctx.ssp_eval(polys, D, x))
+        assert vs == (ws + v0s) % P
+        assert (vs * vs - 1) % P == hs * ts % P
+    # the evaluation kernel itself, against Horner in Python, on one of the 2^20-coefficient polynomials
+    acc = 0
+    for c in vv[::-1]:
+        acc = (acc * 3 + int(c)) % P
+    assert int(ctx.ssp_eval(vv, D, 3)[0]) == acc
