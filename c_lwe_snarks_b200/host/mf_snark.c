@@ -2,12 +2,15 @@
  *
  * The protocol steps, their order, the stream regions (snark.h:8-12) and the order of entropy draws are the
  * reference's; what changes is that each loop over ciphertexts is ONE batched device call:
- *   setup     2D + M Regev encryptions            -> one mfb_encrypt   (snark.c:75-110)
+ *   setup     2D + M Regev encryptions            -> one mfb_encrypt_cb (entropy drawn piece by piece while the
+ *                                                    device encrypts the previous piece)          (snark.c:75-110)
  *   prover    b_w = delta*CT_t + sum_{w_i} CT_v_i -> one mfb_eval_poly with an index list (snark.c:143-155)
- *             v_w, hat_v, h, hat_h                 -> four mfb_eval_poly, or resident lincombs after
- *                                                    mf_crs_make_resident (snark.c:157-174)
+ *             v_w, hat_v, h, hat_h                 -> two two-vector fused passes (mfb_eval_poly2), or — after
+ *                                                    mf_crs_make_resident + mf_ssp_make_resident — ONE device
+ *                                                    pipeline (mfb_prove_resident; mfb_set_prove_resident when the
+ *                                                    regions are sharded over several GPUs)       (snark.c:157-174)
  *   verifier  5 decryptions + the test-error dot  -> one mfb_decrypt   (snark.c:204-208, 238)
- * Polynomial arithmetic over F_p (FLINT in the reference) stays on the host.
+ * Polynomial arithmetic over F_p (FLINT in the reference) runs on the device (k_poly.cu).
  */
 #include "mf_internal.h"
 
