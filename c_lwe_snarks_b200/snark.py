@@ -77,6 +77,11 @@ class Snark:
         self.lib.random_ssp(C.byref(self.witness), self._ssp_ptr())
 
     def setup(self) -> float:
+        if self._vrs_live:  # a repeated setup replaces the previous CRS / verification key
+            self.lib.key_clear(self.vrs.sk)
+            self._vrs_live = False
+        if self._crs_live:
+            self.lib.crs_clear(C.byref(self.crs))
         self.lib.crs_init(C.byref(self.crs))
         self._crs_live = True
         t0 = time.perf_counter()

@@ -56,6 +56,33 @@ def main():
                                            None, d_r1.data_ptr(), st))
     rec("k_evalpoly<2> + 2 finish", ms, D * AES_BLOCKS_PER_CT, "aes_blocks", D=D)
 
+    # host-flavour call (what bench.py's e2e times): pageable and pinned inputs, against the device call + sync
+    import time
+    h64 = h.astype(np.uint64)
+    rop = np.zeros((NC, L64), np.uint64)
+
+    def host_call(c8a, ha, ra):
+        ctx._ck(ctx.lib.mfb_eval_poly(ctx.h, m.api._p8(np.frombuffer(SEED, np.uint8).copy()), 0, m.api._p8(c8a), m.api._p64(ha),
+                                      None, D, m.api._p64(ra)))
+
+    def wall(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    ms = wall(lambda: host_call(c8.reshape(-1), h64, rop))
+    rec("mfb_eval_poly host call, pageable buffers", ms, D, "mac", D=D)
+    p_c8, p_h, p_r = (torch.from_numpy(a.copy()).pin_memory().numpy() for a in (c8.reshape(-1), h64, rop.view(np.uint64).reshape(-1)))
+    ms = wall(lambda: host_call(p_c8, p_h, p_r))
+    rec("mfb_eval_poly host call, pinned buffers", ms, D, "mac", D=D)
+    ms = wall(lambda: (ctx.eval_poly_dev(SEED, 0, d_c8.data_ptr(), d_h.data_ptr(), None, D, None, d_r0.data_ptr(), st),
+                       torch.cuda.synchronize()))
+    rec("mfb_eval_poly_dev + synchronize (wall)", ms, D, "mac", D=D)
+
     d_cts = torch.empty(D * NCP * L64, dtype=torch.int64, device="cuda")
     ms = timeit(lambda: ctx.expand_dev(SEED, 0, d_c8.data_ptr(), D, d_cts.data_ptr(), st), reps=3, warm=1)
     rec("k_expand", ms, D * AES_BLOCKS_PER_CT, "aes_blocks", D=D)
