@@ -515,6 +515,15 @@ def run_gpu_arm(args):
             except Exception as e:  # noqa: BLE001  (reported, the bench line stands)
                 line["snark_box"] = {"error": str(e)[:300]}
         emit(line)
+    if world > 1 and not args.no_snark:
+        # the other ranks wait for rank 0's box leg ON THE CPU (a c10d store key): an NCCL barrier would keep a kernel
+        # spinning on their GPUs, and rank 0's member contexts on those GPUs would be time-sliced against it
+        from datetime import timedelta
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("snark_box_done", "1")
+        else:
+            store.wait(["snark_box_done"], timedelta(seconds=900))
     if peer is not None:
         peer.check()
         peer.close()

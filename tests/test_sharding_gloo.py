@@ -157,3 +157,99 @@ def test_two_rank_exchange_matches_single_process_oracle(oracle):
     for rank, _, _, res in out:
         assert not res[NC:].any()
         assert np.array_equal(res[:NC], want), f"rank {rank}"
+
+
+# ------------------------------------------------------------------------------------------- peer exchange, host side
+class FakePeerGroup:
+    """Test double of api.PeerGroup: a shared-memory "symmetric buffer" is replaced by a file per rank in a directory
+    both ranks see; connect() records the handles, lincomb_dev publishes this rank's partial and adds everybody's."""
+
+    def __init__(self, rank, world, tmpdir, partial):
+        self.rank, self.world, self.dir, self.partial = rank, world, tmpdir, partial
+        self.ipc_handle = np.full(64, rank + 1, np.uint8)
+        self.log = []
+
+    def connect(self, handles):
+        self.log.append(("connect", bytes(handles)))
+
+    def lincomb_dev(self, cts_ptr, coeffs_ptr, d, rop_in_ptr, rop_out_ptr, stream):
+        import ctypes
+        import time
+        np.save(os.path.join(self.dir, f"p{self.rank}.npy"), self.partial)
+        os.replace(os.path.join(self.dir, f"p{self.rank}.npy"), os.path.join(self.dir, f"done{self.rank}.npy"))
+        acc = [0] * NC
+        for r in range(self.world):
+            path = os.path.join(self.dir, f"done{r}.npy")
+            for _ in range(2000):
+                if os.path.exists(path):
+                    break
+                time.sleep(0.01)
+            part = np.load(path)
+            for c in range(NC):
+                acc[c] = (acc[c] + int.from_bytes(part[c].tobytes(), "little")) % (1 << 704)
+        out = np.zeros((NCP, L64), np.uint64)
+        for c in range(NC):
+            out[c] = np.frombuffer(acc[c].to_bytes(88, "little"), "<u8")
+        ctypes.memmove(rop_out_ptr, out.ctypes.data, out.nbytes)
+        self.log.append(("lincomb", d))
+
+    def check(self):
+        self.log.append(("check",))
+
+    def disconnect(self):
+        self.log.append(("disconnect",))
+
+    def close(self):
+        self.log.append(("close",))
+
+
+def _peer_worker(rank, world, port, tmpdir, q):
+    import torch
+    import torch.distributed as dist
+
+    from conftest import SEED, xof_records, xof_scalars
+    from c_lwe_snarks_b200.sharding import PeerShardedLincomb, ShardPlan
+    from oracle.loader import Oracle
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = ShardPlan(world, rank)
+        first, count = plan.ct_range(D_TOTAL)
+        c8, h = xof_records("shard-c8", D_TOTAL), xof_scalars("shard-h", D_TOTAL)
+        partial = Oracle().eval_poly(SEED, first * CTR_CT, c8[first:first + count], h[first:first + count])[:, :L64].copy()
+        group = FakePeerGroup(rank, world, tmpdir, partial)
+        peer = PeerShardedLincomb(plan, group, dist, lambda n: torch.zeros(n, dtype=torch.int64),
+                                  lambda n: torch.zeros(n, dtype=torch.uint8))
+        dummy = torch.zeros(1, dtype=torch.int64)
+        res = peer.step(dummy, dummy, count).numpy().view(np.uint64).reshape(NCP, L64).copy()
+        peer.check()
+        peer.close()
+        q.put((rank, res, group.log))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_peer_exchange_host_logic(oracle, tmp_path):
+    """sharding.PeerShardedLincomb under gloo with a stand-in group: the 64-byte handles are gathered in rank order and
+    handed to connect(); step() returns the all-rank sum; close() runs barrier / disconnect / barrier / close."""
+    import torch.multiprocessing as mp
+
+    from conftest import SEED, xof_records, xof_scalars
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 150
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    c8, h = xof_records("shard-c8", D_TOTAL), xof_scalars("shard-h", D_TOTAL)
+    want = oracle.eval_poly(SEED, 0, c8, h)[:, :L64]
+    for rank, res, log in out:
+        assert np.array_equal(res[:NC], want), f"rank {rank}"
+        assert log[0] == ("connect", bytes([1] * 64 + [2] * 64))
+        assert [e[0] for e in log] == ["connect", "lincomb", "check", "disconnect", "close"]
