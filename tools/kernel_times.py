@@ -1,5 +1,6 @@
 """Device-side timings (CUDA events on the launching stream) of every kernel family at BASELINE sizes.
-Usage: python tools/kernel_times.py [log2d]   -> one JSON line per measurement on stdout."""
+Usage: python tools/kernel_times.py [log2d]   -> one JSON line per measurement on stdout.
+KT_ONCE=1: every kernel family exactly once, no host-call section (the command ncu captures)."""
 import json
 import sys
 from pathlib import Path
@@ -16,7 +17,13 @@ CTR_CT = 92 * 1470
 AES_BLOCKS_PER_CT = CTR_CT / 16
 
 
+import os
+ONCE = os.environ.get("KT_ONCE") == "1"
+
+
 def timeit(fn, reps=5, warm=2):
+    if ONCE:
+        reps, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -74,14 +81,16 @@ def main():
         torch.cuda.synchronize()
         return 1e3 * (time.perf_counter() - t0) / reps
 
-    ms = wall(lambda: host_call(c8.reshape(-1), h64, rop))
-    rec("mfb_eval_poly host call, pageable buffers", ms, D, "mac", D=D)
-    p_c8, p_h, p_r = (torch.from_numpy(a.copy()).pin_memory().numpy() for a in (c8.reshape(-1), h64, rop.view(np.uint64).reshape(-1)))
-    ms = wall(lambda: host_call(p_c8, p_h, p_r))
-    rec("mfb_eval_poly host call, pinned buffers", ms, D, "mac", D=D)
-    ms = wall(lambda: (ctx.eval_poly_dev(SEED, 0, d_c8.data_ptr(), d_h.data_ptr(), None, D, None, d_r0.data_ptr(), st),
-                       torch.cuda.synchronize()))
-    rec("mfb_eval_poly_dev + synchronize (wall)", ms, D, "mac", D=D)
+    if not ONCE:
+        ms = wall(lambda: host_call(c8.reshape(-1), h64, rop))
+        rec("mfb_eval_poly host call, pageable buffers", ms, D, "mac", D=D)
+        p_c8, p_h, p_r = (torch.from_numpy(a.copy()).pin_memory().numpy()
+                          for a in (c8.reshape(-1), h64, rop.view(np.uint64).reshape(-1)))
+        ms = wall(lambda: host_call(p_c8, p_h, p_r))
+        rec("mfb_eval_poly host call, pinned buffers", ms, D, "mac", D=D)
+        ms = wall(lambda: (ctx.eval_poly_dev(SEED, 0, d_c8.data_ptr(), d_h.data_ptr(), None, D, None, d_r0.data_ptr(), st),
+                           torch.cuda.synchronize()))
+        rec("mfb_eval_poly_dev + synchronize (wall)", ms, D, "mac", D=D)
 
     d_cts = torch.empty(D * NCP * L64, dtype=torch.int64, device="cuda")
     ms = timeit(lambda: ctx.expand_dev(SEED, 0, d_c8.data_ptr(), D, d_cts.data_ptr(), st), reps=3, warm=1)
