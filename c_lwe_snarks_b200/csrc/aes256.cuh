@@ -22,6 +22,7 @@ constexpr int AES_TAB_BYTES = 256 * 256;  // 64 KB
 struct AesKey {
   uint32_t rk[60];   // 15 round keys x 4 little-endian column words
   uint32_t nonce[2]; // block bytes 0..7
+  uint32_t rkr[60];  // rotr8(rk[i]): lets the round key ride along inside the rotated half of a column (aes_round)
 };
 
 // ----------------------------------------------------------------------------------- host side
@@ -81,6 +82,7 @@ inline void expand(const uint8_t seed[40], AesKey *out) {
   }
   for (int i = 0; i < 60; i++)
     out->rk[i] = (uint32_t)w[i][0] | (uint32_t)w[i][1] << 8 | (uint32_t)w[i][2] << 16 | (uint32_t)w[i][3] << 24;
+  for (int i = 0; i < 60; i++) out->rkr[i] = out->rk[i] >> 8 | out->rk[i] << 24;
   std::memcpy(out->nonce, seed, 8);
 }
 
@@ -230,9 +232,13 @@ struct AesLut {
   template <int K> __device__ __forceinline__ uint32_t a2(uint32_t w) const { return lds32_t2(addr<K>(w, lbA)); }
 };
 
+// kr0..kr3 = rotr8 of the round key words (AesKey::rkr): in the two-table form a column is
+//   T0[.] ^ T2[.] ^ rotl8(T0[.] ^ T2[.]) ^ k  =  LOP3(a0, a2, rotl8(LOP3(a1, a3, rotr8(k))))
+// — two 3-input LOP3 and one PRMT instead of three LOP3 and one PRMT (the ALU pipe is this kernel's bound).
 template <int TABS, int FM>
 __device__ __forceinline__ void aes_round(const AesLut<TABS, FM> &L, uint32_t &s0, uint32_t &s1, uint32_t &s2, uint32_t &s3,
-                                          uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+                                          uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t kr0, uint32_t kr1,
+                                          uint32_t kr2, uint32_t kr3) {
   if constexpr (TABS == 4) {
     const uint32_t a0 = L.template t0<0>(s0), a1 = L.template t1<1>(s1), a2 = L.template t2<2>(s2), a3 = L.template t3<3>(s3);
     const uint32_t b0 = L.template t0<0>(s1), b1 = L.template t1<1>(s2), b2 = L.template t2<2>(s3), b3 = L.template t3<3>(s0);
@@ -251,10 +257,10 @@ __device__ __forceinline__ void aes_round(const AesLut<TABS, FM> &L, uint32_t &s
     const uint32_t c2 = L.template a2<2>(s0), c3 = L.template a2<3>(s1);
     const uint32_t d0 = L.template a0<0>(s3), d1 = L.template a0<1>(s0);
     const uint32_t d2 = L.template a2<2>(s1), d3 = L.template a2<3>(s2);
-    s0 = a0 ^ a2 ^ k0 ^ rotl8(a1 ^ a3);
-    s1 = b0 ^ b2 ^ k1 ^ rotl8(b1 ^ b3);
-    s2 = c0 ^ c2 ^ k2 ^ rotl8(c1 ^ c3);
-    s3 = d0 ^ d2 ^ k3 ^ rotl8(d1 ^ d3);
+    s0 = a0 ^ a2 ^ rotl8(a1 ^ a3 ^ kr0);
+    s1 = b0 ^ b2 ^ rotl8(b1 ^ b3 ^ kr1);
+    s2 = c0 ^ c2 ^ rotl8(c1 ^ c3 ^ kr2);
+    s3 = d0 ^ d2 ^ rotl8(d1 ^ d3 ^ kr3);
   }
 }
 
@@ -311,7 +317,9 @@ __device__ __forceinline__ AesState aes256_ctr_block_cached(const AesLut<TABS, F
   uint32_t s3 = c.q3 ^ L.template t2<2>(r1) ^ L.template t3<3>(r2);
   uint32_t s2v = t2v;
 #pragma unroll
-  for (int r = 3; r < 14; r++) aes_round<TABS, FM>(L, s0, s1, s2v, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
+  for (int r = 3; r < 14; r++)
+    aes_round<TABS, FM>(L, s0, s1, s2v, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3], k.rkr[4 * r],
+                        k.rkr[4 * r + 1], k.rkr[4 * r + 2], k.rkr[4 * r + 3]);
   return aes_last_round<TABS, FM>(L, k, s0, s1, s2v, s3);
 }
 
@@ -321,7 +329,9 @@ __device__ __forceinline__ AesState aes256_ctr_block_plain(const AesLut<TABS, FM
   uint32_t s0 = k.nonce[0] ^ k.rk[0], s1 = k.nonce[1] ^ k.rk[1];
   uint32_t s2 = (uint32_t)ctr ^ k.rk[2], s3 = (uint32_t)(ctr >> 32) ^ k.rk[3];
 #pragma unroll
-  for (int r = 1; r < 14; r++) aes_round<TABS, FM>(L, s0, s1, s2, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3]);
+  for (int r = 1; r < 14; r++)
+    aes_round<TABS, FM>(L, s0, s1, s2, s3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3], k.rkr[4 * r],
+                        k.rkr[4 * r + 1], k.rkr[4 * r + 2], k.rkr[4 * r + 3]);
   return aes_last_round<TABS, FM>(L, k, s0, s1, s2, s3);
 }
 
