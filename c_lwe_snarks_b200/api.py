@@ -68,6 +68,7 @@ _SIGS = {
     "mfb_lincomb_generic_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp, _vp]),
     "mfb_lincomb": (C.c_int, [_vp, _u64p, _u32p, C.c_size_t, _u64p]),
     "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
+    "mfb_region_create_async": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, _vp, C.POINTER(_vp)]),
     "mfb_region_destroy": (None, [_vp, _vp]),
     "mfb_region_lincomb": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, C.c_size_t, _u64p]),
     "mfb_peer_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), _u8p]),

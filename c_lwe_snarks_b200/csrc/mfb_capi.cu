@@ -816,9 +816,10 @@ int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, 
   return MFB_OK;
 }
 
-int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
-                      mfb_region **out) {
-  MFB_CHECK_CTX(ctx);
+// stream == nullptr: the context's own stream, synchronised before returning; else asynchronous on `stream` (the
+// records are staged in the context's scratch slot 0: one creation in flight per context)
+static int region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                         cudaStream_t stream, bool sync, mfb_region **out) {
   if (!out || !seed || (count && !c8)) return set_err(MFB_EARG, "mfb_region_create: null pointer");
   *out = nullptr;
   mfb_region *r = new (std::nothrow) mfb_region();
@@ -832,12 +833,12 @@ int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   void *d_c8;
   int rc = scratch(ctx, 0, count * CT_BYTES, &d_c8);
   if (rc == MFB_OK && count) {
-    e = cudaMemcpyAsync(d_c8, c8, count * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaMemcpyAsync(d_c8, c8, count * CT_BYTES, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
   }
-  if (rc == MFB_OK) rc = mfb_expand_dev(ctx, seed, offset, (const uint8_t *)d_c8, count, r->cts, ctx->stream);
-  if (rc == MFB_OK) {
-    e = cudaStreamSynchronize(ctx->stream);
+  if (rc == MFB_OK) rc = mfb_expand_dev(ctx, seed, offset, (const uint8_t *)d_c8, count, r->cts, stream);
+  if (rc == MFB_OK && sync) {
+    e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) rc = fail(e, "sync", __FILE__, __LINE__);
   }
   if (rc != MFB_OK) {
@@ -847,6 +848,18 @@ int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, con
   }
   *out = r;
   return MFB_OK;
+}
+
+int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                      mfb_region **out) {
+  MFB_CHECK_CTX(ctx);
+  return region_create(ctx, seed, offset, c8, count, ctx->stream, true, out);
+}
+
+int mfb_region_create_async(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                            void *stream, mfb_region **out) {
+  MFB_CHECK_CTX(ctx);
+  return region_create(ctx, seed, offset, c8, count, (cudaStream_t)stream, false, out);
 }
 
 const void *mfb_region_cts(const mfb_region *r) { return r ? r->cts : nullptr; }

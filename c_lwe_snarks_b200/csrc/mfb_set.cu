@@ -170,10 +170,18 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   for (size_t i = 0; i < world && rc == MFB_OK; i++) {
     r->first[i] = i * base + (i < extra ? i : extra);
     r->count[i] = base + (i < extra ? 1 : 0);
-    // (mfb_region_create expands synchronously: the members' AES expansions run one after the other; making a
-    // region resident is a one-off cost next to the proofs that reuse it)
-    rc = mfb_region_create(s->m[i].ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
-                           r->count[i], &r->shard[i]);
+    // queued on the member's stream: the members' AES expansions run concurrently
+    cudaSetDevice(s->m[i].device);
+    rc = mfb_region_create_async(s->m[i].ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
+                                 r->count[i], s->m[i].stream, &r->shard[i]);
+  }
+  for (size_t i = 0; i < world; i++) {
+    cudaSetDevice(s->m[i].device);
+    const cudaError_t e = cudaStreamSynchronize(s->m[i].stream);
+    if (e != cudaSuccess && rc == MFB_OK) {
+      snprintf(g_set_err, sizeof(g_set_err), "mfb_set_region_create: device %d: %s", s->m[i].device, cudaGetErrorString(e));
+      rc = MFB_ECUDA;
+    }
   }
   if (rc != MFB_OK) {
     char keep[256];

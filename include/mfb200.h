@@ -111,6 +111,10 @@ MFB_API int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *
 typedef struct mfb_region mfb_region;
 MFB_API int mfb_region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
                       mfb_region **out);
+/* the same without waiting: the expansion is queued on `stream`; synchronise it before the region is used or another
+ * region is created on this context (device sets expand their members' shards concurrently this way) */
+MFB_API int mfb_region_create_async(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
+                            void *stream, mfb_region **out);
 MFB_API void mfb_region_destroy(mfb_ctx *ctx, mfb_region *r);
 /* rop += sum_i coeffs[i] * region[first + i], i < d; coeffs/rop in host memory */
 MFB_API int mfb_region_lincomb(mfb_ctx *ctx, const mfb_region *r, size_t first, const uint32_t *coeffs, size_t d,
