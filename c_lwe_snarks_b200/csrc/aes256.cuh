@@ -323,6 +323,36 @@ __device__ __forceinline__ AesState aes256_ctr_block_cached(const AesLut<TABS, F
   return aes_last_round<TABS, FM>(L, k, s0, s1, s2v, s3);
 }
 
+// Two blocks of the SAME 65536-block window in lockstep (ctr_b = ctr_a + stride, both keyed on the same cache): the
+// rounds of the two independent blocks interleave in one instruction stream, doubling the lookups in flight per warp.
+// Falls back to two single calls when the blocks straddle a window boundary.
+template <int TABS, int FM>
+__device__ __forceinline__ void aes256_ctr_block_cached_x2(const AesLut<TABS, FM> &L, const AesKey &k, uint64_t ctr_a,
+                                                           uint64_t ctr_b, AesCtrCache &c, AesState &out_a, AesState &out_b) {
+  if ((ctr_a >> 16) != (ctr_b >> 16)) {
+    out_a = aes256_ctr_block_cached<TABS, FM>(L, k, ctr_a, c);
+    out_b = aes256_ctr_block_cached<TABS, FM>(L, k, ctr_b, c);
+    return;
+  }
+  if ((ctr_a >> 16) != c.window) aes_ctr_cache_fill<TABS, FM>(L, k, ctr_a, c);
+  const uint32_t xa = (uint32_t)ctr_a ^ k.rk[2], xb = (uint32_t)ctr_b ^ k.rk[2];
+  const uint32_t ra1 = c.k1p ^ L.template t1<1>(xa), rb1 = c.k1p ^ L.template t1<1>(xb);
+  const uint32_t ra2 = c.k2p ^ L.template t0<0>(xa), rb2 = c.k2p ^ L.template t0<0>(xb);
+  uint32_t a0 = c.q0 ^ L.template t1<1>(ra1) ^ L.template t2<2>(ra2), b0 = c.q0 ^ L.template t1<1>(rb1) ^ L.template t2<2>(rb2);
+  uint32_t a1 = c.q1 ^ L.template t0<0>(ra1) ^ L.template t1<1>(ra2), b1 = c.q1 ^ L.template t0<0>(rb1) ^ L.template t1<1>(rb2);
+  uint32_t a2 = c.q2 ^ L.template t0<0>(ra2) ^ L.template t3<3>(ra1), b2 = c.q2 ^ L.template t0<0>(rb2) ^ L.template t3<3>(rb1);
+  uint32_t a3 = c.q3 ^ L.template t2<2>(ra1) ^ L.template t3<3>(ra2), b3 = c.q3 ^ L.template t2<2>(rb1) ^ L.template t3<3>(rb2);
+#pragma unroll
+  for (int r = 3; r < 14; r++) {
+    aes_round<TABS, FM>(L, a0, a1, a2, a3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3], k.rkr[4 * r],
+                        k.rkr[4 * r + 1], k.rkr[4 * r + 2], k.rkr[4 * r + 3]);
+    aes_round<TABS, FM>(L, b0, b1, b2, b3, k.rk[4 * r], k.rk[4 * r + 1], k.rk[4 * r + 2], k.rk[4 * r + 3], k.rkr[4 * r],
+                        k.rkr[4 * r + 1], k.rkr[4 * r + 2], k.rkr[4 * r + 3]);
+  }
+  out_a = aes_last_round<TABS, FM>(L, k, a0, a1, a2, a3);
+  out_b = aes_last_round<TABS, FM>(L, k, b0, b1, b2, b3);
+}
+
 // Plain variant (no cache) on the same table abstraction.
 template <int TABS, int FM>
 __device__ __forceinline__ AesState aes256_ctr_block_plain(const AesLut<TABS, FM> &L, const AesKey &k, uint64_t ctr) {

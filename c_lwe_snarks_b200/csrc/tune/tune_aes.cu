@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   extern __shared__ __align__(16) uint8_t dyn[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(dyn);
   const uint32_t tabA = (s0 + 0xffffu) & ~0xffffu;
-  constexpr bool four = (VARIANT >= 3);
+  constexpr bool four = (VARIANT == 3 || VARIANT == 4);
   const uint32_t tabB = tabA + 0x10000;
   const uint32_t buf = s0;  // pad region below the tables
   aes_tables_init(dyn + (tabA - s0), t0g, threadIdx.x, NT);
@@ -32,6 +32,18 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   uint32_t x = 0;
   for (int it = 0; it < items; it++) {
     const uint64_t first = ((uint64_t)blockIdx.x * items + it) * 8453ull + 12345;
+    if constexpr (VARIANT == 5) {  // two blocks per thread in lockstep
+      for (int b = threadIdx.x; b < nblk; b += 2 * AT) {
+        AesState va, vb;
+        if (b + AT < nblk) {
+          aes256_ctr_block_cached_x2(L, key, first + b, first + b + AT, cache, va, vb);
+          sts128(buf + 16u * b, va);
+          sts128(buf + 16u * (b + AT), vb);
+        } else {
+          sts128(buf + 16u * b, aes256_ctr_block_cached(L, key, first + b, cache));
+        }
+      }
+    } else
     if (threadIdx.x < AT)
     for (int b = threadIdx.x; b < nblk; b += AT) {
       AesState v;
@@ -50,7 +62,7 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
 
 template <int VARIANT, int NT, int AT = NT, int FM = 0>
 static void run(const char *name, const AesKey &key, const uint32_t *t0, int nblk, int items, unsigned long long *dig) {
-  const int smem = VARIANT >= 3 ? 0x30000 : 0x20000;
+  const int smem = (VARIANT == 3 || VARIANT == 4) ? 0x30000 : 0x20000;
   CK(cudaFuncSetAttribute(k_aes<VARIANT, NT, AT, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   unsigned long long z = 0, out = 0;
@@ -80,6 +92,11 @@ int main() {
   run<4, 512>("ctr-cached 4-table", key, t0, 2818, items, dig);
   run<2, 512>("ctr-cached 2-table", key, t0, 2560, items, dig);   // 5 full rounds of 512: no ragged last round
   run<4, 512>("ctr-cached 4-table", key, t0, 2560, items, dig);
-  run<2, 512, 512, 0x8>("ctr-cached 2-table", key, t0, 2818, items, dig);
+  run<5, 512>("2-table, 2 blocks/thread", key, t0, 2818, items, dig);
+  run<5, 512>("2-table, 2 blocks/thread", key, t0, 2560, items, dig);
+  run<5, 512>("2-table, 2 blocks/thread", key, t0, 3072, items, dig);
+  run<2, 512>("ctr-cached 2-table", key, t0, 3072, items, dig);
+  run<5, 256>("2-table, 2 blocks/thread", key, t0, 2816, items, dig);
+  run<5, 384>("2-table, 2 blocks/thread", key, t0, 2304, items, dig);
   return 0;
 }
