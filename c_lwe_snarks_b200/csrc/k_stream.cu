@@ -172,7 +172,7 @@ k_expand(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_glo
 // CTA b works on tile b % NTILES as chunk b / NTILES of that tile, so the first ncta % NTILES tiles have one chunk
 // more than the others; a tile's chunks split [0, d) into CONTIGUOUS, balanced ranges (consecutive ciphertexts are
 // 8452.5 blocks apart: the counter-mode cache is refilled every ~8 items instead of every item).  The b coordinate
-// (1470) is handled by thread KS_TILE of the tile-0 CTAs, straight from the wire records.
+// (1470) comes from the wire records, not from the stream: k_bcoord below.
 //
 // Pipeline: THREE keystream buffers and two mbarriers per buffer (full: every warp has stored its blocks; empty:
 // every warp has read its coordinates) instead of a CTA-wide __syncthreads per item.  A tile is 2818 blocks for 512
@@ -209,7 +209,7 @@ __device__ __forceinline__ void ks_fill_rot(const AesKey &key, uint64_t first, i
 template <int NVEC>
 __global__ void __launch_bounds__(KS_THREADS, 1)
 k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
-           const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
+           const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
            const uint32_t *__restrict__ idx, size_t d, int nparts, uint64_t *__restrict__ partial0,
            uint64_t *__restrict__ partial1) {
   // NVEC = 1: tiles of 490 coordinates, thread t < 490 owns coordinate t.
@@ -234,9 +234,7 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
   const int vec = (NVEC == 2 && threadIdx.x >= TILE) ? 1 : 0;
   const int lc = threadIdx.x - vec * TILE;
   const bool is_mac = threadIdx.x < NVEC * TILE;
-  const bool is_b = tile == 0 && threadIdx.x >= NVEC * TILE && threadIdx.x < NVEC * TILE + NVEC;
-  const int my_vec = is_b ? (int)(threadIdx.x - NVEC * TILE) : vec;
-  const uint32_t *coeffs = my_vec ? coeffs1 : coeffs0;
+  const uint32_t *coeffs = vec ? coeffs1 : coeffs0;
 
   auto geom = [&](size_t m) {
     const size_t k = idx ? idx[m] : m;
@@ -281,41 +279,93 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
       uint32_t a[22];
       ks_read_coord(buf_of(b), g.delta + CT_BYTES * lc, a);
       acc_mad(acc, a, coeffs[m]);
-    } else if (is_b) {
-      const size_t k = idx ? idx[m] : m;
-      const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + k * CT_BYTES);  // 92 % 4 == 0
-      uint32_t a[22];
-#pragma unroll
-      for (int l = 0; l < 22; l++) a[l] = rec[l];
-      acc_mad(acc, a, coeffs[m]);
     }
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
     if (!late && t + 2 < nitems) fill(t + 2);
   }
 
-  if (is_mac || is_b) {
+  if (is_mac) {
     // the finish kernel adds `nparts` partials for every coordinate: a tile with one chunk fewer zeroes the last slot
+    const int c = tile * TILE + lc;
     if (chunk == nch - 1 && nch < nparts) {
-      uint64_t *z = (my_vec ? partial1 : partial0) + (size_t)nch * PLANAR_U64;
-      const int c = is_b ? N : tile * TILE + lc;
+      uint64_t *z = (vec ? partial1 : partial0) + (size_t)nch * PLANAR_U64;
 #pragma unroll
       for (int j = 0; j < L64; j++) z[(size_t)j * NCP + c] = 0;
-      if (is_b) {
-#pragma unroll
-        for (int j = 0; j < L64; j++) z[(size_t)j * NCP + N + 1] = 0;
-      }
     }
-    uint64_t *out = (my_vec ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
+    uint64_t *out = (vec ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
     uint32_t r[22];
     acc_fold(acc, r);
-    const int c = is_b ? N : tile * TILE + lc;
 #pragma unroll
     for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
-    if (is_b) {
+  }
+}
+
+// The b coordinate (1470) of the same partial sums, straight from the 92-byte wire records (ct_import lwe.c:125): this is
+// the ONLY consumer of the records, so the host flavour copies them to the device on a second stream WHILE k_evalpoly
+// (which needs only the seed and the scalars) is already running.  CTA k (one per partial slot) takes a balanced
+// contiguous range of the work items, every thread MACs its records, the CTA reduces (REDUX on 16-bit halves, then a
+// 22-step carry chain) and writes coordinate 1470 — and the zero padding coordinate 1471 — of partial slot k.
+constexpr int KB_THREADS = 256;
+template <int NVEC>
+__global__ void __launch_bounds__(KB_THREADS)
+k_bcoord(const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
+         const uint32_t *__restrict__ idx, size_t d, uint64_t *__restrict__ partial0, uint64_t *__restrict__ partial1) {
+  __shared__ uint32_t red[NVEC][KB_THREADS / 32][2 * L32];
+  __shared__ unsigned long long cols[NVEC][L32];
+  const size_t per = d / gridDim.x, rem = d % gridDim.x;
+  const size_t m0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+  const size_t m1 = m0 + per + (blockIdx.x < rem ? 1 : 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Acc704 acc[NVEC];
 #pragma unroll
-      for (int j = 0; j < L64; j++) out[(size_t)j * NCP + N + 1] = 0;
+  for (int v = 0; v < NVEC; v++) acc_zero(acc[v]);
+  for (size_t m = m0 + threadIdx.x; m < m1; m += KB_THREADS) {
+    const size_t k = idx ? idx[m] : m;
+    const uint32_t *rec = reinterpret_cast<const uint32_t *>(c8 + k * CT_BYTES);  // 92 % 4 == 0
+    uint32_t a[22];
+#pragma unroll
+    for (int l = 0; l < 22; l++) a[l] = rec[l];
+    acc_mad(acc[0], a, coeffs0[m]);
+    if constexpr (NVEC == 2) acc_mad(acc[1], a, coeffs1[m]);
+  }
+#pragma unroll
+  for (int v = 0; v < NVEC; v++) {
+    uint32_t r[22];
+    acc_fold(acc[v], r);
+#pragma unroll
+    for (int l = 0; l < 22; l++) {
+      const uint32_t lo = __reduce_add_sync(0xffffffffu, r[l] & 0xffffu);
+      const uint32_t hi = __reduce_add_sync(0xffffffffu, r[l] >> 16);
+      if (lane == 0) {
+        red[v][warp][2 * l] = lo;
+        red[v][warp][2 * l + 1] = hi;
+      }
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < NVEC * L32) {
+    const int v = threadIdx.x / L32, l = threadIdx.x % L32;
+    unsigned long long lo = 0, hi = 0;
+    for (int w = 0; w < KB_THREADS / 32; w++) {
+      lo += red[v][w][2 * l];
+      hi += red[v][w][2 * l + 1];
+    }
+    cols[v][l] = lo + (hi << 16);  // < 2^42
+  }
+  __syncthreads();
+  if (threadIdx.x < NVEC) {
+    const int v = threadIdx.x;
+    uint64_t *out = (v ? partial1 : partial0) + (size_t)blockIdx.x * PLANAR_U64;
+    uint64_t carry = 0;
+    uint32_t prev = 0;
+    for (int l = 0; l < L32; l++) {
+      const uint64_t t = cols[v][l] + carry;
+      carry = t >> 32;
+      if (l & 1) out[(size_t)(l >> 1) * NCP + N] = (uint64_t)prev | (uint64_t)(uint32_t)t << 32;
+      else prev = (uint32_t)t;
+    }
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + N + 1] = 0;
   }
 }
 
@@ -511,17 +561,28 @@ int evalpoly_nchunks(size_t d, int sm_count) {
 }
 
 // writes `nchunks` (= evalpoly_nchunks) canonical planar partial sums to partial_ws
-cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks, int sm_count,
-                                     uint64_t *partial_ws, cudaStream_t st) {
+// (the a coordinates: needs no wire records)
+cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint32_t *coeffs,
+                                     const uint32_t *idx, size_t d, int nchunks, int sm_count, uint64_t *partial_ws,
+                                     cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
   int nparts;
   const int ncta = evalpoly_plan(d, sm_count, KS_NTILES, nchunks, &nparts);
   if (nparts != nchunks) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly<1><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs, nullptr, idx, d, nparts, partial_ws,
-                                                            nullptr);
+  k_evalpoly<1><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, coeffs, nullptr, idx, d, nparts, partial_ws, nullptr);
+  return cudaGetLastError();
+}
+
+// the b coordinate of the same `nchunks` partial sums (coeffs1 / partial1 = nullptr: one scalar vector)
+cudaError_t launch_bcoord_partials(const uint8_t *c8, const uint32_t *coeffs0, const uint32_t *coeffs1, const uint32_t *idx,
+                                   size_t d, int nchunks, uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
+  if (d == 0 || nchunks == 0) return cudaSuccess;
+  if (coeffs1)
+    k_bcoord<2><<<nchunks, KB_THREADS, 0, st>>>(c8, coeffs0, coeffs1, idx, d, partial0, partial1);
+  else
+    k_bcoord<1><<<nchunks, KB_THREADS, 0, st>>>(c8, coeffs0, nullptr, idx, d, partial0, nullptr);
   return cudaGetLastError();
 }
 
@@ -532,7 +593,7 @@ int evalpoly2_nchunks(size_t d, int sm_count) {
 }
 
 // two scalar vectors in one pass: writes nchunks partial sums to partial0 and nchunks to partial1
-cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset,
                                       const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks, int sm_count,
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
@@ -541,7 +602,7 @@ cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uin
   if (nparts != nchunks) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  k_evalpoly<2><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, c8, coeffs0, coeffs1, nullptr, d, nparts, partial0,
+  k_evalpoly<2><<<ncta, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, coeffs0, coeffs1, nullptr, d, nparts, partial0,
                                                             partial1);
   return cudaGetLastError();
 }

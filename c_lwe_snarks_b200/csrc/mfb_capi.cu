@@ -46,11 +46,13 @@ cudaError_t launch_stream_bytes(const AesKey &key, const uint32_t *t0, uint64_t 
 cudaError_t launch_expand(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8, size_t count,
                           uint64_t *cts, int sm_count, cudaStream_t st);
 int evalpoly_nchunks(size_t d, int sm_count);
-cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
-                                     const uint32_t *coeffs, const uint32_t *idx, size_t d, int nchunks, int sm_count,
-                                     uint64_t *partial_ws, cudaStream_t st);
+cudaError_t launch_evalpoly_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint32_t *coeffs,
+                                     const uint32_t *idx, size_t d, int nchunks, int sm_count, uint64_t *partial_ws,
+                                     cudaStream_t st);
+cudaError_t launch_bcoord_partials(const uint8_t *c8, const uint32_t *coeffs0, const uint32_t *coeffs1, const uint32_t *idx,
+                                   size_t d, int nchunks, uint64_t *partial0, uint64_t *partial1, cudaStream_t st);
 int evalpoly2_nchunks(size_t d, int sm_count);
-cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint8_t *c8,
+cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uint64_t offset,
                                       const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d, int nchunks, int sm_count,
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st);
 cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
@@ -90,6 +92,10 @@ struct mfb_ctx {
   uint8_t *bounce[2] = {nullptr, nullptr};
   cudaEvent_t bounce_free[2] = {nullptr, nullptr};
   bool bounce_used[2] = {false, false};  // an H2D from this buffer has been queued at some point
+  // second stream of the host-flavour eval_poly calls: the wire records travel to the device (and the b coordinate is
+  // summed from them) while the AES kernel is already running on `stream`
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   // pinned entropy staging of mfb_encrypt_cb (two pieces in flight)
   uint8_t *ent_pin[2] = {nullptr, nullptr};
   size_t ent_pin_cap = 0;
@@ -285,6 +291,9 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
     if (ctx->ent_pin[k]) cudaFreeHost(ctx->ent_pin[k]);
     if (ctx->ent_free[k]) cudaEventDestroy(ctx->ent_free[k]);
   }
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;
@@ -588,22 +597,60 @@ int mfb_columns_carry_dev(mfb_ctx *ctx, const uint64_t *cols_dev, int c0, int nc
   return MFB_OK;
 }
 
+// eval_poly over one region for one or two scalar vectors (coeffs1 / rop1 = nullptr: one): the AES + MAC kernel for the a
+// coordinates, k_bcoord for the b coordinate, the finish kernel(s) (fused with the peer exchange when `g`).  The wire
+// records are either on the device already (c8_host = nullptr) or are copied from c8_host into c8_dev on the context's
+// second stream while the AES kernel — which does not need them — is running.
+static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *c8_dev, const uint8_t *c8_host,
+                          size_t c8_bytes, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, const uint32_t *idx_dev,
+                          size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
+                          uint64_t *rop1_out_dev, cudaStream_t st, mfb_peer_group *g) {
+  AesKey key;
+  aes_host::expand(seed, &key);
+  const bool two = coeffs1_dev != nullptr;
+  int nchunks = d ? (two ? evalpoly2_nchunks(d, ctx->sm_count) : evalpoly_nchunks(d, ctx->sm_count)) : 0;
+  if ((two ? 2 : 1) * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / (two ? 2 : 1);
+  uint64_t *p0 = ctx->partial_ws, *p1 = two ? ctx->partial_ws + (size_t)nchunks * PLANAR_U64 : nullptr;
+  cudaStream_t st_b = st;
+  if (d && c8_host) {
+    if (!ctx->stream2) MFB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_a) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    if (!ctx->ev_b) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    st_b = ctx->stream2;
+    MFB_CUDA_TRY(cudaEventRecord(ctx->ev_a, st));  // the scalars (queued on st by the caller) are on the device
+  }
+  if (d) prof_mark(ctx, 0, st);
+  if (two)
+    MFB_CUDA_TRY(launch_evalpoly2_partials(key, ctx->t0_dev, offset, coeffs0_dev, coeffs1_dev, d, nchunks, ctx->sm_count, p0, p1, st));
+  else
+    MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, coeffs0_dev, idx_dev, d, nchunks, ctx->sm_count, p0, st));
+  if (d) prof_mark(ctx, 1, st);
+  if (d && c8_host) {
+    MFB_CUDA_TRY(cudaStreamWaitEvent(st_b, ctx->ev_a, 0));
+    MFB_CUDA_TRY(cudaMemcpyAsync(c8_dev, c8_host, c8_bytes, cudaMemcpyHostToDevice, st_b));
+  }
+  MFB_CUDA_TRY(launch_bcoord_partials(c8_dev, coeffs0_dev, coeffs1_dev, idx_dev, d, nchunks, p0, p1, st_b));
+  if (d && c8_host) {
+    MFB_CUDA_TRY(cudaEventRecord(ctx->ev_b, st_b));
+    MFB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_b, 0));
+  }
+  if (g) {
+    MFB_TRY(peer_finish(ctx, g, nchunks, nullptr, rop0_in_dev, rop0_out_dev, nullptr, st));
+  } else {
+    MFB_CUDA_TRY(launch_lincomb_finish(p0, nchunks, rop0_in_dev, rop0_out_dev, nullptr, st));
+    if (two) MFB_CUDA_TRY(launch_lincomb_finish(p1, nchunks, rop1_in_dev, rop1_out_dev, nullptr, st));
+  }
+  ctx->launches += (d ? 2 : 0) + (two ? 2 : 1);
+  return MFB_OK;
+}
+
 int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                       const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
                       uint64_t *rop_out_dev, void *stream) {
   MFB_CHECK_CTX(ctx);
   if (!seed || !rop_out_dev || (d && (!c8_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_eval_poly_dev: null pointer");
-  AesKey key;
-  aes_host::expand(seed, &key);
-  int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
-  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
-  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks, ctx->sm_count,
-                                        ctx->partial_ws, (cudaStream_t)stream));
-  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nchunks, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
-  ctx->launches += d ? 2 : 1;
-  return MFB_OK;
+  return eval_poly_core(ctx, seed, offset, const_cast<uint8_t *>(c8_dev), nullptr, 0, coeffs_dev, nullptr, idx_dev, d, rop_in_dev,
+                        rop_out_dev, nullptr, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
@@ -612,17 +659,8 @@ int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[4
   MFB_CHECK_CTX(ctx);
   if (!g || !g->connected) return set_err(MFB_EARG, "mfb_eval_poly_peer_dev: the peer group is not connected");
   if (!seed || !rop_out_dev || (d && (!c8_dev || !coeffs_dev))) return set_err(MFB_EARG, "mfb_eval_poly_peer_dev: null pointer");
-  AesKey key;
-  aes_host::expand(seed, &key);
-  int nchunks = d ? evalpoly_nchunks(d, ctx->sm_count) : 0;
-  if (nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS;
-  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, c8_dev, coeffs_dev, idx_dev, d, nchunks, ctx->sm_count,
-                                        ctx->partial_ws, (cudaStream_t)stream));
-  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
-  MFB_TRY(peer_finish(ctx, g, nchunks, nullptr, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
-  ctx->launches += d ? 2 : 1;
-  return MFB_OK;
+  return eval_poly_core(ctx, seed, offset, const_cast<uint8_t *>(c8_dev), nullptr, 0, coeffs_dev, nullptr, idx_dev, d, rop_in_dev,
+                        rop_out_dev, nullptr, nullptr, (cudaStream_t)stream, g);
 }
 
 int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
@@ -631,19 +669,8 @@ int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, co
   MFB_CHECK_CTX(ctx);
   if (!seed || !rop0_out_dev || !rop1_out_dev || (d && (!c8_dev || !coeffs0_dev || !coeffs1_dev)))
     return set_err(MFB_EARG, "mfb_eval_poly2_dev: null pointer");
-  AesKey key;
-  aes_host::expand(seed, &key);
-  int nchunks = d ? evalpoly2_nchunks(d, ctx->sm_count) : 0;
-  if (2 * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / 2;
-  uint64_t *p0 = ctx->partial_ws, *p1 = ctx->partial_ws + (size_t)nchunks * PLANAR_U64;
-  if (d) prof_mark(ctx, 0, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_evalpoly2_partials(key, ctx->t0_dev, offset, c8_dev, coeffs0_dev, coeffs1_dev, d, nchunks, ctx->sm_count, p0, p1,
-                                         (cudaStream_t)stream));
-  if (d) prof_mark(ctx, 1, (cudaStream_t)stream);
-  MFB_CUDA_TRY(launch_lincomb_finish(p0, nchunks, rop0_in_dev, rop0_out_dev, nullptr, (cudaStream_t)stream));
-  MFB_CUDA_TRY(launch_lincomb_finish(p1, nchunks, rop1_in_dev, rop1_out_dev, nullptr, (cudaStream_t)stream));
-  ctx->launches += d ? 3 : 2;
-  return MFB_OK;
+  return eval_poly_core(ctx, seed, offset, const_cast<uint8_t *>(c8_dev), nullptr, 0, coeffs0_dev, coeffs1_dev, nullptr, d,
+                        rop0_in_dev, rop0_out_dev, rop1_in_dev, rop1_out_dev, (cudaStream_t)stream, nullptr);
 }
 
 int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
@@ -735,16 +762,15 @@ int mfb_eval_poly(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const u
   if (rc == MFB_OK) {
     cudaError_t e = cudaSuccess;
     do {
-      if (d && (e = cudaMemcpyAsync(d_c8, c8, nrec * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if (d && (e = cudaMemcpyAsync(d_co, co32, d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if (idx && d && (e = cudaMemcpyAsync(d_idx, idx, d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if ((e = cudaMemcpyAsync(d_rop, rop_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
   }
-  if (rc == MFB_OK)
-    rc = mfb_eval_poly_dev(ctx, seed, offset, (const uint8_t *)d_c8, (const uint32_t *)d_co, (const uint32_t *)d_idx, d,
-                           (const uint64_t *)d_rop, (uint64_t *)d_rop, ctx->stream);
+  if (rc == MFB_OK)  // the records follow on the second stream while the AES kernel runs
+    rc = eval_poly_core(ctx, seed, offset, (uint8_t *)d_c8, c8, nrec * CT_BYTES, (const uint32_t *)d_co, nullptr,
+                        (const uint32_t *)d_idx, d, (const uint64_t *)d_rop, (uint64_t *)d_rop, nullptr, nullptr, ctx->stream, nullptr);
   if (rc == MFB_OK) {
     cudaError_t e = cudaMemcpyAsync(rop_flat_inout, d_rop, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -773,7 +799,6 @@ int mfb_eval_poly2(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const 
   if (rc == MFB_OK) {
     cudaError_t e = cudaSuccess;
     do {
-      if (d && (e = cudaMemcpyAsync(d_c8, c8, d * CT_BYTES, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if (d && (e = cudaMemcpyAsync(d_co, co32, 2 * d * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if ((e = cudaMemcpyAsync(r0, rop0_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
       if ((e = cudaMemcpyAsync(r1, rop1_flat_inout, MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
@@ -781,8 +806,8 @@ int mfb_eval_poly2(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const 
     if (e != cudaSuccess) rc = fail(e, "H2D", __FILE__, __LINE__);
   }
   if (rc == MFB_OK)
-    rc = mfb_eval_poly2_dev(ctx, seed, offset, (const uint8_t *)d_c8, (const uint32_t *)d_co, (const uint32_t *)d_co + d, d,
-                            r0, r0, r1, r1, ctx->stream);
+    rc = eval_poly_core(ctx, seed, offset, (uint8_t *)d_c8, c8, d * CT_BYTES, (const uint32_t *)d_co, (const uint32_t *)d_co + d,
+                        nullptr, d, r0, r0, r1, r1, ctx->stream, nullptr);
   if (rc == MFB_OK) {
     cudaError_t e = cudaMemcpyAsync(rop0_flat_inout, r0, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(rop1_flat_inout, r1, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream);
