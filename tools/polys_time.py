@@ -30,6 +30,16 @@ for log2d in [int(a) for a in sys.argv[1:]] or [16, 20]:
         t0 = time.perf_counter()
         res.prover_polys(wl, 12345)
         times.append(1e3 * (time.perf_counter() - t0))
-    print(json.dumps({"D": D, "M": M, "polys_resident_ms": [round(x, 3) for x in times]}), flush=True)
+    # the device-resident variant the fused prover pipeline uses (w | v | h stay on the device: no 24 D bytes of D2H)
+    import ctypes as C
+    ptr = C.c_void_p()
+    wl_p = wl.ctypes.data_as(C.POINTER(C.c_uint64))
+    dev = []
+    for _ in range(6):
+        t0 = time.perf_counter()
+        ctx._ck(ctx.lib.mfb_ssp_prover_polys_resident_dev(ctx.h, res.handle, wl_p, wl.size, 12345, C.byref(ptr)))
+        dev.append(1e3 * (time.perf_counter() - t0))
+    print(json.dumps({"D": D, "M": M, "polys_resident_ms": [round(x, 3) for x in times],
+                      "polys_resident_dev_ms": [round(x, 3) for x in dev[1:]]}), flush=True)
     res.close()
 ctx.close()
