@@ -103,7 +103,10 @@ void mf_crs_release(crs_t crs) {
 }
 
 void mf_crs_make_resident(crs_t crs) {
+  double t0 = mf_now();
   mf_crs_release(crs);
+  mf_trace("make_resident.release_previous", t0);
+  t0 = mf_now();
   struct resident *r = calloc(1, sizeof(*r));
   if (!r) mf_die("malloc");
   r->owner = crs;
@@ -127,7 +130,10 @@ void mf_crs_make_resident(crs_t crs) {
     return;
   }
   int rc = mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s);
+  mf_trace("make_resident.region_s", t0);
+  t0 = mf_now();
   if (rc == MFB_OK) rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
+  mf_trace("make_resident.region_as", t0);
   if (rc != MFB_OK) {
     if (rc != MFB_ENOMEM) mf_die("mfb_region_create");
     fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident: %s; the CRS stays non-resident\n", mfb_last_error());

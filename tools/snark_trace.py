@@ -15,7 +15,16 @@ print("setup", sn.setup(), file=sys.stderr)
 print("setup", sn.setup(), file=sys.stderr)
 print("prove (cold)", sn.prove(), file=sys.stderr)
 print("prove", sn.prove(), file=sys.stderr)
-sn.make_resident()
+import ctypes
+import time
+for label in ("make_resident (cold)", "make_resident"):
+    t0 = time.perf_counter()
+    sn.lib.mf_crs_make_resident(ctypes.byref(sn.crs))
+    t1 = time.perf_counter()
+    sn.lib.mf_ssp_make_resident(sn._ssp_ptr())
+    t2 = time.perf_counter()
+    sn._ssp_resident = True
+    print(label, "crs %.4f ssp %.4f" % (t1 - t0, t2 - t1), file=sys.stderr)
 print("prove_res (cold)", sn.prove(), file=sys.stderr)
 print("prove_res", sn.prove(), file=sys.stderr)
 print("verify", sn.verify(), file=sys.stderr)
