@@ -24,10 +24,12 @@
 namespace mfb {
 
 constexpr int LC_TILE = RT_TILE;  // 64 threads per CTA = coordinates per tile
-constexpr int LC_STAGES = 2;      // ring depth
+// ring depth: 2 stages for one scalar vector (9 CTAs per SM: 203 KB of copies in flight per SM); the two-vector
+// kernel holds two accumulators (157 registers: 6 CTAs per SM), so it gets 3 stages to keep as many bytes in flight
+template <int NVEC> struct LcCfg { static constexpr int STAGES = NVEC == 2 ? 3 : 2; };
 constexpr int LC_G = 2;           // ciphertext blocks per stage
 constexpr int LC_TILE_BYTES = RT_TILE_U64 * 8;  // 5632
-constexpr int LC_SMEM_BYTES = LC_STAGES * LC_G * LC_TILE_BYTES;
+template <int NVEC> constexpr int lc_smem_bytes() { return LcCfg<NVEC>::STAGES * LC_G * LC_TILE_BYTES; }
 constexpr int LC_CTR_STRIDE = 32;  // one queue counter per 128-byte line
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(LC_TILE)
 k_lincomb(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
           size_t d, uint32_t chunk_len, unsigned int *__restrict__ queue, uint64_t *__restrict__ partial,
           size_t partial_stride) {
+  constexpr int LC_STAGES = LcCfg<NVEC>::STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * LC_STAGES];  // [0, S): full (tx), [S, 2S): empty (2 warps)
   __shared__ uint32_t meta_first[LC_STAGES];             // first ciphertext of the stage (d < 2^32 per GPU)
@@ -431,8 +434,8 @@ template <int NVEC>
 static int nslots_for(size_t d, int sm_count) {
   static int occ = 0;
   if (!occ) {
-    cudaFuncSetAttribute(k_lincomb<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb<NVEC>, LC_TILE, LC_SMEM_BYTES) != cudaSuccess || occ < 1)
+    cudaFuncSetAttribute(k_lincomb<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<NVEC>());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb<NVEC>, LC_TILE, lc_smem_bytes<NVEC>()) != cudaSuccess || occ < 1)
       occ = 6;
   }
   size_t n = (size_t)sm_count * occ / RT_NTILES;
@@ -457,14 +460,14 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
     dim3 grid(RT_NTILES, nslots);
     cudaError_t e;
     if (coeffs1) {
-      if ((e = cudaFuncSetAttribute(k_lincomb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k_lincomb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<2>())) != cudaSuccess) return e;
       if (mark) mark(mark_arg, 0, st);
-      k_lincomb<2><<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs0, coeffs1, d, chunk_len, queue, partial_ws,
+      k_lincomb<2><<<grid, LC_TILE, lc_smem_bytes<2>(), st>>>(cts, coeffs0, coeffs1, d, chunk_len, queue, partial_ws,
                                                           (size_t)nslots * PLANAR_U64);
     } else {
-      if ((e = cudaFuncSetAttribute(k_lincomb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM_BYTES)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k_lincomb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<1>())) != cudaSuccess) return e;
       if (mark) mark(mark_arg, 0, st);
-      k_lincomb<1><<<grid, LC_TILE, LC_SMEM_BYTES, st>>>(cts, coeffs0, nullptr, d, chunk_len, queue, partial_ws, 0);
+      k_lincomb<1><<<grid, LC_TILE, lc_smem_bytes<1>(), st>>>(cts, coeffs0, nullptr, d, chunk_len, queue, partial_ws, 0);
     }
     if (mark) mark(mark_arg, 1, st);
   }
