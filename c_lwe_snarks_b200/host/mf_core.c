@@ -98,7 +98,15 @@ int mf_to_flat(uint64_t out[MF_LIMBS], mpz_srcptr z) {
   return SIZ(z) < 0;
 }
 
-void mf_from_flat(mpz_ptr z, const uint64_t in[MF_LIMBS]) { mpz_import(z, MF_LIMBS, -1, sizeof(uint64_t), 0, 0, in); }
+/* z <- the non-negative integer of 11 little-endian limbs: written straight into the limb array (what mpz_import
+ * computes, without its per-call overhead — a proof is 5 x 1471 of these) */
+void mf_from_flat(mpz_ptr z, const uint64_t in[MF_LIMBS]) {
+  if (ALLOC(z) < MF_LIMBS) _mpz_realloc(z, MF_LIMBS);
+  int n = MF_LIMBS;
+  while (n > 0 && in[n - 1] == 0) n--;
+  for (int i = 0; i < n; i++) PTR(z)[i] = in[i];
+  SIZ(z) = n;
+}
 
 void mf_ct_to_flat(uint64_t *out, ct_t ct, const char *who) {
   for (size_t i = 0; i <= GAMMA_N; i++)
