@@ -96,6 +96,7 @@ struct mfb_ctx {
   // summed from them) while the AES kernel is already running on `stream`
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  uint64_t *acc_pin = nullptr;  // pinned staging of the prover pipeline's four flat accumulators (one copy each way)
   // pinned entropy staging of mfb_encrypt_cb (two pieces in flight)
   uint8_t *ent_pin[2] = {nullptr, nullptr};
   size_t ent_pin_cap = 0;
@@ -291,6 +292,7 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
     if (ctx->ent_pin[k]) cudaFreeHost(ctx->ent_pin[k]);
     if (ctx->ent_free[k]) cudaEventDestroy(ctx->ent_free[k]);
   }
+  if (ctx->acc_pin) cudaFreeHost(ctx->acc_pin);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -950,17 +952,19 @@ int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, cons
   MFB_TRY(mfb_ssp_prover_polys_resident_dev(ctx, ssp, witness_limbs, nlimbs, delta, &wvh));
   const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
   void *d_rop;
-  MFB_TRY(scratch(ctx, 2, 4 * MFB_FLAT_CT_U64 * 8, &d_rop));
+  const size_t FL = MFB_FLAT_CT_U64;
+  MFB_TRY(scratch(ctx, 2, 4 * FL * 8, &d_rop));
   uint64_t *r = (uint64_t *)d_rop;
   uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
-  for (int k = 0; k < 4; k++)
-    MFB_CUDA_TRY(cudaMemcpyAsync(r + k * MFB_FLAT_CT_U64, host[k], MFB_FLAT_CT_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
-  MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + MFB_FLAT_CT_U64, r + MFB_FLAT_CT_U64, ctx->stream));
-  MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * MFB_FLAT_CT_U64, r + 2 * MFB_FLAT_CT_U64,
-                           r + 3 * MFB_FLAT_CT_U64, r + 3 * MFB_FLAT_CT_U64, ctx->stream));
-  for (int k = 0; k < 4; k++)
-    MFB_CUDA_TRY(cudaMemcpyAsync(host[k], r + k * MFB_FLAT_CT_U64, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  // the four accumulators travel as ONE pinned copy each way
+  if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 4 * FL * 8, cudaHostAllocDefault));
+  for (int k = 0; k < 4; k++) memcpy(ctx->acc_pin + k * FL, host[k], FL * 8);
+  MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + FL, r + FL, ctx->stream));
+  MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * FL, r + 2 * FL, r + 3 * FL, r + 3 * FL, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(ctx->acc_pin, r, 4 * FL * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 4; k++) memcpy(host[k], ctx->acc_pin + k * FL, FL * 8);
   return MFB_OK;
 }
 

@@ -41,6 +41,7 @@ int set_fail(int code, const char *msg) {
 
 struct mfb_set {
   std::vector<Member> m;
+  uint64_t *acc_pin = nullptr;  // pinned staging of the four flat accumulators of mfb_set_prove_resident
 };
 
 struct mfb_set_region {
@@ -87,6 +88,7 @@ MFB_API void mfb_set_destroy(mfb_set *s) {
     if (mb.owned) mfb_ctx_destroy(mb.ctx);
   }
   if (!s->m.empty()) cudaSetDevice(s->m[0].device);
+  if (s->acc_pin) cudaFreeHost(s->acc_pin);
   delete s;
 }
 
@@ -275,8 +277,10 @@ MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_regio
   const uint32_t *wvh = nullptr;
   SET_TRY(mfb_ssp_prover_polys_resident_dev(p.ctx, ssp, witness_limbs, nlimbs, delta, &wvh));  // stream idle on return
   uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
-  for (int k = 0; k < 4; k++)
-    SET_CUDA(cudaMemcpyAsync(p.res + (size_t)k * MFB_PLANAR_U64, host[k], FLAT * 8, cudaMemcpyHostToDevice, p.stream));
+  // the four accumulators travel as ONE pinned copy each way (slots of MFB_PLANAR_U64, the stride of p.res)
+  if (!s->acc_pin) SET_CUDA(cudaHostAlloc((void **)&s->acc_pin, 4 * MFB_PLANAR_U64 * 8, cudaHostAllocDefault));
+  for (int k = 0; k < 4; k++) memcpy(s->acc_pin + (size_t)k * MFB_PLANAR_U64, host[k], FLAT * 8);
+  SET_CUDA(cudaMemcpyAsync(p.res, s->acc_pin, 4 * MFB_PLANAR_U64 * 8, cudaMemcpyHostToDevice, p.stream));
   // every member: its slices of w, v, h over NVLink, then both two-vector passes over its shards
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
@@ -309,8 +313,7 @@ MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_regio
       SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
     }
   SET_CUDA(cudaSetDevice(p.device));
-  for (int k = 0; k < 4; k++)
-    SET_CUDA(cudaMemcpyAsync(host[k], p.res + (size_t)k * MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, 4 * MFB_PLANAR_U64 * 8, cudaMemcpyDeviceToHost, p.stream));
   int rc = MFB_OK;
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
@@ -320,6 +323,7 @@ MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_regio
     if (st != MFB_OK) rc = st;
   }
   SET_CUDA(cudaSetDevice(p.device));
+  for (int k = 0; k < 4; k++) memcpy(host[k], s->acc_pin + (size_t)k * MFB_PLANAR_U64, FLAT * 8);
   return rc;
 }
 
