@@ -91,6 +91,7 @@ _SIGS = {
     "mfb_set_last_error": (C.c_char_p, []),
     "mfb_set_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_set_region_destroy": (None, [_vp, _vp]),
+    "mfb_set_eval_poly2": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u64p, C.c_size_t, _u64p, _u64p]),
     "mfb_set_region_lincomb2": (C.c_int, [_vp, _vp, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
     "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mfb_columns_carry_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
@@ -268,6 +269,17 @@ class DeviceSet:
     @property
     def size(self) -> int:
         return int(self.ctx.lib.mfb_set_size(self.h))
+
+    def eval_poly2(self, seed, offset: int, c8, coeffs0, coeffs1=None, rop0=None, rop1=None):
+        """eval_poly (coeffs1 None) / eval_poly2 with nothing resident, sharded over the members."""
+        s, rec = _seed(seed), _arr(c8, np.uint8)
+        c0 = _arr(coeffs0, np.uint64)
+        c1 = None if coeffs1 is None else _arr(coeffs1, np.uint64)
+        r0 = np.zeros((NC, L64), np.uint64) if rop0 is None else _arr(rop0, np.uint64).copy()
+        r1 = None if c1 is None else (np.zeros((NC, L64), np.uint64) if rop1 is None else _arr(rop1, np.uint64).copy())
+        self._ck(self.ctx.lib.mfb_set_eval_poly2(self.h, _p8(s), offset, _p8(rec), _p64(c0), None if c1 is None else _p64(c1),
+                                                c0.size, _p64(r0), None if r1 is None else _p64(r1)))
+        return r0 if c1 is None else (r0, r1)
 
     def region(self, seed, offset: int, c8) -> "SetRegion":
         s, rec = _seed(seed), _arr(c8, np.uint8)

@@ -29,6 +29,8 @@ struct Member {
   size_t co_cap = 0;
   uint64_t *part = nullptr;  // 4 x flat
   uint64_t *res = nullptr;   // 4 x flat
+  uint8_t *c8 = nullptr;     // wire records of the member's range (mfb_set_eval_poly2)
+  size_t c8_cap = 0;
 };
 
 thread_local char g_set_err[256] = "";
@@ -82,6 +84,7 @@ MFB_API void mfb_set_destroy(mfb_set *s) {
     cudaSetDevice(mb.device);
     if (mb.group) mfb_peer_destroy(mb.ctx, mb.group);
     if (mb.co) cudaFree(mb.co);
+    if (mb.c8) cudaFree(mb.c8);
     if (mb.part) cudaFree(mb.part);
     if (mb.res) cudaFree(mb.res);
     if (mb.stream) cudaStreamDestroy(mb.stream);
@@ -253,6 +256,82 @@ MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const u
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
     SET_CUDA(cudaStreamSynchronize(mb.stream));
+    const int st = mfb_peer_status(mb.ctx, mb.group);
+    if (st != MFB_OK) rc = st;
+  }
+  SET_CUDA(cudaSetDevice(p.device));
+  return rc;
+}
+
+// eval_poly (one or two scalar vectors) with NOTHING resident, sharded by ciphertext index: member i regenerates the
+// a-vectors of its contiguous range from AES in-kernel (mfb_eval_poly2_dev at its stream offset), one peer all-reduce
+// kernel per vector combines the partial sums.  Host buffers in and out; coefficients as uint64 (< 2^32).
+MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
+                               const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
+  g_set_err[0] = 0;
+  if (!s || !seed || !rop0_flat_inout || (d && (!c8 || !coeffs0)) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
+    return set_fail(MFB_EARG, "mfb_set_eval_poly2: null pointer");
+  const size_t world = s->m.size(), FLAT = MFB_FLAT_CT_U64;
+  const int nvec = coeffs1 ? 2 : 1;
+  std::vector<uint32_t> co32((size_t)nvec * d + 1);
+  for (int v = 0; v < nvec; v++) {
+    const uint64_t *src = v ? coeffs1 : coeffs0;
+    for (size_t i = 0; i < d; i++) {
+      if (src[i] >> 32) return set_fail(MFB_EARG, "mfb_set_eval_poly2: a coefficient does not fit 32 bits");
+      co32[(size_t)v * d + i] = (uint32_t)src[i];
+    }
+  }
+  const size_t base = d / world, extra = d % world;
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    const size_t first = i * base + (i < extra ? i : extra), cnt = base + (i < extra ? 1 : 0);
+    if (mb.co_cap < 2 * cnt + 4) {
+      if (mb.co) SET_CUDA(cudaFree(mb.co));
+      mb.co = nullptr;
+      mb.co_cap = 0;
+      SET_CUDA(cudaMalloc((void **)&mb.co, (2 * cnt + 4) * 4));
+      mb.co_cap = 2 * cnt + 4;
+    }
+    if (mb.c8_cap < cnt * MFB_CT_BYTES + 16) {
+      if (mb.c8) SET_CUDA(cudaFree(mb.c8));
+      mb.c8 = nullptr;
+      mb.c8_cap = 0;
+      SET_CUDA(cudaMalloc((void **)&mb.c8, cnt * MFB_CT_BYTES + 16));
+      mb.c8_cap = cnt * MFB_CT_BYTES + 16;
+    }
+    uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
+    if (cnt) {
+      SET_CUDA(cudaMemcpyAsync(c0, co32.data() + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, co32.data() + d + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+      SET_CUDA(cudaMemcpyAsync(mb.c8, c8 + first * MFB_CT_BYTES, cnt * MFB_CT_BYTES, cudaMemcpyHostToDevice, mb.stream));
+    }
+    if (i == 0) {
+      SET_CUDA(cudaMemcpyAsync(mb.res, rop0_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
+      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(mb.res + MFB_PLANAR_U64, rop1_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
+    }
+    const uint64_t off = offset + first * (uint64_t)MFB_CTR_CT;
+    if (nvec == 2)
+      SET_TRY(mfb_eval_poly2_dev(mb.ctx, seed, off, mb.c8, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + MFB_PLANAR_U64, mb.stream));
+    else
+      SET_TRY(mfb_eval_poly_dev(mb.ctx, seed, off, mb.c8, c0, nullptr, cnt, nullptr, mb.part, mb.stream));
+  }
+  for (int v = 0; v < nvec; v++)
+    for (size_t i = 0; i < world; i++) {
+      Member &mb = s->m[i];
+      SET_CUDA(cudaSetDevice(mb.device));
+      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
+      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
+    }
+  Member &p = s->m[0];
+  SET_CUDA(cudaSetDevice(p.device));
+  SET_CUDA(cudaMemcpyAsync(rop0_flat_inout, p.res, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  if (nvec == 2) SET_CUDA(cudaMemcpyAsync(rop1_flat_inout, p.res + MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
+  int rc = MFB_OK;
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_CUDA(cudaStreamSynchronize(mb.stream));  // (co32 is read by the queued copies until here)
     const int st = mfb_peer_status(mb.ctx, mb.group);
     if (st != MFB_OK) rc = st;
   }

@@ -297,8 +297,17 @@ static void lincomb_pair(ct_t rop0, ct_t rop1, crs_t crs, int which_as, const ui
   if (!acc) mf_die("malloc");
   mf_ct_to_flat(acc, rop0, "prover");
   mf_ct_to_flat(acc + FLAT_CT, rop1, "prover");
-  MF_GPU(mfb_eval_poly2(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S, (const uint8_t *)(which_as ? crs->as : crs->s), poly0,
-                        poly1, GAMMA_D, acc, acc + FLAT_CT));
+  mfb_set *set = device_set();
+  if (set) { /* sharded by ciphertext index: every GPU regenerates the a-vectors of its range */
+    if (mfb_set_eval_poly2(set, crs->seed, which_as ? CTR_AS : CTR_S, (const uint8_t *)(which_as ? crs->as : crs->s), poly0, poly1,
+                           GAMMA_D, acc, acc + FLAT_CT) != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_eval_poly2 failed: %s\n", mfb_set_last_error());
+      abort();
+    }
+  } else {
+    MF_GPU(mfb_eval_poly2(mf_gpu(), crs->seed, which_as ? CTR_AS : CTR_S, (const uint8_t *)(which_as ? crs->as : crs->s), poly0,
+                          poly1, GAMMA_D, acc, acc + FLAT_CT));
+  }
   mf_ct_from_flat(rop0, acc);
   mf_ct_from_flat(rop1, acc + FLAT_CT);
   free(acc);

@@ -199,6 +199,10 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
 MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r);
 MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
                             uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
+/* eval_poly / eval_poly2 with nothing resident, sharded: every member regenerates the a-vectors of its contiguous
+ * ciphertext range from AES in-kernel; coeffs1 / rop1 may both be NULL. */
+MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
+                       const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
 /* mfb_prove_resident over sharded regions: the polynomial step runs on the primary, the members fetch their slices of
  * w, v, h over NVLink, run both two-vector passes over their shards, and four peer all-reduce kernels combine them. */
 MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *reg_s, const mfb_set_region *reg_as,

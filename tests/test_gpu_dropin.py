@@ -112,6 +112,25 @@ def test_prover_with_crs_sharded_over_a_device_set_is_identical(dropin, n):
         assert sha(proof[k]) == g["proof_sha"][k]
 
 
+def test_prover_sharded_over_a_device_set_without_residency(dropin):
+    """mf_set_devices(2) with a NON-resident CRS: both fused passes are sharded by ciphertext index (every member
+    regenerates its a-vectors from AES) — same proof."""
+    import torch
+    g = GOLD["snark_d64_m16"]
+    dropin.set_instance(g["D"], g["M"])
+    dropin.lib.mf_set_devices(2, 1 if torch.cuda.device_count() >= 2 else 0)
+    try:
+        dropin.set_entropy(xof("snark-entropy-d64-m16", g["entropy_bytes"]))
+        ssp, wit = dropin.random_ssp()
+        crs = dropin.setup(ssp)
+        proof, _ = dropin.prover(ssp, crs, wit)
+        dropin.clear_entropy()
+    finally:
+        dropin.lib.mf_set_devices(1, 1)
+    for k in range(5):
+        assert sha(proof[k]) == g["proof_sha"][k]
+
+
 def test_full_snark_beside_compiled_reference(dropin, reference):
     D, M = reference.D, reference.M  # 256, 64
     dropin.set_instance(D, M)

@@ -325,3 +325,25 @@ def test_device_set_over_all_gpus():
     finally:
         dset.close()
         ctx.close()
+
+
+@pytest.mark.parametrize("nmembers,d", [(2, 9), (3, 64), (4, 301)])
+def test_device_set_eval_poly_without_residency(nmembers, d):
+    """mfb_set_eval_poly2: nothing resident, every member regenerates the a-vectors of its range from AES in-kernel."""
+    import c_lwe_snarks_b200 as m
+    off = 11 * CTR_CT + 3
+    c8 = xof_records(f"setf-c8-{d}", d)
+    h0, h1 = xof_scalars(f"setf-h0-{d}", d), xof_scalars(f"setf-h1-{d}", d)
+    rop = xof_records("setf-rop", NC)[:, :88].copy().view("<u8").reshape(NC, L64)
+    ctx = m.Context(0)
+    dset = ctx.device_set([0] * (nmembers - 1))
+    try:
+        want0 = ctx.eval_poly(SEED, off, c8, h0)
+        want1 = ctx.eval_poly(SEED, off, c8, h1, rop=rop)
+        for _ in range(2):
+            r0, r1 = dset.eval_poly2(SEED, off, c8, h0, h1, rop1=rop)
+            assert np.array_equal(r0, want0) and np.array_equal(r1, want1)
+            assert np.array_equal(dset.eval_poly2(SEED, off, c8, h1, rop0=rop), want1)
+    finally:
+        dset.close()
+        ctx.close()
