@@ -24,6 +24,7 @@ static int set_err(int code, const char *fmt, ...) {
 }
 
 int fail(cudaError_t e, const char *what, const char *file, int line) {
+  cudaGetLastError();  // the error is reported through the return code: clear the runtime's per-thread copy of it
   return set_err(MFB_ECUDA, "%s:%d: %s -> %s (%s)", file, line, what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
@@ -127,7 +128,10 @@ static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
     ctx->slot_cap[i] = 0;
     size_t cap = bytes + bytes / 4 + 4096;
     cudaError_t e = cudaMalloc(&ctx->slot[i], cap);
-    if (e != cudaSuccess) return set_err(MFB_ENOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // reported through the return code; do not leave it for a later cudaGetLastError()
+      return set_err(MFB_ENOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+    }
     ctx->slot_cap[i] = cap;
   }
   *out = ctx->slot[i];
@@ -854,6 +858,7 @@ static int region_create(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, 
   r->count = count;
   cudaError_t e = cudaMalloc(&r->cts, (count ? count : 1) * PLANAR_U64 * 8);
   if (e != cudaSuccess) {
+    cudaGetLastError();  // clear it: this failure is reported through the return code, later calls must not see it
     delete r;
     return set_err(MFB_ENOMEM, "cudaMalloc of %zu resident ciphertexts failed: %s", count, cudaGetErrorString(e));
   }

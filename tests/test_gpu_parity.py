@@ -355,3 +355,16 @@ def test_encrypt_cb_equals_encrypt(ctx, oracle, cnt):
     k = cnt - 1
     want = oracle.encrypt(SEED, 7 * CTR_CT + 3 + k * CTR_CT, sk, m[k:k + 1], ent[70 * k: 70 * k + 70])
     assert np.array_equal(got[k], want[0])
+
+
+def test_allocation_failure_is_reported_and_does_not_poison_later_calls(ctx, oracle):
+    """A region that cannot be allocated (2^21 ciphertexts = 272 GB) fails with MFB_ENOMEM and leaves no stale CUDA
+    error behind: the next calls work (mf_crs_make_resident relies on this to fall back to the fused path)."""
+    import c_lwe_snarks_b200 as m
+    big = np.zeros((1 << 21, 92), np.uint8)
+    with pytest.raises(m.api.MfbError, match="cudaMalloc"):
+        ctx.region(SEED, 0, big)
+    c8, h = xof_records("after-oom-c8", 5), xof_scalars("after-oom-h", 5)
+    assert np.array_equal(wide(ctx.eval_poly(SEED, 0, c8, h)), oracle.eval_poly(SEED, 0, c8, h))
+    blob = np.arange(64 * 9, dtype=np.uint64)
+    assert ctx.ssp_eval(blob, 64, 7).shape == (9,)
