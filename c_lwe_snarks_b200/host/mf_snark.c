@@ -132,13 +132,19 @@ void mf_crs_make_resident(crs_t crs) {
   int rc = mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s);
   mf_trace("make_resident.region_s", t0);
   t0 = mf_now();
-  if (rc == MFB_OK) rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
-  mf_trace("make_resident.region_as", t0);
+  if (rc == MFB_OK) {
+    rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
+    mf_trace("make_resident.region_as", t0);
+    if (rc == MFB_ENOMEM) { /* one region fits, two do not (D = 2^20 on one GPU): keep the first, fuse the other */
+      fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident: %s; only the s region is resident\n", mfb_last_error());
+      r->as = NULL;
+      rc = MFB_OK;
+    }
+  }
   if (rc != MFB_OK) {
     if (rc != MFB_ENOMEM) mf_die("mfb_region_create");
     fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident: %s; the CRS stays non-resident\n", mfb_last_error());
     mfb_region_destroy(mf_gpu(), r->s);
-    mfb_region_destroy(mf_gpu(), r->as);
     free(r);
     return;
   }
@@ -324,7 +330,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   double t0 = mf_now();
   mfb_ssp *rssp = resident_ssp_find(ssp);
   struct resident *res = resident_find(crs);
-  const int all_resident = rssp && res && res->d == D;
+  const int all_resident = rssp && res && res->d == D && (res->ms || (res->s && res->as));
 
   /* polynomial step (snark.c:138-169) on the device: w = delta*t + sum_{w_i} v_i, v = w + v_0 (l_u = 0),
    * h = (v^2 - 1) / t  — FLINT's scalar_mul / add / pow / div in the reference.  With the SSP and both CRS regions
@@ -400,14 +406,17 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     mf_ct_from_flat(pi->hat_h, acc + 3 * FLAT_CT);
     free(acc);
   } else {
-    struct resident *r = res;
-    if (r && r->d == D) { /* regions resident in HBM: one pass per region at the HBM roofline, two scalar vectors each */
+    /* per region: resident in HBM -> one pass at the HBM roofline, else a regenerated from AES in-kernel; two scalar
+     * vectors per pass either way */
+    struct resident *r = (res && res->d == D) ? res : NULL;
+    if (r && (r->s || r->ms))
       lincomb_pair_resident(pi->v_w, pi->h, r->s, r->ms, pw, ph);
-      lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, r->mas, pv, ph);
-    } else { /* a regenerated from AES: one pass per region carrying both scalar vectors */
+    else
       lincomb_pair(pi->v_w, pi->h, crs, 0, pw, ph);
+    if (r && (r->as || r->mas))
+      lincomb_pair_resident(pi->hat_v, pi->hat_h, r->as, r->mas, pv, ph);
+    else
       lincomb_pair(pi->hat_v, pi->hat_h, crs, 1, pv, ph);
-    }
   }
   free(pw);
   mf_trace(all_resident ? "prover.polys+lincombs (device pipeline)" : "prover.lincombs", t0);
