@@ -374,17 +374,23 @@ k_bcoord(const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, c
 // e_k = little-endian integer of ent[k*ent_stride .. +ent_nbytes) (69 noise bytes of errdist_uniform lwe.c:60-63;
 // the sign byte that follows is consumed by the host protocol and never used, lwe.c:86-87).
 //
-// A CTA takes a contiguous range of whole ciphertexts; its work items are their 3 coordinate
-// tiles in order, on the same three-buffer mbarrier pipeline as k_evalpoly (no CTA-wide barrier in steady state):
-//   item t:  wait full[t % 3] -> thread c < 490: acc += a_c * sk_c (253 limb products on the FMA pipe, idle during AES)
-//            -> release the buffer -> AES of item t + 2 (ALU + LSU pipes).
-// After a ciphertext's third tile every warp reduces its threads' sums (REDUX on 16-bit halves, no overflow), adds
-// them to per-ciphertext columns in shared memory with 32-bit atomics and counts itself in; the LAST warp to arrive
-// adds e*p + m, propagates the carries (one uniform 22-step chain) and writes the record while the others are already
-// generating the next ciphertext's keystream.
-constexpr int KS_NWARPS = KS_THREADS / 32;
+// A CTA takes a contiguous range of whole ciphertexts; its work items are their 3 coordinate tiles in order, on the
+// three-buffer mbarrier pipeline of k_evalpoly — but WARP-SPECIALISED: 16 producer warps only generate keystream
+// (ALU + LSU pipes) and 4 consumer warps, one per scheduler, only multiply: per coordinate a 22 x 22-limb low product
+// is 253 IMAD.WIDE carry chains, i.e. a long DEPENDENT sequence (one carry flag), so a warp inside it issues about one
+// instruction every 8 cycles.  Measured on the unspecialised version: the keystream rate is proportional to the warp
+// time spent generating it, so every cycle a producer warp spent inside the product was lost (34.4 ms for 131 136
+// ciphertexts against 28.6 ms of pure keystream).  The consumers take ~4 coordinates per thread and tile and sum all
+// their coordinates into ONE accumulator (the dot product adds them anyway); they are about half busy.
+//   producers: wait empty[t % 3] -> AES of item t -> arrive full[t % 3]                 (16 arrivals)
+//   consumers: wait full[t % 3] -> acc += a_c * sk_c for their coordinates -> arrive empty (4 arrivals)
+// After a ciphertext's third tile the consumer warps reduce (REDUX on 16-bit halves, 32-bit shared atomics, a counter);
+// the last one adds e*p + m, propagates the carries (one uniform 22-step chain) and writes the record.
+constexpr int KE_PRODUCERS = KS_THREADS;        // 512 threads = 16 warps
+constexpr int KE_CONSUMERS = 128;               // 4 warps
+constexpr int KE_THREADS = KE_PRODUCERS + KE_CONSUMERS;
 
-__global__ void __launch_bounds__(KS_THREADS, 1)
+__global__ void __launch_bounds__(KE_THREADS, 1)
 k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
           const uint64_t *__restrict__ sk, const uint64_t *__restrict__ msg, const uint8_t *__restrict__ ent,
           int ent_stride, int ent_nbytes, size_t count, uint8_t *__restrict__ out_c8) {
@@ -396,55 +402,57 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   auto buf_of = [&](int b) { return b == 0 ? s.buf[0] : s.buf[1] + (uint32_t)(b - 1) * (uint32_t)KS_BUF_BYTES; };
   const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(bars);
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2 * KS_NBUF; b++) ksb_init(bbase + 8 * b, KS_NWARPS);
+    for (int b = 0; b < KS_NBUF; b++) {
+      ksb_init(bbase + 8 * b, KE_PRODUCERS / 32);              // full: every producer warp has stored its blocks
+      ksb_init(bbase + 8 * (KS_NBUF + b), KE_CONSUMERS / 32);  // empty: every consumer warp has read its coordinates
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     arrived[0] = arrived[1] = 0;
   }
   if (threadIdx.x < 4 * L32) cols[threadIdx.x / (2 * L32)][threadIdx.x % (2 * L32)] = 0;
-  AesCtrCache cache;
-  cache.window = ~0ull;
   const int lane = threadIdx.x & 31;
-  const bool is_mac = threadIdx.x < KS_TILE;
   // contiguous, balanced range of ciphertexts per CTA (keeps the counter-mode cache warm across items)
   const size_t per = count / gridDim.x, rem = count % gridDim.x;
   const size_t k0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
   const size_t nct = per + (blockIdx.x < rem ? 1 : 0);
   const size_t nitems = nct * KS_NTILES;
-  auto ct_of = [&](size_t t) { return k0 + t / KS_NTILES; };
-  auto fill = [&](size_t t) {  // item t of this CTA -> buffer t % 3
-    const int b = (int)(t % KS_NBUF);
-    if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
-    const TileGeom g = tile_geom(offset + ct_of(t) * (uint64_t)CTR_CT, (int)(t % KS_NTILES));
-    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
-    __syncwarp();
-    if (lane == 0) ksb_arrive(bbase + 8 * b);
-  };
+  __syncthreads();  // tables, barriers, columns ready
 
+  if (threadIdx.x < KE_PRODUCERS) {
+    // ---------------------------------------------------------------- producers: keystream only
+    AesCtrCache cache;
+    cache.window = ~0ull;
+    for (size_t t = 0; t < nitems; t++) {
+      const int b = (int)(t % KS_NBUF);
+      if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous readers are done
+      const TileGeom g = tile_geom(offset + (k0 + t / KS_NTILES) * (uint64_t)CTR_CT, (int)(t % KS_NTILES));
+      ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+      __syncwarp();
+      if (lane == 0) ksb_arrive(bbase + 8 * b);
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers: <a, sk> and the record
+  const int ct_id = threadIdx.x - KE_PRODUCERS;  // 0..127
   Acc704 acc;
   acc_zero(acc);
-  __syncthreads();  // tables, barriers, columns ready
-  // staggered like k_evalpoly: early warps MAC item t then AES item t+2, late warps the other way round — here the MAC
-  // is 253 limb products per coordinate, a fifth of the kernel's issue slots, and it must not queue up behind itself
-  const bool late = (threadIdx.x >> 7) & 1;  // warps 4-7, 12-15: two early and two late warps per scheduler
-  if (nitems > 0) fill(0);
-  if (nitems > 1) fill(1);
   for (size_t t = 0; t < nitems; t++) {
     const int b = (int)(t % KS_NBUF);
     const int tile = (int)(t % KS_NTILES);
-    const size_t k = ct_of(t);
-    if (late && t + 2 < nitems) fill(t + 2);
-    ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));  // every warp has stored its blocks of item t
-    if (is_mac) {
-      const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+    const size_t k = k0 + t / KS_NTILES;
+    ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));
+    const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
+    for (int lc = ct_id; lc < KS_TILE; lc += KE_CONSUMERS) {
       uint32_t a[22], w[22];
-      ks_read_coord(buf_of(b), g.delta + CT_BYTES * threadIdx.x, a);
-      const int c = tile * KS_TILE + threadIdx.x;
+      const int c = tile * KS_TILE + lc;
 #pragma unroll
       for (int j = 0; j < L64; j++) {
         const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
         w[2 * j] = (uint32_t)v;
         w[2 * j + 1] = (uint32_t)(v >> 32);
       }
+      ks_read_coord(buf_of(b), g.delta + CT_BYTES * lc, a);
       acc_mul(acc, a, w);
     }
     __syncwarp();
@@ -466,7 +474,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
         }
       }
       if (lane < L32) {
-        atomicAdd(&cols[slot][2 * lane], mylo);  // < 512 * 2^16: no overflow
+        atomicAdd(&cols[slot][2 * lane], mylo);  // < 128 * 2^16: no overflow
         atomicAdd(&cols[slot][2 * lane + 1], myhi);
       }
       __syncwarp();
@@ -476,7 +484,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
         prev = atomicAdd(&arrived[slot], 1u);
       }
       prev = __shfl_sync(0xffffffffu, prev, 0);
-      if (prev == KS_NWARPS - 1) {  // this warp is the last one: all column sums are in
+      if (prev == KE_CONSUMERS / 32 - 1) {  // this warp is the last one: all column sums are in
         __threadfence_block();
         unsigned long long col = 0;
         uint32_t el = 0;
@@ -511,7 +519,6 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
         if (lane <= L32) reinterpret_cast<uint32_t *>(out_c8 + k * CT_BYTES)[lane] = myb;  // 92 % 4 == 0
       }
     }
-    if (!late && t + 2 < nitems) fill(t + 2);
   }
 }
 
@@ -614,7 +621,7 @@ cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offse
   cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
-  k_encrypt<<<(unsigned)grid, KS_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
+  k_encrypt<<<(unsigned)grid, KE_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
                                                                count, out_c8);
   return cudaGetLastError();
 }
