@@ -195,10 +195,13 @@ struct AesCtrCache {
 // FM: bit K set = the address of a byte-K lookup is computed on the FMA pipe (idle otherwise) instead of by the
 // ALU-pipe PRMT: byte = mul.hi(w * 2^(8*(3-K)), 2^8), address = byte * 2^8 + lanebase.  The multipliers are run-time
 // values (m8, m16, m24 come from kernel parameters) so that ptxas keeps IMADs and does not strength-reduce to shifts.
+// FM bits 8..: number of row-0 lookups per full round (a0, b0, c0, d0 in this order) that go through the TEXTURE path
+// (tex1Dfetch on the 1 KB global T0 table, `tex`) instead of shared memory — a development variant (tune_aes.cu).
 template <int TABS, int FM = 0>
 struct AesLut {
   uint32_t lbA, lbB;
   uint32_t m8, m16, m24;
+  unsigned long long tex;  // cudaTextureObject_t of the global T0 table (texture variants only)
   template <int K> __device__ __forceinline__ uint32_t addr(uint32_t w, uint32_t lb) const {
     if constexpr ((FM >> K) & 1) {
       uint32_t b, a;
@@ -249,13 +252,18 @@ __device__ __forceinline__ void aes_round(const AesLut<TABS, FM> &L, uint32_t &s
     s2 = c0 ^ c1 ^ c2 ^ c3 ^ k2;
     s3 = d0 ^ d1 ^ d2 ^ d3 ^ k3;
   } else {
-    const uint32_t a0 = L.template a0<0>(s0), a1 = L.template a0<1>(s1);
+    constexpr int TX = FM >> 8;
+    auto row0 = [&](uint32_t w, bool via_tex) -> uint32_t {
+      if (via_tex) return tex1Dfetch<uint32_t>((cudaTextureObject_t)L.tex, (int)(w & 0xffu));
+      return L.template a0<0>(w);
+    };
+    const uint32_t a0 = row0(s0, TX >= 1), a1 = L.template a0<1>(s1);
     const uint32_t a2 = L.template a2<2>(s2), a3 = L.template a2<3>(s3);
-    const uint32_t b0 = L.template a0<0>(s1), b1 = L.template a0<1>(s2);
+    const uint32_t b0 = row0(s1, TX >= 2), b1 = L.template a0<1>(s2);
     const uint32_t b2 = L.template a2<2>(s3), b3 = L.template a2<3>(s0);
-    const uint32_t c0 = L.template a0<0>(s2), c1 = L.template a0<1>(s3);
+    const uint32_t c0 = row0(s2, TX >= 3), c1 = L.template a0<1>(s3);
     const uint32_t c2 = L.template a2<2>(s0), c3 = L.template a2<3>(s1);
-    const uint32_t d0 = L.template a0<0>(s3), d1 = L.template a0<1>(s0);
+    const uint32_t d0 = row0(s3, TX >= 4), d1 = L.template a0<1>(s0);
     const uint32_t d2 = L.template a2<2>(s1), d3 = L.template a2<3>(s2);
     s0 = a0 ^ a2 ^ rotl8(a1 ^ a3 ^ kr0);
     s1 = b0 ^ b2 ^ rotl8(b1 ^ b3 ^ kr1);

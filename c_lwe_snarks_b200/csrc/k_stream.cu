@@ -42,6 +42,7 @@ __device__ __forceinline__ KsSmem ks_smem_setup(uint8_t *dyn, const uint32_t *__
   s.lut.lbA = s.tab | ((threadIdx.x & 31) << 2);
   s.lut.lbB = 0;
   s.lut.m8 = s.lut.m16 = s.lut.m24 = 0;  // only read by the FMA-addressing variants
+  s.lut.tex = 0;                         // only read by the texture variants
   aes_tables_init(dyn + (s.tab - s0), t0_global, threadIdx.x, blockDim.x);
   return s;
 }

@@ -13,7 +13,8 @@ __device__ __forceinline__ void sts128(uint32_t addr, const AesState &v) {
 // VARIANT 0: shipped (aes256_ctr_block), 1: plain on AesLut<2>, 2: cached TABS=2, 3: plain TABS=4, 4: cached TABS=4
 template <int VARIANT, int NT, int AT, int FM = 0>
 __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0g, int nblk,
-                                              int items, unsigned long long *digest, uint32_t m8, uint32_t m16, uint32_t m24) {
+                                              int items, unsigned long long *digest, uint32_t m8, uint32_t m16, uint32_t m24,
+                                              unsigned long long tex) {
   extern __shared__ __align__(16) uint8_t dyn[];
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(dyn);
   const uint32_t tabA = (s0 + 0xffffu) & ~0xffffu;
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   L.lbA = tabA | ((threadIdx.x & 31) << 2);
   L.lbB = tabB | ((threadIdx.x & 31) << 2);
   L.m8 = m8; L.m16 = m16; L.m24 = m24;
+  L.tex = tex;
   AesCtrCache cache;
   cache.window = ~0ull;
   uint32_t x = 0;
@@ -60,17 +62,18 @@ __global__ void __launch_bounds__(NT, 1) k_aes(const __grid_constant__ AesKey ke
   atomicXor(digest, (unsigned long long)x * 0x9e3779b97f4a7c15ull + blockIdx.x);
 }
 
+static unsigned long long g_tex = 0;
 template <int VARIANT, int NT, int AT = NT, int FM = 0>
 static void run(const char *name, const AesKey &key, const uint32_t *t0, int nblk, int items, unsigned long long *dig) {
   const int smem = (VARIANT == 3 || VARIANT == 4) ? 0x30000 : 0x20000;
   CK(cudaFuncSetAttribute(k_aes<VARIANT, NT, AT, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   unsigned long long z = 0, out = 0;
-  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24);
+  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24, g_tex);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(dig, &z, 8, cudaMemcpyHostToDevice));
   CK(cudaEventRecord(e0));
-  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24);
+  k_aes<VARIANT, NT, AT, FM><<<148, NT, smem>>>(key, t0, nblk, items, dig, 1u << 8, 1u << 16, 1u << 24, g_tex);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   CK(cudaMemcpy(&out, dig, 8, cudaMemcpyDeviceToHost));
@@ -86,17 +89,25 @@ int main() {
   uint32_t t0h[256]; aes_host::t0_table(t0h);
   uint32_t *t0; unsigned long long *dig;
   CK(cudaMalloc(&t0, 1024)); CK(cudaMemcpy(t0, t0h, 1024, cudaMemcpyHostToDevice)); CK(cudaMalloc(&dig, 8));
+  {
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = t0;
+    rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>();
+    rd.res.linear.sizeInBytes = 1024;
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    g_tex = (unsigned long long)tex;
+  }
   const int items = 600;
-  run<0, 512>("first version 2-table", key, t0, 2818, items, dig);
-  run<2, 512>("ctr-cached 2-table", key, t0, 2818, items, dig);   // shipped (round key folded into the rotated half)
-  run<4, 512>("ctr-cached 4-table", key, t0, 2818, items, dig);
-  run<2, 512>("ctr-cached 2-table", key, t0, 2560, items, dig);   // 5 full rounds of 512: no ragged last round
-  run<4, 512>("ctr-cached 4-table", key, t0, 2560, items, dig);
-  run<5, 512>("2-table, 2 blocks/thread", key, t0, 2818, items, dig);
-  run<5, 512>("2-table, 2 blocks/thread", key, t0, 2560, items, dig);
-  run<5, 512>("2-table, 2 blocks/thread", key, t0, 3072, items, dig);
+  run<2, 512>("ctr-cached 2-table", key, t0, 2818, items, dig);   // shipped
+  run<2, 512, 512, 0x100>("2-table, 1 lookup/round via TEX", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x200>("2-table, 2 lookups/round via TEX", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x300>("2-table, 3 lookups/round via TEX", key, t0, 2818, items, dig);
+  run<2, 512, 512, 0x400>("2-table, 4 lookups/round via TEX", key, t0, 2818, items, dig);
   run<2, 512>("ctr-cached 2-table", key, t0, 3072, items, dig);
-  run<5, 256>("2-table, 2 blocks/thread", key, t0, 2816, items, dig);
-  run<5, 384>("2-table, 2 blocks/thread", key, t0, 2304, items, dig);
+  run<2, 512, 512, 0x200>("2-table, 2 lookups/round via TEX", key, t0, 3072, items, dig);
   return 0;
 }
