@@ -91,6 +91,9 @@ def main():
         ms = wall(lambda: (ctx.eval_poly_dev(SEED, 0, d_c8.data_ptr(), d_h.data_ptr(), None, D, None, d_r0.data_ptr(), st),
                            torch.cuda.synchronize()))
         rec("mfb_eval_poly_dev + synchronize (wall)", ms, D, "mac", D=D)
+        h64b = np.roll(h64, 1)
+        ms = wall(lambda: ctx.eval_poly2(SEED, 0, c8, h64, h64b))
+        rec("mfb_eval_poly2 host call (python wrapper, pageable buffers)", ms, 2 * D, "mac", D=D)
 
     d_cts = torch.empty(D * NCP * L64, dtype=torch.int64, device="cuda")
     ms = timeit(lambda: ctx.expand_dev(SEED, 0, d_c8.data_ptr(), D, d_cts.data_ptr(), st), reps=3, warm=1)
