@@ -112,6 +112,8 @@ _SIGS = {
     "mfb_ssp_prover_polys_resident_dev": (C.c_int, [_vp, _vp, _u64p, C.c_size_t, C.c_uint64, C.POINTER(_vp)]),
     "mfb_ssp_degree_bound": (C.c_size_t, [_vp]),
     "mfb_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
+    "mfb_prove_resident_bw": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_size_t,
+                                       _u64p, _u64p, _u64p, _u64p, _u64p]),
     "mfb_set_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "mfb_ssp_eval_resident": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_ssp_eval": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),

@@ -945,32 +945,68 @@ int mfb_region_lincomb2(mfb_ctx *ctx, const mfb_region *r, size_t first, const u
   return MFB_OK;
 }
 
-int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
-                       const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
-                       uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+// b_w = delta * CT_t + sum_{witness bit i-1} CT_v[i-1] (snark.c:143-155) queued on st: ciphertext k of the region at
+// bt_offset is t for k = 0 and v[k-1] after it; only the selected ones are expanded.  Result -> out_dev (flat).
+static int queue_b_w(mfb_ctx *ctx, const uint8_t seed[40], uint64_t bt_offset, const uint8_t *bt_recs, size_t M,
+                     const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *out_dev, cudaStream_t st) {
+  if (delta >> 32) return set_err(MFB_EARG, "b_w: delta does not fit 32 bits");
+  std::vector<uint32_t> co, idx;
+  co.push_back((uint32_t)delta);
+  idx.push_back(0);
+  for (size_t i = 1; i < M; i++)
+    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) {
+      co.push_back(1);
+      idx.push_back((uint32_t)i);
+    }
+  void *d_c8, *d_co, *d_idx;
+  MFB_TRY(scratch(ctx, 0, M * CT_BYTES, &d_c8));
+  MFB_TRY(scratch(ctx, 1, co.size() * 4, &d_co));
+  MFB_TRY(scratch(ctx, 3, idx.size() * 4, &d_idx));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_c8, bt_recs, M * CT_BYTES, cudaMemcpyHostToDevice, st));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_co, co.data(), co.size() * 4, cudaMemcpyHostToDevice, st));
+  MFB_CUDA_TRY(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
+  return eval_poly_core(ctx, seed, bt_offset, (uint8_t *)d_c8, nullptr, 0, (const uint32_t *)d_co, nullptr, (const uint32_t *)d_idx,
+                        co.size(), nullptr, out_dev, nullptr, nullptr, st, nullptr);
+}
+
+int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
+                          const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40], uint64_t bt_offset,
+                          const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout, uint64_t *h_flat_inout,
+                          uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout, uint64_t *b_w_flat_out) {
   MFB_CHECK_CTX(ctx);
   if (!ssp || !reg_s || !reg_as || !witness_limbs || !v_w_flat_inout || !h_flat_inout || !hat_v_flat_inout || !hat_h_flat_inout)
     return set_err(MFB_EARG, "mfb_prove_resident: null pointer");
+  if (b_w_flat_out && (!seed || !bt_recs || M < 1)) return set_err(MFB_EARG, "mfb_prove_resident_bw: b_w needs the seed and the t | v records");
   const size_t D = mfb_ssp_degree_bound(ssp);
   if (reg_s->count != D || reg_as->count != D) return set_err(MFB_EARG, "mfb_prove_resident: the regions must hold D ciphertexts");
+  void *d_rop;
+  const size_t FL = MFB_FLAT_CT_U64;
+  const int nacc = b_w_flat_out ? 5 : 4;
+  MFB_TRY(scratch(ctx, 2, 5 * FL * 8, &d_rop));
+  uint64_t *r = (uint64_t *)d_rop;
+  // b_w first: its few small kernels run while the host prepares the polynomial step
+  if (b_w_flat_out) MFB_TRY(queue_b_w(ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, r + 4 * FL, ctx->stream));
   const uint32_t *wvh = nullptr;
   MFB_TRY(mfb_ssp_prover_polys_resident_dev(ctx, ssp, witness_limbs, nlimbs, delta, &wvh));
   const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
-  void *d_rop;
-  const size_t FL = MFB_FLAT_CT_U64;
-  MFB_TRY(scratch(ctx, 2, 4 * FL * 8, &d_rop));
-  uint64_t *r = (uint64_t *)d_rop;
-  uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
-  // the four accumulators travel as ONE pinned copy each way
-  if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 4 * FL * 8, cudaHostAllocDefault));
+  uint64_t *host[5] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, b_w_flat_out};
+  // the accumulators travel as ONE pinned copy each way
+  if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 5 * FL * 8, cudaHostAllocDefault));
   for (int k = 0; k < 4; k++) memcpy(ctx->acc_pin + k * FL, host[k], FL * 8);
   MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
   MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + FL, r + FL, ctx->stream));
   MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * FL, r + 2 * FL, r + 3 * FL, r + 3 * FL, ctx->stream));
-  MFB_CUDA_TRY(cudaMemcpyAsync(ctx->acc_pin, r, 4 * FL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaMemcpyAsync(ctx->acc_pin, r, (size_t)nacc * FL * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < 4; k++) memcpy(host[k], ctx->acc_pin + k * FL, FL * 8);
+  for (int k = 0; k < nacc; k++) memcpy(host[k], ctx->acc_pin + k * FL, FL * 8);
   return MFB_OK;
+}
+
+int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
+                       const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                       uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+  return mfb_prove_resident_bw(ctx, ssp, reg_s, reg_as, witness_limbs, nlimbs, delta, nullptr, 0, nullptr, 0, v_w_flat_inout,
+                               h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, nullptr);
 }
 
 int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,

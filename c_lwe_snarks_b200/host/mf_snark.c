@@ -367,14 +367,14 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
       idx[nsel++] = (uint32_t)i;
     }
   }
-  {
+  const int b_w_in_pipeline = all_resident && !res->ms; /* one GPU, everything resident: b_w rides in the pipeline below */
+  if (!b_w_in_pipeline) {
     uint64_t *acc = calloc(FLAT_CT, 8); /* ct_import overwrites pi->b_w: start from zero */
     if (!acc) mf_die("malloc");
     MF_GPU(mfb_eval_poly(mf_gpu(), crs->seed, CTR_BT, recs, co, idx, nsel, acc));
     mf_ct_from_flat(pi->b_w, acc);
     free(acc);
   }
-  free(recs);
   free(co);
   free(idx);
 
@@ -384,7 +384,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     /* SSP and regions resident: ONE device pipeline — polynomial step, then both two-vector passes with the
      * coefficients read where they were computed (sharded regions: every GPU fetches its slices over NVLink);
      * only the witness bits and the four accumulators cross PCIe */
-    uint64_t *acc = malloc(4 * FLAT_CT * 8);
+    uint64_t *acc = malloc(5 * FLAT_CT * 8);
     if (!acc) mf_die("malloc");
     mf_ct_to_flat(acc, pi->v_w, "prover");
     mf_ct_to_flat(acc + FLAT_CT, pi->h, "prover");
@@ -397,8 +397,9 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
         abort();
       }
     } else {
-      MF_GPU(mfb_prove_resident(mf_gpu(), rssp, res->s, res->as, PTR(witness), (size_t)SIZ(witness), delta, acc, acc + FLAT_CT,
-                                acc + 2 * FLAT_CT, acc + 3 * FLAT_CT));
+      MF_GPU(mfb_prove_resident_bw(mf_gpu(), rssp, res->s, res->as, PTR(witness), (size_t)SIZ(witness), delta, crs->seed, CTR_BT,
+                                   recs, M, acc, acc + FLAT_CT, acc + 2 * FLAT_CT, acc + 3 * FLAT_CT, acc + 4 * FLAT_CT));
+      mf_ct_from_flat(pi->b_w, acc + 4 * FLAT_CT);
     }
     mf_ct_from_flat(pi->v_w, acc);
     mf_ct_from_flat(pi->h, acc + FLAT_CT);
@@ -419,6 +420,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
       lincomb_pair(pi->hat_v, pi->hat_h, crs, 1, pv, ph);
   }
   free(pw);
+  free(recs);
   mf_trace(all_resident ? "prover.polys+lincombs (device pipeline)" : "prover.lincombs", t0);
   t0 = mf_now();
 

@@ -288,6 +288,13 @@ MFB_API int mfb_ssp_eval_resident(mfb_ctx *ctx, const mfb_ssp *h, size_t first, 
 MFB_API int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
                        const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
                        uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout);
+/* The same including b_w = delta * CT_t + sum_{witness bit i-1} CT_v[i-1] (snark.c:143-155; bt_recs = the t record followed
+ * by the M-1 v records, region at stream offset bt_offset): the whole proof before smudging in one call, one
+ * synchronisation.  b_w_flat_out is written (ct_import semantics), not accumulated; NULL skips it. */
+MFB_API int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
+                          const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40], uint64_t bt_offset,
+                          const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout, uint64_t *h_flat_inout,
+                          uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout, uint64_t *b_w_flat_out);
 /* values[q] = poly_q(x) mod p for npoly polynomials of D u64 coefficients each (setup's nmod_poly_evaluate_nmod
  * calls, snark.c:97-110) */
 MFB_API int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values);
