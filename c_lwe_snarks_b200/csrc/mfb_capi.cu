@@ -959,7 +959,8 @@ static int queue_b_w(mfb_ctx *ctx, const uint8_t seed[40], uint64_t bt_offset, c
       idx.push_back((uint32_t)i);
     }
   void *d_c8, *d_co, *d_idx;
-  MFB_TRY(scratch(ctx, 0, M * CT_BYTES, &d_c8));
+  // (slot 7, not 0: the polynomial step, which runs concurrently on the main stream, stages its index list in slot 0)
+  MFB_TRY(scratch(ctx, 7, M * CT_BYTES, &d_c8));
   MFB_TRY(scratch(ctx, 1, co.size() * 4, &d_co));
   MFB_TRY(scratch(ctx, 3, idx.size() * 4, &d_idx));
   MFB_CUDA_TRY(cudaMemcpyAsync(d_c8, bt_recs, M * CT_BYTES, cudaMemcpyHostToDevice, st));
@@ -984,8 +985,14 @@ int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, c
   const int nacc = b_w_flat_out ? 5 : 4;
   MFB_TRY(scratch(ctx, 2, 5 * FL * 8, &d_rop));
   uint64_t *r = (uint64_t *)d_rop;
-  // b_w first: its few small kernels run while the host prepares the polynomial step
-  if (b_w_flat_out) MFB_TRY(queue_b_w(ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, r + 4 * FL, ctx->stream));
+  // b_w on the second stream: its few small kernels run beside the (launch-latency-bound) polynomial step; they use
+  // the partial-sum workspace, so the first lincomb kernel waits for them
+  if (b_w_flat_out) {
+    if (!ctx->stream2) MFB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_b) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    MFB_TRY(queue_b_w(ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, r + 4 * FL, ctx->stream2));
+    MFB_CUDA_TRY(cudaEventRecord(ctx->ev_b, ctx->stream2));
+  }
   const uint32_t *wvh = nullptr;
   MFB_TRY(mfb_ssp_prover_polys_resident_dev(ctx, ssp, witness_limbs, nlimbs, delta, &wvh));
   const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
@@ -994,6 +1001,7 @@ int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, c
   if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 5 * FL * 8, cudaHostAllocDefault));
   for (int k = 0; k < 4; k++) memcpy(ctx->acc_pin + k * FL, host[k], FL * 8);
   MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (b_w_flat_out) MFB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
   MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + FL, r + FL, ctx->stream));
   MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * FL, r + 2 * FL, r + 3 * FL, r + 3 * FL, ctx->stream));
   MFB_CUDA_TRY(cudaMemcpyAsync(ctx->acc_pin, r, (size_t)nacc * FL * 8, cudaMemcpyDeviceToHost, ctx->stream));
