@@ -93,8 +93,10 @@ void mf_trace(const char *name, double t0) {
 
 /* ------------------------------------------------------------------ conversions */
 int mf_to_flat(uint64_t out[MF_LIMBS], mpz_srcptr z) {
-  const int n = abs(SIZ(z));
-  for (int i = 0; i < MF_LIMBS; i++) out[i] = i < n ? PTR(z)[i] : 0;
+  int n = abs(SIZ(z));
+  if (n > MF_LIMBS) n = MF_LIMBS; /* value mod 2^704 */
+  memcpy(out, PTR(z), (size_t)n * 8);
+  memset(out + n, 0, (size_t)(MF_LIMBS - n) * 8);
   return SIZ(z) < 0;
 }
 
@@ -104,7 +106,7 @@ void mf_from_flat(mpz_ptr z, const uint64_t in[MF_LIMBS]) {
   if (ALLOC(z) < MF_LIMBS) _mpz_realloc(z, MF_LIMBS);
   int n = MF_LIMBS;
   while (n > 0 && in[n - 1] == 0) n--;
-  for (int i = 0; i < n; i++) PTR(z)[i] = in[i];
+  memcpy(PTR(z), in, (size_t)n * 8);
   SIZ(z) = n;
 }
 

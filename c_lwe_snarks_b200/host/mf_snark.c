@@ -384,8 +384,8 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     /* SSP and regions resident: ONE device pipeline — polynomial step, then both two-vector passes with the
      * coefficients read where they were computed (sharded regions: every GPU fetches its slices over NVLink);
      * only the witness bits and the four accumulators cross PCIe */
-    uint64_t *acc = malloc(5 * FLAT_CT * 8);
-    if (!acc) mf_die("malloc");
+    static uint64_t *acc = NULL; /* kept across proofs: 647 KB would be a fresh mmap + page faults every call */
+    if (!acc && !(acc = malloc(5 * FLAT_CT * 8))) mf_die("malloc");
     mf_ct_to_flat(acc, pi->v_w, "prover");
     mf_ct_to_flat(acc + FLAT_CT, pi->h, "prover");
     mf_ct_to_flat(acc + 2 * FLAT_CT, pi->hat_v, "prover");
@@ -405,7 +405,6 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     mf_ct_from_flat(pi->h, acc + FLAT_CT);
     mf_ct_from_flat(pi->hat_v, acc + 2 * FLAT_CT);
     mf_ct_from_flat(pi->hat_h, acc + 3 * FLAT_CT);
-    free(acc);
   } else {
     /* per region: resident in HBM -> one pass at the HBM roofline, else a regenerated from AES in-kernel; two scalar
      * vectors per pass either way */
