@@ -132,7 +132,11 @@ void mf_crs_make_resident(crs_t crs) {
   int rc = mfb_region_create(mf_gpu(), crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->s);
   mf_trace("make_resident.region_s", t0);
   t0 = mf_now();
-  if (rc == MFB_OK) {
+  if (rc == MFB_OK && getenv("MF_B200_ONE_REGION")) {
+    /* test hook: behave as if the second region did not fit, so that the mixed resident / fused prover path (what
+     * D = 2^20 takes on one GPU) can be checked at small sizes */
+    r->as = NULL;
+  } else if (rc == MFB_OK) {
     rc = mfb_region_create(mf_gpu(), crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->as);
     mf_trace("make_resident.region_as", t0);
     if (rc == MFB_ENOMEM) { /* one region fits, two do not (D = 2^20 on one GPU): keep the first, fuse the other */

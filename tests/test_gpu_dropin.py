@@ -131,6 +131,21 @@ def test_prover_sharded_over_a_device_set_without_residency(dropin):
         assert sha(proof[k]) == g["proof_sha"][k]
 
 
+def test_prover_with_only_one_region_resident_is_identical(dropin, monkeypatch):
+    """When only one of the two CRS regions fits in HBM (D = 2^20 on one GPU) mf_crs_make_resident keeps that one and
+    prover() mixes a resident pass with a fused one; $MF_B200_ONE_REGION forces that path at a small size."""
+    g = GOLD["snark_d64_m16"]
+    dropin.set_instance(g["D"], g["M"])
+    monkeypatch.setenv("MF_B200_ONE_REGION", "1")
+    dropin.set_entropy(xof("snark-entropy-d64-m16", g["entropy_bytes"]))
+    ssp, wit = dropin.random_ssp()
+    crs = dropin.setup(ssp)
+    proof, _ = dropin.prover_resident(ssp, crs, wit)
+    dropin.clear_entropy()
+    for k in range(5):
+        assert sha(proof[k]) == g["proof_sha"][k]
+
+
 def test_full_snark_beside_compiled_reference(dropin, reference):
     D, M = reference.D, reference.M  # 256, 64
     dropin.set_instance(D, M)
