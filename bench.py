@@ -233,31 +233,19 @@ def snark_latency(log2d: int, M: int):
 def snark_box_latency(log2d_total: int, M: int, n_dev: int):
     """BASELINE configs[3]: one single-threaded program (the drop-in's setup/prover/verifier) proving a 2^log2d_total-
     constraint SSP with the CRS regions sharded by ciphertext index over n_dev GPUs (mf_set_devices) and every lincomb
-    combined over NVLink peer memory.  Runs on rank 0 after the timed sections; the other ranks wait."""
-    from c_lwe_snarks_b200.snark import Snark
-    D = 1 << log2d_total
-    sn = Snark(D, M)
-    try:
-        sn.random_ssp()
-        sn.setup()  # cold: CUDA contexts of the member devices, first allocations
-        t_setup = sn.setup()
-        sn.set_devices(n_dev)
-        t0 = time.perf_counter()
-        sn.make_resident()
-        t_res = time.perf_counter() - t0
-        sn.prove()
-        t_prove = min(sn.prove() for _ in range(3))
-        ok, t_verify = sn.verify()
-        sn.tamper()
-        bad, _ = sn.verify()
-        import ctypes
-        sn.lib.mf_crs_release(ctypes.byref(sn.crs))
-    finally:
-        sn.close()
-        sn.set_devices(1)
-    return {"D": D, "M": M, "devices": n_dev, "setup_ms": 1e3 * t_setup, "make_resident_ms": 1e3 * t_res,
-            "prove_resident_ms": 1e3 * t_prove, "verify_ms": 1e3 * t_verify, "accept": bool(ok), "tampered_accept": bool(bad),
-            "api": "setup/prover/verifier (snark.h:44-51) via libmangiafuoco_b200.so, one host thread driving all GPUs"}
+    combined over NVLink peer memory.  Runs after the timed sections as a SUBPROCESS of rank 0 (tools/snark_box.py: the
+    drop-in aborts on errors, which must not take the bench line with it); the other ranks wait on the CPU."""
+    import subprocess
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "snark_box.py"), str(log2d_total), str(M), str(n_dev)],
+                       capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"tools/snark_box.py exited {r.returncode}: {(r.stderr or r.stdout)[-300:]}")
+    j = json.loads(lines[-1])
+    return {"D": j["D"], "M": j["M"], "devices": j["devices"], "setup_ms": 1e3 * j["setup_s"],
+            "make_resident_ms": 1e3 * j["make_resident_s"], "prove_nothing_resident_ms": j["prove_nothing_resident_ms"],
+            "prove_resident_ms": min(j["prove_ms"][1:]), "verify_ms": j["verify_ms"], "accept": j["accept"],
+            "tampered_accept": j["tampered_accept"], "api": j["api"]}
 
 
 def run_gpu_arm(args):
