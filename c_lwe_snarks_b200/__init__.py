@@ -8,7 +8,8 @@ it never falls back to a CPU implementation: importing :mod:`c_lwe_snarks_b200.a
 library raises.
 """
 from .api import (ALGO_BYTES_PER_MAC, CT_BYTES, CTR_CT, ENT_BYTES, FLAT_CT_U64, L64, N, NC, NCP, P, PLANAR_U64,
-                  Context, MfbError, Region, build_library, library_path)
+                  Context, DeviceSet, MfbError, PeerGroup, Region, ResidentSsp, SetRegion, build_library, library_path)
 
-__all__ = ["Context", "Region", "MfbError", "build_library", "library_path", "N", "NC", "NCP", "L64", "P",
-           "CT_BYTES", "CTR_CT", "ENT_BYTES", "FLAT_CT_U64", "PLANAR_U64", "ALGO_BYTES_PER_MAC"]
+__all__ = ["Context", "Region", "ResidentSsp", "PeerGroup", "DeviceSet", "SetRegion", "MfbError", "build_library",
+           "library_path", "N", "NC", "NCP", "L64", "P", "CT_BYTES", "CTR_CT", "ENT_BYTES", "FLAT_CT_U64", "PLANAR_U64",
+           "ALGO_BYTES_PER_MAC"]
