@@ -34,6 +34,11 @@ def test_dropin_exports_the_reference_interface():
               "mpz2_urandomb", "mpz2_urandomb2", "aesctr_init", "aesctr_prg", "aesctr_clear",
               "nmod_poly_import", "nmod_poly_export", "random_ssp"]:
         assert hasattr(lib, n), n
+    # the additions of include/mangiafuoco/mangiafuoco_b200.h (INTEGRATION.md "What is new")
+    for n in ["mf_set_instance", "mf_set_entropy_source", "mf_entropy", "mf_set_device", "mf_set_devices",
+              "mf_crs_make_resident", "mf_crs_release", "mf_ssp_make_resident", "mf_ssp_release", "mf_crs_write",
+              "mf_crs_read", "mf_proof_write", "mf_proof_read", "mf_gpu_launches"]:
+        assert hasattr(lib, n), n
 
 
 def test_no_cpu_fallback():
