@@ -1,0 +1,80 @@
+"""CPU: properties of the compiled sm_100a code that the design relies on, read with cuobjdump (no GPU needed).
+
+These are the claims DESIGN.md makes about the machine code — TMA bulk copies completing on mbarriers in K1, carry-chained
+IMAD.WIDE in the MAC, REDUX in the encryption tail, no spills in the hot kernels — checked on the library the tests and
+the bench actually load."""
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "c_lwe_snarks_b200" / "lib" / "libmfb200.so"
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+
+
+@pytest.fixture(scope="module")
+def usage():
+    out = subprocess.run(["cuobjdump", "-res-usage", str(LIB)], capture_output=True, text=True, check=True).stdout
+    res = {}
+    for name, line in re.findall(r"Function (\S+):\n\s*(REG:.*)", out):
+        res[name] = {k: int(v) for k, v in re.findall(r"(\w+)(?:\[\d+\])?:(\d+)", line)}
+    assert res, "no kernels found in the library"
+    return res
+
+
+_SASS = None
+
+
+def sass_of(pattern: str) -> str:
+    global _SASS
+    if _SASS is None:
+        _SASS = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
+    out = _SASS
+    chunks = re.split(r"\n\s*Function : ", out)
+    sel = [c for c in chunks if re.match(pattern, c)]
+    assert sel, f"no kernel matches {pattern}"
+    return "\n".join(sel)
+
+
+def test_built_for_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", str(LIB)], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_(\d+\w?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_hot_kernels_do_not_spill(usage):
+    hot = [n for n in usage if re.search(r"k_lincombILi[12]|k_evalpolyILi[12]|k_expand|k_lincomb_finish|k_peer_allreduce|"
+                                         r"k_ntt_cols|k_ntt_local|k_decrypt|k_bcoord", n)]
+    assert len(hot) >= 12
+    for n in hot:
+        assert usage[n]["STACK"] == 0 and usage[n]["LOCAL"] == 0, (n, usage[n])
+    # 512-thread AES kernels: one CTA per SM needs <= 128 registers; the 640-thread k_encrypt <= 102
+    for n, u in usage.items():
+        if re.search(r"k_evalpolyILi[12]|k_expand|k_stream_bytes", n):
+            assert u["REG"] <= 128, (n, u)
+        if "k_encrypt" in n:
+            assert u["REG"] <= 102 and u["STACK"] <= 64, (n, u)
+
+
+def test_k1_streams_with_tma_bulk_copies_on_mbarriers():
+    s = sass_of(r"_ZN3mfb9k_lincombILi1")
+    assert "UBLKCP" in s, "cp.async.bulk (TMA) missing from k_lincomb"
+    assert "SYNCS" in s, "mbarrier instructions missing from k_lincomb"
+    assert len(re.findall(r"IMAD\.WIDE\.U32(\.X)?", s)) >= 22, "704-bit MAC is not 22 IMAD.WIDE"
+
+
+def test_aes_kernels_use_prmt_addressing_and_shared_tables():
+    s = sass_of(r"_ZN3mfb8k_expand")
+    assert s.count("PRMT") > 400 and s.count("LDS") > 400
+    # the round key folded into the rotated half: fewer LOP3 than LDS (was 373 LOP3 against 471 LDS before the folding)
+    assert s.count("LOP3") < 0.7 * s.count("LDS")
+
+
+def test_encrypt_tail_uses_redux_and_shared_atomics():
+    s = sass_of(r"_ZN3mfb9k_encrypt")
+    assert "REDUX" in s and "ATOMS" in s
+    assert len(re.findall(r"IMAD\.WIDE\.U32", s)) >= 250, "low-half 22x22 product is 253 limb products"
