@@ -91,6 +91,8 @@ _SIGS = {
     "mfb_set_last_error": (C.c_char_p, []),
     "mfb_set_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_set_region_destroy": (None, [_vp, _vp]),
+    "mfb_set_encrypt_cb": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
+                                    C.c_int, C.c_size_t, _u8p]),
     "mfb_set_eval_poly2": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u64p, C.c_size_t, _u64p, _u64p]),
     "mfb_set_region_lincomb2": (C.c_int, [_vp, _vp, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
     "mfb_columns_split_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -271,6 +273,25 @@ class DeviceSet:
     @property
     def size(self) -> int:
         return int(self.ctx.lib.mfb_set_size(self.h))
+
+    def encrypt_cb(self, seed, offset: int, sk_flat, msg, draw, ent_stride: int = ENT_BYTES, ent_nbytes: int = ENT_BYTES - 1):
+        """Context.encrypt_cb with the pieces spread over the members (mfb_set_encrypt_cb)."""
+        s, sk, m = _seed(seed), _arr(sk_flat, np.uint64), _arr(msg, np.uint64)
+        if sk.size != FLAT_SK_U64:
+            raise ValueError("sk_flat must be (1470, 11) uint64")
+        out = np.zeros((m.size, CT_BYTES), np.uint8)
+        fn_t = _SIGS["mfb_set_encrypt_cb"][1][5]
+
+        def _draw(_user, dst, nbytes):
+            data = bytes(draw(nbytes))
+            if len(data) != nbytes:
+                raise ValueError("entropy callback returned the wrong number of bytes")
+            C.memmove(dst, data, nbytes)
+
+        cb = fn_t(_draw)
+        self._ck(self.ctx.lib.mfb_set_encrypt_cb(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes,
+                                                m.size, _p8(out)))
+        return out
 
     def eval_poly2(self, seed, offset: int, c8, coeffs0, coeffs1=None, rop0=None, rop1=None):
         """eval_poly (coeffs1 None) / eval_poly2 with nothing resident, sharded over the members."""

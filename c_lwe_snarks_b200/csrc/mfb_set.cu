@@ -31,6 +31,12 @@ struct Member {
   uint64_t *res = nullptr;   // 4 x flat
   uint8_t *c8 = nullptr;     // wire records of the member's range (mfb_set_eval_poly2)
   size_t c8_cap = 0;
+  // mfb_set_encrypt_cb: the secret key (flat + row-planar), per-piece inputs, the member's records, pinned entropy
+  uint64_t *skf = nullptr, *skp = nullptr;
+  uint8_t *enc_in = nullptr, *enc_out = nullptr, *ent_pin = nullptr;
+  size_t enc_in_cap = 0, enc_out_cap = 0, ent_pin_cap = 0;
+  cudaEvent_t ent_free = nullptr;
+  bool ent_used = false;
 };
 
 thread_local char g_set_err[256] = "";
@@ -85,6 +91,12 @@ MFB_API void mfb_set_destroy(mfb_set *s) {
     if (mb.group) mfb_peer_destroy(mb.ctx, mb.group);
     if (mb.co) cudaFree(mb.co);
     if (mb.c8) cudaFree(mb.c8);
+    if (mb.skf) cudaFree(mb.skf);
+    if (mb.skp) cudaFree(mb.skp);
+    if (mb.enc_in) cudaFree(mb.enc_in);
+    if (mb.enc_out) cudaFree(mb.enc_out);
+    if (mb.ent_pin) cudaFreeHost(mb.ent_pin);
+    if (mb.ent_free) cudaEventDestroy(mb.ent_free);
     if (mb.part) cudaFree(mb.part);
     if (mb.res) cudaFree(mb.res);
     if (mb.stream) cudaStreamDestroy(mb.stream);
@@ -336,6 +348,97 @@ MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offs
     if (st != MFB_OK) rc = st;
   }
   SET_CUDA(cudaSetDevice(p.device));
+  return rc;
+}
+
+// mfb_encrypt_cb over a device set: the entropy is still drawn by the calling thread piece by piece and in order
+// (a hooked, deterministic source sees the reference's sequence), but piece k is encrypted by member k mod size, so
+// the members work on different pieces at the same time and the call becomes entropy-bound instead of AES-bound.
+static int grow(void **p, size_t *cap, size_t need, bool pinned) {
+  if (*cap >= need) return MFB_OK;
+  if (*p) {
+    if (pinned) cudaFreeHost(*p);
+    else cudaFree(*p);
+  }
+  *p = nullptr;
+  *cap = 0;
+  const cudaError_t e = pinned ? cudaHostAlloc(p, need, cudaHostAllocDefault) : cudaMalloc(p, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    snprintf(g_set_err, sizeof(g_set_err), "mfb_set_encrypt_cb: allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
+    return MFB_ENOMEM;
+  }
+  *cap = need;
+  return MFB_OK;
+}
+
+MFB_API int mfb_set_encrypt_cb(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                               mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+  g_set_err[0] = 0;
+  if (count == 0) return MFB_OK;
+  if (!s || !seed || !sk_flat || !msg || !draw || !out_c8) return set_fail(MFB_EARG, "mfb_set_encrypt_cb: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
+    return set_fail(MFB_EARG, "mfb_set_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
+  const size_t world = s->m.size();
+  const size_t piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 110, first_piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 16;
+  const size_t in_per = (size_t)ent_stride + 8;  // per ciphertext in a member's input buffer: entropy, then the message
+  const size_t in_slot = piece * in_per + 8;     // (+ 8: the messages start at the next multiple of 8 bytes)
+  // pieces: [first_piece, piece, piece, ...]; piece k goes to member k % world, at slot k / world of its buffers
+  std::vector<size_t> start, len;
+  for (size_t done = 0; done < count;) {
+    size_t cnt = start.empty() ? first_piece : piece;
+    if (cnt > count - done) cnt = count - done;
+    start.push_back(done);
+    len.push_back(cnt);
+    done += cnt;
+  }
+  const size_t npieces = start.size(), slots = (npieces + world - 1) / world;
+  for (size_t i = 0; i < world && i < npieces; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    size_t cap;
+    cap = mb.skf ? MFB_PLANAR_U64 * 8 : 0;
+    SET_TRY(grow((void **)&mb.skf, &cap, MFB_PLANAR_U64 * 8, false));
+    cap = mb.skp ? MFB_PLANAR_U64 * 8 : 0;
+    SET_TRY(grow((void **)&mb.skp, &cap, MFB_PLANAR_U64 * 8, false));
+    SET_TRY(grow((void **)&mb.enc_in, &mb.enc_in_cap, slots * in_slot, false));
+    SET_TRY(grow((void **)&mb.enc_out, &mb.enc_out_cap, slots * piece * MFB_CT_BYTES, false));
+    SET_TRY(grow((void **)&mb.ent_pin, &mb.ent_pin_cap, piece * (size_t)ent_stride, true));
+    if (!mb.ent_free) SET_CUDA(cudaEventCreateWithFlags(&mb.ent_free, cudaEventDisableTiming));
+    mb.ent_used = false;
+    SET_CUDA(cudaMemcpyAsync(mb.skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, mb.stream));
+    SET_TRY(mfb_flat_to_planar_dev(mb.ctx, mb.skf, MFB_N, 1, mb.skp, mb.stream));
+  }
+  for (size_t k = 0; k < npieces; k++) {
+    Member &mb = s->m[k % world];
+    SET_CUDA(cudaSetDevice(mb.device));
+    const size_t slot = k / world, cnt = len[k];
+    uint8_t *d_ent = mb.enc_in + slot * in_slot;
+    uint64_t *d_msg = (uint64_t *)(d_ent + piece * (size_t)ent_stride + ((8 - (piece * (size_t)ent_stride) % 8) % 8));
+    if (mb.ent_used) SET_CUDA(cudaEventSynchronize(mb.ent_free));  // the copy that last read this pinned buffer is done
+    draw(user, mb.ent_pin, cnt * (size_t)ent_stride);
+    SET_CUDA(cudaMemcpyAsync(d_ent, mb.ent_pin, cnt * (size_t)ent_stride, cudaMemcpyHostToDevice, mb.stream));
+    SET_CUDA(cudaEventRecord(mb.ent_free, mb.stream));
+    mb.ent_used = true;
+    SET_CUDA(cudaMemcpyAsync(d_msg, msg + start[k], cnt * 8, cudaMemcpyHostToDevice, mb.stream));
+    SET_TRY(mfb_encrypt_dev(mb.ctx, seed, offset + start[k] * (uint64_t)MFB_CTR_CT, mb.skp, d_msg, d_ent, ent_stride, ent_nbytes, cnt,
+                            mb.enc_out + slot * piece * MFB_CT_BYTES, mb.stream));
+  }
+  int rc = MFB_OK;
+  for (size_t k = 0; k < npieces; k++) {  // records back, piece by piece (each copy waits for its member's stream)
+    Member &mb = s->m[k % world];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_CUDA(cudaMemcpyAsync(out_c8 + start[k] * MFB_CT_BYTES, mb.enc_out + (k / world) * piece * MFB_CT_BYTES, len[k] * MFB_CT_BYTES,
+                             cudaMemcpyDeviceToHost, mb.stream));
+  }
+  for (size_t i = 0; i < world && i < npieces; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_CUDA(cudaStreamSynchronize(mb.stream));
+    memset(mb.ent_pin, 0, mb.ent_pin_cap);  // the noise is secret
+    SET_CUDA(cudaMemsetAsync(mb.enc_in, 0, mb.enc_in_cap, mb.stream));
+  }
+  SET_CUDA(cudaSetDevice(s->m[0].device));
   return rc;
 }
 

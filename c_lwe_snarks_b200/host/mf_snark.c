@@ -264,7 +264,15 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   uint64_t *skf = malloc(MFB_FLAT_SK_U64 * 8);
   if (!recs || !skf) mf_die("malloc");
   for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
-  MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+  mfb_set *set = device_set();
+  if (set) { /* the pieces spread over the GPUs of the set: entropy-bound instead of AES-bound */
+    if (mfb_set_encrypt_cb(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs) != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_cb failed: %s\n", mfb_set_last_error());
+      abort();
+    }
+  } else {
+    MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+  }
   mf_trace("setup.entropy+encrypt", t0);
   memcpy(crs->s, recs, D * CT_BYTES);
   memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);

@@ -65,6 +65,8 @@ extern "C" {
 
 typedef struct mfb_ctx mfb_ctx;
 typedef struct mfb_ssp mfb_ssp;       /* an SSP blob kept on the device (mfb_ssp_create) */
+/* entropy callback of mfb_encrypt_cb / mfb_set_encrypt_cb: fill dst[0..nbytes) */
+typedef void (*mfb_entropy_fn)(void *user, uint8_t *dst, size_t nbytes);
 
 /* ---- context ------------------------------------------------------------------------------ */
 MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
@@ -199,6 +201,10 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
 MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r);
 MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
                             uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
+/* mfb_encrypt_cb over a device set: the entropy is drawn by the calling thread piece by piece, in order; piece k is
+ * encrypted by member k mod size (setup()'s 2D+M encryptions on a whole box: entropy-bound instead of AES-bound). */
+MFB_API int mfb_set_encrypt_cb(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                       mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
 /* eval_poly / eval_poly2 with nothing resident, sharded: every member regenerates the a-vectors of its contiguous
  * ciphertext range from AES in-kernel; coeffs1 / rop1 may both be NULL. */
 MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
@@ -242,7 +248,6 @@ MFB_API int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, c
  * pieces of the count*ent_stride entropy bytes, in order, exactly once each — so a getrandom-backed callback consumes
  * the OS entropy in the reference's order (per encryption: 69 noise bytes, then 1 sign byte) — while the device
  * encrypts the previous piece: setup()'s 2D+M draws (tens of ms of getrandom) hide behind the kernel. */
-typedef void (*mfb_entropy_fn)(void *user, uint8_t *dst, size_t nbytes);
 MFB_API int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                    mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
 MFB_API int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,

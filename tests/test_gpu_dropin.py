@@ -131,6 +131,23 @@ def test_prover_sharded_over_a_device_set_without_residency(dropin):
         assert sha(proof[k]) == g["proof_sha"][k]
 
 
+def test_setup_over_a_device_set_is_identical(dropin):
+    """mf_set_devices(2): setup()'s encryptions are spread over the members piece by piece; the CRS does not change."""
+    import torch
+    g = GOLD["snark_d64_m16"]
+    dropin.set_instance(g["D"], g["M"])
+    dropin.lib.mf_set_devices(2, 1 if torch.cuda.device_count() >= 2 else 0)
+    try:
+        dropin.set_entropy(xof("snark-entropy-d64-m16", g["entropy_bytes"]))
+        ssp, wit = dropin.random_ssp()
+        crs = dropin.setup(ssp)
+        dropin.clear_entropy()
+    finally:
+        dropin.lib.mf_set_devices(1, 1)
+    assert sha(crs["s"]) == g["crs_s_sha"] and sha(crs["as_"]) == g["crs_as_sha"]
+    assert sha(crs["v"][: g["M"] - 1]) == g["crs_v_sha"] and hexs(crs["t"]) == g["crs_t"]
+
+
 def test_prover_with_only_one_region_resident_is_identical(dropin, monkeypatch):
     """When only one of the two CRS regions fits in HBM (D = 2^20 on one GPU) mf_crs_make_resident keeps that one and
     prover() mixes a resident pass with a fused one; $MF_B200_ONE_REGION forces that path at a small size."""

@@ -347,3 +347,30 @@ def test_device_set_eval_poly_without_residency(nmembers, d):
     finally:
         dset.close()
         ctx.close()
+
+
+@pytest.mark.parametrize("nmembers,cnt", [(1, 7), (2, 148 * 16 + 5), (3, 148 * 16 + 148 * 110 * 2 + 33)])
+def test_device_set_encrypt_cb(nmembers, cnt, oracle):
+    """mfb_set_encrypt_cb: setup's encryptions with the pieces spread over the members == mfb_encrypt on the same entropy,
+    drawn exactly once and in order."""
+    import c_lwe_snarks_b200 as m
+    from conftest import xof
+    sk = oracle.key_gen(xof("sk-setenc", N * CT_BYTES))
+    msg = xof_scalars(f"m-setenc-{cnt}", cnt)
+    ent = xof(f"ent-setenc-{cnt}", cnt * 70)
+    pos = [0]
+
+    def draw(n):
+        out = ent[pos[0]: pos[0] + n].tobytes()
+        pos[0] += n
+        return out
+
+    ctx = m.Context(0)
+    dset = ctx.device_set([0] * (nmembers - 1))
+    try:
+        got = dset.encrypt_cb(SEED, 5 * CTR_CT + 8, sk[:, :11], msg, draw)
+        assert pos[0] == cnt * 70
+        assert np.array_equal(got, ctx.encrypt(SEED, 5 * CTR_CT + 8, sk[:, :11], msg, ent))
+    finally:
+        dset.close()
+        ctx.close()
