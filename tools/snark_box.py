@@ -22,6 +22,8 @@ t_setup_cold = sn.setup()   # includes CUDA initialisation and the first allocat
 t_setup = sn.setup()
 for n in counts:
     sn.set_devices(n)
+    sn.setup()  # warm-up of the members' buffers
+    t_setup_set = sn.setup()  # the encryptions spread over the n GPUs (mfb_set_encrypt_cb): entropy-bound
     sn.prove()  # nothing resident: both fused AES + MAC passes sharded over the n GPUs (mfb_set_eval_poly2)
     t_nonres = min(sn.prove() for _ in range(2))
     t0 = time.perf_counter()
@@ -32,7 +34,7 @@ for n in counts:
     sn.tamper()
     bad, _ = sn.verify()
     print(json.dumps({"D": 1 << log2d, "M": M, "devices": n, "random_ssp_s": round(t_ssp, 3), "setup_cold_s": round(t_setup_cold, 3), "setup_s": round(t_setup, 4),
-                      "prove_nothing_resident_ms": round(1e3 * t_nonres, 2), "make_resident_s": round(t_res, 3),
+                      "setup_over_the_set_s": round(t_setup_set, 4), "prove_nothing_resident_ms": round(1e3 * t_nonres, 2), "make_resident_s": round(t_res, 3),
                       "prove_ms": [round(1e3 * t, 3) for t in proves],
                       "verify_ms": round(1e3 * t_ver, 3), "accept": ok, "tampered_accept": bad,
                       "api": "setup/prover/verifier (snark.h:44-51) via libmangiafuoco_b200.so, one host thread"}), flush=True)
