@@ -18,19 +18,8 @@ struct AccG {
 
 template <int L>
 __device__ __forceinline__ void accg_mad(AccG<L> &x, const uint32_t (&a)[2 * L], uint32_t s) {
-  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(x.E[0]), "+r"(x.E[1]) : "r"(a[0]), "r"(s));
-#pragma unroll
-  for (int k = 1; k < L - 1; k++)
-    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                 : "+r"(x.E[2 * k]), "+r"(x.E[2 * k + 1]) : "r"(a[2 * k]), "r"(s));
-  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
-               : "+r"(x.E[2 * L - 2]), "+r"(x.E[2 * L - 1]) : "r"(a[2 * L - 2]), "r"(s));
-  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(x.O[0]), "+r"(x.O[1]) : "r"(a[1]), "r"(s));
-#pragma unroll
-  for (int k = 1; k < L - 1; k++)
-    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                 : "+r"(x.O[2 * k]), "+r"(x.O[2 * k + 1]) : "r"(a[2 * k + 1]), "r"(s));
-  asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[2 * L - 2]) : "r"(a[2 * L - 1]), "r"(s));
+  MadChain<L, false>::template run<0, 0>(x.E, a, s);
+  MadChain<L - 1, true>::template run<0, 1>(x.O, a, s);
 }
 
 __device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -107,10 +96,7 @@ k_lincomb_g(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeff
   // fold E + (O << 32) and write the partial
   uint32_t r[2 * L];
   r[0] = acc.E[0];
-  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[1]) : "r"(acc.E[1]), "r"(acc.O[0]));
-#pragma unroll
-  for (int i = 2; i < 2 * L - 1; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(acc.E[i]), "r"(acc.O[i - 1]));
-  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r[2 * L - 1]) : "r"(acc.E[2 * L - 1]), "r"(acc.O[2 * L - 2]));
+  AddChain<2 * L - 1>::template run<1, 1, 0>(r, acc.E, acc.O);
   uint64_t *out = partial + (size_t)blockIdx.y * ct_u64 + (size_t)tile * L * 64 + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < L; j++) out[j * 64] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;

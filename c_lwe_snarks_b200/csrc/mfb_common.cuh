@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "mfb_chains.cuh"
+
 namespace mfb {
 
 constexpr int N = 1470;            // GAMMA_N (lwe.h:23)
@@ -72,24 +74,12 @@ __device__ __forceinline__ void acc_zero(Acc704 &x) {
   for (int i = 0; i < 21; i++) x.O[i] = 0;
 }
 
+// The chains below are ONE inline-asm statement each (mfb_chains.cuh, generated): the CC flag that links the limbs
+// never has to survive between statements.
 // acc += s * a   (a = 22 limbs, s < 2^32), mod 2^704
 __device__ __forceinline__ void acc_mad(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
-  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-               : "+r"(x.E[0]), "+r"(x.E[1]) : "r"(a[0]), "r"(s));
-#pragma unroll
-  for (int k = 1; k < 10; k++)
-    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                 : "+r"(x.E[2 * k]), "+r"(x.E[2 * k + 1]) : "r"(a[2 * k]), "r"(s));
-  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
-               : "+r"(x.E[20]), "+r"(x.E[21]) : "r"(a[20]), "r"(s));
-
-  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-               : "+r"(x.O[0]), "+r"(x.O[1]) : "r"(a[1]), "r"(s));
-#pragma unroll
-  for (int k = 1; k < 10; k++)
-    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                 : "+r"(x.O[2 * k]), "+r"(x.O[2 * k + 1]) : "r"(a[2 * k + 1]), "r"(s));
-  asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[21]), "r"(s));
+  MadChain<11, false>::run<0, 0>(x.E, a, s);  // even limbs: E[0..21]
+  MadChain<10, true>::run<0, 1>(x.O, a, s);   // odd limbs: O[0..19], low half of a[21] * s into O[20]
 }
 
 // acc += (a * b) mod 2^704 for two 22-limb operands (schoolbook low half, 253 limb products).
@@ -99,39 +89,22 @@ __device__ __forceinline__ void acc_mad(Acc704 &x, const uint32_t (&a)[22], uint
 // consecutive 64-bit slots of one accumulator and the carry flag links them.  One chain of every row
 // ends at pos 20 (E[20], E[21]), the other at pos 21 (low half into O[20]): both reach the top, where
 // the carry is dropped (that is modq).
-template <int KB, int Lx, bool FIRST>
+template <int KB, int Lx>
 __device__ __forceinline__ void acc_mul_chain(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
-  constexpr int pos = Lx + KB;
+  constexpr int pos = Lx + KB;  // limb position of the chain's first product
   if constexpr (pos <= 21) {
-    if constexpr ((pos & 1) == 0) {
-      if constexpr (FIRST)
-        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                     : "+r"(x.E[pos]), "+r"(x.E[pos + 1]) : "r"(a[Lx]), "r"(s));
-      else
-        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                     : "+r"(x.E[pos]), "+r"(x.E[pos + 1]) : "r"(a[Lx]), "r"(s));
-    } else if constexpr (pos < 21) {
-      if constexpr (FIRST)
-        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                     : "+r"(x.O[pos - 1]), "+r"(x.O[pos]) : "r"(a[Lx]), "r"(s));
-      else
-        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
-                     : "+r"(x.O[pos - 1]), "+r"(x.O[pos]) : "r"(a[Lx]), "r"(s));
-    } else {
-      if constexpr (FIRST)
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[Lx]), "r"(s));
-      else
-        asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(x.O[20]) : "r"(a[Lx]), "r"(s));
-    }
-    acc_mul_chain<KB, Lx + 2, false>(x, a, s);
+    if constexpr ((pos & 1) == 0)
+      MadChain<(20 - pos) / 2 + 1, false>::template run<pos, Lx>(x.E, a, s);
+    else
+      MadChain<(21 - pos) / 2, true>::template run<pos - 1, Lx>(x.O, a, s);
   }
 }
 
 template <int KB>
 __device__ __forceinline__ void acc_mul_rows(Acc704 &x, const uint32_t (&a)[22], const uint32_t (&b)[22]) {
   if constexpr (KB <= 21) {
-    acc_mul_chain<KB, 0, true>(x, a, b[KB]);
-    acc_mul_chain<KB, 1, true>(x, a, b[KB]);
+    acc_mul_chain<KB, 0>(x, a, b[KB]);
+    acc_mul_chain<KB, 1>(x, a, b[KB]);
     acc_mul_rows<KB + 1>(x, a, b);
   }
 }
@@ -143,29 +116,15 @@ __device__ __forceinline__ void acc_mul(Acc704 &x, const uint32_t (&a)[22], cons
 // r[0..21] = (E + (O << 32)) mod 2^704
 __device__ __forceinline__ void acc_fold(const Acc704 &x, uint32_t (&r)[22]) {
   r[0] = x.E[0];
-  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[1]) : "r"(x.E[1]), "r"(x.O[0]));
-#pragma unroll
-  for (int i = 2; i < 21; i++)
-    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(x.E[i]), "r"(x.O[i - 1]));
-  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r[21]) : "r"(x.E[21]), "r"(x.O[20]));
+  AddChain<21>::run<1, 1, 0>(r, x.E, x.O);
 }
 
 // r += b (22 limbs), mod 2^704
-__device__ __forceinline__ void add704(uint32_t (&r)[22], const uint32_t (&b)[22]) {
-  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r[0]) : "r"(b[0]));
-#pragma unroll
-  for (int i = 1; i < 21; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b[i]));
-  asm volatile("addc.u32 %0, %0, %1;" : "+r"(r[21]) : "r"(b[21]));
-}
+__device__ __forceinline__ void add704(uint32_t (&r)[22], const uint32_t (&b)[22]) { AccChain<22>::run(r, b); }
 
 // r = a - b (22 limbs) mod 2^704; returns 1 when a < b (borrow out of the top)
 __device__ __forceinline__ uint32_t sub704(uint32_t (&r)[22], const uint32_t (&a)[22], const uint32_t (&b)[22]) {
-  uint32_t borrow;
-  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(a[0]), "r"(b[0]));
-#pragma unroll
-  for (int i = 1; i < 22; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(a[i]), "r"(b[i]));
-  asm volatile("subc.u32 %0, 0, 0;" : "=r"(borrow));
-  return borrow & 1u;
+  return SubChain<22>::run<0, 0, 0>(r, a, b);
 }
 
 #define MFB_CUDA_TRY(expr)                         \
