@@ -494,6 +494,11 @@ cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, c
   return cudaGetLastError();
 }
 
+cudaError_t probe_kernel_image() {
+  cudaFuncAttributes at;
+  return cudaFuncGetAttributes(&at, k_columns_split);  // cudaErrorInvalidDeviceFunction when no sm_100a image loads
+}
+
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st) {
   k_columns_split<<<(NCP * L32 + 255) / 256, 256, 0, st>>>(flat, cols);
   return cudaGetLastError();

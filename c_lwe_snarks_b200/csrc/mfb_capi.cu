@@ -63,6 +63,7 @@ cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const u
                            uint64_t *out_m, uint64_t *out_dot, cudaStream_t st);
 cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, int tiled,
                                   cudaStream_t st);
+cudaError_t probe_kernel_image();  // k_lincomb.cu: does this device have an image of our kernels?
 
 cudaError_t launch_lincomb_generic(int limbs64, const uint64_t *cts, const uint32_t *coeffs, size_t d, int ntiles, uint64_t *out,
                                    uint64_t *partial_ws, size_t partial_cap_u64, unsigned int *queue, int sm_count,
@@ -119,6 +120,14 @@ struct mfb_region {
   uint64_t *cts = nullptr;  // planar
   size_t count = 0;
 };
+
+// Secret material (keys, noise) staged in a scratch slot is zeroed on the stream that used it before the call
+// returns — on error paths too — so that it does not outlive the call in device memory.
+static void scrub_slot(mfb_ctx *ctx, int i, size_t bytes, cudaStream_t st) {
+  if (!ctx->slot[i] || bytes == 0) return;
+  if (bytes > ctx->slot_cap[i]) bytes = ctx->slot_cap[i];
+  if (cudaMemsetAsync(ctx->slot[i], 0, bytes, st) != cudaSuccess) cudaGetLastError();
+}
 
 static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
   if (bytes == 0) bytes = 16;
@@ -250,9 +259,12 @@ int mfb_ctx_create(mfb_ctx **out, int device) {
   MFB_CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   MFB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return set_err(MFB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+  // the library ships sm_100a cubins only (arch-specific: they load on compute capability 10.0 and nothing else)
+  if (prop.major != 10 || prop.minor != 0 || probe_kernel_image() != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(MFB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
                    prop.minor);
+  }
   mfb_ctx *ctx = new (std::nothrow) mfb_ctx();
   if (!ctx) return set_err(MFB_ENOMEM, "out of host memory");
   ctx->device = device;
@@ -1017,13 +1029,17 @@ int mfb_prove_resident(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, cons
                                h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, nullptr);
 }
 
-int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
-                const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
-  MFB_CHECK_CTX(ctx);
-  if (count == 0) return MFB_OK;
-  if (!seed || !sk_flat || !msg || !ent || !out_c8) return set_err(MFB_EARG, "mfb_encrypt: null pointer");
-  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes)
-    return set_err(MFB_EARG, "mfb_encrypt: need 0 <= ent_nbytes <= 88 and ent_stride >= ent_nbytes");
+// the host-flavour encrypt / decrypt calls stage the secret key in slots 0 (flat) and 4 (row-planar) and the noise in
+// slot 3: all three are zeroed before the call returns, whatever the outcome
+static void scrub_secrets(mfb_ctx *ctx, size_t noise_bytes) {
+  scrub_slot(ctx, 0, MFB_FLAT_SK_U64 * 8, ctx->stream);
+  scrub_slot(ctx, 4, PLANAR_U64 * 8, ctx->stream);
+  scrub_slot(ctx, 3, noise_bytes, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+}
+
+static int encrypt_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                        const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
   void *d_skf, *d_skp, *d_msg, *d_ent, *d_out;
   MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
   MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
@@ -1041,13 +1057,20 @@ int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uin
   return MFB_OK;
 }
 
-int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
-                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
   MFB_CHECK_CTX(ctx);
   if (count == 0) return MFB_OK;
-  if (!seed || !sk_flat || !msg || !draw || !out_c8) return set_err(MFB_EARG, "mfb_encrypt_cb: null pointer");
-  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
-    return set_err(MFB_EARG, "mfb_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
+  if (!seed || !sk_flat || !msg || !ent || !out_c8) return set_err(MFB_EARG, "mfb_encrypt: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes)
+    return set_err(MFB_EARG, "mfb_encrypt: need 0 <= ent_nbytes <= 88 and ent_stride >= ent_nbytes");
+  const int rc = encrypt_body(ctx, seed, offset, sk_flat, msg, ent, ent_stride, ent_nbytes, count, out_c8);
+  scrub_secrets(ctx, count * (size_t)ent_stride);
+  return rc;
+}
+
+static int encrypt_cb_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                           mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
   // pieces: a short first one so that the device starts early, then ~110 ciphertexts per SM and launch
   const size_t piece = (size_t)ctx->sm_count * 110, first_piece = (size_t)ctx->sm_count * 16;
   const size_t cap = piece * (size_t)ent_stride;
@@ -1071,10 +1094,9 @@ int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const 
   MFB_CUDA_TRY(cudaMemcpyAsync(d_skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, ctx->stream));
   MFB_CUDA_TRY(cudaMemcpyAsync(d_msg, msg, count * 8, cudaMemcpyHostToDevice, ctx->stream));
   MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_skf, N, 1, (uint64_t *)d_skp, ctx->stream));
-  int rc = MFB_OK;
   bool used[2] = {false, false};
   int k = 0;
-  for (size_t done = 0; done < count && rc == MFB_OK; k ^= 1) {
+  for (size_t done = 0; done < count; k ^= 1) {
     size_t cnt = done == 0 ? first_piece : piece;
     if (cnt > count - done) cnt = count - done;
     const size_t nb = cnt * (size_t)ent_stride;
@@ -1084,28 +1106,33 @@ int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const 
     MFB_CUDA_TRY(cudaMemcpyAsync(d_e, ctx->ent_pin[k], nb, cudaMemcpyHostToDevice, ctx->stream));
     MFB_CUDA_TRY(cudaEventRecord(ctx->ent_free[k], ctx->stream));
     used[k] = true;
-    rc = mfb_encrypt_dev(ctx, seed, offset + done * (uint64_t)CTR_CT, (const uint64_t *)d_skp, (const uint64_t *)d_msg + done,
-                         d_e, ent_stride, ent_nbytes, cnt, (uint8_t *)d_out + done * CT_BYTES, ctx->stream);
+    MFB_TRY(mfb_encrypt_dev(ctx, seed, offset + done * (uint64_t)CTR_CT, (const uint64_t *)d_skp, (const uint64_t *)d_msg + done,
+                            d_e, ent_stride, ent_nbytes, cnt, (uint8_t *)d_out + done * CT_BYTES, ctx->stream));
     done += cnt;
   }
-  if (rc == MFB_OK) {
-    cudaError_t e = cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = mfb::fail(e, "mfb_encrypt_cb: copy back", __FILE__, __LINE__);
-  } else {
-    cudaStreamSynchronize(ctx->stream);
-  }
-  // the noise is secret: do not leave it in the staging buffers (device scratch is overwritten by later calls)
-  for (int j = 0; j < 2; j++) memset(ctx->ent_pin[j], 0, ctx->ent_pin_cap);
-  cudaMemsetAsync(d_ent, 0, count * (size_t)ent_stride, ctx->stream);
+  MFB_CUDA_TRY(cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MFB_OK;
+}
+
+int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+  MFB_CHECK_CTX(ctx);
+  if (count == 0) return MFB_OK;
+  if (!seed || !sk_flat || !msg || !draw || !out_c8) return set_err(MFB_EARG, "mfb_encrypt_cb: null pointer");
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
+    return set_err(MFB_EARG, "mfb_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
+  const int rc = encrypt_cb_body(ctx, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, count, out_c8);
+  // the key and the noise are secret: nothing of them stays in the staging buffers, on error paths either
+  cudaStreamSynchronize(ctx->stream);  // (the pinned buffers may still be read by a queued copy after an early return)
+  for (int j = 0; j < 2; j++)
+    if (ctx->ent_pin[j]) memset(ctx->ent_pin[j], 0, ctx->ent_pin_cap);
+  scrub_secrets(ctx, count * (size_t)ent_stride);
   return rc;
 }
 
-int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
-                uint64_t *out_m, uint64_t *out_dot) {
-  MFB_CHECK_CTX(ctx);
-  if (count == 0) return MFB_OK;
-  if (!sk_flat || !cts_flat || !out_m) return set_err(MFB_EARG, "mfb_decrypt: null pointer");
+static int decrypt_body(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
+                        uint64_t *out_m, uint64_t *out_dot) {
   void *d_skf, *d_skp, *d_cts, *d_neg = nullptr, *d_m, *d_dot = nullptr;
   MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
   MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
@@ -1123,6 +1150,16 @@ int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat,
   if (out_dot) MFB_CUDA_TRY(cudaMemcpyAsync(out_dot, d_dot, count * L64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MFB_OK;
+}
+
+int mfb_decrypt(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
+                uint64_t *out_m, uint64_t *out_dot) {
+  MFB_CHECK_CTX(ctx);
+  if (count == 0) return MFB_OK;
+  if (!sk_flat || !cts_flat || !out_m) return set_err(MFB_EARG, "mfb_decrypt: null pointer");
+  const int rc = decrypt_body(ctx, sk_flat, cts_flat, b_neg, count, out_m, out_dot);
+  scrub_secrets(ctx, 0);
+  return rc;
 }
 
 }  // extern "C"

@@ -113,6 +113,7 @@ void regev_encrypt2(ct_t c, rng_t rs, sk_t sk, mpz_t m, void (*chi)(mpz_t)) { /*
   uint64_t *skf = sk_flat_new(sk);
   uint8_t rec[CT_BYTES];
   MF_GPU(mfb_encrypt(mf_gpu(), mf_rng_seed(rs), pos, skf, &msg, (const uint8_t *)e_flat, 8 * MF_LIMBS, 8 * MF_LIMBS, 1, rec));
+  explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);
   mf_bytes_to_mpz(c[GAMMA_N], rec, CT_BYTES);
   mpz_clear(e);
@@ -166,6 +167,7 @@ void regev_decrypt(mpz_t m, sk_t sk, ct_t ct) { /* lwe.c:105-111 */
   uint64_t res;
   MF_GPU(mfb_decrypt(mf_gpu(), skf, cf, &neg, 1, &res, NULL));
   mpz_set_ui(m, res);
+  explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);
   free(cf);
 }

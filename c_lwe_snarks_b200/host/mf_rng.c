@@ -125,3 +125,6 @@ void mpz2_urandomb2(mpz_ptr rop, size_t nbits) {
   set_from_bytes(rop, b, nbits);
   if (b != buf) free(b);
 }
+
+/* entropy.h:56 — declared by the reference, defined and called nowhere in it */
+void mpz_entropy_init(void) {}

@@ -228,6 +228,9 @@ static void draw_entropy(void *user, uint8_t *dst, size_t nbytes) {
 void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   const size_t D = GAMMA_D, M = GAMMA_M, count = 2 * D + M;
   double t0 = mf_now();
+  /* the records are about to be rewritten: a resident copy of this crs (mf_crs_make_resident) would be stale, and
+   * prover() finds regions by crs pointer — drop it, as mf_crs_read() does */
+  mf_crs_release(crs);
   vrs->alpha = rand_modp();
   vrs->beta = rand_modp();
   vrs->s = rand_modp();
@@ -279,6 +282,7 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
   memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
   free(recs);
+  explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);
   free(msg);
 }
@@ -474,6 +478,7 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi) {
   uint64_t dec[5], dots[5 * MF_LIMBS];
   MF_GPU(mfb_decrypt(mf_gpu(), skf, cts, neg, 5, dec, dots));
   free(cts);
+  explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);
   const uint64_t h_s = dec[0], hath_s = dec[1], hatv_s = dec[2], w_s = dec[3], b_s = dec[4];
   const uint64_t v_s = (v0_s + w_s) % p;

@@ -35,8 +35,6 @@ class ShardPlan:
     def __post_init__(self):
         if self.world < 1 or not (0 <= self.rank < self.world):
             raise ValueError("bad rank / world size")
-        if NCP % self.world:
-            raise ValueError(f"world size must divide {NCP} (= 2^6 * 23): 1, 2, 4, 8, 16, 23, ...")
 
     def ct_range(self, d_total: int):
         """Contiguous slice [first, first + count) of the ciphertext indices; the remainder goes to the low ranks."""
@@ -46,6 +44,10 @@ class ShardPlan:
 
     @property
     def coords_per_rank(self) -> int:
+        """Coordinates a rank owns after the NCCL reduce-scatter; only that exchange needs an even split (the
+        peer-memory exchange works for any world size <= 16)."""
+        if NCP % self.world:
+            raise ValueError(f"the NCCL exchange needs a world size that divides {NCP} (= 2^6 * 23): 1, 2, 4, 8, 16, 23, ...")
         return NCP // self.world
 
     @property

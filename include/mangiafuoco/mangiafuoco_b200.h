@@ -37,6 +37,17 @@ extern "C" {
 #define PTR(x) ((x)->_mp_d)
 #define ALLOC(x) ((x)->_mp_alloc)
 #define BITS_TO_LIMBS(n) (((n) + (GMP_NUMB_BITS - 1)) / GMP_NUMB_BITS)
+/* gmp-impl.h:15-29.  As in the reference, MPN_NORMALIZE does not stop at NLIMBS == 0: only use it on a non-zero
+ * limb array (the library's own code normalises with a bounded loop instead). */
+#define UNLIKELY(cond) __GMP_UNLIKELY(cond)
+#define MPN_NORMALIZE(DST, NLIMBS)         \
+  do {                                     \
+    while (1) {                            \
+      if ((DST)[(NLIMBS)-1] != 0) break;   \
+      (NLIMBS)--;                          \
+    }                                      \
+  } while (0)
+#define MPZ_NEWALLOC(z, n) (UNLIKELY((n) > ALLOC(z)) ? (mp_ptr)_mpz_realloc(z, n) : PTR(z))
 
 /* ---- parameters (lwe.h:14-31) ------------------------------------------------------------------------- */
 #define GAMMA_N 1470
@@ -119,6 +130,8 @@ static inline void rng_gen(rng_t prg, void *out, size_t count) { aesctr_prg((aes
     rng_init(rs, rseed_);          \
   } while (0)
 
+/* entropy.h:56 declares it, no reference source defines or calls it: kept for link compatibility, does nothing */
+void mpz_entropy_init(void);
 void mpz2_urandomb(mpz_ptr rop, rng_t prg, size_t nbits);
 void mpz2_urandomb2(mpz_ptr rop, size_t nbits);
 #define mpz2_urandommv(vs, rng, bits, len)                                   \
@@ -230,7 +243,10 @@ bool verifier(ssp_t ssp, vrs_t vrs, proof_t pi);
 
 /* ---- additions (not in the reference) ------------------------------------------------------------------ */
 /* Keep the two big CRS regions (s, as) expanded in HBM across prover() calls for this crs: the AES
- * regeneration of the a-vectors is then paid once instead of per proof.  mf_crs_release frees them. */
+ * regeneration of the a-vectors is then paid once instead of per proof.  mf_crs_release frees them.
+ * The resident copy is a snapshot of crs->seed / crs->s / crs->as at the time of the call: call it AFTER setup()
+ * or mf_crs_read().  Both of those (and crs_clear) drop a resident copy of the crs they overwrite, so a stale
+ * copy is never used; a caller that rewrites the record arrays by hand must call mf_crs_release itself. */
 void mf_crs_make_resident(crs_t crs);
 void mf_crs_release(crs_t crs);
 /* Number of GPUs the resident regions are sharded over (by ciphertext index), all driven by the calling thread:

@@ -31,7 +31,7 @@ def test_dropin_exports_the_reference_interface():
               "key_gen", "key_clear", "errdist_uniform", "ct_init", "ct_clear", "ct_export", "ct_import",
               "decompress_encryption", "regev_encrypt2", "mpz_add_dotp", "regev_decrypt", "ct_smudge", "ct_add",
               "ct_mul_ui", "ct_addmul_ui", "ct_zero", "eval_poly", "rng_init", "rng_clear", "rng_seek",
-              "mpz2_urandomb", "mpz2_urandomb2", "aesctr_init", "aesctr_prg", "aesctr_clear",
+              "mpz2_urandomb", "mpz2_urandomb2", "mpz_entropy_init", "aesctr_init", "aesctr_prg", "aesctr_clear",
               "nmod_poly_import", "nmod_poly_export", "random_ssp"]:
         assert hasattr(lib, n), n
     # the additions of include/mangiafuoco/mangiafuoco_b200.h (INTEGRATION.md "What is new")

@@ -284,3 +284,27 @@ def test_python_snark_binding_roundtrip():
         assert sn.gpu_launches() > 0
     finally:
         sn.close()
+
+
+def test_setup_over_a_resident_crs_drops_the_stale_regions():
+    """setup() rewrites crs->s / crs->as in place: a resident copy made before it (mf_crs_make_resident) would be stale,
+    and prover() finds regions by crs pointer.  setup() must drop it — the proof over the NEW records verifies."""
+    import ctypes as C
+
+    from c_lwe_snarks_b200.snark import Snark
+    sn = Snark(128, 16)
+    try:
+        sn.random_ssp()
+        sn.setup()
+        sn.make_resident()
+        sn.prove()
+        assert sn.verify()[0]
+        sn.lib.key_clear(sn.vrs.sk)
+        sn.lib.setup(C.byref(sn.crs), C.byref(sn.vrs), sn._ssp_ptr())  # same crs object, new alpha / beta / s / sk / records
+        sn.prove()  # must not use the regions expanded from the old records
+        assert sn.verify()[0]
+        sn.make_resident()
+        sn.prove()
+        assert sn.verify()[0]
+    finally:
+        sn.close()

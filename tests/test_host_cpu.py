@@ -139,3 +139,39 @@ def test_proof_file_roundtrip(tmp_path):
     assert other.proof.v_w[N].size < 0
     sn.close()
     other.close()
+
+
+def test_gmp_impl_macros_of_the_reference_compile_and_work(tmp_path):
+    """gmp-impl.h:15-29 (UNLIKELY, MPN_NORMALIZE, MPZ_NEWALLOC) and entropy.h:56 (mpz_entropy_init) are part of the
+    reference's header surface: a program using them compiles against the drop-in headers, links and runs."""
+    src = tmp_path / "macros.c"
+    src.write_text(r'''
+#include "gmp-impl.h"
+#include "entropy.h"
+#include <stdio.h>
+int main(void) {
+  mpz_t z;
+  mpz_init(z);
+  mp_ptr p = MPZ_NEWALLOC(z, 5);            /* grows the limb array */
+  p[0] = 7; p[1] = 0; p[2] = 9; p[3] = 0; p[4] = 0;
+  mp_size_t n = 5;
+  MPN_NORMALIZE(p, n);                      /* strips the two zero high limbs */
+  SIZ(z) = (int)n;
+  if (UNLIKELY(n != 3)) return 1;
+  if (ALLOC(z) < 5 || PTR(z) != p) return 2;
+  if (MPZ_NEWALLOC(z, 2) != p) return 3;    /* no reallocation when it already fits */
+  mpz_entropy_init();
+  mpz_clear(z);
+  puts("ok");
+  return 0;
+}
+''')
+    lib = ROOT / "c_lwe_snarks_b200" / "lib"
+    exe = tmp_path / "macros"
+    cmd = ["gcc", "-std=gnu11", "-O1", f"-I{ROOT / 'include' / 'mangiafuoco'}", f"-I{ROOT / 'include' / 'compat'}",
+           f"-I{ROOT / 'include'}", str(src), f"-L{lib}", "-lmangiafuoco_b200", "-lmfb200", "-l:libgmp.so.10",
+           f"-Wl,-rpath,{lib}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr[-500:])

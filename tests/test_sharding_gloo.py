@@ -128,8 +128,11 @@ def test_shard_plan():
             assert ShardPlan(world, r).coords_per_rank * world == NCP
         assert covered[0][0] == 0 and sum(c for _, c in covered) == 1000003
         assert all(covered[i][0] + covered[i][1] == covered[i + 1][0] for i in range(world - 1))
+    # world sizes that do not divide 1472 shard the ciphertexts fine (the peer-memory exchange takes any world <= 16);
+    # only the NCCL exchange, which scatters the coordinates evenly, refuses them
+    assert [ShardPlan(3, r).ct_range(10) for r in range(3)] == [(0, 4), (4, 3), (7, 3)]
     with pytest.raises(ValueError):
-        ShardPlan(3, 0)
+        ShardPlan(3, 0).coords_per_rank
     with pytest.raises(ValueError):
         ShardPlan(2, 2)
     assert ShardPlan(8, 7).ct_range(5) == (5, 0)  # more ranks than ciphertexts: empty shard
