@@ -116,6 +116,16 @@ _SIGS = {
     "mfb_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "mfb_prove_resident_bw": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_size_t,
                                        _u64p, _u64p, _u64p, _u64p, _u64p]),
+    "mfb_lincomb2_partials_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "mfb_lincomb_finish4_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "mfb_peer_allreduce_lanes_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp, _vp, C.c_size_t, _vp]),
+    "mfb_peer_finish4_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mfb_ssp_prover_polys_resident_async": (C.c_int, [_vp, _vp, _u64p, C.c_size_t, C.c_uint64, _vp, C.POINTER(_vp)]),
+    "mfb_b_w_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _vp, _vp]),
+    "mfb_set_encrypt_par": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
+                                     C.c_int, C.c_size_t, _u8p, _vp, C.c_int]),
+    "mfb_set_prove_resident_bw": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_size_t,
+                                           _u64p, _u64p, _u64p, _u64p, _u64p]),
     "mfb_set_prove_resident": (C.c_int, [_vp, _vp, _vp, _vp, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "mfb_ssp_eval_resident": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),
     "mfb_ssp_eval": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p]),

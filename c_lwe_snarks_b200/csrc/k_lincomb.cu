@@ -200,11 +200,22 @@ __device__ __forceinline__ void fin_add_flat(uint32_t (&r)[22], const uint64_t *
   add704(r, b);
 }
 
+// One launch finishes up to PEER_LANES accumulators: grid (23 tiles, lanes); lane l adds the partials at
+// partial + l * lane_stride and reads / writes its flat ciphertext at rop + l * rop_stride.  (The prover's two
+// two-vector passes leave four sets of partials: one finish launch instead of four.)  queue / queue2: chunk queues
+// to re-arm (one per pass that fed this finish), nullable.
 __global__ void __launch_bounds__(64 * FIN_SLICES)
-k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                 unsigned int *queue) {
+k_lincomb_finish(const uint64_t *__restrict__ partial, size_t lane_stride, int nparts, const uint64_t *rop_in,
+                 uint64_t *rop_out, size_t rop_stride, unsigned int *queue, unsigned int *queue2) {
   __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
-  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;  // one CTA per tile: re-arm its chunk queue
+  const int lane = blockIdx.y;
+  if (threadIdx.x == 0 && lane == 0) {  // one CTA per tile: re-arm its chunk queues
+    if (queue) queue[blockIdx.x * LC_CTR_STRIDE] = 0;
+    if (queue2) queue2[blockIdx.x * LC_CTR_STRIDE] = 0;
+  }
+  partial += (size_t)lane * lane_stride;
+  if (rop_in) rop_in += (size_t)lane * rop_stride;
+  rop_out += (size_t)lane * rop_stride;
   const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const int c = blockIdx.x * 64 + cl;
   uint32_t r[22];
@@ -218,18 +229,19 @@ k_lincomb_finish(const uint64_t *__restrict__ partial, int nparts, const uint64_
 
 // --- multi-GPU: the finish step FUSED with the exchange over NVLink peer memory -----------------
 // Every rank owns a "symmetric" buffer that its peers map (CUDA IPC between processes, plain peer access inside
-// one); mfb_common.cuh: PEER_*.  For the call with sequence number `epoch` (parity q = epoch & 1), CTA `tile`
+// one); mfb_common.cuh: PEER_*.  For the call with sequence number `epoch` (parity q = epoch & 1), CTA (tile, lane)
 //   1. adds this rank's row-planar partials for its 64 coordinates (as k_lincomb_finish does);
-//   2. PUSHES the 5632-byte flat tile into slot [q][rank] of EVERY rank's buffer (coalesced 16-byte stores that
+//   2. PUSHES the 5632-byte flat tile into slot [q][rank][lane] of EVERY rank's buffer (coalesced 16-byte stores that
 //      travel over NVLink / NVSwitch; its own copy is a local store), fences at system scope and then releases
-//      flag [q][rank][tile] = epoch in every rank's buffer;
-//   3. waits until the flags [q][s][tile] of its OWN buffer carry `epoch` for every source rank s (acquire loads
-//      of local memory, written remotely), and
+//      flag [q][rank][lane][tile] = epoch in every rank's buffer;
+//   3. waits until the flags [q][s][lane][tile] of its OWN buffer carry `epoch` for every source rank s (acquire
+//      loads of local memory, written remotely), and
 //   4. adds the `world` tiles now sitting in local HBM/L2 (exact mod 2^704: the order does not matter), adds the
 //      incoming rop and writes the result — every rank ends with the full sum, with one NVLink store latency
 //      on the critical path instead of the four launches of split -> reduce-scatter -> carry -> all-gather.
 // Two parities suffice: a rank can only push call e+2 after it has seen every peer's flags of call e+1, which a
-// peer raises in the kernel that follows (in stream order) its own reads of call e.
+// peer raises in the kernel that follows (in stream order) its own reads of call e.  All lanes of one launch share
+// the epoch: every rank must pass the same number of lanes.
 struct PeerTable {
   uint8_t *base[PEER_MAX];
 };
@@ -258,13 +270,20 @@ __device__ __forceinline__ bool peer_wait_u32(const uint32_t *f, uint32_t want, 
 }
 
 __global__ void __launch_bounds__(64 * FIN_SLICES)
-k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                      unsigned int *queue, const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch,
-                      uint64_t timeout_ns, int *status) {
+k_lincomb_finish_peer(const uint64_t *__restrict__ partial, size_t lane_stride, int nparts, const uint64_t *rop_in,
+                      uint64_t *rop_out, size_t rop_stride, unsigned int *queue, unsigned int *queue2,
+                      const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, uint64_t timeout_ns,
+                      int *status) {
   __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
   __shared__ __align__(16) uint64_t stage[RT_TILE * L64];  // the flat tile: [64][11] u64
-  if (queue && threadIdx.x == 0) queue[blockIdx.x * LC_CTR_STRIDE] = 0;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x, lane = blockIdx.y;
+  if (threadIdx.x == 0 && lane == 0) {
+    if (queue) queue[tile * LC_CTR_STRIDE] = 0;
+    if (queue2) queue2[tile * LC_CTR_STRIDE] = 0;
+  }
+  partial += (size_t)lane * lane_stride;
+  if (rop_in) rop_in += (size_t)lane * rop_stride;
+  rop_out += (size_t)lane * rop_stride;
   const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const int c = tile * 64 + cl;
   const uint32_t q = epoch & 1u;
@@ -281,17 +300,17 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const ui
     const uint4 v = reinterpret_cast<const uint4 *>(stage)[threadIdx.x];
     for (int i = 0; i < world; i++) {
       const int p = (rank + 1 + i) % world;  // remote destinations first, the local copy last
-      uint8_t *dst = peers.base[p] + peer_slot_offset(q, world, rank) + (size_t)tile * TILE_FLAT_BYTES + 16 * threadIdx.x;
+      uint8_t *dst = peers.base[p] + peer_slot_offset(q, world, rank, lane) + (size_t)tile * TILE_FLAT_BYTES + 16 * threadIdx.x;
       *reinterpret_cast<uint4 *>(dst) = v;
     }
   }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world)
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, tile)), epoch);
+    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
   // 3. wait for every source rank's tile
   if ((int)threadIdx.x < world) {
-    const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, tile));
+    const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, lane, tile));
     // a peer that never arrives is reported instead of hanging the GPU
     if (!peer_wait_u32(f, epoch, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
   }
@@ -300,7 +319,7 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const ui
 #pragma unroll
   for (int j = 0; j < 22; j++) r[j] = 0;
   for (int src = slice; src < world; src += FIN_SLICES) {
-    const uint64_t *t = reinterpret_cast<const uint64_t *>(peers.base[rank] + peer_slot_offset(q, world, src)) + (size_t)c * L64;
+    const uint64_t *t = reinterpret_cast<const uint64_t *>(peers.base[rank] + peer_slot_offset(q, world, src, lane)) + (size_t)c * L64;
     uint32_t b[22];
 #pragma unroll
     for (int j = 0; j < L64; j++) {
@@ -329,13 +348,17 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, int nparts, const ui
   }
 }
 
-// The exchange alone (mfb_peer_allreduce_dev): this rank's contribution is already a flat ciphertext.  64 threads per
-// tile and no shared memory, so that the kernel is co-resident with a running k_lincomb (which fills the SMs' shared
-// memory): on a side stream it overlaps the NEXT lincomb kernel completely.
+// The exchange alone (mfb_peer_allreduce_dev): this rank's contribution is already a flat ciphertext (per lane, at
+// flat_partial + lane * in_stride).  64 threads per (tile, lane) and no shared memory, so that the kernel is co-resident
+// with a running k_lincomb (which fills the SMs' shared memory): on a side stream it overlaps the NEXT lincomb kernel.
 __global__ void __launch_bounds__(RT_TILE)
-k_peer_allreduce(const uint64_t *__restrict__ flat_partial, const uint64_t *rop_in, uint64_t *rop_out,
-                 const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status) {
-  const int tile = blockIdx.x;
+k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, const uint64_t *rop_in, uint64_t *rop_out,
+                 size_t rop_stride, const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch,
+                 uint64_t timeout_ns, int *status) {
+  const int tile = blockIdx.x, lane = blockIdx.y;
+  flat_partial += (size_t)lane * in_stride;
+  if (rop_in) rop_in += (size_t)lane * rop_stride;
+  rop_out += (size_t)lane * rop_stride;
   const int c = tile * RT_TILE + threadIdx.x;
   const uint32_t q = epoch & 1u;
   constexpr int TILE_FLAT_U64 = RT_TILE * L64;  // 704 u64 = 352 x 16 bytes
@@ -350,14 +373,14 @@ k_peer_allreduce(const uint64_t *__restrict__ flat_partial, const uint64_t *rop_
     v.w = (uint32_t)(hi >> 32);
     for (int k = 0; k < world; k++) {
       const int p = (rank + 1 + k) % world;
-      *reinterpret_cast<uint4 *>(peers.base[p] + peer_slot_offset(q, world, rank) + e * 8) = v;
+      *reinterpret_cast<uint4 *>(peers.base[p] + peer_slot_offset(q, world, rank, lane) + e * 8) = v;
     }
   }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, tile)), epoch);
-    const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, tile));
+    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
+    const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, lane, tile));
     if (!peer_wait_u32(f, epoch, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
   }
   __syncthreads();
@@ -365,7 +388,7 @@ k_peer_allreduce(const uint64_t *__restrict__ flat_partial, const uint64_t *rop_
 #pragma unroll
   for (int j = 0; j < 22; j++) r[j] = 0;
   for (int src = 0; src < world; src++) {
-    const uint64_t *t = reinterpret_cast<const uint64_t *>(peers.base[rank] + peer_slot_offset(q, world, src)) + (size_t)c * L64;
+    const uint64_t *t = reinterpret_cast<const uint64_t *>(peers.base[rank] + peer_slot_offset(q, world, src, lane)) + (size_t)c * L64;
     uint32_t b[22];
 #pragma unroll
     for (int j = 0; j < L64; j++) {
@@ -475,22 +498,32 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
   return cudaGetLastError();
 }
 
-cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                  unsigned int *queue, cudaStream_t st) {
-  k_lincomb_finish<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue);
+// finish `lanes` accumulators in one launch: lane l = partials at partial_ws + l * lane_stride (u64), flat ciphertext at
+// rop + l * rop_stride (u64)
+cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts, const uint64_t *rop_in,
+                                  uint64_t *rop_out, size_t rop_stride, unsigned int *queue, unsigned int *queue2,
+                                  cudaStream_t st) {
+  if (lanes < 1 || lanes > PEER_LANES) return cudaErrorInvalidValue;
+  k_lincomb_finish<<<dim3(RT_NTILES, lanes), 64 * FIN_SLICES, 0, st>>>(partial_ws, lane_stride, nparts, rop_in, rop_out, rop_stride,
+                                                                     queue, queue2);
   return cudaGetLastError();
 }
 
-cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *flat_partial,
-                                       const uint64_t *rop_in, uint64_t *rop_out, unsigned int *queue, uint8_t *const *bases,
-                                       int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st) {
+// flat_partial != nullptr: the exchange alone (k_peer_allreduce; lane l contributes flat_partial + l * lane_stride);
+// else the finish of the row-planar partials fused with the exchange
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts,
+                                       const uint64_t *flat_partial, const uint64_t *rop_in, uint64_t *rop_out, size_t rop_stride,
+                                       unsigned int *queue, unsigned int *queue2, uint8_t *const *bases, int world, int rank,
+                                       uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st) {
+  if (lanes < 1 || lanes > PEER_LANES) return cudaErrorInvalidValue;
   PeerTable t = {};
   for (int i = 0; i < world; i++) t.base[i] = bases[i];
   if (flat_partial)
-    k_peer_allreduce<<<RT_NTILES, RT_TILE, 0, st>>>(flat_partial, rop_in, rop_out, t, world, rank, epoch, timeout_ns, status);
+    k_peer_allreduce<<<dim3(RT_NTILES, lanes), RT_TILE, 0, st>>>(flat_partial, lane_stride, rop_in, rop_out, rop_stride, t, world, rank,
+                                                                epoch, timeout_ns, status);
   else
-    k_lincomb_finish_peer<<<RT_NTILES, 64 * FIN_SLICES, 0, st>>>(partial_ws, nparts, rop_in, rop_out, queue, t, world, rank, epoch,
-                                                                 timeout_ns, status);
+    k_lincomb_finish_peer<<<dim3(RT_NTILES, lanes), 64 * FIN_SLICES, 0, st>>>(partial_ws, lane_stride, nparts, rop_in, rop_out, rop_stride,
+                                                                            queue, queue2, t, world, rank, epoch, timeout_ns, status);
   return cudaGetLastError();
 }
 

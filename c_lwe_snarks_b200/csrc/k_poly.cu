@@ -617,6 +617,23 @@ static cudaError_t poly_mul(PolyEngine &E, const uint32_t *a, uint32_t la, uint3
   return cudaGetLastError();
 }
 
+// The same with the second operand given as its forward transform of n points (bhat[3][n], Montgomery form): an operand
+// that does not change between calls (the cached rev(t)^-1 of a resident SSP) is lifted and transformed once.
+static cudaError_t poly_mul_bhat(PolyEngine &E, const uint32_t *a, uint32_t la, uint32_t a_src_len, int a_rev, const uint32_t *bhat,
+                                 uint32_t n, uint32_t lo, uint32_t out_len, uint32_t *out, cudaStream_t st) {
+  if (n > E.nmax) return cudaErrorInvalidValue;
+  k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(a, la, a_src_len, a_rev, E.fa, n);
+  E.launches++;
+  cudaError_t ne = ntt_forward(E, E.fa, n, st);
+  if (ne != cudaSuccess) return ne;
+  k_pointwise<<<dim3(gridfor(n), NPR), 256, 0, st>>>(E.fa, bhat, n);
+  E.launches++;
+  if ((ne = ntt_inverse(E, E.fa, n, st)) != cudaSuccess) return ne;
+  k_crt<<<gridfor(out_len), 256, 0, st>>>(E.fa, n, lo, out_len, E.crt, 0, out);
+  E.launches++;
+  return cudaGetLastError();
+}
+
 // g[0..m) = f^-1 mod x^m for f of lf coefficients (f[0] != 0), Newton: g <- g * (2 - f g) mod x^2k
 static cudaError_t poly_inv_series(PolyEngine &E, const uint32_t *f, uint32_t lf, uint32_t m, uint32_t *g, cudaStream_t st) {
   k_set_inv0<<<1, 32, 0, st>>>(f, g);
@@ -708,12 +725,20 @@ struct mfb_ssp {
   uint32_t lt = 0;           // normalised length of t
   uint32_t *binv = nullptr;  // rev(t)^-1 mod x^binv_len
   uint32_t binv_len = 0, binv_cap = 0;
+  // forward transform (bhat_n points, three primes) of rev(t)^-1 mod x^bhat_lq: what the device-resident pipeline divides with
+  uint32_t *bhat = nullptr;
+  uint32_t bhat_n = 0, bhat_lq = 0;
+  // pinned staging of the witness-selected polynomial indices (so that their upload is a true asynchronous copy) and the
+  // event after which the staging may be overwritten
+  uint32_t *sel_pin = nullptr;
+  cudaEvent_t sel_free = nullptr;
+  bool sel_used = false;
 };
 
-// v (D residues, device) and t (lt residues, stable device pointer) -> h = (v^2 - 1) / t truncated to D, then w | v | h
-// back to the host as u64.  d_w, d_v, d_h are consecutive D-element u32 arrays.
+// Host-blob path: v (D residues, device) and t (lt residues, stable device pointer) -> h = (v^2 - 1) / t truncated to D,
+// then w | v | h back to the host as u64.  d_w, d_v, d_h are consecutive D-element u32 arrays.
 static int polys_tail(mfb_ctx *ctx, PolyEngine &E, cudaStream_t st, uint32_t Du, uint32_t n, uint32_t *d_w, uint32_t *d_a,
-                      uint64_t *d_wide, const uint32_t *t32, uint32_t lt, mfb_ssp *cache, uint64_t *w_out, uint64_t *v_out,
+                      uint64_t *d_wide, const uint32_t *t32, uint32_t lt, uint64_t *w_out, uint64_t *v_out,
                       uint64_t *h_out) {
   uint32_t *d_v = d_w + Du, *d_h = d_w + 2 * Du;
   uint32_t lv = 0;
@@ -751,29 +776,8 @@ static int polys_tail(mfb_ctx *ctx, PolyEngine &E, cudaStream_t st, uint32_t Du,
   }
   if (la < lt) {
     PTRY(cudaMemsetAsync(d_h, 0, (size_t)Du * 4, st));
-  } else if (cache) {
-    const uint32_t lq = la - lt + 1;
-    if (cache->binv_len < lq) {  // (re)build the cached inverse to the precision this quotient needs
-      if (cache->binv_cap < lq) {
-        if (cache->binv) PTRY(cudaFree(cache->binv));
-        cache->binv = nullptr;
-        cache->binv_cap = cache->binv_len = 0;
-        const uint32_t cap = lq > Du ? lq : Du;
-        PTRY(cudaMalloc(&cache->binv, (size_t)cap * 4));
-        cache->binv_cap = cap;
-      }
-      const uint32_t prec = cache->binv_cap;
-      PTRY(poly_rev_inverse(E, t32, lt, prec, cache->binv, st));
-      cache->binv_len = prec;
-    }
-    PTRY(poly_quot_from_inverse(E, d_a, la, lq, cache->binv, d_h, Du, st));
   } else {
     PTRY(poly_div(E, d_a, la, t32, lt, d_h, Du, st));
-  }
-  if (!w_out) {  // device-resident pipeline (mfb_prove_resident): w | v | h stay on the device as u32 residues
-    PTRY(cudaStreamSynchronize(st));
-    (void)ctx;
-    return MFB_OK;
   }
   // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
   k_widen<<<gridfor(3 * Du), 256, 0, st>>>(d_w, 3 * Du, d_wide);
@@ -845,7 +849,7 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
   PTRY(cudaMemcpyAsync(&lt, E.d_len, 4, cudaMemcpyDeviceToHost, st));
   PTRY(cudaStreamSynchronize(st));
   if (lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys: t(x) is the zero polynomial");
-  rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, t32, lt, nullptr, w_out, v_out, h_out);
+  rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, t32, lt, w_out, v_out, h_out);
   ctx_count_launches(ctx, E.launches - L0);
   return rc;
 }
@@ -903,59 +907,135 @@ extern "C" void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h) {
   if (ctx) ctx_enter(ctx);
   cudaFree(h->blob);
   cudaFree(h->binv);
+  cudaFree(h->bhat);
+  if (h->sel_pin) cudaFreeHost(h->sel_pin);
+  if (h->sel_free) cudaEventDestroy(h->sel_free);
   delete h;
 }
 
-static int polys_resident_impl(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta,
-                               uint64_t *w_out, uint64_t *v_out, uint64_t *h_out, const uint32_t **wvh_dev) {
-  int rc = ctx_enter(ctx);
-  if (rc) return rc;
-  if (!h || !witness_limbs) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
+// The polynomial step over a RESIDENT blob, queued on `st` without any host round trip: *wvh = w | v | h as three
+// consecutive arrays of D u32 residues in the context's scratch.
+//   w = delta t + sum of the selected v_i, v = w + v_0            one kernel over the blob
+//   a = v^2 - 1                                                  one product of 2D - 1 coefficients
+//   h = a / t = rev( rev(a) * rev(t)^-1 mod x^lq ), lq = 2D - lt one product against the CACHED TRANSFORM of rev(t)^-1
+// a is taken with its nominal length 2D - 1 (leading zeros when v has lower degree: the Euclidean quotient does not
+// change, its top coefficients are zero), so that no length has to be read back from the device and rev(t)^-1 and its
+// transform depend on the instance only.
+static int polys_resident_queue(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta,
+                                cudaStream_t st, uint32_t **wvh) {
   if (h->lt == 0) return ctx_bad_arg("mfb_ssp_prover_polys_resident: t(x) is the zero polynomial");
   PolyEngine &E = *poly_engine_of(ctx);
-  cudaStream_t st = ctx_stream_of(ctx);
-  const uint64_t L0 = E.launches;
   const size_t D = h->D, M = h->M;
-  const uint32_t Du = (uint32_t)D;
-  uint32_t n = 2;
+  const uint32_t Du = (uint32_t)D, la = 2 * Du - 1, lq = la - h->lt + 1;
+  uint32_t n = 2, n2 = 2;
   while (n < 2 * D) n <<= 1;
-  PTRY(engine_reserve(E, n, st));
-  void *d_idx, *d_w, *d_a, *d_wide;
+  while (n2 < 2 * lq - 1) n2 <<= 1;
+  {  // transforms of the Newton iteration / of the quotient product need up to 2 lq points
+    const uint64_t need = 2 * (uint64_t)lq > (uint64_t)lq + lq / 2 + h->lt + 8 ? 2 * (uint64_t)lq : (uint64_t)lq + lq / 2 + h->lt + 8;
+    uint32_t nn = n > n2 ? n : n2;
+    while (nn < need) nn <<= 1;
+    PTRY(engine_reserve(E, nn, st));
+  }
+  int rc;
+  void *d_idx, *d_w, *d_a;
   if ((rc = ctx_scratch(ctx, 0, M * 4, &d_idx))) return rc;
   if ((rc = ctx_scratch(ctx, 4, (size_t)n * 4, &d_a))) return rc;
   if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;
-  if ((rc = ctx_scratch(ctx, 6, D * 8 * 3, &d_wide))) return rc;
-  uint32_t *sel = (uint32_t *)malloc(M * 4);
-  if (!sel) return ctx_bad_arg("out of host memory");
+  uint32_t *dw = (uint32_t *)d_w, *dv = dw + D, *dh = dw + 2 * D;
+  if (h->bhat_lq != lq || h->bhat_n != n2) {  // first proof over this blob: Newton inverse of rev(t), then its transform
+    if (h->binv_cap < lq) {
+      if (h->binv) PTRY(cudaFree(h->binv));
+      h->binv = nullptr;
+      h->binv_cap = h->binv_len = 0;
+      PTRY(cudaMalloc(&h->binv, (size_t)lq * 4));
+      h->binv_cap = lq;
+    }
+    if (h->binv_len < lq) {
+      PTRY(poly_rev_inverse(E, h->blob, h->lt, h->binv_cap, h->binv, st));
+      h->binv_len = h->binv_cap;
+    }
+    if (h->bhat) PTRY(cudaFree(h->bhat));
+    h->bhat = nullptr;
+    h->bhat_n = h->bhat_lq = 0;
+    PTRY(cudaMalloc(&h->bhat, (size_t)NPR * n2 * 4));
+    k_lift<<<dim3(gridfor(n2), NPR), 256, 0, st>>>(h->binv, lq, lq, 0, h->bhat, n2);
+    E.launches++;
+    PTRY(ntt_forward(E, h->bhat, n2, st));
+    h->bhat_n = n2;
+    h->bhat_lq = lq;
+  }
+  // witness bit i-1 selects v_i = polynomial i+1 of the blob
+  if (!h->sel_pin) PTRY(cudaHostAlloc((void **)&h->sel_pin, (M ? M : 1) * 4, cudaHostAllocDefault));
+  if (!h->sel_free) PTRY(cudaEventCreateWithFlags(&h->sel_free, cudaEventDisableTiming));
+  if (h->sel_used) PTRY(cudaEventSynchronize(h->sel_free));  // the previous proof's upload has read the staging
   uint32_t nsel = 0;
   for (size_t i = 1; i < M; i++)
-    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) sel[nsel++] = (uint32_t)(i + 1);
-  cudaError_t e = nsel ? cudaMemcpyAsync(d_idx, sel, (size_t)nsel * 4, cudaMemcpyHostToDevice, st) : cudaSuccess;
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // sel is about to be freed
-  free(sel);
-  PTRY(e);
-  k_ssp_accumulate_res<<<gridfor(Du), 256, 0, st>>>(h->blob, Du, (const uint32_t *)d_idx, nsel, delta, (uint32_t *)d_w,
-                                                     (uint32_t *)d_w + D);
+    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) h->sel_pin[nsel++] = (uint32_t)(i + 1);
+  if (nsel) PTRY(cudaMemcpyAsync(d_idx, h->sel_pin, (size_t)nsel * 4, cudaMemcpyHostToDevice, st));
+  PTRY(cudaEventRecord(h->sel_free, st));
+  h->sel_used = true;
+  k_ssp_accumulate_res<<<gridfor(Du), 256, 0, st>>>(h->blob, Du, (const uint32_t *)d_idx, nsel, delta, dw, dv);
   E.launches++;
   PTRY(cudaGetLastError());
-  rc = polys_tail(ctx, E, st, Du, n, (uint32_t *)d_w, (uint32_t *)d_a, (uint64_t *)d_wide, h->blob, h->lt, h, w_out, v_out, h_out);
-  ctx_count_launches(ctx, E.launches - L0);
-  if (wvh_dev) *wvh_dev = (const uint32_t *)d_w;
-  return rc;
+  PTRY(poly_mul(E, dv, Du, Du, 0, dv, Du, Du, 0, 0, la, 0, (uint32_t *)d_a, st));
+  k_sub_one<<<1, 32, 0, st>>>((uint32_t *)d_a);
+  E.launches++;
+  PTRY(poly_mul_bhat(E, (const uint32_t *)d_a, lq, la, 1, h->bhat, n2, 0, lq, E.t3, st));
+  k_reverse<<<gridfor(Du), 256, 0, st>>>(E.t3, lq, dh, Du);
+  E.launches++;
+  PTRY(cudaGetLastError());
+  *wvh = dw;
+  return MFB_OK;
 }
 
 extern "C" int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
                                              uint64_t delta, uint64_t *w_out, uint64_t *v_out, uint64_t *h_out) {
-  if (!w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
-  return polys_resident_impl(ctx, h, witness_limbs, nlimbs, delta, w_out, v_out, h_out, nullptr);
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (!h || !witness_limbs || !w_out || !v_out || !h_out) return ctx_bad_arg("mfb_ssp_prover_polys_resident: null pointer");
+  PolyEngine &E = *poly_engine_of(ctx);
+  cudaStream_t st = ctx_stream_of(ctx);
+  const uint64_t L0 = E.launches;
+  const size_t D = h->D;
+  void *d_wide;
+  if ((rc = ctx_scratch(ctx, 6, D * 8 * 3, &d_wide))) return rc;
+  uint32_t *d_w = nullptr;
+  if ((rc = polys_resident_queue(ctx, h, witness_limbs, nlimbs, delta, st, &d_w))) return rc;
+  // back to the host as u64 coefficient arrays (what nmod_poly / eval_poly consume)
+  k_widen<<<gridfor(3 * (uint32_t)D), 256, 0, st>>>(d_w, 3 * (uint32_t)D, (uint64_t *)d_wide);
+  E.launches++;
+  PTRY(cudaMemcpyAsync(w_out, d_wide, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(v_out, (uint64_t *)d_wide + D, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaMemcpyAsync(h_out, (uint64_t *)d_wide + 2 * D, D * 8, cudaMemcpyDeviceToHost, st));
+  PTRY(cudaStreamSynchronize(st));
+  ctx_count_launches(ctx, E.launches - L0);
+  return MFB_OK;
 }
 
-// The same, results left ON THE DEVICE: *wvh_dev = three consecutive arrays of D u32 residues (w, v, h) in the context's
-// scratch, valid until the next polynomial / encrypt / decrypt call on this context.  The stream is idle on return.
+// The same with the results left ON THE DEVICE, queued on `stream` WITHOUT waiting: *wvh_dev = three consecutive arrays of
+// D u32 residues (w, v, h) in the context's scratch, valid (in stream order) until the next polynomial / encrypt /
+// decrypt call on this context.
+extern "C" int mfb_ssp_prover_polys_resident_async(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                                   uint64_t delta, void *stream, const uint32_t **wvh_dev) {
+  int rc = ctx_enter(ctx);
+  if (rc) return rc;
+  if (!h || !witness_limbs || !wvh_dev) return ctx_bad_arg("mfb_ssp_prover_polys_resident_async: null pointer");
+  PolyEngine &E = *poly_engine_of(ctx);
+  const uint64_t L0 = E.launches;
+  uint32_t *d_w = nullptr;
+  rc = polys_resident_queue(ctx, h, witness_limbs, nlimbs, delta, (cudaStream_t)stream, &d_w);
+  ctx_count_launches(ctx, E.launches - L0);
+  *wvh_dev = d_w;
+  return rc;
+}
+
+// ... on the context's own stream, which is idle on return
 extern "C" int mfb_ssp_prover_polys_resident_dev(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
                                                  uint64_t delta, const uint32_t **wvh_dev) {
-  if (!wvh_dev) return ctx_bad_arg("mfb_ssp_prover_polys_resident_dev: null pointer");
-  return polys_resident_impl(ctx, h, witness_limbs, nlimbs, delta, nullptr, nullptr, nullptr, wvh_dev);
+  int rc = mfb_ssp_prover_polys_resident_async(ctx, h, witness_limbs, nlimbs, delta, ctx ? ctx_stream_of(ctx) : nullptr, wvh_dev);
+  if (rc) return rc;
+  PTRY(cudaStreamSynchronize(ctx_stream_of(ctx)));
+  return MFB_OK;
 }
 
 extern "C" size_t mfb_ssp_degree_bound(const mfb_ssp *h) { return h ? h->D : 0; }

@@ -34,11 +34,13 @@ typedef void (*mark_fn)(void *, int, cudaStream_t);
 cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0, const uint32_t *coeffs1, size_t d,
                                     uint64_t *partial_ws, unsigned int *queue, int *nslots_inout, cudaStream_t st,
                                     mark_fn mark, void *mark_arg);
-cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, int nparts, const uint64_t *rop_in, uint64_t *rop_out,
-                                  unsigned int *queue, cudaStream_t st);
-cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, int nparts, const uint64_t *flat_partial,
-                                       const uint64_t *rop_in, uint64_t *rop_out, unsigned int *queue, uint8_t *const *bases,
-                                       int world, int rank, uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st);
+cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts, const uint64_t *rop_in,
+                                  uint64_t *rop_out, size_t rop_stride, unsigned int *queue, unsigned int *queue2,
+                                  cudaStream_t st);
+cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts,
+                                       const uint64_t *flat_partial, const uint64_t *rop_in, uint64_t *rop_out, size_t rop_stride,
+                                       unsigned int *queue, unsigned int *queue2, uint8_t *const *bases, int world, int rank,
+                                       uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
 cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
                                  cudaStream_t st);
@@ -74,6 +76,7 @@ void poly_engine_delete(PolyEngine *e);
 
 constexpr int MAX_CHUNKS = 256;
 constexpr int NSLOTS = 8;
+constexpr int QUEUE_U32 = 32 * 32;  // one chunk-queue set: 32 counters, one per 128-byte line
 
 }  // namespace mfb
 
@@ -85,7 +88,9 @@ struct mfb_ctx {
   cudaStream_t stream = nullptr;   // the context's own stream (host flavour)
   uint32_t *t0_dev = nullptr;      // 256-entry T0 table
   uint64_t *partial_ws = nullptr;  // MAX_CHUNKS row-planar partial sums
-  unsigned int *queue = nullptr;   // K1's per-tile chunk queues (23 counters, one per 128 B line), zero between calls
+  unsigned int *queue = nullptr;   // K1's per-tile chunk queues (23 counters, one per 128 B line), zero between calls;
+                                   // two sets (QUEUE_U32 apart): the prover pipeline runs two passes before ONE finish
+  int pass_nslots[2] = {-1, -1};   // partial sums per vector left in the workspace by mfb_lincomb2_partials_dev(pass)
   void *slot[NSLOTS] = {};         // growable device scratch for the host flavour
   size_t slot_cap[NSLOTS] = {};
   uint64_t launches = 0;
@@ -277,8 +282,8 @@ int mfb_ctx_create(mfb_ctx **out, int device) {
     if ((e = cudaMalloc(&ctx->t0_dev, sizeof(t0))) != cudaSuccess) break;
     if ((e = cudaMemcpy(ctx->t0_dev, t0, sizeof(t0), cudaMemcpyHostToDevice)) != cudaSuccess) break;
     if ((e = cudaMalloc(&ctx->partial_ws, (size_t)MAX_CHUNKS * PLANAR_U64 * 8)) != cudaSuccess) break;
-    if ((e = cudaMalloc(&ctx->queue, 32 * 32 * sizeof(unsigned int))) != cudaSuccess) break;
-    if ((e = cudaMemset(ctx->queue, 0, 32 * 32 * sizeof(unsigned int))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&ctx->queue, 2 * QUEUE_U32 * sizeof(unsigned int))) != cudaSuccess) break;
+    if ((e = cudaMemset(ctx->queue, 0, 2 * QUEUE_U32 * sizeof(unsigned int))) != cudaSuccess) break;
   } while (0);
   if (e != cudaSuccess) {
     rc = fail(e, "context setup", __FILE__, __LINE__);
@@ -383,7 +388,8 @@ int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeff
   MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
                                        (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nslots, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, 0, 1, nslots, rop_in_dev, rop_out_dev, 0, ctx->queue, nullptr,
+                                     (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
   return MFB_OK;
 }
@@ -531,12 +537,15 @@ void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g) {
   delete g;
 }
 
-static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, int nparts, const uint64_t *flat_partial_dev, const uint64_t *rop_in_dev,
-                       uint64_t *rop_out_dev, unsigned int *queue, cudaStream_t st) {
+static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, size_t lane_stride, int lanes, int nparts, const uint64_t *flat_partial_dev,
+                       const uint64_t *rop_in_dev, uint64_t *rop_out_dev, size_t rop_stride, unsigned int *queue,
+                       unsigned int *queue2, cudaStream_t st) {
   if (g->epoch == 0xffffffffu) return set_err(MFB_EARG, "peer exchange: 2^32 calls on one group; create a new one");
+  if (lanes < 1 || lanes > PEER_LANES) return set_err(MFB_EARG, "peer exchange: 1 <= lanes <= %d", PEER_LANES);
   g->epoch += 1;
-  MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, nparts, flat_partial_dev, rop_in_dev, rop_out_dev, queue, g->base,
-                                          g->world, g->rank, g->epoch, g->timeout_ns, g->status, st));
+  MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, lane_stride, lanes, nparts, flat_partial_dev, rop_in_dev, rop_out_dev,
+                                          rop_stride, queue, queue2, g->base, g->world, g->rank, g->epoch, g->timeout_ns, g->status,
+                                          st));
   return MFB_OK;
 }
 
@@ -550,19 +559,37 @@ int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *cts_de
   MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs_dev, nullptr, d, ctx->partial_ws, ctx->queue, &nslots,
                                        (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  MFB_TRY(peer_finish(ctx, g, nslots, nullptr, rop_in_dev, rop_out_dev, ctx->queue, (cudaStream_t)stream));
+  MFB_TRY(peer_finish(ctx, g, 0, 1, nslots, nullptr, rop_in_dev, rop_out_dev, 0, ctx->queue, nullptr, (cudaStream_t)stream));
   ctx->launches += d ? 2 : 1;
+  return MFB_OK;
+}
+
+int mfb_peer_allreduce_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, size_t in_stride_u64, int lanes,
+                                 const uint64_t *rop_in_dev, uint64_t *rop_out_dev, size_t rop_stride_u64, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: the peer group is not connected");
+  if (!partial_flat_dev || !rop_out_dev) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: null pointer");
+  MFB_TRY(peer_finish(ctx, g, in_stride_u64, lanes, 0, partial_flat_dev, rop_in_dev, rop_out_dev, rop_stride_u64, nullptr, nullptr,
+                      (cudaStream_t)stream));
+  ctx->launches += 1;
   return MFB_OK;
 }
 
 int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, const uint64_t *rop_in_dev,
                            uint64_t *rop_out_dev, void *stream) {
-  MFB_CHECK_CTX(ctx);
-  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: the peer group is not connected");
-  if (!partial_flat_dev || !rop_out_dev) return set_err(MFB_EARG, "mfb_peer_allreduce_dev: null pointer");
-  MFB_TRY(peer_finish(ctx, g, 0, partial_flat_dev, rop_in_dev, rop_out_dev, nullptr, (cudaStream_t)stream));
-  ctx->launches += 1;
-  return MFB_OK;
+  return mfb_peer_allreduce_lanes_dev(ctx, g, partial_flat_dev, 0, 1, rop_in_dev, rop_out_dev, 0, stream);
+}
+
+// Two accumulators whose partial sums sit `lane_stride` apart: ONE finish launch when the flat ciphertexts are laid out
+// with a common stride (rop1 - rop0 the same for the inputs and the outputs), else one launch each.
+static cudaError_t finish_pair(const uint64_t *p0, size_t lane_stride, int nparts, const uint64_t *in0, uint64_t *out0,
+                               const uint64_t *in1, uint64_t *out1, unsigned int *queue, cudaStream_t st, mfb_ctx *ctx) {
+  const bool strided = out1 > out0 && ((in0 == nullptr && in1 == nullptr) || (in0 && in1 && in1 - in0 == out1 - out0));
+  ctx->launches += strided ? 1 : 2;
+  if (strided) return launch_lincomb_finish(p0, lane_stride, 2, nparts, in0, out0, (size_t)(out1 - out0), queue, nullptr, st);
+  cudaError_t e = launch_lincomb_finish(p0, 0, 1, nparts, in0, out0, 0, nullptr, nullptr, st);
+  if (e != cudaSuccess) return e;
+  return launch_lincomb_finish(p0 + lane_stride, 0, 1, nparts, in1, out1, 0, queue, nullptr, st);
 }
 
 int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
@@ -576,10 +603,58 @@ int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coef
   MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs0_dev, coeffs1_dev, d, ctx->partial_ws, ctx->queue, &nslots,
                                        (cudaStream_t)stream,
                                        [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, nslots, rop0_in_dev, rop0_out_dev, nullptr, (cudaStream_t)stream));
-  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws + (size_t)nslots * PLANAR_U64, nslots, rop1_in_dev, rop1_out_dev,
-                                     ctx->queue, (cudaStream_t)stream));
-  ctx->launches += d ? 3 : 2;
+  MFB_CUDA_TRY(finish_pair(ctx->partial_ws, (size_t)nslots * PLANAR_U64, nslots, rop0_in_dev, rop0_out_dev, rop1_in_dev,
+                           rop1_out_dev, ctx->queue, (cudaStream_t)stream, ctx));
+  ctx->launches += d ? 1 : 0;
+  return MFB_OK;
+}
+
+/* ---- the prover pipeline's building blocks: two two-vector passes, then ONE finish for the four accumulators ------ */
+int mfb_lincomb2_partials_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
+                              size_t d, int pass, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (pass < 0 || pass > 1) return set_err(MFB_EARG, "mfb_lincomb2_partials_dev: pass must be 0 or 1");
+  if (d && (!cts_dev || !coeffs0_dev || !coeffs1_dev)) return set_err(MFB_EARG, "mfb_lincomb2_partials_dev: null pointer");
+  int nslots = lincomb_nslots(d, ctx->sm_count, 2);
+  if (4 * nslots > MAX_CHUNKS) nslots = MAX_CHUNKS / 4;
+  // pass p writes the partials of its two vectors to workspace lanes 2p and 2p+1 and pulls chunks from queue set p
+  MFB_CUDA_TRY(launch_lincomb_partials(cts_dev, coeffs0_dev, coeffs1_dev, d, ctx->partial_ws + (size_t)(2 * pass) * nslots * PLANAR_U64,
+                                       ctx->queue + pass * QUEUE_U32, &nslots, (cudaStream_t)stream,
+                                       [](void *c, int w, cudaStream_t s) { prof_mark((mfb_ctx *)c, w, s); }, ctx));
+  ctx->pass_nslots[pass] = nslots;
+  if (d) ctx->launches += 1;
+  return MFB_OK;
+}
+
+static int finish4_check(mfb_ctx *ctx, const char *who) {
+  if (ctx->pass_nslots[0] < 0 || ctx->pass_nslots[0] != ctx->pass_nslots[1])
+    return set_err(MFB_EARG, "%s: needs mfb_lincomb2_partials_dev for pass 0 and pass 1 over equally many ciphertexts first", who);
+  return MFB_OK;
+}
+
+int mfb_lincomb_finish4_dev(mfb_ctx *ctx, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev, size_t rop_stride_u64, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!rop_out4_dev || rop_stride_u64 < MFB_FLAT_CT_U64) return set_err(MFB_EARG, "mfb_lincomb_finish4_dev: bad argument");
+  MFB_TRY(finish4_check(ctx, "mfb_lincomb_finish4_dev"));
+  const int ns = ctx->pass_nslots[0];
+  MFB_CUDA_TRY(launch_lincomb_finish(ctx->partial_ws, (size_t)ns * PLANAR_U64, 4, ns, rop_in4_dev, rop_out4_dev, rop_stride_u64,
+                                     ctx->queue, ctx->queue + QUEUE_U32, (cudaStream_t)stream));
+  ctx->pass_nslots[0] = ctx->pass_nslots[1] = -1;
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_peer_finish4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev, size_t rop_stride_u64,
+                         void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_finish4_dev: the peer group is not connected");
+  if (!rop_out4_dev || rop_stride_u64 < MFB_FLAT_CT_U64) return set_err(MFB_EARG, "mfb_peer_finish4_dev: bad argument");
+  MFB_TRY(finish4_check(ctx, "mfb_peer_finish4_dev"));
+  const int ns = ctx->pass_nslots[0];
+  MFB_TRY(peer_finish(ctx, g, (size_t)ns * PLANAR_U64, 4, ns, nullptr, rop_in4_dev, rop_out4_dev, rop_stride_u64, ctx->queue,
+                      ctx->queue + QUEUE_U32, (cudaStream_t)stream));
+  ctx->pass_nslots[0] = ctx->pass_nslots[1] = -1;
+  ctx->launches += 1;
   return MFB_OK;
 }
 
@@ -653,12 +728,14 @@ static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset,
     MFB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_b, 0));
   }
   if (g) {
-    MFB_TRY(peer_finish(ctx, g, nchunks, nullptr, rop0_in_dev, rop0_out_dev, nullptr, st));
+    MFB_TRY(peer_finish(ctx, g, 0, 1, nchunks, nullptr, rop0_in_dev, rop0_out_dev, 0, nullptr, nullptr, st));
+  } else if (two) {
+    MFB_CUDA_TRY(finish_pair(p0, (size_t)nchunks * PLANAR_U64, nchunks, rop0_in_dev, rop0_out_dev, rop1_in_dev, rop1_out_dev, nullptr, st, ctx));
+    ctx->launches -= 1;  // (counted once more below)
   } else {
-    MFB_CUDA_TRY(launch_lincomb_finish(p0, nchunks, rop0_in_dev, rop0_out_dev, nullptr, st));
-    if (two) MFB_CUDA_TRY(launch_lincomb_finish(p1, nchunks, rop1_in_dev, rop1_out_dev, nullptr, st));
+    MFB_CUDA_TRY(launch_lincomb_finish(p0, 0, 1, nchunks, rop0_in_dev, rop0_out_dev, 0, nullptr, nullptr, st));
   }
-  ctx->launches += (d ? 2 : 0) + (two ? 2 : 1);
+  ctx->launches += (d ? 2 : 0) + 1;
   return MFB_OK;
 }
 
@@ -982,6 +1059,13 @@ static int queue_b_w(mfb_ctx *ctx, const uint8_t seed[40], uint64_t bt_offset, c
                         co.size(), nullptr, out_dev, nullptr, nullptr, st, nullptr);
 }
 
+int mfb_b_w_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t bt_offset, const uint8_t *bt_recs, size_t M,
+                const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *b_w_flat_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || !bt_recs || !witness_limbs || !b_w_flat_out_dev || M < 1) return set_err(MFB_EARG, "mfb_b_w_dev: bad argument");
+  return queue_b_w(ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, b_w_flat_out_dev, (cudaStream_t)stream);
+}
+
 int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, const mfb_region *reg_as,
                           const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40], uint64_t bt_offset,
                           const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout, uint64_t *h_flat_inout,
@@ -1005,17 +1089,22 @@ int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, c
     MFB_TRY(queue_b_w(ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, r + 4 * FL, ctx->stream2));
     MFB_CUDA_TRY(cudaEventRecord(ctx->ev_b, ctx->stream2));
   }
-  const uint32_t *wvh = nullptr;
-  MFB_TRY(mfb_ssp_prover_polys_resident_dev(ctx, ssp, witness_limbs, nlimbs, delta, &wvh));
-  const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
   uint64_t *host[5] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, b_w_flat_out};
-  // the accumulators travel as ONE pinned copy each way
+  // the accumulators travel as ONE pinned copy each way; accumulators that are all zero (the usual case: a proof
+  // starts from proof_init) are not sent at all
   if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 5 * FL * 8, cudaHostAllocDefault));
-  for (int k = 0; k < 4; k++) memcpy(ctx->acc_pin + k * FL, host[k], FL * 8);
-  MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t any = 0;
+  for (int k = 0; k < 4; k++)
+    for (size_t i = 0; i < FL; i++) any |= (ctx->acc_pin[k * FL + i] = host[k][i]);
+  if (any) MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // polynomial step, both two-vector passes and ONE finish for the four accumulators, all queued without a host round trip
+  const uint32_t *wvh = nullptr;
+  MFB_TRY(mfb_ssp_prover_polys_resident_async(ctx, ssp, witness_limbs, nlimbs, delta, ctx->stream, &wvh));
+  const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
   if (b_w_flat_out) MFB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
-  MFB_TRY(mfb_lincomb2_dev(ctx, reg_s->cts, d_w, d_h, D, r, r, r + FL, r + FL, ctx->stream));
-  MFB_TRY(mfb_lincomb2_dev(ctx, reg_as->cts, d_v, d_h, D, r + 2 * FL, r + 2 * FL, r + 3 * FL, r + 3 * FL, ctx->stream));
+  MFB_TRY(mfb_lincomb2_partials_dev(ctx, reg_s->cts, d_w, d_h, D, 0, ctx->stream));
+  MFB_TRY(mfb_lincomb2_partials_dev(ctx, reg_as->cts, d_v, d_h, D, 1, ctx->stream));
+  MFB_TRY(mfb_lincomb_finish4_dev(ctx, any ? r : nullptr, r, FL, ctx->stream));
   MFB_CUDA_TRY(cudaMemcpyAsync(ctx->acc_pin, r, (size_t)nacc * FL * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < nacc; k++) memcpy(host[k], ctx->acc_pin + k * FL, FL * 8);

@@ -37,18 +37,21 @@ __host__ __device__ __forceinline__ size_t resident_index(int c, int j) {
 }
 // "Row-planar" layout (secret keys, partial sums): limb row j, coordinate c at j*1472 + c.
 
-// Symmetric exchange buffer of one rank for the peer-memory finish (k_lincomb_finish_peer): for each call parity q
-// and each source rank s, a flat [1472][11] u64 slot, followed by the arrival flags [q][s][23 tiles] (u32).
+// Symmetric exchange buffer of one rank for the peer-memory finish (k_lincomb_finish_peer): for each call parity q,
+// each source rank s and each LANE (one exchange call combines up to PEER_LANES ciphertexts at once — the prover's
+// four accumulators), a flat [1472][11] u64 slot, followed by the arrival flags [q][s][lane][23 tiles] (u32).
 constexpr int PEER_MAX = 16;
+constexpr int PEER_LANES = 4;
 constexpr size_t PEER_SLOT_BYTES = PLANAR_U64 * 8;  // 129536
-__host__ __device__ __forceinline__ size_t peer_slot_offset(uint32_t q, int world, int src) {
-  return ((size_t)q * world + src) * PEER_SLOT_BYTES;
+__host__ __device__ __forceinline__ size_t peer_slot_offset(uint32_t q, int world, int src, int lane) {
+  return (((size_t)q * world + src) * PEER_LANES + lane) * PEER_SLOT_BYTES;
 }
-__host__ __device__ __forceinline__ size_t peer_flag_offset(uint32_t q, int world, int src, int tile) {
-  return (size_t)2 * world * PEER_SLOT_BYTES + (((size_t)q * world + src) * RT_NTILES + tile) * 4;
+__host__ __device__ __forceinline__ size_t peer_flag_offset(uint32_t q, int world, int src, int lane, int tile) {
+  return (size_t)2 * world * PEER_LANES * PEER_SLOT_BYTES +
+         ((((size_t)q * world + src) * PEER_LANES + lane) * RT_NTILES + tile) * 4;
 }
 __host__ __device__ __forceinline__ size_t peer_buffer_bytes(int world) {
-  return (size_t)2 * world * PEER_SLOT_BYTES + (size_t)2 * world * RT_NTILES * 4;
+  return (size_t)2 * world * PEER_LANES * PEER_SLOT_BYTES + (size_t)2 * world * PEER_LANES * RT_NTILES * 4;
 }
 
 // ---------------------------------------------------------------------------------------------

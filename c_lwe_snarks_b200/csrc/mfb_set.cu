@@ -5,11 +5,18 @@
 // (same-process peer access, mfb_peer_connect_local).  A set region is a CRS region sharded by ciphertext index
 // (SURVEY.md §8e): member i holds a contiguous range resident in its HBM.  A lincomb over the region runs
 // k_lincomb<2> on every member over its range (launches are asynchronous, the members work in parallel) and then
-// one k_peer_allreduce per scalar vector; the result is read from the primary.  Built on the public C-ABI only.
+// ONE exchange kernel per member combines all the accumulators of the call (lanes); the result is read from the
+// primary.  Built on the public C-ABI only.
+//
+// Failure handling: any error inside a set call leaves the members' exchange sequence numbers possibly out of step, so
+// the set is marked POISONED (every later call fails with MFB_EPEER until it is destroyed and created again); results
+// travel through pinned staging and reach the caller's buffers only when every member finished cleanly.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -17,6 +24,9 @@
 #include "../../include/mfb200.h"
 
 namespace {
+
+constexpr size_t SLOT = MFB_PLANAR_U64;  // stride (u64) between the flat accumulators of a member's part / res arrays
+constexpr int NACC = 5;                  // v_w, h, hat_v, hat_h, b_w
 
 struct Member {
   mfb_ctx *ctx = nullptr;
@@ -27,16 +37,18 @@ struct Member {
   // device scratch of the lincomb: coefficients, the member's flat partial sums, the reduced results
   uint32_t *co = nullptr;
   size_t co_cap = 0;
-  uint64_t *part = nullptr;  // 4 x flat
-  uint64_t *res = nullptr;   // 4 x flat
+  uint64_t *part = nullptr;  // NACC x flat
+  uint64_t *res = nullptr;   // NACC x flat
   uint8_t *c8 = nullptr;     // wire records of the member's range (mfb_set_eval_poly2)
   size_t c8_cap = 0;
-  // mfb_set_encrypt_cb: the secret key (flat + row-planar), per-piece inputs, the member's records, pinned entropy
+  // encryption: the secret key (flat + row-planar), entropy / messages / records of the member's range, pinned staging
   uint64_t *skf = nullptr, *skp = nullptr;
-  uint8_t *enc_in = nullptr, *enc_out = nullptr, *ent_pin = nullptr;
-  size_t enc_in_cap = 0, enc_out_cap = 0, ent_pin_cap = 0;
-  cudaEvent_t ent_free = nullptr;
-  bool ent_used = false;
+  uint8_t *enc_ent = nullptr, *enc_out = nullptr;
+  uint64_t *enc_msg = nullptr;
+  size_t enc_ent_cap = 0, enc_out_cap = 0, enc_msg_cap = 0;
+  uint8_t *ent_pin[2] = {nullptr, nullptr};
+  size_t ent_pin_cap = 0;
+  cudaEvent_t ent_free[2] = {nullptr, nullptr};
 };
 
 thread_local char g_set_err[256] = "";
@@ -49,7 +61,9 @@ int set_fail(int code, const char *msg) {
 
 struct mfb_set {
   std::vector<Member> m;
-  uint64_t *acc_pin = nullptr;  // pinned staging of the four flat accumulators of mfb_set_prove_resident
+  uint64_t *acc_pin = nullptr;  // pinned staging of the flat accumulators (NACC slots of SLOT u64)
+  cudaEvent_t ev_polys = nullptr;
+  bool poisoned = false;
 };
 
 struct mfb_set_region {
@@ -68,9 +82,106 @@ struct mfb_set_region {
     cudaError_t _e = (expr);                                                                  \
     if (_e != cudaSuccess) {                                                                  \
       snprintf(g_set_err, sizeof(g_set_err), "%s -> %s", #expr, cudaGetErrorString(_e));      \
+      cudaGetLastError();                                                                     \
       return MFB_ECUDA;                                                                       \
     }                                                                                         \
   } while (0)
+
+namespace {
+
+int check_usable(mfb_set *s, const char *who) {
+  if (!s) return set_fail(MFB_EARG, "null set");
+  if (s->poisoned) {
+    snprintf(g_set_err, sizeof(g_set_err), "%s: an earlier call on this device set failed; destroy it and create a new one", who);
+    return MFB_EPEER;
+  }
+  return MFB_OK;
+}
+
+// Ends a set call: waits for every member, collects the peer status words.  rc != MFB_OK (the body failed) or a member
+// that did not finish cleanly poisons the set; the error text of the first failure is kept.
+int finish_call(mfb_set *s, int rc) {
+  char keep[256];
+  snprintf(keep, sizeof(keep), "%s", rc != MFB_OK ? (g_set_err[0] ? g_set_err : mfb_last_error()) : "");
+  for (auto &mb : s->m) {
+    if (!mb.ctx) continue;
+    if (cudaSetDevice(mb.device) != cudaSuccess || cudaStreamSynchronize(mb.stream) != cudaSuccess) {
+      if (rc == MFB_OK) {
+        snprintf(keep, sizeof(keep), "device %d: %s", mb.device, cudaGetErrorString(cudaGetLastError()));
+        rc = MFB_ECUDA;
+      }
+      cudaGetLastError();
+      continue;
+    }
+    if (mb.group) {
+      const int st = mfb_peer_status(mb.ctx, mb.group);
+      if (st != MFB_OK && rc == MFB_OK) {
+        snprintf(keep, sizeof(keep), "%s", mfb_last_error());
+        rc = st;
+      }
+    }
+  }
+  cudaSetDevice(s->m[0].device);
+  if (rc != MFB_OK) {
+    s->poisoned = true;
+    snprintf(g_set_err, sizeof(g_set_err), "%s", keep);
+  }
+  return rc;
+}
+
+int grow(void **p, size_t *cap, size_t need, bool pinned) {
+  if (*cap >= need) return MFB_OK;
+  if (*p) {
+    if (pinned) cudaFreeHost(*p);
+    else cudaFree(*p);
+  }
+  *p = nullptr;
+  *cap = 0;
+  const cudaError_t e = pinned ? cudaHostAlloc(p, need, cudaHostAllocDefault) : cudaMalloc(p, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    snprintf(g_set_err, sizeof(g_set_err), "device set: allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
+    return MFB_ENOMEM;
+  }
+  *cap = need;
+  return MFB_OK;
+}
+
+int ensure_acc_pin(mfb_set *s) {
+  if (!s->acc_pin) SET_CUDA(cudaHostAlloc((void **)&s->acc_pin, NACC * SLOT * 8, cudaHostAllocDefault));
+  return MFB_OK;
+}
+
+// flat accumulators of the caller -> pinned staging slots; returns whether any limb is non-zero
+bool stage_in(mfb_set *s, uint64_t *const *host, int n) {
+  uint64_t any = 0;
+  for (int k = 0; k < n; k++)
+    for (size_t i = 0; i < MFB_FLAT_CT_U64; i++) any |= (s->acc_pin[(size_t)k * SLOT + i] = host[k][i]);
+  return any != 0;
+}
+void stage_out(mfb_set *s, uint64_t *const *host, int n) {
+  for (int k = 0; k < n; k++) memcpy(host[k], s->acc_pin + (size_t)k * SLOT, MFB_FLAT_CT_U64 * 8);
+}
+
+// contiguous, balanced split of [0, total) over the members (the remainder goes to the low ranks)
+void split_range(size_t total, size_t world, size_t i, size_t *first, size_t *count) {
+  const size_t base = total / world, extra = total % world;
+  *first = i * base + (i < extra ? i : extra);
+  *count = base + (i < extra ? 1 : 0);
+}
+
+void scrub_member_secrets(Member &mb) {
+  cudaSetDevice(mb.device);
+  if (mb.skf) cudaMemsetAsync(mb.skf, 0, MFB_PLANAR_U64 * 8, mb.stream);
+  if (mb.skp) cudaMemsetAsync(mb.skp, 0, MFB_PLANAR_U64 * 8, mb.stream);
+  if (mb.enc_ent) cudaMemsetAsync(mb.enc_ent, 0, mb.enc_ent_cap, mb.stream);
+  cudaStreamSynchronize(mb.stream);
+  for (int k = 0; k < 2; k++)
+    if (mb.ent_pin[k]) memset(mb.ent_pin[k], 0, mb.ent_pin_cap);
+  cudaGetLastError();
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -87,16 +198,20 @@ MFB_API void mfb_set_destroy(mfb_set *s) {
     if (mb.ctx && mb.group) mfb_peer_disconnect(mb.ctx, mb.group);
   for (auto &mb : s->m) {
     if (!mb.ctx) continue;
+    if (mb.stream) scrub_member_secrets(mb);  // keys and noise do not outlive the set in device or pinned memory
     cudaSetDevice(mb.device);
     if (mb.group) mfb_peer_destroy(mb.ctx, mb.group);
     if (mb.co) cudaFree(mb.co);
     if (mb.c8) cudaFree(mb.c8);
     if (mb.skf) cudaFree(mb.skf);
     if (mb.skp) cudaFree(mb.skp);
-    if (mb.enc_in) cudaFree(mb.enc_in);
+    if (mb.enc_ent) cudaFree(mb.enc_ent);
+    if (mb.enc_msg) cudaFree(mb.enc_msg);
     if (mb.enc_out) cudaFree(mb.enc_out);
-    if (mb.ent_pin) cudaFreeHost(mb.ent_pin);
-    if (mb.ent_free) cudaEventDestroy(mb.ent_free);
+    for (int k = 0; k < 2; k++) {
+      if (mb.ent_pin[k]) cudaFreeHost(mb.ent_pin[k]);
+      if (mb.ent_free[k]) cudaEventDestroy(mb.ent_free[k]);
+    }
     if (mb.part) cudaFree(mb.part);
     if (mb.res) cudaFree(mb.res);
     if (mb.stream) cudaStreamDestroy(mb.stream);
@@ -104,6 +219,7 @@ MFB_API void mfb_set_destroy(mfb_set *s) {
   }
   if (!s->m.empty()) cudaSetDevice(s->m[0].device);
   if (s->acc_pin) cudaFreeHost(s->acc_pin);
+  if (s->ev_polys) cudaEventDestroy(s->ev_polys);
   delete s;
 }
 
@@ -131,8 +247,8 @@ MFB_API int mfb_set_create(mfb_ctx *primary, const int *devices, int ndev, mfb_s
     if (rc != MFB_OK) break;
     cudaError_t e = cudaSetDevice(mb.device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&mb.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.part, 4 * MFB_PLANAR_U64 * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.res, 4 * MFB_PLANAR_U64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.part, NACC * SLOT * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&mb.res, NACC * SLOT * 8);
     if (e != cudaSuccess) {
       snprintf(g_set_err, sizeof(g_set_err), "mfb_set_create: device %d: %s", mb.device, cudaGetErrorString(e));
       rc = MFB_ECUDA;
@@ -145,6 +261,13 @@ MFB_API int mfb_set_create(mfb_ctx *primary, const int *devices, int ndev, mfb_s
     void *bases[MFB_PEER_MAX];
     for (int i = 0; i < world; i++) bases[i] = mfb_peer_base(s->m[i].group);
     for (int i = 0; i < world && rc == MFB_OK; i++) rc = mfb_peer_connect_local(s->m[i].ctx, s->m[i].group, bases);
+  }
+  if (rc == MFB_OK) {
+    cudaSetDevice(s->m[0].device);
+    if (cudaEventCreateWithFlags(&s->ev_polys, cudaEventDisableTiming) != cudaSuccess) {
+      snprintf(g_set_err, sizeof(g_set_err), "mfb_set_create: cudaEventCreate failed");
+      rc = MFB_ECUDA;
+    }
   }
   if (rc != MFB_OK) {
     char keep[256];
@@ -173,7 +296,8 @@ MFB_API void mfb_set_region_destroy(mfb_set *s, mfb_set_region *r) {
 MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, size_t count,
                                   mfb_set_region **out) {
   g_set_err[0] = 0;
-  if (!s || !seed || !out || (count && !c8)) return set_fail(MFB_EARG, "mfb_set_region_create: null pointer");
+  SET_TRY(check_usable(s, "mfb_set_region_create"));
+  if (!seed || !out || (count && !c8)) return set_fail(MFB_EARG, "mfb_set_region_create: null pointer");
   *out = nullptr;
   mfb_set_region *r = new (std::nothrow) mfb_set_region();
   if (!r) return set_fail(MFB_ENOMEM, "out of host memory");
@@ -182,11 +306,9 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   r->first.assign(world, 0);
   r->count.assign(world, 0);
   r->total = count;
-  const size_t base = count / world, extra = count % world;
   int rc = MFB_OK;
   for (size_t i = 0; i < world && rc == MFB_OK; i++) {
-    r->first[i] = i * base + (i < extra ? i : extra);
-    r->count[i] = base + (i < extra ? 1 : 0);
+    split_range(count, world, i, &r->first[i], &r->count[i]);
     // queued on the member's stream: the members' AES expansions run concurrently
     cudaSetDevice(s->m[i].device);
     rc = mfb_region_create_async(s->m[i].ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
@@ -200,7 +322,7 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
       rc = MFB_ECUDA;
     }
   }
-  if (rc != MFB_OK) {
+  if (rc != MFB_OK) {  // (no exchange was started: the set itself stays usable)
     char keep[256];
     snprintf(keep, sizeof(keep), "%s", mfb_set_last_error());
     mfb_set_region_destroy(s, r);
@@ -212,78 +334,102 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   return MFB_OK;
 }
 
-// rop0 += sum coeffs0[i] * CT_i, rop1 += sum coeffs1[i] * CT_i over the WHOLE region (d = its ciphertext count);
-// coeffs1 / rop1 may both be NULL for a single scalar vector.  Host buffers in, host buffers out, synchronous.
-MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1,
-                                    size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
-  g_set_err[0] = 0;
-  if (!s || !r || !rop0_flat_inout || (d && !coeffs0) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
-    return set_fail(MFB_EARG, "mfb_set_region_lincomb2: null pointer");
-  if (d != r->total) return set_fail(MFB_EARG, "mfb_set_region_lincomb2: d must be the region's ciphertext count");
+static int region_lincomb2_body(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, int nvec,
+                                bool any) {
   const size_t world = s->m.size();
-  const int nvec = coeffs1 ? 2 : 1;
-  const size_t FLAT = MFB_FLAT_CT_U64;
-  // 1. every member: coefficients to the device, lincomb over its shard into its flat partial(s)
+  // every member: coefficients to the device, lincomb over its shard into its flat partial(s), then ONE exchange kernel
+  // for all the vectors of the call; only the primary's result (which also adds the incoming accumulators) is read back
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
     const size_t cnt = r->count[i], first = r->first[i];
-    if (mb.co_cap < 2 * cnt + 4) {
-      if (mb.co) SET_CUDA(cudaFree(mb.co));
-      mb.co = nullptr;
-      mb.co_cap = 0;
-      SET_CUDA(cudaMalloc((void **)&mb.co, (2 * cnt + 4) * 4));
-      mb.co_cap = 2 * cnt + 4;
+    {
+      size_t cap = mb.co_cap * 4;
+      SET_TRY(grow((void **)&mb.co, &cap, (3 * cnt + 4) * 4, false));
+      mb.co_cap = cap / 4;
     }
     uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
     if (cnt) {
       SET_CUDA(cudaMemcpyAsync(c0, coeffs0 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
       if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, coeffs1 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
     }
-    if (i == 0) {  // the incoming accumulators join the sum on the primary
-      SET_CUDA(cudaMemcpyAsync(mb.res, rop0_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
-      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(mb.res + MFB_PLANAR_U64, rop1_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
-    }
+    if (i == 0 && any) SET_CUDA(cudaMemcpyAsync(mb.res, s->acc_pin, (size_t)nvec * SLOT * 8, cudaMemcpyHostToDevice, mb.stream));
     const uint64_t *cts = (const uint64_t *)mfb_region_cts(r->shard[i]);
     if (nvec == 2)
-      SET_TRY(mfb_lincomb2_dev(mb.ctx, cts, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + MFB_PLANAR_U64, mb.stream));
+      SET_TRY(mfb_lincomb2_dev(mb.ctx, cts, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + SLOT, mb.stream));
     else
       SET_TRY(mfb_lincomb_dev(mb.ctx, cts, c0, cnt, nullptr, mb.part, mb.stream));
+    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
+                                         mb.stream));
   }
-  // 2. every member: one all-reduce kernel per vector (push to all members, wait, add); only the primary's result
-  //    (which also adds the incoming accumulator) is read back
-  for (int v = 0; v < nvec; v++)
-    for (size_t i = 0; i < world; i++) {
-      Member &mb = s->m[i];
-      SET_CUDA(cudaSetDevice(mb.device));
-      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
-      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
-    }
   Member &p = s->m[0];
   SET_CUDA(cudaSetDevice(p.device));
-  SET_CUDA(cudaMemcpyAsync(rop0_flat_inout, p.res, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
-  if (nvec == 2) SET_CUDA(cudaMemcpyAsync(rop1_flat_inout, p.res + MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
-  int rc = MFB_OK;
-  for (size_t i = 0; i < world; i++) {
-    Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    SET_CUDA(cudaStreamSynchronize(mb.stream));
-    const int st = mfb_peer_status(mb.ctx, mb.group);
-    if (st != MFB_OK) rc = st;
-  }
-  SET_CUDA(cudaSetDevice(p.device));
+  SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, (size_t)nvec * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));
+  return MFB_OK;
+}
+
+// rop0 += sum coeffs0[i] * CT_i, rop1 += sum coeffs1[i] * CT_i over the WHOLE region (d = its ciphertext count);
+// coeffs1 / rop1 may both be NULL for a single scalar vector.  Host buffers in, host buffers out, synchronous.
+MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1,
+                                    size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
+  g_set_err[0] = 0;
+  SET_TRY(check_usable(s, "mfb_set_region_lincomb2"));
+  if (!r || !rop0_flat_inout || (d && !coeffs0) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
+    return set_fail(MFB_EARG, "mfb_set_region_lincomb2: null pointer");
+  if (d != r->total) return set_fail(MFB_EARG, "mfb_set_region_lincomb2: d must be the region's ciphertext count");
+  const int nvec = coeffs1 ? 2 : 1;
+  SET_TRY(ensure_acc_pin(s));
+  uint64_t *host[2] = {rop0_flat_inout, rop1_flat_inout};
+  const bool any = stage_in(s, host, nvec);
+  const int rc = finish_call(s, region_lincomb2_body(s, r, coeffs0, coeffs1, nvec, any));
+  if (rc == MFB_OK) stage_out(s, host, nvec);
   return rc;
 }
 
+static int eval_poly2_body(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint32_t *co32, size_t d,
+                           int nvec, bool any) {
+  const size_t world = s->m.size();
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    size_t first, cnt;
+    split_range(d, world, i, &first, &cnt);
+    {
+      size_t cap = mb.co_cap * 4;
+      SET_TRY(grow((void **)&mb.co, &cap, (3 * cnt + 4) * 4, false));
+      mb.co_cap = cap / 4;
+    }
+    SET_TRY(grow((void **)&mb.c8, &mb.c8_cap, cnt * MFB_CT_BYTES + 16, false));
+    uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
+    if (cnt) {
+      SET_CUDA(cudaMemcpyAsync(c0, co32 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, co32 + d + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
+      SET_CUDA(cudaMemcpyAsync(mb.c8, c8 + first * MFB_CT_BYTES, cnt * MFB_CT_BYTES, cudaMemcpyHostToDevice, mb.stream));
+    }
+    if (i == 0 && any) SET_CUDA(cudaMemcpyAsync(mb.res, s->acc_pin, (size_t)nvec * SLOT * 8, cudaMemcpyHostToDevice, mb.stream));
+    const uint64_t off = offset + first * (uint64_t)MFB_CTR_CT;
+    if (nvec == 2)
+      SET_TRY(mfb_eval_poly2_dev(mb.ctx, seed, off, mb.c8, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + SLOT, mb.stream));
+    else
+      SET_TRY(mfb_eval_poly_dev(mb.ctx, seed, off, mb.c8, c0, nullptr, cnt, nullptr, mb.part, mb.stream));
+    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
+                                         mb.stream));
+  }
+  Member &p = s->m[0];
+  SET_CUDA(cudaSetDevice(p.device));
+  SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, (size_t)nvec * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));
+  return MFB_OK;
+}
+
 // eval_poly (one or two scalar vectors) with NOTHING resident, sharded by ciphertext index: member i regenerates the
-// a-vectors of its contiguous range from AES in-kernel (mfb_eval_poly2_dev at its stream offset), one peer all-reduce
-// kernel per vector combines the partial sums.  Host buffers in and out; coefficients as uint64 (< 2^32).
+// a-vectors of its contiguous range from AES in-kernel (mfb_eval_poly2_dev at its stream offset), one exchange kernel
+// per member combines the partial sums.  Host buffers in and out; coefficients as uint64 (< 2^32).
 MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
                                const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout) {
   g_set_err[0] = 0;
-  if (!s || !seed || !rop0_flat_inout || (d && (!c8 || !coeffs0)) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
+  SET_TRY(check_usable(s, "mfb_set_eval_poly2"));
+  if (!seed || !rop0_flat_inout || (d && (!c8 || !coeffs0)) || ((coeffs1 == nullptr) != (rop1_flat_inout == nullptr)))
     return set_fail(MFB_EARG, "mfb_set_eval_poly2: null pointer");
-  const size_t world = s->m.size(), FLAT = MFB_FLAT_CT_U64;
   const int nvec = coeffs1 ? 2 : 1;
   std::vector<uint32_t> co32((size_t)nvec * d + 1);
   for (int v = 0; v < nvec; v++) {
@@ -293,96 +439,109 @@ MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offs
       co32[(size_t)v * d + i] = (uint32_t)src[i];
     }
   }
-  const size_t base = d / world, extra = d % world;
-  for (size_t i = 0; i < world; i++) {
-    Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    const size_t first = i * base + (i < extra ? i : extra), cnt = base + (i < extra ? 1 : 0);
-    if (mb.co_cap < 2 * cnt + 4) {
-      if (mb.co) SET_CUDA(cudaFree(mb.co));
-      mb.co = nullptr;
-      mb.co_cap = 0;
-      SET_CUDA(cudaMalloc((void **)&mb.co, (2 * cnt + 4) * 4));
-      mb.co_cap = 2 * cnt + 4;
-    }
-    if (mb.c8_cap < cnt * MFB_CT_BYTES + 16) {
-      if (mb.c8) SET_CUDA(cudaFree(mb.c8));
-      mb.c8 = nullptr;
-      mb.c8_cap = 0;
-      SET_CUDA(cudaMalloc((void **)&mb.c8, cnt * MFB_CT_BYTES + 16));
-      mb.c8_cap = cnt * MFB_CT_BYTES + 16;
-    }
-    uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
-    if (cnt) {
-      SET_CUDA(cudaMemcpyAsync(c0, co32.data() + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
-      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, co32.data() + d + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
-      SET_CUDA(cudaMemcpyAsync(mb.c8, c8 + first * MFB_CT_BYTES, cnt * MFB_CT_BYTES, cudaMemcpyHostToDevice, mb.stream));
-    }
-    if (i == 0) {
-      SET_CUDA(cudaMemcpyAsync(mb.res, rop0_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
-      if (nvec == 2) SET_CUDA(cudaMemcpyAsync(mb.res + MFB_PLANAR_U64, rop1_flat_inout, FLAT * 8, cudaMemcpyHostToDevice, mb.stream));
-    }
-    const uint64_t off = offset + first * (uint64_t)MFB_CTR_CT;
-    if (nvec == 2)
-      SET_TRY(mfb_eval_poly2_dev(mb.ctx, seed, off, mb.c8, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + MFB_PLANAR_U64, mb.stream));
-    else
-      SET_TRY(mfb_eval_poly_dev(mb.ctx, seed, off, mb.c8, c0, nullptr, cnt, nullptr, mb.part, mb.stream));
-  }
-  for (int v = 0; v < nvec; v++)
-    for (size_t i = 0; i < world; i++) {
-      Member &mb = s->m[i];
-      SET_CUDA(cudaSetDevice(mb.device));
-      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
-      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
-    }
-  Member &p = s->m[0];
-  SET_CUDA(cudaSetDevice(p.device));
-  SET_CUDA(cudaMemcpyAsync(rop0_flat_inout, p.res, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
-  if (nvec == 2) SET_CUDA(cudaMemcpyAsync(rop1_flat_inout, p.res + MFB_PLANAR_U64, FLAT * 8, cudaMemcpyDeviceToHost, p.stream));
-  int rc = MFB_OK;
-  for (size_t i = 0; i < world; i++) {
-    Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    SET_CUDA(cudaStreamSynchronize(mb.stream));  // (co32 is read by the queued copies until here)
-    const int st = mfb_peer_status(mb.ctx, mb.group);
-    if (st != MFB_OK) rc = st;
-  }
-  SET_CUDA(cudaSetDevice(p.device));
+  SET_TRY(ensure_acc_pin(s));
+  uint64_t *host[2] = {rop0_flat_inout, rop1_flat_inout};
+  const bool any = stage_in(s, host, nvec);
+  // (finish_call waits for every member: co32 is read by the queued copies until then)
+  const int rc = finish_call(s, eval_poly2_body(s, seed, offset, c8, co32.data(), d, nvec, any));
+  if (rc == MFB_OK) stage_out(s, host, nvec);
   return rc;
 }
 
-// mfb_encrypt_cb over a device set: the entropy is still drawn by the calling thread piece by piece and in order
-// (a hooked, deterministic source sees the reference's sequence), but piece k is encrypted by member k mod size, so
-// the members work on different pieces at the same time and the call becomes entropy-bound instead of AES-bound.
-static int grow(void **p, size_t *cap, size_t need, bool pinned) {
-  if (*cap >= need) return MFB_OK;
-  if (*p) {
-    if (pinned) cudaFreeHost(*p);
-    else cudaFree(*p);
+// ---------------------------------------------------------------------------------------------------- encryption
+// One member's share of an encryption call: ciphertexts [first, first + cnt) of the call, cut into pieces; the entropy of
+// piece k+1 is drawn into pinned memory while the device encrypts piece k.  Everything is queued on the member's stream;
+// the records stay on the device (mb.enc_out) until collect_records().
+static int member_encrypt(Member &mb, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                          mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t first, size_t cnt, size_t piece,
+                          size_t first_piece) {
+  SET_CUDA(cudaSetDevice(mb.device));
+  if (cnt == 0) return MFB_OK;
+  size_t cap;
+  cap = mb.skf ? MFB_PLANAR_U64 * 8 : 0;
+  SET_TRY(grow((void **)&mb.skf, &cap, MFB_PLANAR_U64 * 8, false));
+  cap = mb.skp ? MFB_PLANAR_U64 * 8 : 0;
+  SET_TRY(grow((void **)&mb.skp, &cap, MFB_PLANAR_U64 * 8, false));
+  SET_TRY(grow((void **)&mb.enc_ent, &mb.enc_ent_cap, cnt * (size_t)ent_stride, false));
+  cap = mb.enc_msg_cap;
+  SET_TRY(grow((void **)&mb.enc_msg, &cap, cnt * 8, false));
+  mb.enc_msg_cap = cap;
+  SET_TRY(grow((void **)&mb.enc_out, &mb.enc_out_cap, cnt * MFB_CT_BYTES, false));
+  const size_t pin_need = piece * (size_t)ent_stride;
+  if (mb.ent_pin_cap < pin_need) {
+    for (int k = 0; k < 2; k++) {
+      size_t c2 = mb.ent_pin_cap;
+      SET_TRY(grow((void **)&mb.ent_pin[k], &c2, pin_need, true));
+    }
+    mb.ent_pin_cap = pin_need;
   }
-  *p = nullptr;
-  *cap = 0;
-  const cudaError_t e = pinned ? cudaHostAlloc(p, need, cudaHostAllocDefault) : cudaMalloc(p, need);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    snprintf(g_set_err, sizeof(g_set_err), "mfb_set_encrypt_cb: allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
-    return MFB_ENOMEM;
+  for (int k = 0; k < 2; k++)
+    if (!mb.ent_free[k]) SET_CUDA(cudaEventCreateWithFlags(&mb.ent_free[k], cudaEventDisableTiming));
+  SET_CUDA(cudaMemcpyAsync(mb.skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, mb.stream));
+  SET_TRY(mfb_flat_to_planar_dev(mb.ctx, mb.skf, MFB_N, 1, mb.skp, mb.stream));
+  SET_CUDA(cudaMemcpyAsync(mb.enc_msg, msg + first, cnt * 8, cudaMemcpyHostToDevice, mb.stream));  // all messages up front
+  bool used[2] = {false, false};
+  int k = 0;
+  for (size_t done = 0; done < cnt; k ^= 1) {
+    size_t n = done == 0 ? first_piece : piece;
+    if (n > cnt - done) n = cnt - done;
+    if (used[k]) SET_CUDA(cudaEventSynchronize(mb.ent_free[k]));  // the copy that last read this pinned buffer is done
+    draw(user, mb.ent_pin[k], n * (size_t)ent_stride);
+    uint8_t *d_e = mb.enc_ent + done * (size_t)ent_stride;
+    SET_CUDA(cudaMemcpyAsync(d_e, mb.ent_pin[k], n * (size_t)ent_stride, cudaMemcpyHostToDevice, mb.stream));
+    SET_CUDA(cudaEventRecord(mb.ent_free[k], mb.stream));
+    used[k] = true;
+    SET_TRY(mfb_encrypt_dev(mb.ctx, seed, offset + (first + done) * (uint64_t)MFB_CTR_CT, mb.skp, mb.enc_msg + done, d_e, ent_stride,
+                            ent_nbytes, n, mb.enc_out + done * MFB_CT_BYTES, mb.stream));
+    done += n;
   }
-  *cap = need;
   return MFB_OK;
 }
 
+// records [first, first + cnt) of the call, from the member's device buffer to their destinations: out_c8 (contiguous)
+// or the caller's segments (record k of segment g goes to g.dst + (k - g.first) * 92)
+static int collect_records(Member &mb, size_t first, size_t cnt, uint8_t *out_c8, const mfb_c8_segment *segs, int nsegs) {
+  SET_CUDA(cudaSetDevice(mb.device));
+  if (cnt == 0) return MFB_OK;
+  if (out_c8) {
+    SET_CUDA(cudaMemcpyAsync(out_c8 + first * MFB_CT_BYTES, mb.enc_out, cnt * MFB_CT_BYTES, cudaMemcpyDeviceToHost, mb.stream));
+    return MFB_OK;
+  }
+  for (int g = 0; g < nsegs; g++) {
+    const size_t lo = segs[g].first > first ? segs[g].first : first;
+    const size_t hi_s = segs[g].first + segs[g].count, hi_m = first + cnt, hi = hi_s < hi_m ? hi_s : hi_m;
+    if (lo >= hi) continue;
+    SET_CUDA(cudaMemcpyAsync(segs[g].dst + (lo - segs[g].first) * MFB_CT_BYTES, mb.enc_out + (lo - first) * MFB_CT_BYTES,
+                             (hi - lo) * MFB_CT_BYTES, cudaMemcpyDeviceToHost, mb.stream));
+  }
+  return MFB_OK;
+}
+
+static int encrypt_args_ok(const char *who, const void *seed, const void *sk, const void *msg, mfb_entropy_fn draw, int ent_stride,
+                           int ent_nbytes) {
+  if (!seed || !sk || !msg || !draw) {
+    snprintf(g_set_err, sizeof(g_set_err), "%s: null pointer", who);
+    return MFB_EARG;
+  }
+  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0) {
+    snprintf(g_set_err, sizeof(g_set_err), "%s: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)", who);
+    return MFB_EARG;
+  }
+  return MFB_OK;
+}
+
+// mfb_encrypt_cb over a device set, entropy in the REFERENCE'S ORDER: the calling thread draws it piece by piece and in
+// order (a hooked, deterministic source sees the reference's sequence); piece k is encrypted by member k mod size, so
+// the members work on different pieces at the same time and the call is entropy-bound instead of AES-bound.
 MFB_API int mfb_set_encrypt_cb(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                                mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
   g_set_err[0] = 0;
   if (count == 0) return MFB_OK;
-  if (!s || !seed || !sk_flat || !msg || !draw || !out_c8) return set_fail(MFB_EARG, "mfb_set_encrypt_cb: null pointer");
-  if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
-    return set_fail(MFB_EARG, "mfb_set_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
+  SET_TRY(check_usable(s, "mfb_set_encrypt_cb"));
+  SET_TRY(encrypt_args_ok("mfb_set_encrypt_cb", seed, sk_flat, msg, draw, ent_stride, ent_nbytes));
+  if (!out_c8) return set_fail(MFB_EARG, "mfb_set_encrypt_cb: null pointer");
   const size_t world = s->m.size();
   const size_t piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 110, first_piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 16;
-  const size_t in_per = (size_t)ent_stride + 8;  // per ciphertext in a member's input buffer: entropy, then the message
-  const size_t in_slot = piece * in_per + 8;     // (+ 8: the messages start at the next multiple of 8 bytes)
   // pieces: [first_piece, piece, piece, ...]; piece k goes to member k % world, at slot k / world of its buffers
   std::vector<size_t> start, len;
   for (size_t done = 0; done < count;) {
@@ -393,120 +552,207 @@ MFB_API int mfb_set_encrypt_cb(mfb_set *s, const uint8_t seed[40], uint64_t offs
     done += cnt;
   }
   const size_t npieces = start.size(), slots = (npieces + world - 1) / world;
-  for (size_t i = 0; i < world && i < npieces; i++) {
+  auto body = [&]() -> int {
+    for (size_t i = 0; i < world && i < npieces; i++) {
+      Member &mb = s->m[i];
+      SET_CUDA(cudaSetDevice(mb.device));
+      size_t cap;
+      cap = mb.skf ? MFB_PLANAR_U64 * 8 : 0;
+      SET_TRY(grow((void **)&mb.skf, &cap, MFB_PLANAR_U64 * 8, false));
+      cap = mb.skp ? MFB_PLANAR_U64 * 8 : 0;
+      SET_TRY(grow((void **)&mb.skp, &cap, MFB_PLANAR_U64 * 8, false));
+      SET_TRY(grow((void **)&mb.enc_ent, &mb.enc_ent_cap, slots * piece * (size_t)ent_stride, false));
+      cap = mb.enc_msg_cap;
+      SET_TRY(grow((void **)&mb.enc_msg, &cap, slots * piece * 8, false));  // separate buffer: always 8-byte aligned
+      mb.enc_msg_cap = cap;
+      SET_TRY(grow((void **)&mb.enc_out, &mb.enc_out_cap, slots * piece * MFB_CT_BYTES, false));
+      if (mb.ent_pin_cap < piece * (size_t)ent_stride) {
+        for (int k = 0; k < 2; k++) {
+          size_t c2 = mb.ent_pin_cap;
+          SET_TRY(grow((void **)&mb.ent_pin[k], &c2, piece * (size_t)ent_stride, true));
+        }
+        mb.ent_pin_cap = piece * (size_t)ent_stride;
+      }
+      for (int k = 0; k < 2; k++)
+        if (!mb.ent_free[k]) SET_CUDA(cudaEventCreateWithFlags(&mb.ent_free[k], cudaEventDisableTiming));
+      SET_CUDA(cudaMemcpyAsync(mb.skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, mb.stream));
+      SET_TRY(mfb_flat_to_planar_dev(mb.ctx, mb.skf, MFB_N, 1, mb.skp, mb.stream));
+      // the member's messages, all its pieces up front (not one pageable copy per piece between the kernels)
+      for (size_t k = i; k < npieces; k += world)
+        SET_CUDA(cudaMemcpyAsync(mb.enc_msg + (k / world) * piece, msg + start[k], len[k] * 8, cudaMemcpyHostToDevice, mb.stream));
+    }
+    std::vector<int> uses(world, 0);
+    for (size_t k = 0; k < npieces; k++) {
+      Member &mb = s->m[k % world];
+      SET_CUDA(cudaSetDevice(mb.device));
+      const size_t slot = k / world, cnt = len[k];
+      const int b = uses[k % world] & 1;
+      if (uses[k % world] >= 2) SET_CUDA(cudaEventSynchronize(mb.ent_free[b]));  // the copy that last read this buffer is done
+      uses[k % world]++;
+      draw(user, mb.ent_pin[b], cnt * (size_t)ent_stride);
+      uint8_t *d_ent = mb.enc_ent + slot * piece * (size_t)ent_stride;
+      SET_CUDA(cudaMemcpyAsync(d_ent, mb.ent_pin[b], cnt * (size_t)ent_stride, cudaMemcpyHostToDevice, mb.stream));
+      SET_CUDA(cudaEventRecord(mb.ent_free[b], mb.stream));
+      SET_TRY(mfb_encrypt_dev(mb.ctx, seed, offset + start[k] * (uint64_t)MFB_CTR_CT, mb.skp, mb.enc_msg + slot * piece, d_ent, ent_stride,
+                              ent_nbytes, cnt, mb.enc_out + slot * piece * MFB_CT_BYTES, mb.stream));
+    }
+    for (size_t k = 0; k < npieces; k++) {  // records back, piece by piece (each copy waits for its member's stream)
+      Member &mb = s->m[k % world];
+      SET_CUDA(cudaSetDevice(mb.device));
+      SET_CUDA(cudaMemcpyAsync(out_c8 + start[k] * MFB_CT_BYTES, mb.enc_out + (k / world) * piece * MFB_CT_BYTES, len[k] * MFB_CT_BYTES,
+                               cudaMemcpyDeviceToHost, mb.stream));
+    }
+    return MFB_OK;
+  };
+  int rc = body();
+  // (no exchange kernels here: a failure does not desynchronise the members, the set stays usable)
+  char keep[256];
+  snprintf(keep, sizeof(keep), "%s", rc != MFB_OK ? mfb_set_last_error() : "");
+  for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    size_t cap;
-    cap = mb.skf ? MFB_PLANAR_U64 * 8 : 0;
-    SET_TRY(grow((void **)&mb.skf, &cap, MFB_PLANAR_U64 * 8, false));
-    cap = mb.skp ? MFB_PLANAR_U64 * 8 : 0;
-    SET_TRY(grow((void **)&mb.skp, &cap, MFB_PLANAR_U64 * 8, false));
-    SET_TRY(grow((void **)&mb.enc_in, &mb.enc_in_cap, slots * in_slot, false));
-    SET_TRY(grow((void **)&mb.enc_out, &mb.enc_out_cap, slots * piece * MFB_CT_BYTES, false));
-    SET_TRY(grow((void **)&mb.ent_pin, &mb.ent_pin_cap, piece * (size_t)ent_stride, true));
-    if (!mb.ent_free) SET_CUDA(cudaEventCreateWithFlags(&mb.ent_free, cudaEventDisableTiming));
-    mb.ent_used = false;
-    SET_CUDA(cudaMemcpyAsync(mb.skf, sk_flat, MFB_FLAT_SK_U64 * 8, cudaMemcpyHostToDevice, mb.stream));
-    SET_TRY(mfb_flat_to_planar_dev(mb.ctx, mb.skf, MFB_N, 1, mb.skp, mb.stream));
+    cudaSetDevice(mb.device);
+    const cudaError_t e = cudaStreamSynchronize(mb.stream);
+    if (e != cudaSuccess && rc == MFB_OK) {
+      snprintf(keep, sizeof(keep), "mfb_set_encrypt_cb: device %d: %s", mb.device, cudaGetErrorString(e));
+      rc = MFB_ECUDA;
+    }
+    scrub_member_secrets(mb);  // the key and the noise are secret, on error paths too
   }
-  for (size_t k = 0; k < npieces; k++) {
-    Member &mb = s->m[k % world];
-    SET_CUDA(cudaSetDevice(mb.device));
-    const size_t slot = k / world, cnt = len[k];
-    uint8_t *d_ent = mb.enc_in + slot * in_slot;
-    uint64_t *d_msg = (uint64_t *)(d_ent + piece * (size_t)ent_stride + ((8 - (piece * (size_t)ent_stride) % 8) % 8));
-    if (mb.ent_used) SET_CUDA(cudaEventSynchronize(mb.ent_free));  // the copy that last read this pinned buffer is done
-    draw(user, mb.ent_pin, cnt * (size_t)ent_stride);
-    SET_CUDA(cudaMemcpyAsync(d_ent, mb.ent_pin, cnt * (size_t)ent_stride, cudaMemcpyHostToDevice, mb.stream));
-    SET_CUDA(cudaEventRecord(mb.ent_free, mb.stream));
-    mb.ent_used = true;
-    SET_CUDA(cudaMemcpyAsync(d_msg, msg + start[k], cnt * 8, cudaMemcpyHostToDevice, mb.stream));
-    SET_TRY(mfb_encrypt_dev(mb.ctx, seed, offset + start[k] * (uint64_t)MFB_CTR_CT, mb.skp, d_msg, d_ent, ent_stride, ent_nbytes, cnt,
-                            mb.enc_out + slot * piece * MFB_CT_BYTES, mb.stream));
-  }
-  int rc = MFB_OK;
-  for (size_t k = 0; k < npieces; k++) {  // records back, piece by piece (each copy waits for its member's stream)
-    Member &mb = s->m[k % world];
-    SET_CUDA(cudaSetDevice(mb.device));
-    SET_CUDA(cudaMemcpyAsync(out_c8 + start[k] * MFB_CT_BYTES, mb.enc_out + (k / world) * piece * MFB_CT_BYTES, len[k] * MFB_CT_BYTES,
-                             cudaMemcpyDeviceToHost, mb.stream));
-  }
-  for (size_t i = 0; i < world && i < npieces; i++) {
-    Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    SET_CUDA(cudaStreamSynchronize(mb.stream));
-    memset(mb.ent_pin, 0, mb.ent_pin_cap);  // the noise is secret
-    SET_CUDA(cudaMemsetAsync(mb.enc_in, 0, mb.enc_in_cap, mb.stream));
-  }
-  SET_CUDA(cudaSetDevice(s->m[0].device));
+  cudaSetDevice(s->m[0].device);
+  if (rc != MFB_OK) snprintf(g_set_err, sizeof(g_set_err), "%s", keep);
   return rc;
 }
 
-// mfb_prove_resident over sharded regions (see mfb200.h)
-MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras,
-                                   const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
-                                   uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+// The same for an entropy source WITHOUT an order to preserve (the OS: getrandom(2)): member i takes the contiguous range
+// i of the ciphertexts and is driven by ITS OWN host thread, which draws that range's entropy (draw is called
+// concurrently from the member threads and must be thread-safe) while its device encrypts — entropy, upload, AES and
+// download all scale with the number of members.  The records go straight to their destinations: out_c8, or nsegs
+// segments of the record index space (setup(): crs->s, crs->as, crs->t, crs->v).
+MFB_API int mfb_set_encrypt_par(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                                mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8,
+                                const mfb_c8_segment *segs, int nsegs) {
   g_set_err[0] = 0;
-  if (!s || !ssp || !rs || !ras || !witness_limbs || !v_w_flat_inout || !h_flat_inout || !hat_v_flat_inout || !hat_h_flat_inout)
-    return set_fail(MFB_EARG, "mfb_set_prove_resident: null pointer");
-  const size_t D = mfb_ssp_degree_bound(ssp), world = s->m.size(), FLAT = MFB_FLAT_CT_U64;
-  if (rs->total != D || ras->total != D) return set_fail(MFB_EARG, "mfb_set_prove_resident: the regions must hold D ciphertexts");
+  if (count == 0) return MFB_OK;
+  SET_TRY(check_usable(s, "mfb_set_encrypt_par"));
+  SET_TRY(encrypt_args_ok("mfb_set_encrypt_par", seed, sk_flat, msg, draw, ent_stride, ent_nbytes));
+  if ((out_c8 == nullptr) == (segs == nullptr) || (segs && nsegs < 1))
+    return set_fail(MFB_EARG, "mfb_set_encrypt_par: give either out_c8 or segments");
+  const size_t world = s->m.size();
+  const size_t piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 110, first_piece = (size_t)mfb_device_sm_count(s->m[0].ctx) * 16;
+  std::vector<int> rcs(world, MFB_OK);
+  std::vector<std::string> errs(world);
+  auto work = [&](size_t i) {
+    g_set_err[0] = 0;
+    Member &mb = s->m[i];
+    size_t first, cnt;
+    split_range(count, world, i, &first, &cnt);
+    int rc = member_encrypt(mb, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, first, cnt, piece, first_piece);
+    if (rc == MFB_OK) rc = collect_records(mb, first, cnt, out_c8, segs, nsegs);
+    if (rc == MFB_OK && cudaStreamSynchronize(mb.stream) != cudaSuccess) {
+      snprintf(g_set_err, sizeof(g_set_err), "mfb_set_encrypt_par: device %d: %s", mb.device, cudaGetErrorString(cudaGetLastError()));
+      rc = MFB_ECUDA;
+    }
+    if (rc != MFB_OK) errs[i] = mfb_set_last_error();  // (thread-local: copy it out before the thread ends)
+    scrub_member_secrets(mb);
+    rcs[i] = rc;
+  };
+  std::vector<std::thread> pool;
+  for (size_t i = 1; i < world; i++) pool.emplace_back(work, i);
+  work(0);
+  for (auto &t : pool) t.join();
+  cudaSetDevice(s->m[0].device);
   for (size_t i = 0; i < world; i++)
-    if (rs->first[i] != ras->first[i] || rs->count[i] != ras->count[i])
-      return set_fail(MFB_EARG, "mfb_set_prove_resident: the two regions are sharded differently");
+    if (rcs[i] != MFB_OK) {
+      snprintf(g_set_err, sizeof(g_set_err), "%s", errs[i].c_str());
+      return rcs[i];
+    }
+  return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- prover pipeline
+static int prove_body(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras, const uint64_t *witness_limbs,
+                      size_t nlimbs, uint64_t delta, const uint8_t *seed, uint64_t bt_offset, const uint8_t *bt_recs, size_t M,
+                      bool any, bool want_bw) {
+  const size_t D = mfb_ssp_degree_bound(ssp), world = s->m.size();
   Member &p = s->m[0];
   SET_CUDA(cudaSetDevice(p.device));
+  if (any) SET_CUDA(cudaMemcpyAsync(p.res, s->acc_pin, 4 * SLOT * 8, cudaMemcpyHostToDevice, p.stream));
+  // b_w (a few selected ciphertexts regenerated from AES) on a member that would otherwise wait for the polynomial step
+  Member &bm = s->m[world > 1 ? 1 : 0];
+  if (want_bw) {
+    SET_CUDA(cudaSetDevice(bm.device));
+    SET_TRY(mfb_b_w_dev(bm.ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, bm.res + 4 * SLOT, bm.stream));
+  }
+  // polynomial step on the primary, queued without a host round trip; the other members wait for it ON THE DEVICE
+  SET_CUDA(cudaSetDevice(p.device));
   const uint32_t *wvh = nullptr;
-  SET_TRY(mfb_ssp_prover_polys_resident_dev(p.ctx, ssp, witness_limbs, nlimbs, delta, &wvh));  // stream idle on return
-  uint64_t *host[4] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout};
-  // the four accumulators travel as ONE pinned copy each way (slots of MFB_PLANAR_U64, the stride of p.res)
-  if (!s->acc_pin) SET_CUDA(cudaHostAlloc((void **)&s->acc_pin, 4 * MFB_PLANAR_U64 * 8, cudaHostAllocDefault));
-  for (int k = 0; k < 4; k++) memcpy(s->acc_pin + (size_t)k * MFB_PLANAR_U64, host[k], FLAT * 8);
-  SET_CUDA(cudaMemcpyAsync(p.res, s->acc_pin, 4 * MFB_PLANAR_U64 * 8, cudaMemcpyHostToDevice, p.stream));
-  // every member: its slices of w, v, h over NVLink, then both two-vector passes over its shards
+  SET_TRY(mfb_ssp_prover_polys_resident_async(p.ctx, ssp, witness_limbs, nlimbs, delta, p.stream, &wvh));
+  SET_CUDA(cudaEventRecord(s->ev_polys, p.stream));
+  // every member: its slices of w, v, h over NVLink, both two-vector passes over its shards, then ONE
+  // kernel that finishes its four partial sums and exchanges them with the other members
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
     const size_t cnt = rs->count[i], first = rs->first[i];
-    if (mb.co_cap < 3 * cnt + 4) {
-      if (mb.co) SET_CUDA(cudaFree(mb.co));
-      mb.co = nullptr;
-      mb.co_cap = 0;
-      SET_CUDA(cudaMalloc((void **)&mb.co, (3 * cnt + 4) * 4));
-      mb.co_cap = 3 * cnt + 4;
+    const uint32_t *cw, *cv, *ch;
+    if (i == 0) {
+      cw = wvh + first;
+      cv = wvh + D + first;
+      ch = wvh + 2 * D + first;
+    } else {
+      size_t cap = mb.co_cap * 4;
+      SET_TRY(grow((void **)&mb.co, &cap, (3 * cnt + 4) * 4, false));
+      mb.co_cap = cap / 4;
+      SET_CUDA(cudaStreamWaitEvent(mb.stream, s->ev_polys, 0));
+      for (int k = 0; k < 3 && cnt; k++)
+        SET_CUDA(cudaMemcpyPeerAsync(mb.co + k * cnt, mb.device, wvh + k * D + first, p.device, cnt * 4, mb.stream));
+      cw = mb.co;
+      cv = mb.co + cnt;
+      ch = mb.co + 2 * cnt;
     }
-    uint32_t *cw = mb.co, *cv = mb.co + cnt, *ch = mb.co + 2 * cnt;
-    if (cnt) {
-      SET_CUDA(cudaMemcpyPeerAsync(cw, mb.device, wvh + first, p.device, cnt * 4, mb.stream));
-      SET_CUDA(cudaMemcpyPeerAsync(cv, mb.device, wvh + D + first, p.device, cnt * 4, mb.stream));
-      SET_CUDA(cudaMemcpyPeerAsync(ch, mb.device, wvh + 2 * D + first, p.device, cnt * 4, mb.stream));
-    }
-    uint64_t *pt = mb.part;
-    SET_TRY(mfb_lincomb2_dev(mb.ctx, (const uint64_t *)mfb_region_cts(rs->shard[i]), cw, ch, cnt, nullptr, pt, nullptr,
-                             pt + MFB_PLANAR_U64, mb.stream));
-    SET_TRY(mfb_lincomb2_dev(mb.ctx, (const uint64_t *)mfb_region_cts(ras->shard[i]), cv, ch, cnt, nullptr, pt + 2 * MFB_PLANAR_U64,
-                             nullptr, pt + 3 * MFB_PLANAR_U64, mb.stream));
-  }
-  for (int v = 0; v < 4; v++)
-    for (size_t i = 0; i < world; i++) {
-      Member &mb = s->m[i];
-      SET_CUDA(cudaSetDevice(mb.device));
-      uint64_t *res = mb.res + (size_t)v * MFB_PLANAR_U64;
-      SET_TRY(mfb_peer_allreduce_dev(mb.ctx, mb.group, mb.part + (size_t)v * MFB_PLANAR_U64, i == 0 ? res : nullptr, res, mb.stream));
-    }
-  SET_CUDA(cudaSetDevice(p.device));
-  SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, 4 * MFB_PLANAR_U64 * 8, cudaMemcpyDeviceToHost, p.stream));
-  int rc = MFB_OK;
-  for (size_t i = 0; i < world; i++) {
-    Member &mb = s->m[i];
-    SET_CUDA(cudaSetDevice(mb.device));
-    SET_CUDA(cudaStreamSynchronize(mb.stream));
-    const int st = mfb_peer_status(mb.ctx, mb.group);
-    if (st != MFB_OK) rc = st;
+    SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(rs->shard[i]), cw, ch, cnt, 0, mb.stream));
+    SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(ras->shard[i]), cv, ch, cnt, 1, mb.stream));
+    SET_TRY(mfb_peer_finish4_dev(mb.ctx, mb.group, i == 0 && any ? mb.res : nullptr, mb.res, SLOT, mb.stream));
   }
   SET_CUDA(cudaSetDevice(p.device));
-  for (int k = 0; k < 4; k++) memcpy(host[k], s->acc_pin + (size_t)k * MFB_PLANAR_U64, FLAT * 8);
+  SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, 4 * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));
+  if (want_bw) {
+    SET_CUDA(cudaSetDevice(bm.device));
+    SET_CUDA(cudaMemcpyAsync(s->acc_pin + 4 * SLOT, bm.res + 4 * SLOT, MFB_FLAT_CT_U64 * 8, cudaMemcpyDeviceToHost, bm.stream));
+  }
+  return MFB_OK;
+}
+
+// mfb_prove_resident_bw over sharded regions (see mfb200.h)
+MFB_API int mfb_set_prove_resident_bw(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras,
+                                      const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40],
+                                      uint64_t bt_offset, const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout,
+                                      uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout,
+                                      uint64_t *b_w_flat_out) {
+  g_set_err[0] = 0;
+  SET_TRY(check_usable(s, "mfb_set_prove_resident"));
+  if (!ssp || !rs || !ras || !witness_limbs || !v_w_flat_inout || !h_flat_inout || !hat_v_flat_inout || !hat_h_flat_inout)
+    return set_fail(MFB_EARG, "mfb_set_prove_resident: null pointer");
+  if (b_w_flat_out && (!seed || !bt_recs || M < 1)) return set_fail(MFB_EARG, "mfb_set_prove_resident_bw: b_w needs the seed and the t | v records");
+  const size_t D = mfb_ssp_degree_bound(ssp), world = s->m.size();
+  if (rs->total != D || ras->total != D) return set_fail(MFB_EARG, "mfb_set_prove_resident: the regions must hold D ciphertexts");
+  for (size_t i = 0; i < world; i++)
+    if (rs->first[i] != ras->first[i] || rs->count[i] != ras->count[i])
+      return set_fail(MFB_EARG, "mfb_set_prove_resident: the two regions are sharded differently");
+  SET_TRY(ensure_acc_pin(s));
+  uint64_t *host[NACC] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, b_w_flat_out};
+  const bool any = stage_in(s, host, 4);
+  const int rc = finish_call(s, prove_body(s, ssp, rs, ras, witness_limbs, nlimbs, delta, seed, bt_offset, bt_recs, M, any,
+                                           b_w_flat_out != nullptr));
+  if (rc == MFB_OK) stage_out(s, host, b_w_flat_out ? NACC : 4);
   return rc;
+}
+
+MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras,
+                                   const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
+                                   uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout) {
+  return mfb_set_prove_resident_bw(s, ssp, rs, ras, witness_limbs, nlimbs, delta, nullptr, 0, nullptr, 0, v_w_flat_inout, h_flat_inout,
+                                   hat_v_flat_inout, hat_h_flat_inout, nullptr);
 }
 
 }  // extern "C"

@@ -33,6 +33,8 @@ void mf_set_entropy_source(mf_entropy_fn fn, void *arg) {
   g_ent_arg = arg;
 }
 
+int mf_entropy_hooked(void) { return g_ent_fn != NULL; }
+
 void mf_entropy(void *buf, size_t len) {
   if (g_ent_fn) {
     g_ent_fn(buf, len, g_ent_arg);

@@ -20,6 +20,9 @@ void mf_die(const char *what) __attribute__((noreturn));
     if ((call) != MFB_OK) mf_die(#call);                                         \
   } while (0)
 
+/* is an entropy hook installed (mf_set_entropy_source)?  Then draws must happen serially, in the reference's order. */
+int mf_entropy_hooked(void);
+
 /* stream position of an rng (aes.c bookkeeping: 16*ctr - rem) and the seed it was built from */
 uint64_t mf_rng_pos(rng_t rng);
 void mf_rng_advance(rng_t rng, uint64_t nbytes);

@@ -225,6 +225,27 @@ static void draw_entropy(void *user, uint8_t *dst, size_t nbytes) {
   mf_entropy(dst, nbytes);
 }
 
+/* out[i] = x0 * r^i mod p for i < n, as 8 interleaved chains (chain c starts at c * n/8 with x0 * r^(c n/8)) */
+static uint64_t powmod_p(uint64_t b, uint64_t e) {
+  uint64_t acc = 1;
+  for (b %= GAMMA_P; e; e >>= 1, b = b * b % GAMMA_P)
+    if (e & 1) acc = acc * b % GAMMA_P;
+  return acc;
+}
+static void geometric(uint64_t *out, size_t n, uint64_t x0, uint64_t r) {
+  enum { CH = 8 };
+  const size_t per = n / CH;
+  uint64_t x[CH];
+  for (int c = 0; c < CH; c++) x[c] = x0 % GAMMA_P * powmod_p(r, (uint64_t)c * per) % GAMMA_P;
+  for (size_t i = 0; i < per; i++)
+    for (int c = 0; c < CH; c++) {
+      out[c * per + i] = x[c];
+      x[c] = x[c] * r % GAMMA_P;
+    }
+  uint64_t y = per ? out[CH * per - 1] * r % GAMMA_P : x0 % GAMMA_P; /* the n % 8 elements after the last chain */
+  for (size_t i = CH * per; i < n; i++, y = y * r % GAMMA_P) out[i] = y;
+}
+
 void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   const size_t D = GAMMA_D, M = GAMMA_M, count = 2 * D + M;
   double t0 = mf_now();
@@ -238,13 +259,13 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   mf_trace("setup.key_gen", t0);
   t0 = mf_now();
 
-  /* plaintexts in stream order (snark.h:8-12): s^i, alpha*s^i, beta*t(s), beta*v_i(s) for i = 1..M-1 */
+  /* plaintexts in stream order (snark.h:8-12): s^i, alpha*s^i, beta*t(s), beta*v_i(s) for i = 1..M-1.  The two
+   * geometric sequences are cut into 8 independent chains each (x_{i+1} = x_i * s is one dependent multiply + reduce per
+   * element: 2^21 of them in a row would cost ~10 ms at D = 2^20) */
   uint64_t *msg = malloc(count * 8);
   if (!msg) mf_die("malloc");
-  uint64_t x = 1;
-  for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[i] = x;
-  x = vrs->alpha;
-  for (size_t i = 0; i < D; i++, x = (x * vrs->s) % GAMMA_P) msg[D + i] = x;
+  geometric(msg, D, 1, vrs->s);
+  geometric(msg + D, D, vrs->alpha, vrs->s);
   /* t(s) and v_i(s): the reference's M Horner passes (snark.c:97-110) as one batched device evaluation over the
    * dense blob [t, v_0, ..., v_{M-1}] (ssp.h:6-9); v_0(s) is computed and not used, as its slot is skipped there */
   uint64_t *vals = malloc((M + 1) * 8);
@@ -261,27 +282,41 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
   t0 = mf_now();
 
   /* per encryption the reference draws 69 noise bytes, then 1 sign byte (lwe.c:85-87): 70 bytes each, in order.
-   * The draws go through mfb_encrypt_cb's callback piece by piece — same bytes, same order — so that getrandom(2)
-   * for the next piece runs while the device encrypts the previous one. */
-  uint8_t *recs = malloc(count * CT_BYTES);
+   * The draws go through a callback piece by piece, so that getrandom(2) for the next piece runs while the device
+   * encrypts the previous one.  Record k of the call is ciphertext k of the stream: s, as, t, v. */
   uint64_t *skf = malloc(MFB_FLAT_SK_U64 * 8);
-  if (!recs || !skf) mf_die("malloc");
+  if (!skf) mf_die("malloc");
   for (size_t i = 0; i < GAMMA_N; i++) mf_to_flat(skf + i * MF_LIMBS, vrs->sk[i]);
   mfb_set *set = device_set();
-  if (set) { /* the pieces spread over the GPUs of the set: entropy-bound instead of AES-bound */
-    if (mfb_set_encrypt_cb(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs) != MFB_OK) {
-      fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_cb failed: %s\n", mfb_set_last_error());
+  if (set && !mf_entropy_hooked()) {
+    /* OS entropy has no order to preserve: every GPU of the set takes a contiguous range of the ciphertexts, driven by
+     * its own host thread that draws that range's entropy, and writes its records straight into the CRS arrays */
+    const mfb_c8_segment segs[4] = {{0, D, (uint8_t *)crs->s}, {D, D, (uint8_t *)crs->as}, {2 * D, 1, crs->t},
+                                    {2 * D + 1, M - 1, (uint8_t *)crs->v}};
+    if (mfb_set_encrypt_par(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, NULL, segs, 4) !=
+        MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_par failed: %s\n", mfb_set_last_error());
       abort();
     }
+    mf_trace("setup.entropy+encrypt (one thread per GPU)", t0);
   } else {
-    MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+    uint8_t *recs = malloc(count * CT_BYTES);
+    if (!recs) mf_die("malloc");
+    if (set) { /* hooked entropy: drawn by this thread in the reference's order, the pieces spread over the GPUs */
+      if (mfb_set_encrypt_cb(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs) != MFB_OK) {
+        fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_cb failed: %s\n", mfb_set_last_error());
+        abort();
+      }
+    } else {
+      MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+    }
+    mf_trace("setup.entropy+encrypt", t0);
+    memcpy(crs->s, recs, D * CT_BYTES);
+    memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);
+    memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
+    memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
+    free(recs);
   }
-  mf_trace("setup.entropy+encrypt", t0);
-  memcpy(crs->s, recs, D * CT_BYTES);
-  memcpy(crs->as, recs + D * CT_BYTES, D * CT_BYTES);
-  memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
-  memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
-  free(recs);
   explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);
   free(msg);
@@ -383,7 +418,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
       idx[nsel++] = (uint32_t)i;
     }
   }
-  const int b_w_in_pipeline = all_resident && !res->ms; /* one GPU, everything resident: b_w rides in the pipeline below */
+  const int b_w_in_pipeline = all_resident; /* everything resident: b_w rides in the device pipeline below */
   if (!b_w_in_pipeline) {
     uint64_t *acc = calloc(FLAT_CT, 8); /* ct_import overwrites pi->b_w: start from zero */
     if (!acc) mf_die("malloc");
@@ -407,16 +442,16 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
     mf_ct_to_flat(acc + 2 * FLAT_CT, pi->hat_v, "prover");
     mf_ct_to_flat(acc + 3 * FLAT_CT, pi->hat_h, "prover");
     if (res->ms) {
-      if (mfb_set_prove_resident(g_set, rssp, res->ms, res->mas, PTR(witness), (size_t)SIZ(witness), delta, acc, acc + FLAT_CT,
-                                 acc + 2 * FLAT_CT, acc + 3 * FLAT_CT) != MFB_OK) {
-        fprintf(stderr, "mangiafuoco_b200: mfb_set_prove_resident failed: %s\n", mfb_set_last_error());
+      if (mfb_set_prove_resident_bw(g_set, rssp, res->ms, res->mas, PTR(witness), (size_t)SIZ(witness), delta, crs->seed, CTR_BT, recs,
+                                    M, acc, acc + FLAT_CT, acc + 2 * FLAT_CT, acc + 3 * FLAT_CT, acc + 4 * FLAT_CT) != MFB_OK) {
+        fprintf(stderr, "mangiafuoco_b200: mfb_set_prove_resident_bw failed: %s\n", mfb_set_last_error());
         abort();
       }
     } else {
       MF_GPU(mfb_prove_resident_bw(mf_gpu(), rssp, res->s, res->as, PTR(witness), (size_t)SIZ(witness), delta, crs->seed, CTR_BT,
                                    recs, M, acc, acc + FLAT_CT, acc + 2 * FLAT_CT, acc + 3 * FLAT_CT, acc + 4 * FLAT_CT));
-      mf_ct_from_flat(pi->b_w, acc + 4 * FLAT_CT);
     }
+    mf_ct_from_flat(pi->b_w, acc + 4 * FLAT_CT);
     mf_ct_from_flat(pi->v_w, acc);
     mf_ct_from_flat(pi->h, acc + FLAT_CT);
     mf_ct_from_flat(pi->hat_v, acc + 2 * FLAT_CT);

@@ -106,6 +106,15 @@ MFB_API int mfb_lincomb_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_
 MFB_API int mfb_lincomb2_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
                      size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
                      uint64_t *rop1_out_dev, void *stream);
+/* Building blocks of the prover pipeline (snark.c:157-174: two regions, two scalar vectors each): the two two-vector
+ * passes leave their partial sums in the context's workspace (pass = 0, 1; both over equally many ciphertexts), then ONE
+ * finish launch produces the four flat accumulators rop_out4 + k * rop_stride_u64, k = 0..3 in the order (pass 0 vector
+ * 0, pass 0 vector 1, pass 1 vector 0, pass 1 vector 1); rop_in4 (same layout) may be NULL (zero).  mfb_peer_finish4_dev
+ * is that finish fused with the peer-memory exchange of all four (see below): one kernel per rank. */
+MFB_API int mfb_lincomb2_partials_dev(mfb_ctx *ctx, const uint64_t *cts_dev, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev,
+                              size_t d, int pass, void *stream);
+MFB_API int mfb_lincomb_finish4_dev(mfb_ctx *ctx, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev, size_t rop_stride_u64,
+                            void *stream);
 /* host flavour over flat host ciphertexts (d small: ct_add / ct_mul_ui / ct_addmul_ui on ct_t objects) */
 MFB_API int mfb_lincomb(mfb_ctx *ctx, const uint64_t *cts_flat, const uint32_t *coeffs, size_t d, uint64_t *rop_flat_inout);
 
@@ -178,6 +187,12 @@ MFB_API int mfb_lincomb_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t
  * the main stream nothing (sharding.PipelinedPeerShardedLincomb). */
 MFB_API int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, const uint64_t *rop_in_dev,
                            uint64_t *rop_out_dev, void *stream);
+/* Up to 4 flat ciphertexts per rank in ONE exchange kernel ("lanes": partial_flat_dev + l * in_stride_u64 in, rop +
+ * l * rop_stride_u64 in / out, l < lanes); every rank must pass the same number of lanes. */
+MFB_API int mfb_peer_allreduce_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, size_t in_stride_u64, int lanes,
+                                 const uint64_t *rop_in_dev, uint64_t *rop_out_dev, size_t rop_stride_u64, void *stream);
+MFB_API int mfb_peer_finish4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev,
+                         size_t rop_stride_u64, void *stream);
 /* the same for the fused AES + MAC path (mfb_eval_poly_dev over this rank's ciphertexts) */
 MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                            const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
@@ -205,15 +220,35 @@ MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const u
  * encrypted by member k mod size (setup()'s 2D+M encryptions on a whole box: entropy-bound instead of AES-bound). */
 MFB_API int mfb_set_encrypt_cb(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                        mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
+/* The same when the entropy source has no order to preserve (the OS): member i takes the contiguous range i of the
+ * ciphertexts and is driven by its own host thread, which draws that range's entropy — draw is called CONCURRENTLY and
+ * must be thread-safe — while its device encrypts: entropy, upload, AES and download all scale with the members.  The
+ * records go to out_c8, or (out_c8 == NULL) to nsegs segments of the record index space: record k of segment g goes to
+ * g.dst + (k - g.first) * 92 (setup(): crs->s, crs->as, crs->t, crs->v without an intermediate copy). */
+typedef struct mfb_c8_segment {
+  size_t first, count;
+  uint8_t *dst;
+} mfb_c8_segment;
+MFB_API int mfb_set_encrypt_par(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                        mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8,
+                        const mfb_c8_segment *segs, int nsegs);
 /* eval_poly / eval_poly2 with nothing resident, sharded: every member regenerates the a-vectors of its contiguous
  * ciphertext range from AES in-kernel; coeffs1 / rop1 may both be NULL. */
 MFB_API int mfb_set_eval_poly2(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint64_t *coeffs0,
                        const uint64_t *coeffs1, size_t d, uint64_t *rop0_flat_inout, uint64_t *rop1_flat_inout);
-/* mfb_prove_resident over sharded regions: the polynomial step runs on the primary, the members fetch their slices of
- * w, v, h over NVLink, run both two-vector passes over their shards, and four peer all-reduce kernels combine them. */
+/* mfb_prove_resident[_bw] over sharded regions: the polynomial step is queued on the primary (no host round trip), the
+ * other members wait for it on the device, fetch their slices of w, v, h over NVLink, run both two-vector passes over
+ * their shards and ONE finish + exchange kernel each for the four accumulators; b_w is computed meanwhile by a member
+ * that would otherwise wait for the polynomial step.  One synchronisation, one pinned copy back.
+ * A failed set call poisons the set (later calls return MFB_EPEER): destroy it and create a new one. */
 MFB_API int mfb_set_prove_resident(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *reg_s, const mfb_set_region *reg_as,
                            const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *v_w_flat_inout,
                            uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout);
+MFB_API int mfb_set_prove_resident_bw(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *reg_s, const mfb_set_region *reg_as,
+                              const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40],
+                              uint64_t bt_offset, const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout,
+                              uint64_t *h_flat_inout, uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout,
+                              uint64_t *b_w_flat_out);
 
 /* ---- K2+K1 fused: eval_poly with a regenerated in-kernel ----------------------------------- */
 /* rop += sum_{m<d} coeffs[m] * CT_{k(m)},  k(m) = idx ? idx[m] : m, where CT_k = ct_import(stream at
@@ -282,6 +317,10 @@ MFB_API int mfb_ssp_prover_polys_resident(mfb_ctx *ctx, mfb_ssp *h, const uint64
  * valid until the next polynomial / encrypt / decrypt call on this context. */
 MFB_API int mfb_ssp_prover_polys_resident_dev(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
                                       uint64_t delta, const uint32_t **wvh_dev);
+/* The same queued on `stream` WITHOUT waiting (no host round trip at all: the selection indices travel through pinned
+ * staging, the quotient uses the cached transform of rev(t)^-1): *wvh_dev is valid in stream order. */
+MFB_API int mfb_ssp_prover_polys_resident_async(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witness_limbs, size_t nlimbs,
+                                        uint64_t delta, void *stream, const uint32_t **wvh_dev);
 MFB_API size_t mfb_ssp_degree_bound(const mfb_ssp *h);
 /* values[q] = poly_{first+q}(x) mod p over a resident blob [t, v_0, ..., v_{M-1}] (polynomial 0 = t): setup's and the
  * verifier's evaluations (snark.c:97-110, 197-201, 214-215) without shipping the coefficients again. */
@@ -300,6 +339,10 @@ MFB_API int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *
                           const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, const uint8_t seed[40], uint64_t bt_offset,
                           const uint8_t *bt_recs, size_t M, uint64_t *v_w_flat_inout, uint64_t *h_flat_inout,
                           uint64_t *hat_v_flat_inout, uint64_t *hat_h_flat_inout, uint64_t *b_w_flat_out);
+/* b_w alone, queued on `stream`: b_w_flat_out_dev (device) = delta * CT_t + sum_{witness bit i-1} CT_v[i-1]; bt_recs
+ * are host records (t, then the M-1 v records). */
+MFB_API int mfb_b_w_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t bt_offset, const uint8_t *bt_recs, size_t M,
+                const uint64_t *witness_limbs, size_t nlimbs, uint64_t delta, uint64_t *b_w_flat_out_dev, void *stream);
 /* values[q] = poly_q(x) mod p for npoly polynomials of D u64 coefficients each (setup's nmod_poly_evaluate_nmod
  * calls, snark.c:97-110) */
 MFB_API int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_t npoly, uint64_t x, uint64_t *values);
