@@ -120,6 +120,8 @@ _SIGS = {
     "mfb_lincomb_finish4_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "mfb_peer_allreduce_lanes_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "mfb_peer_finish4_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mfb_peer_finish4_push_dev": (C.c_int, [_vp, _vp, _vp]),
+    "mfb_peer_wait4_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mfb_ssp_prover_polys_resident_async": (C.c_int, [_vp, _vp, _u64p, C.c_size_t, C.c_uint64, _vp, C.POINTER(_vp)]),
     "mfb_b_w_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _vp, _vp]),
     "mfb_set_encrypt_par": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
@@ -302,6 +304,38 @@ class DeviceSet:
         self._ck(self.ctx.lib.mfb_set_encrypt_cb(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes,
                                                 m.size, _p8(out)))
         return out
+
+    def encrypt_par(self, seed, offset: int, sk_flat, msg, draw, ent_stride: int = ENT_BYTES, ent_nbytes: int = ENT_BYTES - 1,
+                    segments=None):
+        """mfb_set_encrypt_par: one host thread per member, contiguous ranges; `draw(nbytes)` is called concurrently from the
+        member threads.  segments = [(first, count), ...] partitions the record index space: the records are then returned
+        as one array per segment (written by the library straight into them), else as one (count, 92) array."""
+        s, sk, m = _seed(seed), _arr(sk_flat, np.uint64), _arr(msg, np.uint64)
+        if sk.size != FLAT_SK_U64:
+            raise ValueError("sk_flat must be (1470, 11) uint64")
+        fn_t = _SIGS["mfb_set_encrypt_par"][1][5]
+
+        def _draw(_user, dst, nbytes):
+            data = bytes(draw(nbytes))
+            if len(data) != nbytes:
+                raise ValueError("entropy callback returned the wrong number of bytes")
+            C.memmove(dst, data, nbytes)
+
+        cb = fn_t(_draw)
+        if segments is None:
+            out = np.zeros((m.size, CT_BYTES), np.uint8)
+            self._ck(self.ctx.lib.mfb_set_encrypt_par(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes,
+                                                     m.size, _p8(out), None, 0))
+            return out
+
+        class Seg(C.Structure):
+            _fields_ = [("first", C.c_size_t), ("count", C.c_size_t), ("dst", C.c_void_p)]
+
+        outs = [np.zeros((cnt, CT_BYTES), np.uint8) for _, cnt in segments]
+        segs = (Seg * len(segments))(*[Seg(f, c, o.ctypes.data) for (f, c), o in zip(segments, outs)])
+        self._ck(self.ctx.lib.mfb_set_encrypt_par(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes,
+                                                 m.size, None, C.cast(segs, C.c_void_p), len(segments)))
+        return outs
 
     def eval_poly2(self, seed, offset: int, c8, coeffs0, coeffs1=None, rop0=None, rop1=None):
         """eval_poly (coeffs1 None) / eval_poly2 with nothing resident, sharded over the members."""

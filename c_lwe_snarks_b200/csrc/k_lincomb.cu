@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(64 * FIN_SLICES)
 k_lincomb_finish_peer(const uint64_t *__restrict__ partial, size_t lane_stride, int nparts, const uint64_t *rop_in,
                       uint64_t *rop_out, size_t rop_stride, unsigned int *queue, unsigned int *queue2,
                       const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch, uint64_t timeout_ns,
-                      int *status) {
+                      int *status, int push_only) {
   __shared__ uint32_t sm[FIN_SLICES - 1][22][64];
   __shared__ __align__(16) uint64_t stage[RT_TILE * L64];  // the flat tile: [64][11] u64
   const int tile = blockIdx.x, lane = blockIdx.y;
@@ -308,6 +308,7 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, size_t lane_stride, 
   __syncthreads();
   if ((int)threadIdx.x < world)
     st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
+  if (push_only) return;  // steps 3 and 4 are a separate, small kernel (k_peer_allreduce, wait_only): this one never blocks
   // 3. wait for every source rank's tile
   if ((int)threadIdx.x < world) {
     const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, lane, tile));
@@ -354,7 +355,7 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, size_t lane_stride, 
 __global__ void __launch_bounds__(RT_TILE)
 k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, const uint64_t *rop_in, uint64_t *rop_out,
                  size_t rop_stride, const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch,
-                 uint64_t timeout_ns, int *status) {
+                 uint64_t timeout_ns, int *status, int wait_only) {
   const int tile = blockIdx.x, lane = blockIdx.y;
   flat_partial += (size_t)lane * in_stride;
   if (rop_in) rop_in += (size_t)lane * rop_stride;
@@ -362,8 +363,9 @@ k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, co
   const int c = tile * RT_TILE + threadIdx.x;
   const uint32_t q = epoch & 1u;
   constexpr int TILE_FLAT_U64 = RT_TILE * L64;  // 704 u64 = 352 x 16 bytes
-  // push: the tile as 16-byte pieces (the flat input ends at coordinate 1470: the padding coordinate is sent as zeros)
-  for (int i = threadIdx.x; i < TILE_FLAT_U64 / 2; i += RT_TILE) {
+  // push: the tile as 16-byte pieces (the flat input ends at coordinate 1470: the padding coordinate is sent as zeros);
+  // wait_only: the tiles were pushed (and the flags raised) by k_lincomb_finish_peer(push_only) of the same epoch
+  for (int i = threadIdx.x; i < (wait_only ? 0 : TILE_FLAT_U64 / 2); i += RT_TILE) {
     const size_t e = (size_t)tile * TILE_FLAT_U64 + 2 * (size_t)i;
     uint4 v;
     const uint64_t lo = e < (size_t)NC * L64 ? flat_partial[e] : 0, hi = e + 1 < (size_t)NC * L64 ? flat_partial[e + 1] : 0;
@@ -379,7 +381,8 @@ k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, co
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
-    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
+    if (!wait_only)
+      st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
     const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, lane, tile));
     if (!peer_wait_u32(f, epoch, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
   }
@@ -509,21 +512,27 @@ cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, size_t lane_stride
   return cudaGetLastError();
 }
 
-// flat_partial != nullptr: the exchange alone (k_peer_allreduce; lane l contributes flat_partial + l * lane_stride);
-// else the finish of the row-planar partials fused with the exchange
+// mode 0: flat_partial != nullptr: the exchange alone (k_peer_allreduce; lane l contributes flat_partial + l * lane_stride),
+//         else the finish of the row-planar partials fused with the exchange (one kernel that pushes, waits and adds);
+// mode 1: finish + push only (never blocks);  mode 2: wait + add only (a small kernel: 64 threads per tile and lane) —
+//         the two halves of one exchange (same epoch) when the ranks' kernels cannot be assumed co-resident
 cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts,
                                        const uint64_t *flat_partial, const uint64_t *rop_in, uint64_t *rop_out, size_t rop_stride,
                                        unsigned int *queue, unsigned int *queue2, uint8_t *const *bases, int world, int rank,
-                                       uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st) {
+                                       uint32_t epoch, uint64_t timeout_ns, int *status, int mode, cudaStream_t st) {
   if (lanes < 1 || lanes > PEER_LANES) return cudaErrorInvalidValue;
   PeerTable t = {};
   for (int i = 0; i < world; i++) t.base[i] = bases[i];
-  if (flat_partial)
+  if (mode == 2)
+    k_peer_allreduce<<<dim3(RT_NTILES, lanes), RT_TILE, 0, st>>>(rop_out, 0, rop_in, rop_out, rop_stride, t, world, rank, epoch, timeout_ns,
+                                                                status, 1);
+  else if (flat_partial)
     k_peer_allreduce<<<dim3(RT_NTILES, lanes), RT_TILE, 0, st>>>(flat_partial, lane_stride, rop_in, rop_out, rop_stride, t, world, rank,
-                                                                epoch, timeout_ns, status);
+                                                                epoch, timeout_ns, status, 0);
   else
     k_lincomb_finish_peer<<<dim3(RT_NTILES, lanes), 64 * FIN_SLICES, 0, st>>>(partial_ws, lane_stride, nparts, rop_in, rop_out, rop_stride,
-                                                                            queue, queue2, t, world, rank, epoch, timeout_ns, status);
+                                                                            queue, queue2, t, world, rank, epoch, timeout_ns, status,
+                                                                            mode == 1);
   return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, size_t lane_stride
 cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts,
                                        const uint64_t *flat_partial, const uint64_t *rop_in, uint64_t *rop_out, size_t rop_stride,
                                        unsigned int *queue, unsigned int *queue2, uint8_t *const *bases, int world, int rank,
-                                       uint32_t epoch, uint64_t timeout_ns, int *status, cudaStream_t st);
+                                       uint32_t epoch, uint64_t timeout_ns, int *status, int mode, cudaStream_t st);
 cudaError_t launch_columns_split(const uint64_t *flat, uint64_t *cols, cudaStream_t st);
 cudaError_t launch_columns_carry(const uint64_t *cols, int c0, int ncoord, const uint64_t *flat_in, uint64_t *flat_out,
                                  cudaStream_t st);
@@ -537,15 +537,16 @@ void mfb_peer_destroy(mfb_ctx *ctx, mfb_peer_group *g) {
   delete g;
 }
 
+// mode 0: one kernel (push, wait, add); mode 1: finish + push (starts a new exchange); mode 2: wait + add (completes it)
 static int peer_finish(mfb_ctx *ctx, mfb_peer_group *g, size_t lane_stride, int lanes, int nparts, const uint64_t *flat_partial_dev,
                        const uint64_t *rop_in_dev, uint64_t *rop_out_dev, size_t rop_stride, unsigned int *queue,
-                       unsigned int *queue2, cudaStream_t st) {
+                       unsigned int *queue2, cudaStream_t st, int mode = 0) {
   if (g->epoch == 0xffffffffu) return set_err(MFB_EARG, "peer exchange: 2^32 calls on one group; create a new one");
   if (lanes < 1 || lanes > PEER_LANES) return set_err(MFB_EARG, "peer exchange: 1 <= lanes <= %d", PEER_LANES);
-  g->epoch += 1;
+  if (mode != 2) g->epoch += 1;
   MFB_CUDA_TRY(launch_lincomb_finish_peer(ctx->partial_ws, lane_stride, lanes, nparts, flat_partial_dev, rop_in_dev, rop_out_dev,
                                           rop_stride, queue, queue2, g->base, g->world, g->rank, g->epoch, g->timeout_ns, g->status,
-                                          st));
+                                          mode, st));
   return MFB_OK;
 }
 
@@ -654,6 +655,28 @@ int mfb_peer_finish4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in
   MFB_TRY(peer_finish(ctx, g, (size_t)ns * PLANAR_U64, 4, ns, nullptr, rop_in4_dev, rop_out4_dev, rop_stride_u64, ctx->queue,
                       ctx->queue + QUEUE_U32, (cudaStream_t)stream));
   ctx->pass_nslots[0] = ctx->pass_nslots[1] = -1;
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_peer_finish4_push_dev(mfb_ctx *ctx, mfb_peer_group *g, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_finish4_push_dev: the peer group is not connected");
+  MFB_TRY(finish4_check(ctx, "mfb_peer_finish4_push_dev"));
+  const int ns = ctx->pass_nslots[0];
+  MFB_TRY(peer_finish(ctx, g, (size_t)ns * PLANAR_U64, 4, ns, nullptr, nullptr, ctx->partial_ws /* unused */, 0, ctx->queue,
+                      ctx->queue + QUEUE_U32, (cudaStream_t)stream, 1));
+  ctx->pass_nslots[0] = ctx->pass_nslots[1] = -1;
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_peer_wait4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev, size_t rop_stride_u64,
+                       void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_wait4_dev: the peer group is not connected");
+  if (!rop_out4_dev || rop_stride_u64 < MFB_FLAT_CT_U64) return set_err(MFB_EARG, "mfb_peer_wait4_dev: bad argument");
+  MFB_TRY(peer_finish(ctx, g, 0, 4, 0, nullptr, rop_in4_dev, rop_out4_dev, rop_stride_u64, nullptr, nullptr, (cudaStream_t)stream, 2));
   ctx->launches += 1;
   return MFB_OK;
 }

@@ -334,6 +334,19 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   return MFB_OK;
 }
 
+// Second phase of a set call: the members' exchange kernels, which WAIT for each other on the device.  They are enqueued
+// only after every member's compute work of the call is in its stream (members may share a GPU, where a waiting kernel
+// must never sit in front of work that another member's kernel is waiting for).
+static int exchange_all(mfb_set *s, int nvec, bool any) {
+  for (size_t i = 0; i < s->m.size(); i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
+                                         mb.stream));
+  }
+  return MFB_OK;
+}
+
 static int region_lincomb2_body(mfb_set *s, const mfb_set_region *r, const uint32_t *coeffs0, const uint32_t *coeffs1, int nvec,
                                 bool any) {
   const size_t world = s->m.size();
@@ -359,9 +372,8 @@ static int region_lincomb2_body(mfb_set *s, const mfb_set_region *r, const uint3
       SET_TRY(mfb_lincomb2_dev(mb.ctx, cts, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + SLOT, mb.stream));
     else
       SET_TRY(mfb_lincomb_dev(mb.ctx, cts, c0, cnt, nullptr, mb.part, mb.stream));
-    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
-                                         mb.stream));
   }
+  SET_TRY(exchange_all(s, nvec, any));
   Member &p = s->m[0];
   SET_CUDA(cudaSetDevice(p.device));
   SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, (size_t)nvec * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));
@@ -412,9 +424,8 @@ static int eval_poly2_body(mfb_set *s, const uint8_t seed[40], uint64_t offset, 
       SET_TRY(mfb_eval_poly2_dev(mb.ctx, seed, off, mb.c8, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + SLOT, mb.stream));
     else
       SET_TRY(mfb_eval_poly_dev(mb.ctx, seed, off, mb.c8, c0, nullptr, cnt, nullptr, mb.part, mb.stream));
-    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
-                                         mb.stream));
   }
+  SET_TRY(exchange_all(s, nvec, any));
   Member &p = s->m[0];
   SET_CUDA(cudaSetDevice(p.device));
   SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, (size_t)nvec * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));
@@ -688,8 +699,8 @@ static int prove_body(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const 
   const uint32_t *wvh = nullptr;
   SET_TRY(mfb_ssp_prover_polys_resident_async(p.ctx, ssp, witness_limbs, nlimbs, delta, p.stream, &wvh));
   SET_CUDA(cudaEventRecord(s->ev_polys, p.stream));
-  // every member: its slices of w, v, h over NVLink, both two-vector passes over its shards, then ONE
-  // kernel that finishes its four partial sums and exchanges them with the other members
+  // every member: its slices of w, v, h over NVLink, both two-vector passes over its shards, then ONE kernel that
+  // finishes its four partial sums and pushes them to every member; a small second kernel waits for the others' and adds
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
@@ -712,7 +723,12 @@ static int prove_body(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const 
     }
     SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(rs->shard[i]), cw, ch, cnt, 0, mb.stream));
     SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(ras->shard[i]), cv, ch, cnt, 1, mb.stream));
-    SET_TRY(mfb_peer_finish4_dev(mb.ctx, mb.group, i == 0 && any ? mb.res : nullptr, mb.res, SLOT, mb.stream));
+    SET_TRY(mfb_peer_finish4_push_dev(mb.ctx, mb.group, mb.stream));  // never blocks
+  }
+  for (size_t i = 0; i < world; i++) {  // the waiting halves, after every member's pushes are queued
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_TRY(mfb_peer_wait4_dev(mb.ctx, mb.group, i == 0 && any ? mb.res : nullptr, mb.res, SLOT, mb.stream));
   }
   SET_CUDA(cudaSetDevice(p.device));
   SET_CUDA(cudaMemcpyAsync(s->acc_pin, p.res, 4 * SLOT * 8, cudaMemcpyDeviceToHost, p.stream));

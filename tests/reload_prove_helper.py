@@ -30,13 +30,13 @@ def main():
         C.memmove(buf, ent.ctypes.data + pos[0], n)
         pos[0] += n
 
+    sn.load_crs(crs_file)  # (crs_init draws a throw-away seed from the OS: before the hook is installed)
     sn.lib.mf_set_entropy_source(draw, None)
     sn.ssp[:] = np.load(ssp_file)
     wl = np.load(wit_file).astype(np.uint64)
     imp = getattr(sn.gmp, "__gmpz_import")
     imp.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p]
     imp(C.byref(sn.witness), wl.size, -1, 8, 0, 0, wl.ctypes.data)
-    sn.load_crs(crs_file)
     if devices > 1:
         import torch
         sn.set_devices(devices, spread=torch.cuda.device_count() >= devices)

@@ -374,3 +374,38 @@ def test_device_set_encrypt_cb(nmembers, cnt, oracle):
     finally:
         dset.close()
         ctx.close()
+
+
+@pytest.mark.parametrize("nmembers,cnt", [(1, 7), (2, 5), (3, 148 * 16 + 148 * 110 * 3 + 33), (4, 3)])
+def test_device_set_encrypt_par(nmembers, cnt, oracle):
+    """mfb_set_encrypt_par (what setup() uses with OS entropy): one host thread per member over contiguous ranges, the
+    records written straight into the caller's segments.  With an entropy source that hands every caller the same
+    bytes the result must equal mfb_encrypt on that entropy, whatever thread drew what."""
+    import c_lwe_snarks_b200 as m
+    from conftest import xof
+    sk = oracle.key_gen(xof("sk-setenc", N * CT_BYTES))
+    msg = xof_scalars(f"m-setpar-{cnt}", cnt)
+    unit = xof("ent-setpar-unit", 70)
+    ent = np.tile(unit, cnt)
+    calls = []
+
+    def draw(n):  # called concurrently from the member threads (ctypes takes the GIL for each call)
+        assert n % 70 == 0
+        calls.append(n)
+        return np.tile(unit, n // 70).tobytes()
+
+    ctx = m.Context(0)
+    dset = ctx.device_set([0] * (nmembers - 1))
+    try:
+        want = ctx.encrypt(SEED, 5 * CTR_CT + 8, sk[:, :11], msg, ent)
+        got = dset.encrypt_par(SEED, 5 * CTR_CT + 8, sk[:, :11], msg, draw)
+        assert sum(calls) == cnt * 70
+        assert np.array_equal(got, want)
+        # segments: a ragged partition of the record index space, as setup() passes (s | as | t | v)
+        cuts = sorted({0, cnt // 3, cnt // 3 + 1, (2 * cnt) // 3, cnt})
+        segs = [(a, b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+        outs = dset.encrypt_par(SEED, 5 * CTR_CT + 8, sk[:, :11], msg, draw, segments=segs)
+        assert np.array_equal(np.concatenate(outs), want)
+    finally:
+        dset.close()
+        ctx.close()
