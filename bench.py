@@ -60,6 +60,12 @@ def synth_inputs(d: int, rank: int = 0):
     return c8, h
 
 
+def workload_string(log2d: int) -> str:
+    """config.workload — the SAME string in both arms (residency / sampling are described under their own keys)."""
+    return (f"prover lincomb (eval_poly, lwe.c:176-186), D=2^{log2d} Regev ciphertexts per GPU, n=1470, logq=736 (eff. 704), "
+            f"p=2^32-5")
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -186,9 +192,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts per GPU, n=1470, logq=736 "
-                                   f"(eff. 704), p=2^32-5",
-                       "reference_path": "eval_poly of the unmodified reference (oracle/_ref): AES-CTR regeneration + GMP MAC",
+            "config": {"workload": workload_string(args.log2d),
+                       "path": "eval_poly of the unmodified reference (oracle/_ref): AES-CTR regeneration + GMP MAC on the host cores",
                        "sample_ciphertexts_per_step": total},
             "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
                              "sample": f"{total} ciphertexts per step ({per_core} per core x {cores} processes over disjoint "
@@ -234,7 +239,9 @@ def snark_box_latency(log2d_total: int, M: int, n_dev: int):
     """BASELINE configs[3]: one single-threaded program (the drop-in's setup/prover/verifier) proving a 2^log2d_total-
     constraint SSP with the CRS regions sharded by ciphertext index over n_dev GPUs (mf_set_devices) and every lincomb
     combined over NVLink peer memory.  Runs after the timed sections as a SUBPROCESS of rank 0 (tools/snark_box.py: the
-    drop-in aborts on errors, which must not take the bench line with it); the other ranks wait on the CPU."""
+    drop-in aborts on errors, which must not take the bench line with it); the other ranks wait on the CPU.
+    setup_ms = setup() with its encryptions spread over the n_dev GPUs (one host thread per GPU draws the entropy of its
+    range); setup_one_gpu_ms = the same call before mf_set_devices."""
     import subprocess
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "snark_box.py"), str(log2d_total), str(M), str(n_dev)],
                        capture_output=True, text=True, timeout=600)
@@ -242,10 +249,85 @@ def snark_box_latency(log2d_total: int, M: int, n_dev: int):
     if r.returncode != 0 or not lines:
         raise RuntimeError(f"tools/snark_box.py exited {r.returncode}: {(r.stderr or r.stdout)[-300:]}")
     j = json.loads(lines[-1])
-    return {"D": j["D"], "M": j["M"], "devices": j["devices"], "setup_ms": 1e3 * j["setup_s"],
+    return {"D": j["D"], "M": j["M"], "devices": j["devices"], "setup_ms": 1e3 * j["setup_over_the_set_s"],
+            "setup_one_gpu_ms": 1e3 * j["setup_s"],
             "make_resident_ms": 1e3 * j["make_resident_s"], "prove_nothing_resident_ms": j["prove_nothing_resident_ms"],
             "prove_resident_ms": min(j["prove_ms"][1:]), "verify_ms": j["verify_ms"], "accept": j["accept"],
             "tampered_accept": j["tampered_accept"], "api": j["api"]}
+
+
+def strong_2e20_leg(ctx, torch, dist, world, rank, steps, peer, ppipe, sl, barrier, st):
+    """BASELINE configs[3] / north_star: ONE lincomb over D = 2^20 ciphertexts (snark.c:157-174 at GAMMA_D = 2^20) split by
+    ciphertext index over the N GPUs — rank r holds the contiguous range r of 2^20 / N ciphertexts resident (N = 1: the whole
+    136 GB region on one B200).  Two timings per lincomb: `latency` = lincomb + exchange back to back, the exchange on the
+    critical path (what one proof sees); `pipelined` = the exchange of lincomb i overlapped with lincomb i + 1 (throughput of
+    a stream of proofs).  Parity: rank 0 recomputes the whole sum alone through the fused AES + MAC kernel."""
+    Dt = 1 << 20
+    if Dt % world:
+        return {"skipped": f"2^20 is not divisible by {world} ranks"}
+    Dg, first = Dt // world, rank * (Dt // world)
+    c8g, hg = synth_inputs(Dt, 0)  # the same global instance on every rank
+    try:
+        d_c8 = torch.from_numpy(c8g[first: first + Dg].reshape(-1).copy()).cuda()
+        d_h = torch.from_numpy(hg[first: first + Dg].astype(np.uint32).view(np.int32)).cuda()
+        d_big = torch.empty(Dg * PLANAR_BYTES, dtype=torch.uint8, device="cuda")
+    except RuntimeError as e:  # (another tenant on the GPU: report, do not fail the bench line)
+        return {"skipped": f"allocation of {Dg * PLANAR_BYTES / 1e9:.1f} GB failed: {str(e)[:120]}"}
+    ctx.expand_dev(SEED, first * CTR_CT, d_c8.data_ptr(), Dg, d_big.data_ptr(), st)
+    torch.cuda.synchronize()
+
+    def one(coeffs):
+        if peer is not None:
+            return peer.step(d_big, coeffs, Dg)
+        return sl.step(d_big, coeffs, Dg)
+
+    for _ in range(3):
+        res = one(d_h)
+    barrier()
+    ctx.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        res = one(d_h)
+    e1.record()
+    barrier()
+    k_ms, k_n = ctx.profile_end()
+    lat_ms = e0.elapsed_time(e1) / steps
+    got = res.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64).copy()
+    pipe_ms = lat_ms
+    if ppipe is not None:
+        for _ in range(3):
+            ppipe.submit(d_big, d_h, Dg)
+        ppipe.drain()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(steps):
+            ppipe.submit(d_big, d_h, Dg)
+        ppipe.drain()
+        e3.record()
+        barrier()
+        pipe_ms = e2.elapsed_time(e3) / steps
+    t_all = torch.tensor([lat_ms, pipe_ms, k_ms / max(1, k_n)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    lat_ms, pipe_ms, kern_ms = (float(x) for x in t_all.tolist())
+    ok = None
+    if rank == 0:  # independent of the exchange: the whole 2^20-ciphertext sum on this GPU alone, a regenerated from AES
+        ok = bool(np.array_equal(ctx.eval_poly(SEED, 0, c8g, hg), got))
+        if not ok:
+            raise SystemExit("bench.py: strong_2e20: the sharded result differs from rank 0's own computation — numbers withheld")
+    barrier()
+    del d_big
+    torch.cuda.empty_cache()
+    return {"D_total": Dt, "ciphertexts_per_gpu": Dg, "resident_gb_per_gpu": Dg * PLANAR_BYTES / 1e9,
+            "ms_per_lincomb_latency": lat_ms, "mac_per_s_latency": Dt / (lat_ms * 1e-3),
+            "ms_per_lincomb_pipelined": pipe_ms, "mac_per_s_pipelined": Dt / (pipe_ms * 1e-3),
+            "kernel_ms": kern_ms, "kernel_gbs": Dg * ALGO_BYTES / (kern_ms * 1e-3) / 1e9,
+            "parity_independent_recompute": ok, "scaling": "strong",
+            "note": "latency: k_lincomb + finish (N > 1: fused with the peer-memory exchange) back to back, max over ranks; "
+                    "pipelined: exchange on a side stream under the next lincomb; kernel_*: k_lincomb alone (CUDA events in the library)"}
 
 
 def run_gpu_arm(args):
@@ -357,6 +439,48 @@ def run_gpu_arm(args):
     ms = float(t_all.item())
     result = d_rop.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64).copy()
 
+    def sync_step(coeffs, cts=None, d_local=None):
+        """one sharded lincomb with the exchange ON the critical path (no pipelining across steps)"""
+        cts = d_cts if cts is None else cts
+        d_local = D if d_local is None else d_local
+        if peer is not None:
+            return peer.step(cts, coeffs, d_local)   # k_lincomb + the finish kernel fused with the peer exchange
+        return sl.step(cts, coeffs, d_local)           # one GPU, or the NCCL exchange
+
+    # ---- parity outside the timed regions (1): a 64-ciphertext sample against the CPU oracle, through the SAME sharded
+    # resident path (scalars zero outside the sample: every rank contributes a run of 64 / N ciphertexts)
+    n_s = max(1, 64 // world)
+    run_at = lambda r: (7919 * (r + 1)) % (D - n_s)  # noqa: E731
+    h_sp = np.zeros(D, np.uint32)
+    h_sp[run_at(rank): run_at(rank) + n_s] = h[run_at(rank): run_at(rank) + n_s].astype(np.uint32)
+    d_hs = torch.from_numpy(h_sp.view(np.int32)).cuda()
+    got_s = sync_step(d_hs)
+    torch.cuda.synchronize()
+    got_s = got_s.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64).copy()
+    oracle_ok = multi_ok = None
+    if rank == 0:
+        from oracle.loader import Oracle  # the CPU restatement, here only as the checker
+        orc = Oracle()
+        want = None
+        for r in range(world):
+            c8_r, h_r = (c8, h) if r == rank else synth_inputs(D, r)
+            j = run_at(r)
+            want = orc.eval_poly(SEED, (r * D + j) * CTR_CT, c8_r[j: j + n_s], h_r[j: j + n_s], rop=want)
+        oracle_ok = bool(np.array_equal(got_s, want[:, :L64]))
+        if not oracle_ok:
+            raise SystemExit("bench.py: the sharded resident lincomb differs from the CPU oracle on the 64-ciphertext sample — numbers withheld")
+        # (2) N > 1: rank 0 ALONE recomputes the global sum of the timed step — every rank's ciphertext range through the
+        # fused AES + MAC kernel on this one GPU, no exchange involved — and compares it bit for bit with the exchanged result
+        if world > 1:
+            acc = np.zeros((NC, L64), np.uint64)
+            for r in range(world):
+                c8_r, h_r = (c8, h) if r == rank else synth_inputs(D, r)
+                acc = ctx.eval_poly(SEED, r * D * CTR_CT, c8_r, h_r, rop=acc)
+            multi_ok = bool(np.array_equal(acc, result))
+            if not multi_ok:
+                raise SystemExit("bench.py: the exchanged result differs from rank 0's own computation of the global sum — numbers withheld")
+    barrier()
+
     # ---- informational: the two-scalar-vector pass the prover uses over a resident region (k_lincomb<2>)
     d_r0 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
     d_r1 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
@@ -455,6 +579,21 @@ def run_gpu_arm(args):
     if rank == 0 and not check:
         raise SystemExit("bench.py: resident lincomb and fused eval_poly disagree — numbers withheld")
 
+    parity = {"resident_equals_fused": check, "oracle_sample_64_ciphertexts": oracle_ok,
+              "multi_gpu_independent_recompute": multi_ok,
+              "what": "resident lincomb == fused AES+MAC eval_poly (two independent kernels); a 64-ciphertext sample through the "
+                      "sharded resident path == the CPU oracle; N > 1: the exchanged result == rank 0 recomputing the global sum "
+                      "alone (mfb_eval_poly over every rank's range, no exchange)"}
+
+    # ---- BASELINE configs[3]: the 2^20-ciphertext lincomb split by ciphertext index over the N GPUs (strong scaling)
+    strong = None
+    if not args.no_strong:
+        if reg is not None:
+            reg = None
+        del d_cts, d_c8_e, d_h_e, d_co_r
+        torch.cuda.empty_cache()
+        strong = strong_2e20_leg(ctx, torch, dist, world, rank, steps, peer, ppipe, sl, barrier, st)
+
     if rank == 0:
         peak, peak_src = peaks()
         per_launch_ms = k_ms / max(1, k_n)
@@ -470,11 +609,11 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": world * D * steps / (ms * 1e-3), "unit": METRIC, "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"prover lincomb (eval_poly), D=2^{args.log2d} Regev ciphertexts per GPU resident in HBM "
-                                   f"({D * PLANAR_BYTES / 1e9:.2f} GB planar), n=1470, logq=736 (eff. 704), p=2^32-5",
+            "config": {"workload": workload_string(args.log2d),
+                       "path": f"ciphertexts resident in HBM ({D * PLANAR_BYTES / 1e9:.2f} GB tile-planar per GPU), k_lincomb + finish",
                        "ciphertexts_per_gpu": D, "l2": "inputs (8.49 GB per step) exceed the 126 MB L2; no flush needed",
                        "exchange": exchange,
-                       "parity_check": check},
+                       "parity_check": parity},
             "roofline": {"bound": "hbm", "kernel": "k_lincomb", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": D * ALGO_BYTES, "kernel_ms": per_launch_ms, "launches_timed": k_n},
@@ -492,16 +631,25 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world > 1:
+            line["parity_multi_gpu"] = bool(multi_ok)
+        if strong is not None:
+            peak_s = peak
+            strong["roofline_frac"] = strong["kernel_gbs"] / peak_s
+            line["strong_2e20"] = strong
         if world == 1 and not args.no_snark:
             line["snark"] = snark_latency(args.log2d, 64)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
             line["config1_reference_cpu"] = config1_reference()
         if world > 1 and not args.no_snark:
-            try:
-                line["snark_box"] = snark_box_latency(args.log2d + (world - 1).bit_length(), 64, world)
-            except Exception as e:  # noqa: BLE001  (reported, the bench line stands)
-                line["snark_box"] = {"error": str(e)[:300]}
+            # the full drop-in SNARK from ONE host thread over the N GPUs: the north-star instance (D = 2^20), and the
+            # weak-scaling instance (D = N * 2^16: per-GPU work as in the N = 1 `snark` leg)
+            for key, lg in (("snark_box", 20), ("snark_box_weak", args.log2d + (world - 1).bit_length())):
+                try:
+                    line[key] = snark_box_latency(lg, 64, world)
+                except Exception as e:  # noqa: BLE001  (reported, the bench line stands)
+                    line[key] = {"error": str(e)[:300]}
         emit(line)
     if world > 1 and not args.no_snark:
         # the other ranks wait for rank 0's box leg ON THE CPU (a c10d store key): an NCCL barrier would keep a kernel
@@ -544,6 +692,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=6000, help="ciphertexts timed by the 1-core cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-snark", action="store_true", help="skip the full setup/prove/verify latency leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 2^20-ciphertext strong-scaling leg")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = exchange fused into the finish kernel over NVLink peer memory (CUDA IPC); "
                          "nccl = u64-column reduce-scatter + carry + all-gather")
