@@ -826,7 +826,7 @@ extern "C" int mfb_ssp_prover_polys(mfb_ctx *ctx, const uint64_t *ssp, size_t D,
   size_t done = 0;
   do {
     const size_t cnt = pieces.size() - done < BATCH ? pieces.size() - done : BATCH;
-    if (done) PTRY(cudaStreamSynchronize(st));  // the staging area is reused: the previous accumulate must have read it
+    // (the staging area is reused in stream order: the previous accumulate has read it before the next copy lands)
     if (cnt && (rc = ctx_h2d_pieces(ctx, d_sel, pieces.data() + done, D * 8, cnt, st))) return rc;
     k_ssp_accumulate<<<gridfor(Du), 256, 0, st>>>((const uint64_t *)d_t, delta, (const uint64_t *)d_sel, (uint32_t)cnt, Du, first,
                                                    (uint32_t *)d_w);
@@ -881,9 +881,11 @@ extern "C" int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_
   for (size_t o = 0; rc == MFB_OK && o < total; o += STAGE) {
     const size_t cnt = total - o < STAGE ? total - o : STAGE;
     if ((rc = ctx_h2d(ctx, d_stage, ssp + o, cnt * 8, st)) != MFB_OK) break;
+    // (no synchronisation between batches: the staging area is reused in stream order, and the host packs the next
+    // batch into the pinned bounce buffers while this one is on the DMA engine)
     k_reduce_u64poly<<<gridfor((uint32_t)cnt), 256, 0, st>>>((const uint64_t *)d_stage, (uint32_t)cnt, h->blob + o);
     E.launches++;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
   }
   if (rc == MFB_OK && e == cudaSuccess) {
     e = cudaMemsetAsync(E.d_len, 0, 16, st);
@@ -1064,7 +1066,7 @@ extern "C" int mfb_ssp_eval(mfb_ctx *ctx, const uint64_t *polys, size_t D, size_
     k_eval<<<(unsigned)cnt, 256, 0, st>>>((const uint64_t *)d_p, (uint32_t)D, (const uint32_t *)d_pw, (uint64_t *)d_val + q);
     E.launches++;
     PTRY(cudaGetLastError());
-    if (q + per < npoly) PTRY(cudaStreamSynchronize(st));  // staging buffer reuse
+    // (the staging buffer is reused in stream order: no synchronisation between batches)
   }
   PTRY(cudaMemcpyAsync(values, d_val, npoly * 8, cudaMemcpyDeviceToHost, st));
   PTRY(cudaStreamSynchronize(st));

@@ -168,15 +168,22 @@ static int scratch(mfb_ctx *ctx, int i, size_t bytes, void **out) {
 // Pageable sources make cudaMemcpyAsync stage through a small driver buffer at 4-5 GB/s; here the pieces are packed
 // into two 64 MB pinned bounce buffers by a few host threads while the previous buffer is in flight on the DMA engine.
 static const size_t BOUNCE_BYTES = (size_t)64 << 20;
-static int h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces,
-                      cudaStream_t st) {
-  if (npieces == 0 || piece_bytes == 0) return MFB_OK;
+static int bounce_ready(mfb_ctx *ctx) {
   for (int k = 0; k < 2; k++) {
     if (!ctx->bounce[k]) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->bounce[k], BOUNCE_BYTES, cudaHostAllocDefault));
     if (!ctx->bounce_free[k]) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->bounce_free[k], cudaEventDisableTiming));
   }
+  return MFB_OK;
+}
+
+static int h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces,
+                      cudaStream_t st) {
+  if (npieces == 0 || piece_bytes == 0) return MFB_OK;
+  MFB_TRY(bounce_ready(ctx));
+  // measured on the B200 box (csrc/tune/h2d_probe.cu, 16 host threads): packing with 1 / 4 / 8 / 16 threads moves
+  // 14 / 27 / 34 / 43 GB/s end to end (cudaMemcpy from pageable memory: 11, cudaHostRegister + copy: 6)
   unsigned hw = std::thread::hardware_concurrency();
-  const unsigned nthreads = hw >= 16 ? 8 : hw >= 4 ? 4 : 1;
+  const unsigned nthreads = hw >= 16 ? 16 : hw >= 8 ? 8 : hw >= 4 ? 4 : 1;
   uint8_t *dst = (uint8_t *)dst_dev;
   size_t piece = 0, in_piece = 0;  // cursor over the logical concatenation
   int k = 0;
@@ -320,6 +327,14 @@ void mfb_ctx_destroy(mfb_ctx *ctx) {
   for (int i = 0; i < 2 * PROF_MAX; i++)
     if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
   delete ctx;
+}
+
+// pre-allocates the pinned staging a first call would otherwise pay for (2 x 64 MB bounce buffers, the accumulator staging)
+int mfb_ctx_warm(mfb_ctx *ctx) {
+  MFB_CHECK_CTX(ctx);
+  MFB_TRY(bounce_ready(ctx));
+  if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 5 * MFB_FLAT_CT_U64 * 8, cudaHostAllocDefault));
+  return MFB_OK;
 }
 
 int mfb_ctx_device(mfb_ctx *ctx) { return ctx ? ctx->device : -1; }

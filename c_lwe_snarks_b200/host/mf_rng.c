@@ -74,6 +74,7 @@ void aesctr_prg(aesctr_ptr stream, void *outbuf, size_t count) {
 }
 
 void rng_init(rng_t rs, uint8_t *rseed) {
+  mf_gpu_prefetch();
   uint64_t nonce;
   memcpy(&nonce, rseed, 8);
   aesctr_init((aesctr_ptr)rs, rseed + 8, nonce);

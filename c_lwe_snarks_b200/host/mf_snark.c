@@ -17,6 +17,7 @@
 #define FLAT_CT (MFB_FLAT_CT_U64)
 
 void proof_init(proof_t pi) {
+  mf_gpu_prefetch();
   ct_init(pi->h);
   ct_init(pi->hat_h);
   ct_init(pi->hat_v);
@@ -157,13 +158,32 @@ void mf_crs_make_resident(crs_t crs) {
 }
 
 /* ------------------------------------------------------------------ resident SSP blobs (addition) */
+/* A resident copy is keyed on the blob's address and instance size, and carries a FINGERPRINT of the blob (FNV-1a over
+ * 66 samples of 64 bytes spread over it).  Every use re-computes the fingerprint (a few microseconds): a blob that was
+ * rewritten, or freed and re-allocated at the same address, no longer matches, the stale copy is dropped and the caller
+ * falls back to the host blob.  (A modification that misses every sample is not detected: callers that edit single
+ * coefficients in place must call mf_ssp_release themselves — documented in the header.) */
 struct resident_ssp {
   const uint8_t *owner;
   mfb_ssp *h;
   size_t d, m;
+  uint64_t fp;
   struct resident_ssp *next;
 };
 static struct resident_ssp *g_resident_ssp = NULL;
+
+static uint64_t ssp_fingerprint(const uint8_t *blob, size_t D, size_t M) {
+  const size_t bytes = 8 * D * (M + 1), chunk = 64;
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  const size_t nsamp = 66;
+  for (size_t k = 0; k < nsamp; k++) {
+    size_t off = bytes <= chunk ? 0 : (size_t)((unsigned __int128)(bytes - chunk) * k / (nsamp - 1));
+    off &= ~(size_t)7;
+    const size_t n = bytes < chunk ? bytes : chunk;
+    for (size_t i = 0; i < n; i++) hsh = (hsh ^ blob[off + i]) * 0x100000001b3ull;
+  }
+  return hsh ^ (uint64_t)D ^ ((uint64_t)M << 32);
+}
 
 void mf_ssp_release(ssp_t ssp) {
   struct resident_ssp **pp = &g_resident_ssp;
@@ -179,30 +199,50 @@ void mf_ssp_release(ssp_t ssp) {
   }
 }
 
-void mf_ssp_make_resident(ssp_t ssp) {
+static mfb_ssp *ssp_make_resident(ssp_t ssp, int quiet) {
   mf_ssp_release(ssp);
   struct resident_ssp *r = calloc(1, sizeof(*r));
   if (!r) mf_die("malloc");
   r->owner = ssp;
   r->d = GAMMA_D;
   r->m = GAMMA_M;
+  r->fp = ssp_fingerprint(ssp, r->d, r->m);
   const int rc = mfb_ssp_create(mf_gpu(), (const uint64_t *)ssp, r->d, r->m, &r->h);
   if (rc != MFB_OK) {
-    fprintf(stderr, "mangiafuoco_b200: mf_ssp_make_resident: %s; the SSP stays on the host\n", mfb_last_error());
+    if (!quiet) fprintf(stderr, "mangiafuoco_b200: mf_ssp_make_resident: %s; the SSP stays on the host\n", mfb_last_error());
     free(r);
-    return;
+    return NULL;
   }
   r->next = g_resident_ssp;
   g_resident_ssp = r;
+  return r->h;
 }
+
+void mf_ssp_make_resident(ssp_t ssp) { (void)ssp_make_resident(ssp, 0); }
 
 static mfb_ssp *resident_ssp_find(ssp_t ssp) {
   for (struct resident_ssp *r = g_resident_ssp; r; r = r->next)
-    if (r->owner == ssp && r->d == GAMMA_D && r->m == GAMMA_M) return r->h;
+    if (r->owner == ssp && r->d == GAMMA_D && r->m == GAMMA_M) {
+      if (ssp_fingerprint(ssp, r->d, r->m) == r->fp) return r->h;
+      mf_ssp_release(ssp); /* the blob changed under the resident copy: drop it, use the host blob */
+      return NULL;
+    }
   return NULL;
 }
 
+/* setup(), prover() and verifier() all read the same dense blob (8 D (M + 3) bytes: 5.7 GB at the reference's default
+ * instance).  Unless $MF_B200_NO_AUTO_SSP is set, the first of them to see a blob uploads it ONCE (as u32 residues) and
+ * the others find it resident — the reference's own programs, which cannot call mf_ssp_make_resident, then pay the PCIe
+ * transfer once instead of in every call.  Returns NULL when disabled or when the blob does not fit. */
+static mfb_ssp *resident_ssp_auto(ssp_t ssp) {
+  mfb_ssp *h = resident_ssp_find(ssp);
+  if (h) return h;
+  if (getenv("MF_B200_NO_AUTO_SSP")) return NULL;
+  return ssp_make_resident(ssp, 1);
+}
+
 void crs_init(crs_t crs) { /* snark.c:35-48 */
+  mf_gpu_prefetch();
   mf_entropy(crs->seed, sizeof(rseed_t));
   crs->s = malloc(CT_BYTES * GAMMA_D);
   crs->as = malloc(CT_BYTES * GAMMA_D);
@@ -270,7 +310,8 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
    * dense blob [t, v_0, ..., v_{M-1}] (ssp.h:6-9); v_0(s) is computed and not used, as its slot is skipped there */
   uint64_t *vals = malloc((M + 1) * 8);
   if (!vals) mf_die("malloc");
-  mfb_ssp *rssp = resident_ssp_find(ssp);
+  mfb_ssp *rssp = resident_ssp_auto(ssp); /* uploads the blob once; prover() and verifier() then find it on the device */
+  mf_trace("setup.ssp_resident", t0);
   if (rssp)
     MF_GPU(mfb_ssp_eval_resident(mf_gpu(), rssp, 0, M + 1, vrs->s, vals));
   else
@@ -379,7 +420,7 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
   }
 
   double t0 = mf_now();
-  mfb_ssp *rssp = resident_ssp_find(ssp);
+  mfb_ssp *rssp = resident_ssp_auto(ssp);
   struct resident *res = resident_find(crs);
   const int all_resident = rssp && res && res->d == D && (res->ms || (res->s && res->as));
 

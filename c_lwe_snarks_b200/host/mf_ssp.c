@@ -17,6 +17,7 @@ void nmod_poly_import(nmod_poly_t *pp, void *buf, size_t degree) { /* ssp.c:28-3
 /* ssp.c:37-77.  Entropy, in order: M/8 bytes for the witness, then M draws of 8*D bytes (v_0 .. v_{M-1}).
  * t := v_0 + sum_{i>=1, w_{i-1}=1} v_i - 1, so that t | (v^2 - 1) with v = v_0 + sum w_i v_i. */
 void random_ssp(mpz_t input, uint8_t *circuit) {
+  mf_gpu_prefetch();
   const size_t D = GAMMA_D, M = GAMMA_M;
   uint8_t *buf = malloc(8 * D);
   if (!buf) mf_die("malloc");

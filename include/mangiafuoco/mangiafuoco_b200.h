@@ -257,8 +257,13 @@ void mf_crs_release(crs_t crs);
  * (testing on a one-GPU box). */
 void mf_set_devices(int n, int spread);
 /* The same for the SSP instance: the dense blob is uploaded once (as u32 residues) and the Newton inverse that the
- * prover's division h = (v^2 - 1)/t needs is cached with it; prover() then only ships the witness.  The blob must not
- * change while it is resident (mf_ssp_release before modifying or freeing it). */
+ * prover's division h = (v^2 - 1)/t needs is cached with it; prover() then only ships the witness.
+ * setup() and prover() do this BY THEMSELVES for the blob they are given (unless $MF_B200_NO_AUTO_SSP is set): the
+ * reference's own programs, which know nothing of this call, then move the blob over PCIe once instead of in every
+ * call.  Staleness rule: a resident copy is keyed on the blob's address and instance size and carries a fingerprint
+ * (FNV-1a over 66 samples of 64 bytes spread over the blob) that is re-checked on every use — a blob that was
+ * regenerated, or freed and re-allocated at the same address, is detected, the copy is dropped and the host blob is
+ * used.  An in-place edit that misses every sample is NOT detected: call mf_ssp_release(ssp) after such an edit. */
 void mf_ssp_make_resident(ssp_t ssp);
 void mf_ssp_release(ssp_t ssp);
 /* Persistence (the reference only sketches a "crs.mfuoco" mmap, benchmark_snark.c:23-24): the CRS file is a 24-byte

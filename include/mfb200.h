@@ -71,6 +71,8 @@ typedef void (*mfb_entropy_fn)(void *user, uint8_t *dst, size_t nbytes);
 /* ---- context ------------------------------------------------------------------------------ */
 MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
 MFB_API void mfb_ctx_destroy(mfb_ctx *ctx);
+/* optional: allocate the pinned staging buffers now instead of inside the first call that needs them */
+MFB_API int mfb_ctx_warm(mfb_ctx *ctx);
 MFB_API const char *mfb_last_error(void);
 MFB_API int mfb_device_sm_count(mfb_ctx *ctx);
 MFB_API int mfb_ctx_device(mfb_ctx *ctx);

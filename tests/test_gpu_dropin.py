@@ -308,3 +308,35 @@ def test_setup_over_a_resident_crs_drops_the_stale_regions():
         assert sn.verify()[0]
     finally:
         sn.close()
+
+
+def test_auto_resident_ssp_detects_a_regenerated_blob():
+    """setup() / prover() keep the SSP blob they are given resident on the device by themselves.  A blob that is
+    REGENERATED IN PLACE (same address, new contents) must not be served from the stale copy: the fingerprint check
+    drops it and the new instance proves and verifies."""
+    from c_lwe_snarks_b200.snark import Snark
+    sn = Snark(128, 16)
+    try:
+        for _ in range(3):  # same buffer, three different instances
+            sn.random_ssp()
+            sn.setup()
+            sn.prove()
+            assert sn.verify()[0]
+        sn.tamper()
+        assert not sn.verify()[0]
+    finally:
+        sn.lib.mf_ssp_release(sn._ssp_ptr())
+        sn.close()
+
+
+def test_host_blob_path_without_auto_residency(dropin, monkeypatch):
+    """$MF_B200_NO_AUTO_SSP: setup() and prover() stream the dense blob from host memory on every call (the path a blob
+    too large for the device takes) — same CRS, same proof."""
+    g = GOLD["snark_d64_m16"]
+    dropin.set_instance(g["D"], g["M"])
+    monkeypatch.setenv("MF_B200_NO_AUTO_SSP", "1")
+    r = run_snark(dropin, g["D"], g["M"], xof("snark-entropy-d64-m16", g["entropy_bytes"]))
+    assert sha(r["crs"]["s"]) == g["crs_s_sha"] and sha(r["crs"]["as_"]) == g["crs_as_sha"]
+    for k in range(5):
+        assert sha(r["proof"][k]) == g["proof_sha"][k]
+    assert r["ok"] and not r["ok_bad"]
