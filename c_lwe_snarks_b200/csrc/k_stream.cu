@@ -390,6 +390,10 @@ k_bcoord(const uint8_t *__restrict__ c8, const uint32_t *__restrict__ coeffs0, c
 constexpr int KE_PRODUCERS = KS_THREADS;        // 512 threads = 16 warps
 constexpr int KE_CONSUMERS = 128;               // 4 warps
 constexpr int KE_THREADS = KE_PRODUCERS + KE_CONSUMERS;
+// register budget per thread after the re-balancing: 640 threads x 96 = 61440 registers at launch;
+// 512 x 80 + 128 x 160 = 61440
+constexpr int KE_PRODUCER_REGS = 80;
+constexpr int KE_CONSUMER_REGS = 160;
 
 __global__ void __launch_bounds__(KE_THREADS, 1)
 k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
@@ -421,6 +425,11 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
 
   if (threadIdx.x < KE_PRODUCERS) {
     // ---------------------------------------------------------------- producers: keystream only
+    // The CTA's register file is re-balanced between the two roles (setmaxnreg, warpgroup-wide): the 16 producer warps
+    // give registers back, the consumer warpgroup takes them — its 22 x 22-limb product needs the accumulator (43), one
+    // operand (22) and the other operand's limbs in flight at once, which does not fit the 96 registers a 640-thread
+    // CTA starts with.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(KE_PRODUCER_REGS));
     AesCtrCache cache;
     cache.window = ~0ull;
     for (size_t t = 0; t < nitems; t++) {
@@ -435,6 +444,7 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   }
 
   // ------------------------------------------------------------------ consumers: <a, sk> and the record
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(KE_CONSUMER_REGS));
   const int ct_id = threadIdx.x - KE_PRODUCERS;  // 0..127
   Acc704 acc;
   acc_zero(acc);
@@ -445,16 +455,10 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
     ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));
     const TileGeom g = tile_geom(offset + k * (uint64_t)CTR_CT, tile);
     for (int lc = ct_id; lc < KS_TILE; lc += KE_CONSUMERS) {
-      uint32_t a[22], w[22];
+      uint32_t a[22];
       const int c = tile * KS_TILE + lc;
-#pragma unroll
-      for (int j = 0; j < L64; j++) {
-        const uint64_t v = __ldg(sk + (size_t)j * NCP + c);
-        w[2 * j] = (uint32_t)v;
-        w[2 * j + 1] = (uint32_t)(v >> 32);
-      }
       ks_read_coord(buf_of(b), g.delta + CT_BYTES * lc, a);
-      acc_mul(acc, a, w);
+      acc_mul_ld(acc, a, sk + c, NCP);  // the key's limbs are read (L1 / L2) as the rows need them
     }
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
