@@ -116,24 +116,6 @@ __device__ __forceinline__ void acc_mul(Acc704 &x, const uint32_t (&a)[22], cons
   acc_mul_rows<0>(x, a, b);
 }
 
-// The same with the second operand read from memory limb by limb (64-bit limb row j of coordinate-planar data at
-// b64[j * stride]): the 22 limbs of b never sit in registers together — what keeps the consumer warps of k_encrypt
-// (accumulator 43 + a 22 registers) under the 102-register ceiling of a 640-thread CTA without spilling.
-template <int J>
-__device__ __forceinline__ void acc_mul_rows_ld(Acc704 &x, const uint32_t (&a)[22], const uint64_t *__restrict__ b64, size_t stride) {
-  if constexpr (J < L64) {
-    const uint64_t v = __ldg(b64 + (size_t)J * stride);
-    acc_mul_chain<2 * J, 0>(x, a, (uint32_t)v);
-    acc_mul_chain<2 * J, 1>(x, a, (uint32_t)v);
-    acc_mul_chain<2 * J + 1, 0>(x, a, (uint32_t)(v >> 32));
-    acc_mul_chain<2 * J + 1, 1>(x, a, (uint32_t)(v >> 32));
-    acc_mul_rows_ld<J + 1>(x, a, b64, stride);
-  }
-}
-__device__ __forceinline__ void acc_mul_ld(Acc704 &x, const uint32_t (&a)[22], const uint64_t *__restrict__ b64, size_t stride) {
-  acc_mul_rows_ld<0>(x, a, b64, stride);
-}
-
 // r[0..21] = (E + (O << 32)) mod 2^704
 __device__ __forceinline__ void acc_fold(const Acc704 &x, uint32_t (&r)[22]) {
   r[0] = x.E[0];
