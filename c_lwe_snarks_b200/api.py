@@ -67,6 +67,8 @@ _SIGS = {
     "mfb_lincomb2_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "mfb_region_lincomb2": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, _u32p, C.c_size_t, _u64p, _u64p]),
     "mfb_lincomb_generic_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "mfb_encrypt_generic_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _u8p, C.c_uint64, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                         C.c_size_t, _vp, _vp]),
     "mfb_lincomb": (C.c_int, [_vp, _u64p, _u32p, C.c_size_t, _u64p]),
     "mfb_region_create": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, C.POINTER(_vp)]),
     "mfb_region_create_async": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, _vp, C.POINTER(_vp)]),
@@ -589,6 +591,11 @@ class Context:
                      rop1_out: int, stream: int = 0):
         self._ck(self.lib.mfb_lincomb2_dev(self.h, cts_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in, rop0_out, rop1_in, rop1_out,
                                            stream))
+
+    def encrypt_generic_dev(self, limbs64: int, n: int, ct_bytes: int, seed, offset: int, sk_ptr: int, sk_stride: int, msg_ptr: int,
+                            ent_ptr: int, ent_stride: int, ent_nbytes: int, count: int, out_ptr: int, stream: int = 0):
+        self._ck(self.lib.mfb_encrypt_generic_dev(self.h, limbs64, n, ct_bytes, _p8(_seed(seed)), offset, sk_ptr, sk_stride, msg_ptr,
+                                                  ent_ptr, ent_stride, ent_nbytes, count, out_ptr, stream))
 
     def lincomb_generic_dev(self, limbs64: int, ncoords: int, cts_ptr: int, coeffs_ptr: int, d: int, out_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_lincomb_generic_dev(self.h, limbs64, ncoords, cts_ptr, coeffs_ptr, d, out_ptr, stream))

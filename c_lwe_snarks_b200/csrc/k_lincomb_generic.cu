@@ -10,18 +10,6 @@
 
 namespace mfb {
 
-template <int L>  // L = 64-bit limbs
-struct AccG {
-  uint32_t E[2 * L];
-  uint32_t O[2 * L - 1];
-};
-
-template <int L>
-__device__ __forceinline__ void accg_mad(AccG<L> &x, const uint32_t (&a)[2 * L], uint32_t s) {
-  MadChain<L, false>::template run<0, 0>(x.E, a, s);
-  MadChain<L - 1, true>::template run<0, 1>(x.O, a, s);
-}
-
 __device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void g_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -32,7 +20,10 @@ __device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-constexpr int GS = 2, GG = 2;  // ring: stages x blocks per stage
+// ring: GS stages x GG blocks (ciphertext tiles of L * 512 bytes) per stage, ~11 KB per stage as in K1: short limb
+// vectors get more blocks per stage so that as many bytes stay in flight
+constexpr int GS = 2;
+template <int L> struct GgOf { static constexpr int value = 11264 / (L * 512) >= 4 ? 4 : 2; };
 
 // grid (ntiles, nslots); queue[tile*32]; partial[slot][tile][L][64] (same tile-planar shape as one ciphertext)
 template <int L>
@@ -40,6 +31,7 @@ __global__ void __launch_bounds__(64)
 k_lincomb_g(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeffs, size_t d, uint32_t chunk_len,
             unsigned int *__restrict__ queue, uint64_t *__restrict__ partial) {
   constexpr int TB = L * 64 * 8;  // tile bytes
+  constexpr int GG = GgOf<L>::value;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * GS];
   __shared__ uint32_t meta_first[GS], meta_n[GS];
@@ -70,11 +62,8 @@ k_lincomb_g(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeff
   };
   if (threadIdx.x == 0)
     for (int s = 0; s < GS; s++) issue(s);
-  AccG<L> acc;
-#pragma unroll
-  for (int i = 0; i < 2 * L; i++) acc.E[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 2 * L - 1; i++) acc.O[i] = 0;
+  AccN<2 * L> acc;
+  acc_zero(acc);
   for (uint32_t it = 0;; it++) {
     const int s = (int)(it % GS);
     const uint32_t ph = (it / GS) & 1;
@@ -87,7 +76,7 @@ k_lincomb_g(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeff
       uint32_t a[2 * L];
 #pragma unroll
       for (int j = 0; j < L; j++) { const uint64_t v = sp[j * 64]; a[2 * j] = (uint32_t)v; a[2 * j + 1] = (uint32_t)(v >> 32); }
-      accg_mad<L>(acc, a, __ldg(coeffs + first + g));
+      acc_mad(acc, a, __ldg(coeffs + first + g));
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) g_mbar_arrive(bbase + 8 * (GS + s));
@@ -95,57 +84,80 @@ k_lincomb_g(const uint64_t *__restrict__ cts, const uint32_t *__restrict__ coeff
   }
   // fold E + (O << 32) and write the partial
   uint32_t r[2 * L];
-  r[0] = acc.E[0];
-  AddChain<2 * L - 1>::template run<1, 1, 0>(r, acc.E, acc.O);
+  acc_fold(acc, r);
   uint64_t *out = partial + (size_t)blockIdx.y * ct_u64 + (size_t)tile * L * 64 + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < L; j++) out[j * 64] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
 }
 
-// out (tile-planar, one ciphertext shape) = sum of nparts partials mod 2^(64 L); also re-arms the queues
+// out (tile-planar, one ciphertext shape) = sum of nparts partials mod 2^(64 L); also re-arms the queues.
+// CTA = 64 coordinates x GF_SLICES slices of the partial index (independent loads in flight), met in shared memory.
+template <int L> struct GfSlices { static constexpr int value = L > 12 ? 4 : 8; };  // (static shared memory <= 48 KB)
 template <int L>
-__global__ void __launch_bounds__(64) k_finish_g(const uint64_t *__restrict__ partial, int nparts, uint64_t *out, unsigned int *queue) {
-  const int tile = blockIdx.x;
+__device__ __forceinline__ void addL(uint64_t (&r)[L], const uint64_t (&b)[L]) {
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+    const uint64_t s1 = r[j] + b[j];
+    const uint64_t c1 = s1 < b[j];
+    const uint64_t s2 = s1 + carry;
+    const uint64_t c2 = s2 < carry;
+    r[j] = s2;
+    carry = c1 + c2;
+  }
+}
+template <int L>
+__global__ void __launch_bounds__(64 * GfSlices<L>::value) k_finish_g(const uint64_t *__restrict__ partial, int nparts, uint64_t *out, unsigned int *queue) {
+  constexpr int GF_SLICES = GfSlices<L>::value;
+  __shared__ uint64_t sm[GF_SLICES - 1][L][64];
+  const int tile = blockIdx.x, cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const size_t ct_u64 = (size_t)gridDim.x * L * 64;
   if (threadIdx.x == 0) queue[tile * 32] = 0;
   uint64_t r[L];
 #pragma unroll
   for (int j = 0; j < L; j++) r[j] = 0;
-  for (int k = 0; k < nparts; k++) {
-    const uint64_t *p = partial + (size_t)k * ct_u64 + (size_t)tile * L * 64 + threadIdx.x;
-    unsigned long long carry = 0;
+  for (int k = slice; k < nparts; k += GF_SLICES) {
+    const uint64_t *p = partial + (size_t)k * ct_u64 + (size_t)tile * L * 64 + cl;
+    uint64_t b[L];
 #pragma unroll
-    for (int j = 0; j < L; j++) {
-      const uint64_t b = p[j * 64];
-      const uint64_t s1 = r[j] + b;
-      const uint64_t c1 = s1 < b;
-      const uint64_t s2 = s1 + carry;
-      const uint64_t c2 = s2 < carry;
-      r[j] = s2;
-      carry = c1 + c2;
-    }
+    for (int j = 0; j < L; j++) b[j] = p[j * 64];
+    addL<L>(r, b);
   }
-  uint64_t *o = out + (size_t)tile * L * 64 + threadIdx.x;
+  if (slice > 0) {
 #pragma unroll
-  for (int j = 0; j < L; j++) o[j * 64] = r[j];
+    for (int j = 0; j < L; j++) sm[slice - 1][j][cl] = r[j];
+  }
+  __syncthreads();
+  if (slice == 0) {
+    for (int s2 = 0; s2 < GF_SLICES - 1; s2++) {
+      uint64_t b[L];
+#pragma unroll
+      for (int j = 0; j < L; j++) b[j] = sm[s2][j][cl];
+      addL<L>(r, b);
+    }
+    uint64_t *o = out + (size_t)tile * L * 64 + cl;
+#pragma unroll
+    for (int j = 0; j < L; j++) o[j * 64] = r[j];
+  }
 }
 
 template <int L>
 static cudaError_t run_generic(const uint64_t *cts, const uint32_t *coeffs, size_t d, int ntiles, uint64_t *out, uint64_t *partial_ws,
                                size_t partial_cap_u64, unsigned int *queue, int sm_count, cudaStream_t st) {
+  constexpr int GG = GgOf<L>::value;
   const int smem = GS * GG * L * 64 * 8;
   cudaError_t e = cudaFuncSetAttribute(k_lincomb_g<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lincomb_g<L>, 64, smem) != cudaSuccess || occ < 1) occ = 4;
   size_t nslots = (size_t)sm_count * occ / ntiles;
-  const size_t chunks = (d + 3) / 4;
+  const size_t chunks = (d + GS * GG - 1) / (GS * GG);
   if (nslots > chunks) nslots = chunks;
   const size_t ct_u64 = (size_t)ntiles * L * 64;
   if (nslots * ct_u64 > partial_cap_u64) nslots = partial_cap_u64 / ct_u64;
   if (nslots < 1) nslots = 1;
-  k_lincomb_g<L><<<dim3(ntiles, (unsigned)nslots), 64, smem, st>>>(cts, coeffs, d, 4, queue, partial_ws);
-  k_finish_g<L><<<ntiles, 64, 0, st>>>(partial_ws, (int)nslots, out, queue);
+  k_lincomb_g<L><<<dim3(ntiles, (unsigned)nslots), 64, smem, st>>>(cts, coeffs, d, GS * GG, queue, partial_ws);
+  k_finish_g<L><<<ntiles, 64 * GfSlices<L>::value, 0, st>>>(partial_ws, (int)nslots, out, queue);
   return cudaGetLastError();
 }
 

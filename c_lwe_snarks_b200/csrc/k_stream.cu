@@ -535,6 +535,170 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
   }
 }
 
+// ------------------------------------------------------------------------------------ Regev encryption, other (n, log q)
+// BASELINE configs[4]: the reference implements ONE parameter set (lwe.h:23-31; any other GAMMA_LOGQ is `#error "Not
+// implemented"`, lwe.h:119-121), so this kernel has no reference output to match: it is the design of k_encrypt with the
+// limb count a template parameter and n, the coordinate width and the tiling run-time values, checked against plain
+// integer arithmetic:
+//   coordinate j of ciphertext k = little-endian integer of the ctb = log q / 8 stream bytes at offset + (k n + j) ctb,
+//   reduced mod q_eff = 2^(64 L), L = floor(log q / 64) (what lwe.h:108-118 does for 736: mask, then drop the top limb);
+//   b_k = (e_k p + <sk, a_k> + m_k) mod q_eff, written as a ctb-byte record.
+// A ciphertext is cut into `ntiles` tiles of at most `tile` coordinates (tile * ctb <= the 45 KB keystream buffer).
+template <int L>
+__global__ void __launch_bounds__(KE_THREADS, 1)
+k_encrypt_g(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
+            const uint64_t *__restrict__ sk, int sk_stride, const uint64_t *__restrict__ msg, const uint8_t *__restrict__ ent,
+            int ent_stride, int ent_nbytes, size_t count, int n, int ctb, int tile, int ntiles, uint8_t *__restrict__ out_c8) {
+  constexpr int NL = 2 * L;
+  extern __shared__ __align__(16) uint8_t dyn[];
+  __shared__ __align__(8) uint64_t bars[2 * KS_NBUF];
+  __shared__ uint32_t cols[2][2 * NL];
+  __shared__ uint32_t arrived[2];
+  KsSmem s = ks_smem_setup(dyn, t0_global);
+  auto buf_of = [&](int b) { return b == 0 ? s.buf[0] : s.buf[1] + (uint32_t)(b - 1) * (uint32_t)KS_BUF_BYTES; };
+  const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(bars);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < KS_NBUF; b++) {
+      ksb_init(bbase + 8 * b, KE_PRODUCERS / 32);
+      ksb_init(bbase + 8 * (KS_NBUF + b), KE_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    arrived[0] = arrived[1] = 0;
+  }
+  if (threadIdx.x < 4 * NL) cols[threadIdx.x / (2 * NL)][threadIdx.x % (2 * NL)] = 0;
+  const int lane = threadIdx.x & 31;
+  const size_t per = count / gridDim.x, rem = count % gridDim.x;
+  const size_t k0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+  const size_t nct = per + (blockIdx.x < rem ? 1 : 0);
+  const size_t nitems = nct * (size_t)ntiles;
+  const uint64_t ct_stream = (uint64_t)n * (uint64_t)ctb;  // stream bytes per ciphertext
+  auto geom = [&](size_t t) {
+    const size_t k = k0 + t / ntiles;
+    const int tl = (int)(t % ntiles);
+    const uint64_t off = offset + k * ct_stream + (uint64_t)tl * tile * ctb;
+    const int nco = n - tl * tile < tile ? n - tl * tile : tile;
+    TileGeom g;
+    g.first = off >> 4;
+    g.delta = (uint32_t)(off & 15);
+    g.nblk = (int)((g.delta + (uint32_t)nco * ctb + 15) >> 4);
+    return g;
+  };
+  __syncthreads();
+
+  if (threadIdx.x < KE_PRODUCERS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(KE_PRODUCER_REGS));
+    AesCtrCache cache;
+    cache.window = ~0ull;
+    for (size_t t = 0; t < nitems; t++) {
+      const int b = (int)(t % KS_NBUF);
+      if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));
+      const TileGeom g = geom(t);
+      ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+      __syncwarp();
+      if (lane == 0) ksb_arrive(bbase + 8 * b);
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(KE_CONSUMER_REGS));
+  const int ct_id = threadIdx.x - KE_PRODUCERS;
+  AccN<NL> acc;
+  acc_zero(acc);
+  for (size_t t = 0; t < nitems; t++) {
+    const int b = (int)(t % KS_NBUF);
+    const int tl = (int)(t % ntiles);
+    const size_t k = k0 + t / ntiles;
+    ksb_wait(bbase + 8 * b, (uint32_t)((t / KS_NBUF) & 1));
+    const TileGeom g = geom(t);
+    const int nco = n - tl * tile < tile ? n - tl * tile : tile;
+    for (int lc = ct_id; lc < nco; lc += KE_CONSUMERS) {
+      uint32_t a[NL], w[NL];
+      const int c = tl * tile + lc;
+#pragma unroll
+      for (int j = 0; j < L; j++) {
+        const uint64_t v = __ldg(sk + (size_t)j * sk_stride + c);
+        w[2 * j] = (uint32_t)v;
+        w[2 * j + 1] = (uint32_t)(v >> 32);
+      }
+      {  // the NL live limbs of the coordinate that starts at byte pos of the keystream buffer
+        const uint32_t pos = g.delta + (uint32_t)ctb * lc;
+        const uint32_t wa = buf_of(b) + (pos & ~3u), sh = (pos & 3u) * 8;
+        uint32_t lo = lds32(wa);
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+          const uint32_t hi = lds32(wa + 4 * (l + 1));
+          a[l] = __funnelshift_r(lo, hi, sh);
+          lo = hi;
+        }
+      }
+      acc_mul(acc, a, w);
+    }
+    __syncwarp();
+    if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
+
+    if (tl == ntiles - 1) {
+      const int slot = (int)((t / ntiles) & 1);
+      uint32_t r[NL];
+      acc_fold(acc, r);
+      acc_zero(acc);
+      uint32_t mylo = 0, myhi = 0;
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, r[l] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, r[l] >> 16);
+        if (lane == l) {
+          mylo = lo;
+          myhi = hi;
+        }
+      }
+      if (lane < NL) {
+        atomicAdd(&cols[slot][2 * lane], mylo);
+        atomicAdd(&cols[slot][2 * lane + 1], myhi);
+      }
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        prev = atomicAdd(&arrived[slot], 1u);
+      }
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == KE_CONSUMERS / 32 - 1) {
+        __threadfence_block();
+        unsigned long long col = 0;
+        uint32_t el = 0;
+        if (lane < NL) {
+          volatile uint32_t *cv = cols[slot];
+          col = (unsigned long long)cv[2 * lane] + ((unsigned long long)cv[2 * lane + 1] << 16);
+          cv[2 * lane] = 0;
+          cv[2 * lane + 1] = 0;
+          const uint8_t *e8 = ent + k * (size_t)ent_stride;
+          for (int i = 0; i < 4; i++) {
+            const int byte = 4 * lane + i;
+            if (byte < ent_nbytes) el |= (uint32_t)e8[byte] << (8 * i);
+          }
+        }
+        if (lane == 0) *(volatile uint32_t *)&arrived[slot] = 0;
+        const uint64_t mm = msg[k];
+        uint64_t carry = 0;
+        uint32_t myb = 0;
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+          uint64_t tt = __shfl_sync(0xffffffffu, col, l) + carry;
+          if (l == 0) tt += mm & 0xffffffffu;
+          if (l == 1) tt += mm >> 32;
+          const uint64_t prod = (uint64_t)__shfl_sync(0xffffffffu, el, l) * P;
+          const uint64_t sum = tt + prod;
+          const uint64_t c_out = sum < prod ? 1 : 0;
+          carry = (sum >> 32) + (c_out << 32);
+          if (lane == l) myb = (uint32_t)sum;
+        }
+        // the record: NL live words, then zero up to ctb bytes (ctb is a multiple of 4, ctb / 4 <= 32)
+        if (lane < ctb / 4) reinterpret_cast<uint32_t *>(out_c8 + k * (size_t)ctb)[lane] = lane < NL ? myb : 0u;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ launchers
 static cudaError_t ks_attr(const void *fn) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_SMEM_BYTES);
@@ -637,6 +801,34 @@ cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offse
   k_encrypt<<<(unsigned)grid, KE_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, msg, ent, ent_stride, ent_nbytes,
                                                                count, out_c8);
   return cudaGetLastError();
+}
+
+template <int L>
+static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk, int sk_stride,
+                                 const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, int n, int ctb,
+                                 uint8_t *out_c8, int sm_count, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt_g<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const int max_tile = KS_TILE_BYTES / ctb;  // coordinates whose keystream fits one buffer
+  const int ntiles = (n + max_tile - 1) / max_tile;
+  const int tile = (n + ntiles - 1) / ntiles;  // balanced
+  const size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
+  k_encrypt_g<L><<<(unsigned)grid, KE_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, sk_stride, msg, ent, ent_stride, ent_nbytes,
+                                                                      count, n, ctb, tile, ntiles, out_c8);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt_generic(int limbs64, const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
+                                   int sk_stride, const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes,
+                                   size_t count, int n, int ctb, uint8_t *out_c8, int sm_count, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  switch (limbs64) {
+#define MFB_CASE(Lv) \
+  case Lv: return run_encrypt_g<Lv>(key, t0, offset, sk, sk_stride, msg, ent, ent_stride, ent_nbytes, count, n, ctb, out_c8, sm_count, st);
+    MFB_CASE(4) MFB_CASE(6) MFB_CASE(8) MFB_CASE(10) MFB_CASE(11) MFB_CASE(12) MFB_CASE(13) MFB_CASE(14) MFB_CASE(16)
+#undef MFB_CASE
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace mfb

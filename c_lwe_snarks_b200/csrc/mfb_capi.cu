@@ -61,6 +61,9 @@ cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uin
 cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
                            const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
                            uint8_t *out_c8, int sm_count, cudaStream_t st);
+cudaError_t launch_encrypt_generic(int limbs64, const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
+                                   int sk_stride, const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes,
+                                   size_t count, int n, int ctb, uint8_t *out_c8, int sm_count, cudaStream_t st);
 cudaError_t launch_decrypt(const uint64_t *sk, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,
                            uint64_t *out_m, uint64_t *out_dot, cudaStream_t st);
 cudaError_t launch_flat_to_planar(const uint64_t *flat, int n, size_t count, uint64_t *planar, int tiled,
@@ -818,6 +821,27 @@ int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const
   aes_host::expand(seed, &key);
   MFB_CUDA_TRY(launch_encrypt(key, ctx->t0_dev, offset, sk_planar_dev, msg_dev, ent_dev, ent_stride, ent_nbytes, count,
                               out_c8_dev, ctx->sm_count, (cudaStream_t)stream));
+  if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_encrypt_generic_dev(mfb_ctx *ctx, int limbs64, int n, int ct_bytes, const uint8_t seed[40], uint64_t offset,
+                            const uint64_t *sk_planar_dev, int sk_stride, const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride,
+                            int ent_nbytes, size_t count, uint8_t *out_c8_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || (count && (!sk_planar_dev || !msg_dev || !ent_dev || !out_c8_dev)))
+    return set_err(MFB_EARG, "mfb_encrypt_generic_dev: null pointer");
+  if (n < 1 || n > 4096 || sk_stride < n) return set_err(MFB_EARG, "mfb_encrypt_generic_dev: need 1 <= n <= 4096 and sk_stride >= n");
+  if (ct_bytes % 4 || ct_bytes < 8 * limbs64 || ct_bytes > 128)
+    return set_err(MFB_EARG, "mfb_encrypt_generic_dev: ct_bytes (log q / 8) must be a multiple of 4 with 8 * limbs64 <= ct_bytes <= 128");
+  if (ent_nbytes < 0 || ent_nbytes > 8 * limbs64 || ent_stride < ent_nbytes)
+    return set_err(MFB_EARG, "mfb_encrypt_generic_dev: need 0 <= ent_nbytes <= 8 * limbs64 and ent_stride >= ent_nbytes");
+  AesKey key;
+  aes_host::expand(seed, &key);
+  cudaError_t e = launch_encrypt_generic(limbs64, key, ctx->t0_dev, offset, sk_planar_dev, sk_stride, msg_dev, ent_dev, ent_stride,
+                                         ent_nbytes, count, n, ct_bytes, out_c8_dev, ctx->sm_count, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return set_err(MFB_EARG, "mfb_encrypt_generic_dev: limbs64 must be one of 4,6,8,10,11,12,13,14,16");
+  MFB_CUDA_TRY(e);
   if (count) ctx->launches += 1;
   return MFB_OK;
 }

@@ -65,61 +65,69 @@ __host__ __device__ __forceinline__ size_t peer_buffer_bytes(int world) {
 // value = (E + (O << 32)) mod 2^704.  Carries out of the top are dropped: that IS modq.
 // The lo/hi pairs below are fused by ptxas into IMAD.WIDE.U32 with carry-in/-out (one per limb).
 // ---------------------------------------------------------------------------------------------
-struct Acc704 {
-  uint32_t E[22];
-  uint32_t O[21];
+// NL = number of 32-bit limbs (22 for the reference's parameter set; other even values for the (n, log q) sweep).
+template <int NL>
+struct AccN {
+  uint32_t E[NL];
+  uint32_t O[NL - 1];
 };
+using Acc704 = AccN<22>;
 
-__device__ __forceinline__ void acc_zero(Acc704 &x) {
+template <int NL>
+__device__ __forceinline__ void acc_zero(AccN<NL> &x) {
 #pragma unroll
-  for (int i = 0; i < 22; i++) x.E[i] = 0;
+  for (int i = 0; i < NL; i++) x.E[i] = 0;
 #pragma unroll
-  for (int i = 0; i < 21; i++) x.O[i] = 0;
+  for (int i = 0; i < NL - 1; i++) x.O[i] = 0;
 }
 
 // The chains below are ONE inline-asm statement each (mfb_chains.cuh, generated): the CC flag that links the limbs
 // never has to survive between statements.
-// acc += s * a   (a = 22 limbs, s < 2^32), mod 2^704
-__device__ __forceinline__ void acc_mad(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
-  MadChain<11, false>::run<0, 0>(x.E, a, s);  // even limbs: E[0..21]
-  MadChain<10, true>::run<0, 1>(x.O, a, s);   // odd limbs: O[0..19], low half of a[21] * s into O[20]
+// acc += s * a   (a = NL limbs, s < 2^32), mod 2^(32 NL)
+template <int NL>
+__device__ __forceinline__ void acc_mad(AccN<NL> &x, const uint32_t (&a)[NL], uint32_t s) {
+  static_assert(NL % 2 == 0, "even limb count");
+  MadChain<NL / 2, false>::template run<0, 0>(x.E, a, s);     // even limbs: E[0..NL-1]
+  MadChain<NL / 2 - 1, true>::template run<0, 1>(x.O, a, s);  // odd limbs: O[0..NL-3], low half of a[NL-1] * s into O[NL-2]
 }
 
-// acc += (a * b) mod 2^704 for two 22-limb operands (schoolbook low half, 253 limb products).
-// Row KB adds a[0..21-KB] * b[KB] at limb offset KB as two carry chains (l even, l odd).  A product at
+// acc += (a * b) mod 2^(32 NL) for two NL-limb operands (schoolbook low half: NL (NL + 1) / 2 limb products, 253 for 22).
+// Row KB adds a[0..NL-1-KB] * b[KB] at limb offset KB as two carry chains (l even, l odd).  A product at
 // limb position pos = l + KB goes to E[pos], E[pos+1] when pos is even and to O[pos-1], O[pos] when
 // pos is odd; along a chain pos keeps its parity and advances by 2, so consecutive products occupy
 // consecutive 64-bit slots of one accumulator and the carry flag links them.  One chain of every row
-// ends at pos 20 (E[20], E[21]), the other at pos 21 (low half into O[20]): both reach the top, where
+// ends at pos NL-2 (E[NL-2], E[NL-1]), the other at pos NL-1 (low half into O[NL-2]): both reach the top, where
 // the carry is dropped (that is modq).
-template <int KB, int Lx>
-__device__ __forceinline__ void acc_mul_chain(Acc704 &x, const uint32_t (&a)[22], uint32_t s) {
+template <int NL, int KB, int Lx>
+__device__ __forceinline__ void acc_mul_chain(AccN<NL> &x, const uint32_t (&a)[NL], uint32_t s) {
   constexpr int pos = Lx + KB;  // limb position of the chain's first product
-  if constexpr (pos <= 21) {
+  if constexpr (pos <= NL - 1) {
     if constexpr ((pos & 1) == 0)
-      MadChain<(20 - pos) / 2 + 1, false>::template run<pos, Lx>(x.E, a, s);
+      MadChain<(NL - 2 - pos) / 2 + 1, false>::template run<pos, Lx>(x.E, a, s);
     else
-      MadChain<(21 - pos) / 2, true>::template run<pos - 1, Lx>(x.O, a, s);
+      MadChain<(NL - 1 - pos) / 2, true>::template run<pos - 1, Lx>(x.O, a, s);
   }
 }
 
-template <int KB>
-__device__ __forceinline__ void acc_mul_rows(Acc704 &x, const uint32_t (&a)[22], const uint32_t (&b)[22]) {
-  if constexpr (KB <= 21) {
-    acc_mul_chain<KB, 0>(x, a, b[KB]);
-    acc_mul_chain<KB, 1>(x, a, b[KB]);
-    acc_mul_rows<KB + 1>(x, a, b);
+template <int NL, int KB>
+__device__ __forceinline__ void acc_mul_rows(AccN<NL> &x, const uint32_t (&a)[NL], const uint32_t (&b)[NL]) {
+  if constexpr (KB <= NL - 1) {
+    acc_mul_chain<NL, KB, 0>(x, a, b[KB]);
+    acc_mul_chain<NL, KB, 1>(x, a, b[KB]);
+    acc_mul_rows<NL, KB + 1>(x, a, b);
   }
 }
 
-__device__ __forceinline__ void acc_mul(Acc704 &x, const uint32_t (&a)[22], const uint32_t (&b)[22]) {
-  acc_mul_rows<0>(x, a, b);
+template <int NL>
+__device__ __forceinline__ void acc_mul(AccN<NL> &x, const uint32_t (&a)[NL], const uint32_t (&b)[NL]) {
+  acc_mul_rows<NL, 0>(x, a, b);
 }
 
-// r[0..21] = (E + (O << 32)) mod 2^704
-__device__ __forceinline__ void acc_fold(const Acc704 &x, uint32_t (&r)[22]) {
+// r[0..NL-1] = (E + (O << 32)) mod 2^(32 NL)
+template <int NL>
+__device__ __forceinline__ void acc_fold(const AccN<NL> &x, uint32_t (&r)[NL]) {
   r[0] = x.E[0];
-  AddChain<21>::run<1, 1, 0>(r, x.E, x.O);
+  AddChain<NL - 1>::template run<1, 1, 0>(r, x.E, x.O);
 }
 
 // r += b (22 limbs), mod 2^704

@@ -148,6 +148,14 @@ MFB_API size_t mfb_region_count(const mfb_region *r);
 MFB_API int mfb_lincomb_generic_dev(mfb_ctx *ctx, int limbs64, int ncoords, const uint64_t *cts_dev, const uint32_t *coeffs_dev,
                             size_t d, uint64_t *out_dev, void *stream);
 
+/* Regev encryption at other parameter points (same design as mfb_encrypt_dev; no reference counterpart either):
+ * coordinate j of ciphertext k = the ct_bytes = log q / 8 stream bytes at offset + (k n + j) ct_bytes, reduced mod
+ * q_eff = 2^(64 limbs64); out record k (ct_bytes bytes) = (e_k p + <sk, a_k> + msg[k]) mod q_eff, p = 2^32 - 5.
+ * sk_planar_dev: limb row j of coordinate c at j * sk_stride + c.  e_k as in mfb_encrypt_dev (ent_nbytes <= 8 limbs64). */
+MFB_API int mfb_encrypt_generic_dev(mfb_ctx *ctx, int limbs64, int n, int ct_bytes, const uint8_t seed[40], uint64_t offset,
+                            const uint64_t *sk_planar_dev, int sk_stride, const uint64_t *msg_dev, const uint8_t *ent_dev,
+                            int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8_dev, void *stream);
+
 /* ---- multi-GPU exchange helpers (one process per GPU; the collective itself is NCCL) ------ */
 /* cols_dev[1472][22] u64 <- the 32-bit limbs of flat_dev, widened, so that an elementwise integer sum over
  * ranks is exact; carry: flat_out[c] = (flat_in[c] + sum_l cols[c - c0][l] << 32l) mod 2^704 for the
