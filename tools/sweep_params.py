@@ -62,7 +62,7 @@ def main():
         torch.cuda.empty_cache()
         # encrypt: ~64 ciphertexts per SM
         ctb = logq // 8
-        cnt = 148 * 64
+        cnt = 148 * 256
         stride = (n + 63) // 64 * 64
         sk = torch.randint(-2**62, 2**62, (L * stride,), dtype=torch.int64, device="cuda")
         msg = torch.randint(0, 2**31 - 1, (cnt,), dtype=torch.int64, device="cuda")
