@@ -196,14 +196,10 @@ def test_lincomb_resident_vs_fused_and_oracle(ctx, oracle, torch):
     assert np.array_equal(wide(d_rop.cpu().numpy().view(np.uint64).reshape(NC, L64)), want)
 
 
-@pytest.mark.parametrize("clusters", [True, False])
 @pytest.mark.parametrize("d,off", [(1, 0), (2, 8), (3, 16), (7, 3 * CTR_CT + 8), (60, 11), (147, 5), (149, 2 * CTR_CT), (333, 2**36 + 5 * CTR_CT),
                                    (1000, 77)])
-def test_eval_poly2_vs_oracle(ctx, oracle, d, off, clusters, monkeypatch):
-    """two scalar vectors in one pass == two eval_poly calls == the oracle (prover pairs v_w/h and hat_v/hat_h); both
-    kernels: CTA pairs sharing a full tile through distributed shared memory (k_evalpoly2c), and the half-tile fallback"""
-    if not clusters:
-        monkeypatch.setenv("MFB_NO_CLUSTERS", "1")
+def test_eval_poly2_vs_oracle(ctx, oracle, d, off):
+    """two scalar vectors in one pass == two eval_poly calls == the oracle (prover pairs v_w/h and hat_v/hat_h)"""
     c8 = xof_records(f"ev2-c8-{d}", d)
     h0, h1 = xof_scalars(f"ev2-h0-{d}", d), xof_scalars(f"ev2-h1-{d}", d)
     h1[0] = 0
