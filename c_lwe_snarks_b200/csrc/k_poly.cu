@@ -16,6 +16,8 @@
 // written twice per transform instead of once per stage; both kernels do two radix-2 stages per pass in registers
 // (radix-4 steps).  The prover's polynomial step at D = 2^20 went from 1.68 ms to 0.81 ms, at 2^18 from 0.61 to 0.33 ms.
 // All three primes share a launch (grid.y).
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "mfb_common.cuh"
@@ -79,15 +81,29 @@ __global__ void k_twiddle_fill(uint32_t *tw, uint32_t *twi, uint32_t nmax_half, 
   }
 }
 
+// tw_loc[k][e] = w_NTT_B^e = tw[k][e * nmax / NTT_B] for e < NTT_B / 2 (and the inverse table likewise)
+__global__ void k_twiddle_compact(const uint32_t *__restrict__ tw, const uint32_t *__restrict__ twi, uint32_t nmax_half,
+                                  uint32_t *tw_loc, uint32_t *twi_loc) {
+  const int k = blockIdx.y;
+  const uint32_t step = nmax_half / (NTT_B / 2);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < NTT_B / 2; e += gridDim.x * blockDim.x) {
+    tw_loc[(size_t)k * (NTT_B / 2) + e] = tw[(size_t)k * nmax_half + (size_t)e * step];
+    twi_loc[(size_t)k * (NTT_B / 2) + e] = twi[(size_t)k * nmax_half + (size_t)e * step];
+  }
+}
+
 // all stages with span < NTT_B inside shared memory; one CTA per contiguous block of blk = min(n, NTT_B) elements.
 // The twiddles of these stages are the blk/2 powers of w_blk: staged once per CTA in shared memory (twl[e] =
 // w_blk^e = tw[e * nmax / blk]); stage `half` reads twl[j * (blk/2/half)] — no strided global loads in the loop.
 // Two radix-2 stages at a time in registers (a radix-4 step on elements i, i + h/2, i + h, i + 3h/2): half the
 // barriers and half the shared-memory traffic of a stage-by-stage loop; an odd stage count leaves one radix-2 stage.
 constexpr int NTTL_T = NTT_B / 4;  // threads: one radix-4 step each per pass
+// twloc: the COMPACT table of the NTT_B / 2 powers of w_NTT_B per prime (k_twiddle_compact): contiguous, so that the
+// 3072 CTAs of a 2^21-point transform read 4 KB each in full lines instead of gathering 1024 sectors from the big table
+// (that gather was two thirds of this kernel's L2 traffic).
 template <bool INVERSE>
-__global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ tw,
-                                                      uint32_t nmax_half, uint32_t sc0, uint32_t sc1, uint32_t sc2) {
+__global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ twloc,
+                                                      uint32_t sc0, uint32_t sc1, uint32_t sc2) {
   __shared__ uint32_t s[NTT_B];
   __shared__ uint32_t twl[NTT_B / 2];
   const int k = blockIdx.y;
@@ -96,9 +112,9 @@ __global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, c
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
   const uint32_t bh = blk >> 1;
   uint32_t *xk = x + (size_t)k * n + (size_t)blockIdx.x * blk;
-  const uint32_t *twk = tw + (size_t)k * nmax_half;
+  const uint32_t *twk = twloc + (size_t)k * (NTT_B / 2);
   for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) s[i] = xk[i];
-  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twk[(size_t)e * (nmax_half / bh)];
+  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twk[(size_t)e * ((NTT_B / 2) / bh)];  // w_blk^e = w_NTT_B^(e NTT_B / blk)
   __syncthreads();
   auto radix2 = [&](uint32_t half) {  // one plain stage (half = 1 when the stage count is odd)
     const uint32_t ts = bh / half;
@@ -365,8 +381,13 @@ __global__ void k_ssp_accumulate(const uint64_t *__restrict__ t, uint64_t delta,
   }
 }
 // resident SSP (u32 residues, polynomial k at blob[k*D .. (k+1)*D)): w = delta*t + sum of the selected polynomials, v = w + v_0
-__global__ void k_ssp_accumulate_res(const uint32_t *__restrict__ blob, uint32_t D, const uint32_t *__restrict__ sel,
-                                     uint32_t nsel, uint64_t delta, uint32_t *w, uint32_t *v) {
+// hdr = [number of selected polynomials, delta (< p), their indices ...]: everything that changes from proof to proof sits
+// in device memory, so that the launch parameters are constants of the instance (the step is replayed as a CUDA graph)
+__global__ void k_ssp_accumulate_res(const uint32_t *__restrict__ blob, uint32_t D, const uint32_t *__restrict__ hdr,
+                                     uint32_t *w, uint32_t *v) {
+  const uint32_t nsel = hdr[0];
+  const uint64_t delta = hdr[1];
+  const uint32_t *__restrict__ sel = hdr + 2;
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
     uint64_t acc = (uint64_t)blob[c] * (delta % FP) % FP;
     for (uint32_t k = 0; k < nsel; k++) acc += blob[(size_t)sel[k] * D + c];  // nsel < 2^31 terms below 2^32
@@ -459,6 +480,7 @@ __global__ void __launch_bounds__(256) k_eval32(const uint32_t *__restrict__ pol
 struct PolyEngine {
   uint32_t nmax = 0;  // twiddle tables cover transforms up to this size
   uint32_t *tw = nullptr, *twi = nullptr;
+  uint32_t *tw_loc = nullptr, *twi_loc = nullptr;  // [3][NTT_B / 2]: powers of w_NTT_B, contiguous (k_ntt_local)
   uint32_t *fa = nullptr, *fb = nullptr;  // [3][nmax] work arrays
   uint32_t *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;  // coefficient scratch (u32, nmax each)
   uint32_t *d_len = nullptr;
@@ -496,7 +518,7 @@ static cudaError_t engine_consts(PolyEngine &E) {
 }
 
 static void engine_free(PolyEngine &E) {
-  cudaFree(E.tw); cudaFree(E.twi); cudaFree(E.fa); cudaFree(E.fb); cudaFree(E.t1); cudaFree(E.t2); cudaFree(E.t3);
+  cudaFree(E.tw); cudaFree(E.twi); cudaFree(E.tw_loc); cudaFree(E.twi_loc); cudaFree(E.fa); cudaFree(E.fb); cudaFree(E.t1); cudaFree(E.t2); cudaFree(E.t3);
   cudaFree(E.d_len);
   E = PolyEngine();
 }
@@ -504,6 +526,7 @@ static void engine_free(PolyEngine &E) {
 static cudaError_t engine_reserve(PolyEngine &E, uint32_t n, cudaStream_t st) {
   cudaError_t e = engine_consts(E);
   if (e != cudaSuccess) return e;
+  if (n < (uint32_t)NTT_B) n = NTT_B;  // the compact table of k_ntt_local holds the powers of w_NTT_B
   if (n <= E.nmax) return cudaSuccess;
   if (n > (1u << 23)) return cudaErrorInvalidValue;  // 2-adicity of the NTT primes
   const bool had_consts = E.consts_ready;
@@ -514,6 +537,8 @@ static cudaError_t engine_reserve(PolyEngine &E, uint32_t n, cudaStream_t st) {
   const size_t half = n / 2;
   if ((e = cudaMalloc(&E.tw, NPR * half * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&E.twi, NPR * half * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.tw_loc, (size_t)NPR * (NTT_B / 2) * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&E.twi_loc, (size_t)NPR * (NTT_B / 2) * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&E.fa, (size_t)NPR * n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&E.fb, (size_t)NPR * n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&E.t1, (size_t)n * 4)) != cudaSuccess) return e;
@@ -527,6 +552,8 @@ static cudaError_t engine_reserve(PolyEngine &E, uint32_t n, cudaStream_t st) {
   }
   dim3 g(gridfor((uint32_t)half), NPR);
   k_twiddle_fill<<<g, 256, 0, st>>>(E.tw, E.twi, (uint32_t)half, w[0], w[1], w[2], wi[0], wi[1], wi[2]);
+  E.launches++;
+  k_twiddle_compact<<<dim3(4, NPR), 256, 0, st>>>(E.tw, E.twi, (uint32_t)half, E.tw_loc, E.twi_loc);
   E.launches++;
   E.nmax = n;
   return cudaGetLastError();
@@ -565,7 +592,7 @@ static cudaError_t ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStrea
     E.launches++;
   }
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
-  k_ntt_local<false><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.tw, nh, 0, 0, 0);
+  k_ntt_local<false><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.tw_loc, 0, 0, 0);
   E.launches++;
   return cudaGetLastError();
 }
@@ -579,7 +606,7 @@ static cudaError_t ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStrea
   const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
   const bool cols = n > (uint32_t)NTT_B;
   // the 1/n scaling rides in the last kernel of the transform
-  k_ntt_local<true><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.twi, nh, cols ? 0 : sc[0], cols ? 0 : sc[1], cols ? 0 : sc[2]);
+  k_ntt_local<true><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.twi_loc, cols ? 0 : sc[0], cols ? 0 : sc[1], cols ? 0 : sc[2]);
   E.launches++;
   if (cols) {
     cudaError_t e = launch_ntt_cols<true>(x, n, E.twi, nh, sc, st);
@@ -733,6 +760,11 @@ struct mfb_ssp {
   uint32_t *sel_pin = nullptr;
   cudaEvent_t sel_free = nullptr;
   bool sel_used = false;
+  // the polynomial step as an instantiated CUDA graph (one launch instead of ~17), valid for the pointers in graph_key
+  cudaGraphExec_t gexec = nullptr;
+  const void *graph_key[8] = {};
+  uint64_t graph_kernels = 0;
+  bool graph_off = false;  // capture failed once: plain launches from then on
 };
 
 // Host-blob path: v (D residues, device) and t (lt residues, stable device pointer) -> h = (v^2 - 1) / t truncated to D,
@@ -912,6 +944,7 @@ extern "C" void mfb_ssp_destroy(mfb_ctx *ctx, mfb_ssp *h) {
   cudaFree(h->bhat);
   if (h->sel_pin) cudaFreeHost(h->sel_pin);
   if (h->sel_free) cudaEventDestroy(h->sel_free);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
   delete h;
 }
 
@@ -940,7 +973,7 @@ static int polys_resident_queue(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witnes
   }
   int rc;
   void *d_idx, *d_w, *d_a;
-  if ((rc = ctx_scratch(ctx, 0, M * 4, &d_idx))) return rc;
+  if ((rc = ctx_scratch(ctx, 0, (M + 2) * 4, &d_idx))) return rc;
   if ((rc = ctx_scratch(ctx, 4, (size_t)n * 4, &d_a))) return rc;
   if ((rc = ctx_scratch(ctx, 5, D * 4 * 3, &d_w))) return rc;
   uint32_t *dw = (uint32_t *)d_w, *dv = dw + D, *dh = dw + 2 * D;
@@ -966,26 +999,65 @@ static int polys_resident_queue(mfb_ctx *ctx, mfb_ssp *h, const uint64_t *witnes
     h->bhat_n = n2;
     h->bhat_lq = lq;
   }
-  // witness bit i-1 selects v_i = polynomial i+1 of the blob
-  if (!h->sel_pin) PTRY(cudaHostAlloc((void **)&h->sel_pin, (M ? M : 1) * 4, cudaHostAllocDefault));
+  // witness bit i-1 selects v_i = polynomial i+1 of the blob; header + index list through pinned staging
+  const size_t hdr_bytes = (M + 2) * 4;
+  if (!h->sel_pin) PTRY(cudaHostAlloc((void **)&h->sel_pin, hdr_bytes, cudaHostAllocDefault));
   if (!h->sel_free) PTRY(cudaEventCreateWithFlags(&h->sel_free, cudaEventDisableTiming));
   if (h->sel_used) PTRY(cudaEventSynchronize(h->sel_free));  // the previous proof's upload has read the staging
   uint32_t nsel = 0;
   for (size_t i = 1; i < M; i++)
-    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) h->sel_pin[nsel++] = (uint32_t)(i + 1);
-  if (nsel) PTRY(cudaMemcpyAsync(d_idx, h->sel_pin, (size_t)nsel * 4, cudaMemcpyHostToDevice, st));
+    if ((i - 1) / 64 < nlimbs && (witness_limbs[(i - 1) / 64] >> ((i - 1) % 64) & 1)) h->sel_pin[2 + nsel++] = (uint32_t)(i + 1);
+  h->sel_pin[0] = nsel;
+  h->sel_pin[1] = (uint32_t)(delta % FP);
+  // the step itself: upload, w | v, a = v^2 - 1, h = a / t.  Every launch parameter is a constant of (instance, buffers).
+  auto body = [&](cudaStream_t s2) -> int {
+    PTRY(cudaMemcpyAsync(d_idx, h->sel_pin, hdr_bytes, cudaMemcpyHostToDevice, s2));
+    k_ssp_accumulate_res<<<gridfor(Du), 256, 0, s2>>>(h->blob, Du, (const uint32_t *)d_idx, dw, dv);
+    E.launches++;
+    PTRY(cudaGetLastError());
+    PTRY(poly_mul(E, dv, Du, Du, 0, dv, Du, Du, 0, 0, la, 0, (uint32_t *)d_a, s2));
+    k_sub_one<<<1, 32, 0, s2>>>((uint32_t *)d_a);
+    E.launches++;
+    PTRY(poly_mul_bhat(E, (const uint32_t *)d_a, lq, la, 1, h->bhat, n2, 0, lq, E.t3, s2));
+    k_reverse<<<gridfor(Du), 256, 0, s2>>>(E.t3, lq, dh, Du);
+    E.launches++;
+    PTRY(cudaGetLastError());
+    return MFB_OK;
+  };
+  bool launched = false;
+  if (st != nullptr && !h->graph_off && !getenv("MFB_NO_GRAPHS")) {
+    const void *key[8] = {d_idx, d_a, d_w, E.fa, E.t3, h->bhat, h->sel_pin, (const void *)(uintptr_t)E.nmax};
+    if (!h->gexec || memcmp(key, h->graph_key, sizeof(key)) != 0) {  // (re)capture: first replayable proof, or a buffer moved
+      if (h->gexec) cudaGraphExecDestroy(h->gexec);
+      h->gexec = nullptr;
+      cudaGraph_t g = nullptr;
+      const uint64_t l0 = E.launches;
+      bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int brc = body(st);
+        ok = cudaStreamEndCapture(st, &g) == cudaSuccess && brc == MFB_OK && g != nullptr;
+      }
+      h->graph_kernels = E.launches - l0;
+      E.launches = l0;  // (captured, not run)
+      if (ok) ok = cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+      if (!ok) {
+        cudaGetLastError();
+        h->gexec = nullptr;
+        h->graph_off = true;
+      } else {
+        memcpy(h->graph_key, key, sizeof(key));
+      }
+    }
+    if (h->gexec) {
+      PTRY(cudaGraphLaunch(h->gexec, st));
+      E.launches += h->graph_kernels;
+      launched = true;
+    }
+  }
+  if (!launched && (rc = body(st))) return rc;
   PTRY(cudaEventRecord(h->sel_free, st));
   h->sel_used = true;
-  k_ssp_accumulate_res<<<gridfor(Du), 256, 0, st>>>(h->blob, Du, (const uint32_t *)d_idx, nsel, delta, dw, dv);
-  E.launches++;
-  PTRY(cudaGetLastError());
-  PTRY(poly_mul(E, dv, Du, Du, 0, dv, Du, Du, 0, 0, la, 0, (uint32_t *)d_a, st));
-  k_sub_one<<<1, 32, 0, st>>>((uint32_t *)d_a);
-  E.launches++;
-  PTRY(poly_mul_bhat(E, (const uint32_t *)d_a, lq, la, 1, h->bhat, n2, 0, lq, E.t3, st));
-  k_reverse<<<gridfor(Du), 256, 0, st>>>(E.t3, lq, dh, Du);
-  E.launches++;
-  PTRY(cudaGetLastError());
   *wvh = dw;
   return MFB_OK;
 }

@@ -149,19 +149,28 @@ def test_low_degree_t_on_a_fresh_context():
         c.close()
 
 
+@pytest.mark.parametrize("graphs", [True, False])
 @pytest.mark.parametrize("D,M,t_len", [(64, 16, 64), (1000, 8, 1000), (1000, 8, 40), (4096, 4, 4096)])
-def test_resident_ssp_matches_host_blob_path(ctx, D, M, t_len):
-    """mfb_ssp_create + mfb_ssp_prover_polys_resident (cached inverse) == mfb_ssp_prover_polys, for several witnesses."""
+def test_resident_ssp_matches_host_blob_path(ctx, D, M, t_len, graphs, monkeypatch):
+    """mfb_ssp_create + mfb_ssp_prover_polys_resident (cached transform of the inverse; the step replayed as a CUDA graph
+    whose only per-proof input is the selection header) == mfb_ssp_prover_polys, for several witnesses and deltas; also
+    with plain launches ($MFB_NO_GRAPHS)."""
+    if not graphs:
+        monkeypatch.setenv("MFB_NO_GRAPHS", "1")
     blob, wl, bits, t, v = make_ssp(D, M, f"poly-res-{D}-{t_len}", exact=(t_len == D), t_len=t_len)
     res = ctx.ssp_resident(blob.view(np.uint8), D, M)
     try:
-        for k, delta in enumerate([1, 0x9E3779B9 % P, P - 1]):
+        for k, delta in enumerate([1, 0x9E3779B9 % P, P - 1, 12345, 7]):
             wit = wl.copy()
             wit[0] ^= np.uint64(0x5555 * k)
             a = ctx.ssp_prover_polys(blob.view(np.uint8), D, M, wit, delta)
             b = res.prover_polys(wit, delta)
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
+            if k >= 3:  # twice in a row without the host-blob call in between: the graph is replayed, not re-captured
+                b2 = res.prover_polys(wit, delta)
+                for x, y in zip(a, b2):
+                    assert np.array_equal(x, y)
     finally:
         res.close()
 
