@@ -60,10 +60,11 @@ def synth_inputs(d: int, rank: int = 0):
     return c8, h
 
 
-def workload_string(log2d: int) -> str:
-    """config.workload — the SAME string in both arms (residency / sampling are described under their own keys)."""
-    return (f"prover lincomb (eval_poly, lwe.c:176-186), D=2^{log2d} Regev ciphertexts per GPU, n=1470, logq=736 (eff. 704), "
-            f"p=2^32-5")
+def workload_config(log2d: int) -> dict:
+    """`config` — IDENTICAL in both arms (how each arm runs the workload is described under `config_details`)."""
+    return {"workload": f"prover lincomb (eval_poly, lwe.c:176-186), D=2^{log2d} Regev ciphertexts per GPU, n=1470, logq=736 "
+                        f"(eff. 704), p=2^32-5",
+            "log2_ciphertexts_per_gpu": log2d, "n": 1470, "logq": 736, "q_eff_bits": 704, "p": P}
 
 
 def peaks():
@@ -192,9 +193,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_string(args.log2d),
-                       "path": "eval_poly of the unmodified reference (oracle/_ref): AES-CTR regeneration + GMP MAC on the host cores",
-                       "sample_ciphertexts_per_step": total},
+            "config": workload_config(args.log2d),
+            "config_details": {"path": "eval_poly of the unmodified reference (oracle/_ref): AES-CTR regeneration + GMP MAC on the "
+                                       "host cores", "sample_ciphertexts_per_step": total},
             "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
                              "sample": f"{total} ciphertexts per step ({per_core} per core x {cores} processes over disjoint "
                                        f"ranges via rng_seek, partials folded with ct_add); wall {wall:.1f} s"},
@@ -641,11 +642,12 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": world * D * steps / (ms * 1e-3), "unit": METRIC, "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_string(args.log2d),
-                       "path": f"ciphertexts resident in HBM ({D * PLANAR_BYTES / 1e9:.2f} GB tile-planar per GPU), k_lincomb + finish",
-                       "ciphertexts_per_gpu": D, "l2": "inputs (8.49 GB per step) exceed the 126 MB L2; no flush needed",
-                       "exchange": exchange,
-                       "parity_check": parity},
+            "config": workload_config(args.log2d),
+            "config_details": {"path": f"ciphertexts resident in HBM ({D * PLANAR_BYTES / 1e9:.2f} GB tile-planar per GPU), "
+                                       f"k_lincomb + finish",
+                               "ciphertexts_per_gpu": D, "l2": "inputs (8.49 GB per step) exceed the 126 MB L2; no flush needed",
+                               "exchange": exchange},
+            "parity_check": parity,
             "roofline": {"bound": "hbm", "kernel": "k_lincomb", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": D * ALGO_BYTES, "kernel_ms": per_launch_ms, "launches_timed": k_n},

@@ -200,34 +200,35 @@ __device__ __forceinline__ uint32_t ntt_root_pow(const uint32_t *__restrict__ tw
 }
 
 template <bool INVERSE>
-__global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, uint32_t m, int logm, uint32_t C,
+__global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, uint32_t m, int logm, int logC,
                                                      const uint32_t *__restrict__ tw, uint32_t nmax_half, uint32_t sc0,
                                                      uint32_t sc1, uint32_t sc2) {
   extern __shared__ uint32_t sh[];
   uint32_t *s = sh;              // [m][C]
-  uint32_t *twm = sh + m * C;    // [m/2]: w_m^e
+  uint32_t *twm = sh + ((size_t)m << logC);  // [m/2]: w_m^e
   const int k = blockIdx.y;
   const uint32_t P = c_P[k], pinv = c_PINV[k];
   const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;
+  const uint32_t C = 1u << logC, Cm = C - 1;    // columns per tile: a power of two, so t / C and t % C are a shift and a mask
   const uint32_t c = n / m;                     // columns of the whole array (= NTT_B)
   const uint32_t l0 = blockIdx.x * C;           // first column of this tile
   uint32_t *xk = x + (size_t)k * n;
   const uint32_t *twk = tw + (size_t)k * nmax_half;
   const uint32_t mh = m >> 1;
-  for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) s[t] = xk[(size_t)(t / C) * c + l0 + (t % C)];
+  for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) s[t] = xk[(size_t)(t >> logC) * c + l0 + (t & Cm)];
   for (uint32_t e = threadIdx.x; e < mh; e += NTTC_T) twm[e] = twk[(size_t)e * (nmax_half / mh)];
   __syncthreads();
 
   // column factors: thread (lc, g) walks output indices p = g, g + G, g + 2G, ... of column l0 + lc
   auto col_factors = [&]() {
-    const uint32_t G = NTTC_T / C ? NTTC_T / C : 1;  // rows covered per sweep (C <= NTTC_T: see the launcher)
-    const uint32_t lc = threadIdx.x % C, g = threadIdx.x / C;
+    const uint32_t G = NTTC_T >> logC ? NTTC_T >> logC : 1;  // rows covered per sweep (C <= NTTC_T: see the launcher)
+    const uint32_t lc = threadIdx.x & Cm, g = threadIdx.x >> logC;
     if (g >= G || g >= m) return;
     const uint32_t l = l0 + lc;
     uint32_t f = ntt_root_pow(twk, (uint32_t)(((uint64_t)l * g) & (n - 1)), n, nmax_half, P);       // w^(l*g)
     const uint32_t r = ntt_root_pow(twk, (uint32_t)(((uint64_t)l * G) & (n - 1)), n, nmax_half, P);  // w^(l*G)
     for (uint32_t pp = g; pp < m; pp += G) {
-      uint32_t *e = s + ntt_bitrev(pp, logm) * C + lc;
+      uint32_t *e = s + (ntt_bitrev(pp, logm) << logC) + lc;
       *e = mont_mul(*e, f, P, pinv);
       f = mont_mul(f, r, P, pinv);
     }
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, ui
   auto radix2 = [&](uint32_t half) {
     const uint32_t ts = mh / half;
     for (uint32_t t = threadIdx.x; t < mh * C; t += NTTC_T) {
-      const uint32_t bt = t / C, lc = t % C;
+      const uint32_t bt = t >> logC, lc = t & Cm;
       const uint32_t j = bt & (half - 1), i = ((bt - j) << 1) + j;
-      uint32_t *pa = s + i * C + lc, *pb = pa + half * C;
+      uint32_t *pa = s + (i << logC) + lc, *pb = pa + (half << logC);
       const uint32_t a = *pa, b = *pb;
       if (!INVERSE) {
         *pa = add_mod(a, b, P);
@@ -256,10 +257,10 @@ __global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, ui
   auto radix4 = [&](uint32_t h) {
     const uint32_t q4 = h >> 1, ts = mh / h;
     for (uint32_t t = threadIdx.x; t < (m >> 2) * C; t += NTTC_T) {
-      const uint32_t bt = t / C, lc = t % C;
+      const uint32_t bt = t >> logC, lc = t & Cm;
       const uint32_t j = bt & (q4 - 1), i = ((bt - j) << 2) + j;
       const uint32_t t1 = twm[j * ts], t2 = twm[(j + q4) * ts], t3 = twm[2 * j * ts];
-      uint32_t *p0 = s + i * C + lc, *p1 = p0 + q4 * C, *p2 = p0 + h * C, *p3 = p2 + q4 * C;
+      uint32_t *p0 = s + (i << logC) + lc, *p1 = p0 + (q4 << logC), *p2 = p0 + (h << logC), *p3 = p2 + (q4 << logC);
       uint32_t a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
       if (!INVERSE) {
         const uint32_t b0 = add_mod(a0, a2, P), b2 = mont_mul(sub_mod(a0, a2, P), t1, P, pinv);
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, ui
     if (h == 1) radix2(1);
     col_factors();
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) xk[(size_t)(t / C) * c + l0 + (t % C)] = s[t];
+    for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T) xk[(size_t)(t >> logC) * c + l0 + (t & Cm)] = s[t];
   } else {
     col_factors();  // tw is the inverse table here: w_n^-(l*p)
     __syncthreads();
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(NTTC_T) k_ntt_cols(uint32_t *x, uint32_t n, ui
     }
     for (; h <= mh; h <<= 2) radix4(h);
     for (uint32_t t = threadIdx.x; t < m * C; t += NTTC_T)
-      xk[(size_t)(t / C) * c + l0 + (t % C)] = mont_mul(s[t], scale, P, pinv);
+      xk[(size_t)(t >> logC) * c + l0 + (t & Cm)] = mont_mul(s[t], scale, P, pinv);
   }
 }
 
@@ -580,7 +581,9 @@ static cudaError_t launch_ntt_cols(uint32_t *x, uint32_t n, const uint32_t *tw, 
     cudaError_t e = cudaFuncSetAttribute(k_ntt_cols<INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k_ntt_cols<INVERSE><<<dim3(NTT_B / C, NPR), NTTC_T, smem, st>>>(x, n, m, logm, C, tw, nh, sc[0], sc[1], sc[2]);
+  int logC = 0;
+  while ((1u << logC) < C) logC++;
+  k_ntt_cols<INVERSE><<<dim3(NTT_B / C, NPR), NTTC_T, smem, st>>>(x, n, m, logm, logC, tw, nh, sc[0], sc[1], sc[2]);
   return cudaGetLastError();
 }
 static cudaError_t ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
