@@ -125,6 +125,8 @@ _SIGS = {
     "mfb_peer_finish4_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mfb_peer_finish4_push_dev": (C.c_int, [_vp, _vp, _vp]),
     "mfb_peer_wait4_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mfb_peer_push_lanes_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "mfb_peer_wait_lanes_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "mfb_ssp_prover_polys_resident_async": (C.c_int, [_vp, _vp, _u64p, C.c_size_t, C.c_uint64, _vp, C.POINTER(_vp)]),
     "mfb_b_w_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _vp, _vp]),
     "mfb_set_encrypt_par": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,

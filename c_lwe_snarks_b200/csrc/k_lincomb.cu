@@ -355,7 +355,7 @@ k_lincomb_finish_peer(const uint64_t *__restrict__ partial, size_t lane_stride, 
 __global__ void __launch_bounds__(RT_TILE)
 k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, const uint64_t *rop_in, uint64_t *rop_out,
                  size_t rop_stride, const __grid_constant__ PeerTable peers, int world, int rank, uint32_t epoch,
-                 uint64_t timeout_ns, int *status, int wait_only) {
+                 uint64_t timeout_ns, int *status, int wait_only, int push_only) {
   const int tile = blockIdx.x, lane = blockIdx.y;
   flat_partial += (size_t)lane * in_stride;
   if (rop_in) rop_in += (size_t)lane * rop_stride;
@@ -380,9 +380,10 @@ k_peer_allreduce(const uint64_t *__restrict__ flat_partial, size_t in_stride, co
   }
   __threadfence_system();
   __syncthreads();
+  if ((int)threadIdx.x < world && !wait_only)
+    st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
+  if (push_only) return;  // the waiting half is a second launch of this kernel (wait_only)
   if ((int)threadIdx.x < world) {
-    if (!wait_only)
-      st_release_sys_u32(reinterpret_cast<uint32_t *>(peers.base[threadIdx.x] + peer_flag_offset(q, world, rank, lane, tile)), epoch);
     const uint32_t *f = reinterpret_cast<const uint32_t *>(peers.base[rank] + peer_flag_offset(q, world, (int)threadIdx.x, lane, tile));
     if (!peer_wait_u32(f, epoch, timeout_ns)) *reinterpret_cast<volatile int *>(status) = 1 + (int)threadIdx.x;
   }
@@ -514,8 +515,10 @@ cudaError_t launch_lincomb_finish(const uint64_t *partial_ws, size_t lane_stride
 
 // mode 0: flat_partial != nullptr: the exchange alone (k_peer_allreduce; lane l contributes flat_partial + l * lane_stride),
 //         else the finish of the row-planar partials fused with the exchange (one kernel that pushes, waits and adds);
-// mode 1: finish + push only (never blocks);  mode 2: wait + add only (a small kernel: 64 threads per tile and lane) —
-//         the two halves of one exchange (same epoch) when the ranks' kernels cannot be assumed co-resident
+// mode 1: push only (never blocks): the finish of the row-planar partials + push, or (flat_partial) the push of flat
+//         ciphertexts;  mode 2: wait + add only (a small kernel: 64 threads per tile and lane) — the two halves of one
+//         exchange (same epoch) when the ranks' kernels cannot be assumed to run concurrently (members of a device set
+//         sharing a GPU; a profiler or debugger that serialises launches)
 cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_stride, int lanes, int nparts,
                                        const uint64_t *flat_partial, const uint64_t *rop_in, uint64_t *rop_out, size_t rop_stride,
                                        unsigned int *queue, unsigned int *queue2, uint8_t *const *bases, int world, int rank,
@@ -525,10 +528,10 @@ cudaError_t launch_lincomb_finish_peer(const uint64_t *partial_ws, size_t lane_s
   for (int i = 0; i < world; i++) t.base[i] = bases[i];
   if (mode == 2)
     k_peer_allreduce<<<dim3(RT_NTILES, lanes), RT_TILE, 0, st>>>(rop_out, 0, rop_in, rop_out, rop_stride, t, world, rank, epoch, timeout_ns,
-                                                                status, 1);
+                                                                status, 1, 0);
   else if (flat_partial)
     k_peer_allreduce<<<dim3(RT_NTILES, lanes), RT_TILE, 0, st>>>(flat_partial, lane_stride, rop_in, rop_out, rop_stride, t, world, rank,
-                                                                epoch, timeout_ns, status, 0);
+                                                                epoch, timeout_ns, status, 0, mode == 1);
   else
     k_lincomb_finish_peer<<<dim3(RT_NTILES, lanes), 64 * FIN_SLICES, 0, st>>>(partial_ws, lane_stride, nparts, rop_in, rop_out, rop_stride,
                                                                             queue, queue2, t, world, rank, epoch, timeout_ns, status,

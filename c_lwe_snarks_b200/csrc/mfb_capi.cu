@@ -594,6 +594,28 @@ int mfb_peer_allreduce_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t
   return MFB_OK;
 }
 
+// the same exchange in two launches (push, then wait + add: see mfb_peer_finish4_push_dev); mfb_peer_wait_lanes_dev completes it
+int mfb_peer_push_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, size_t in_stride_u64, int lanes,
+                            void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_push_lanes_dev: the peer group is not connected");
+  if (!partial_flat_dev) return set_err(MFB_EARG, "mfb_peer_push_lanes_dev: null pointer");
+  MFB_TRY(peer_finish(ctx, g, in_stride_u64, lanes, 0, partial_flat_dev, nullptr, const_cast<uint64_t *>(partial_flat_dev), 0, nullptr,
+                      nullptr, (cudaStream_t)stream, 1));
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_peer_wait_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, int lanes, const uint64_t *rop_in_dev, uint64_t *rop_out_dev,
+                            size_t rop_stride_u64, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_wait_lanes_dev: the peer group is not connected");
+  if (!rop_out_dev) return set_err(MFB_EARG, "mfb_peer_wait_lanes_dev: null pointer");
+  MFB_TRY(peer_finish(ctx, g, 0, lanes, 0, nullptr, rop_in_dev, rop_out_dev, rop_stride_u64, nullptr, nullptr, (cudaStream_t)stream, 2));
+  ctx->launches += 1;
+  return MFB_OK;
+}
+
 int mfb_peer_allreduce_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, const uint64_t *rop_in_dev,
                            uint64_t *rop_out_dev, void *stream) {
   return mfb_peer_allreduce_lanes_dev(ctx, g, partial_flat_dev, 0, 1, rop_in_dev, rop_out_dev, 0, stream);
@@ -694,9 +716,7 @@ int mfb_peer_wait4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in4_
   MFB_CHECK_CTX(ctx);
   if (!g || !g->connected) return set_err(MFB_EARG, "mfb_peer_wait4_dev: the peer group is not connected");
   if (!rop_out4_dev || rop_stride_u64 < MFB_FLAT_CT_U64) return set_err(MFB_EARG, "mfb_peer_wait4_dev: bad argument");
-  MFB_TRY(peer_finish(ctx, g, 0, 4, 0, nullptr, rop_in4_dev, rop_out4_dev, rop_stride_u64, nullptr, nullptr, (cudaStream_t)stream, 2));
-  ctx->launches += 1;
-  return MFB_OK;
+  return mfb_peer_wait_lanes_dev(ctx, g, 4, rop_in4_dev, rop_out4_dev, rop_stride_u64, stream);
 }
 
 int mfb_lincomb_generic_dev(mfb_ctx *ctx, int limbs64, int ncoords, const uint64_t *cts_dev, const uint32_t *coeffs_dev,

@@ -334,15 +334,20 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   return MFB_OK;
 }
 
-// Second phase of a set call: the members' exchange kernels, which WAIT for each other on the device.  They are enqueued
-// only after every member's compute work of the call is in its stream (members may share a GPU, where a waiting kernel
-// must never sit in front of work that another member's kernel is waiting for).
+// Second phase of a set call: the members' exchange.  Every member first PUSHES its flat partial sums to all members (a
+// kernel that never waits), then a small kernel per member waits for the others' tiles and adds them.  No kernel of a
+// set call ever waits for work that is not yet in some stream: members may share a GPU, and a profiler that serialises
+// launches (ncu) can capture the path.
 static int exchange_all(mfb_set *s, int nvec, bool any) {
   for (size_t i = 0; i < s->m.size(); i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
-    SET_TRY(mfb_peer_allreduce_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT,
-                                         mb.stream));
+    SET_TRY(mfb_peer_push_lanes_dev(mb.ctx, mb.group, mb.part, SLOT, nvec, mb.stream));
+  }
+  for (size_t i = 0; i < s->m.size(); i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    SET_TRY(mfb_peer_wait_lanes_dev(mb.ctx, mb.group, nvec, i == 0 && any ? mb.res : nullptr, mb.res, SLOT, mb.stream));
   }
   return MFB_OK;
 }

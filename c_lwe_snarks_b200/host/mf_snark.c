@@ -117,7 +117,10 @@ void mf_crs_make_resident(crs_t crs) {
   mfb_set *set = device_set();
   if (set) { /* sharded by ciphertext index over the set's GPUs */
     int rc = mfb_set_region_create(set, crs->seed, CTR_S, (const uint8_t *)crs->s, r->d, &r->ms);
+    mf_trace("make_resident.set_region_s", t0);
+    t0 = mf_now();
     if (rc == MFB_OK) rc = mfb_set_region_create(set, crs->seed, CTR_AS, (const uint8_t *)crs->as, r->d, &r->mas);
+    mf_trace("make_resident.set_region_as", t0);
     if (rc != MFB_OK) {
       fprintf(stderr, "mangiafuoco_b200: mf_crs_make_resident over %d devices: %s; the CRS stays non-resident\n",
               mfb_set_size(set), mfb_set_last_error());
@@ -218,7 +221,12 @@ static mfb_ssp *ssp_make_resident(ssp_t ssp, int quiet) {
   return r->h;
 }
 
-void mf_ssp_make_resident(ssp_t ssp) { (void)ssp_make_resident(ssp, 0); }
+static mfb_ssp *resident_ssp_find(ssp_t ssp);
+void mf_ssp_make_resident(ssp_t ssp) {
+  double t0 = mf_now();
+  if (!resident_ssp_find(ssp)) (void)ssp_make_resident(ssp, 0); /* (already resident and unchanged: nothing to do) */
+  mf_trace("ssp_make_resident", t0);
+}
 
 static mfb_ssp *resident_ssp_find(ssp_t ssp) {
   for (struct resident_ssp *r = g_resident_ssp; r; r = r->next)

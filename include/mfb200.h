@@ -209,6 +209,11 @@ MFB_API int mfb_peer_finish4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t
 MFB_API int mfb_peer_finish4_push_dev(mfb_ctx *ctx, mfb_peer_group *g, void *stream);
 MFB_API int mfb_peer_wait4_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *rop_in4_dev, uint64_t *rop_out4_dev,
                        size_t rop_stride_u64, void *stream);
+/* ... and for flat ciphertexts (mfb_peer_allreduce_lanes_dev in two launches) */
+MFB_API int mfb_peer_push_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint64_t *partial_flat_dev, size_t in_stride_u64, int lanes,
+                            void *stream);
+MFB_API int mfb_peer_wait_lanes_dev(mfb_ctx *ctx, mfb_peer_group *g, int lanes, const uint64_t *rop_in_dev, uint64_t *rop_out_dev,
+                            size_t rop_stride_u64, void *stream);
 /* the same for the fused AES + MAC path (mfb_eval_poly_dev over this rank's ciphertexts) */
 MFB_API int mfb_eval_poly_peer_dev(mfb_ctx *ctx, mfb_peer_group *g, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                            const uint32_t *coeffs_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop_in_dev,
