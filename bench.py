@@ -618,13 +618,33 @@ def run_gpu_arm(args):
                       "sharded resident path == the CPU oracle; N > 1: the exchanged result == rank 0 recomputing the global sum "
                       "alone (mfb_eval_poly over every rank's range, no exchange)"}
 
+    # ---- N > 1: the full drop-in SNARK from ONE host thread over the N GPUs (a subprocess of rank 0): the north-star
+    # instance (D = 2^20) and the weak-scaling instance (D = N * 2^16: per-GPU work as in the N = 1 `snark` leg).  The other
+    # ranks free their big buffers and wait ON THE CPU (a c10d store key): an NCCL barrier would keep a kernel spinning
+    # on their GPUs, and rank 0's member contexts on those GPUs would be time-sliced against it.  (Runs before the
+    # strong-scaling leg: memory another process has just freed is scrubbed by the driver when it is allocated again,
+    # which would sit in make_resident_ms.)
+    if reg is not None:
+        reg = None
+    del d_cts, d_c8_e, d_h_e, d_co_r
+    torch.cuda.empty_cache()
+    boxes = {}
+    if world > 1 and not args.no_snark:
+        from datetime import timedelta
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            for key, lg in (("snark_box", 20), ("snark_box_weak", args.log2d + (world - 1).bit_length())):
+                try:
+                    boxes[key] = snark_box_latency(lg, 64, world)
+                except Exception as e:  # noqa: BLE001  (reported, the bench line stands)
+                    boxes[key] = {"error": str(e)[:300]}
+            store.set("snark_box_done", "1")
+        else:
+            store.wait(["snark_box_done"], timedelta(seconds=1500))
+
     # ---- BASELINE configs[3]: the 2^20-ciphertext lincomb split by ciphertext index over the N GPUs (strong scaling)
     strong = None
     if not args.no_strong:
-        if reg is not None:
-            reg = None
-        del d_cts, d_c8_e, d_h_e, d_co_r
-        torch.cuda.empty_cache()
         strong = strong_2e20_leg(ctx, torch, dist, world, rank, steps, peer, ppipe, sl, barrier, st)
 
     if rank == 0:
@@ -678,24 +698,8 @@ def run_gpu_arm(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
             line["config1_reference_cpu"] = config1_reference()
-        if world > 1 and not args.no_snark:
-            # the full drop-in SNARK from ONE host thread over the N GPUs: the north-star instance (D = 2^20), and the
-            # weak-scaling instance (D = N * 2^16: per-GPU work as in the N = 1 `snark` leg)
-            for key, lg in (("snark_box", 20), ("snark_box_weak", args.log2d + (world - 1).bit_length())):
-                try:
-                    line[key] = snark_box_latency(lg, 64, world)
-                except Exception as e:  # noqa: BLE001  (reported, the bench line stands)
-                    line[key] = {"error": str(e)[:300]}
+        line.update(boxes)
         emit(line)
-    if world > 1 and not args.no_snark:
-        # the other ranks wait for rank 0's box leg ON THE CPU (a c10d store key): an NCCL barrier would keep a kernel
-        # spinning on their GPUs, and rank 0's member contexts on those GPUs would be time-sliced against it
-        from datetime import timedelta
-        store = dist.distributed_c10d._get_default_store()
-        if rank == 0:
-            store.set("snark_box_done", "1")
-        else:
-            store.wait(["snark_box_done"], timedelta(seconds=900))
     if peer is not None:
         peer.check()
         peer.close()
