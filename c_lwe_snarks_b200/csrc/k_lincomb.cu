@@ -474,6 +474,20 @@ int lincomb_nslots(size_t d, int sm_count, int nvec) {
   return nvec == 2 ? nslots_for<2>(d, sm_count) : nslots_for<1>(d, sm_count);
 }
 
+// the opt-in to > 48 KB of dynamic shared memory is per device and per kernel: done once, not on every launch (a launch
+// sequence over 8 GPUs from one host thread is latency-critical)
+template <int NVEC>
+static cudaError_t lincomb_smem_optin() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(k_lincomb<NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<NVEC>());
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
 typedef void (*mark_fn)(void *, int, cudaStream_t);
 // launches the main kernel only; *nslots_inout returns the number of partial sums written per vector.
 // coeffs1 == nullptr: one scalar vector; else two (partials of vector 1 start at partial_ws + nslots * PLANAR_U64).
@@ -487,12 +501,12 @@ cudaError_t launch_lincomb_partials(const uint64_t *cts, const uint32_t *coeffs0
     dim3 grid(RT_NTILES, nslots);
     cudaError_t e;
     if (coeffs1) {
-      if ((e = cudaFuncSetAttribute(k_lincomb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<2>())) != cudaSuccess) return e;
+      if ((e = lincomb_smem_optin<2>()) != cudaSuccess) return e;
       if (mark) mark(mark_arg, 0, st);
       k_lincomb<2><<<grid, LC_TILE, lc_smem_bytes<2>(), st>>>(cts, coeffs0, coeffs1, d, chunk_len, queue, partial_ws,
                                                           (size_t)nslots * PLANAR_U64);
     } else {
-      if ((e = cudaFuncSetAttribute(k_lincomb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc_smem_bytes<1>())) != cudaSuccess) return e;
+      if ((e = lincomb_smem_optin<1>()) != cudaSuccess) return e;
       if (mark) mark(mark_arg, 0, st);
       k_lincomb<1><<<grid, LC_TILE, lc_smem_bytes<1>(), st>>>(cts, coeffs0, nullptr, d, chunk_len, queue, partial_ws, 0);
     }

@@ -1163,8 +1163,13 @@ int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, c
   const int nacc = b_w_flat_out ? 5 : 4;
   MFB_TRY(scratch(ctx, 2, 5 * FL * 8, &d_rop));
   uint64_t *r = (uint64_t *)d_rop;
-  // b_w on the second stream: its few small kernels run beside the (launch-latency-bound) polynomial step; they use
-  // the partial-sum workspace, so the first lincomb kernel waits for them
+  // 1. the polynomial step first (it needs only the witness), queued without a host round trip: everything the host does
+  //    next — b_w's uploads, staging the accumulators — runs beside it
+  const uint32_t *wvh = nullptr;
+  MFB_TRY(mfb_ssp_prover_polys_resident_async(ctx, ssp, witness_limbs, nlimbs, delta, ctx->stream, &wvh));
+  const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
+  // 2. b_w on the second stream: its few small kernels run beside the polynomial step; they use the partial-sum
+  //    workspace, so the first lincomb kernel waits for them
   if (b_w_flat_out) {
     if (!ctx->stream2) MFB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     if (!ctx->ev_b) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
@@ -1172,17 +1177,14 @@ int mfb_prove_resident_bw(mfb_ctx *ctx, mfb_ssp *ssp, const mfb_region *reg_s, c
     MFB_CUDA_TRY(cudaEventRecord(ctx->ev_b, ctx->stream2));
   }
   uint64_t *host[5] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, b_w_flat_out};
-  // the accumulators travel as ONE pinned copy each way; accumulators that are all zero (the usual case: a proof
-  // starts from proof_init) are not sent at all
+  // 3. the accumulators travel as ONE pinned copy each way; accumulators that are all zero (the usual case: a proof
+  //    starts from proof_init) are not sent at all
   if (!ctx->acc_pin) MFB_CUDA_TRY(cudaHostAlloc((void **)&ctx->acc_pin, 5 * FL * 8, cudaHostAllocDefault));
   uint64_t any = 0;
   for (int k = 0; k < 4; k++)
     for (size_t i = 0; i < FL; i++) any |= (ctx->acc_pin[k * FL + i] = host[k][i]);
   if (any) MFB_CUDA_TRY(cudaMemcpyAsync(r, ctx->acc_pin, 4 * FL * 8, cudaMemcpyHostToDevice, ctx->stream));
-  // polynomial step, both two-vector passes and ONE finish for the four accumulators, all queued without a host round trip
-  const uint32_t *wvh = nullptr;
-  MFB_TRY(mfb_ssp_prover_polys_resident_async(ctx, ssp, witness_limbs, nlimbs, delta, ctx->stream, &wvh));
-  const uint32_t *d_w = wvh, *d_v = wvh + D, *d_h = wvh + 2 * D;
+  // 4. both two-vector passes and ONE finish for the four accumulators
   if (b_w_flat_out) MFB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
   MFB_TRY(mfb_lincomb2_partials_dev(ctx, reg_s->cts, d_w, d_h, D, 0, ctx->stream));
   MFB_TRY(mfb_lincomb2_partials_dev(ctx, reg_as->cts, d_v, d_h, D, 1, ctx->stream));

@@ -688,24 +688,23 @@ MFB_API int mfb_set_encrypt_par(mfb_set *s, const uint8_t seed[40], uint64_t off
 // ---------------------------------------------------------------------------------------------------- prover pipeline
 static int prove_body(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const mfb_set_region *ras, const uint64_t *witness_limbs,
                       size_t nlimbs, uint64_t delta, const uint8_t *seed, uint64_t bt_offset, const uint8_t *bt_recs, size_t M,
-                      bool any, bool want_bw) {
+                      uint64_t *const *host, bool want_bw) {
   const size_t D = mfb_ssp_degree_bound(ssp), world = s->m.size();
   Member &p = s->m[0];
+  // 1. the polynomial step on the primary FIRST (it needs only the witness): queued without a host round trip; everything
+  //    the host does from here on runs beside it, and the other members wait for it ON THE DEVICE
   SET_CUDA(cudaSetDevice(p.device));
-  if (any) SET_CUDA(cudaMemcpyAsync(p.res, s->acc_pin, 4 * SLOT * 8, cudaMemcpyHostToDevice, p.stream));
-  // b_w (a few selected ciphertexts regenerated from AES) on a member that would otherwise wait for the polynomial step
+  const uint32_t *wvh = nullptr;
+  SET_TRY(mfb_ssp_prover_polys_resident_async(p.ctx, ssp, witness_limbs, nlimbs, delta, p.stream, &wvh));
+  SET_CUDA(cudaEventRecord(s->ev_polys, p.stream));
+  // 2. b_w (a few selected ciphertexts regenerated from AES) on a member that would otherwise wait for the polynomial step
   Member &bm = s->m[world > 1 ? 1 : 0];
   if (want_bw) {
     SET_CUDA(cudaSetDevice(bm.device));
     SET_TRY(mfb_b_w_dev(bm.ctx, seed, bt_offset, bt_recs, M, witness_limbs, nlimbs, delta, bm.res + 4 * SLOT, bm.stream));
   }
-  // polynomial step on the primary, queued without a host round trip; the other members wait for it ON THE DEVICE
-  SET_CUDA(cudaSetDevice(p.device));
-  const uint32_t *wvh = nullptr;
-  SET_TRY(mfb_ssp_prover_polys_resident_async(p.ctx, ssp, witness_limbs, nlimbs, delta, p.stream, &wvh));
-  SET_CUDA(cudaEventRecord(s->ev_polys, p.stream));
-  // every member: its slices of w, v, h over NVLink, both two-vector passes over its shards, then ONE kernel that
-  // finishes its four partial sums and pushes them to every member; a small second kernel waits for the others' and adds
+  // 3. every member: its slices of w, v, h over NVLink (one strided copy), both two-vector passes over its shards, then ONE
+  //    kernel that finishes its four partial sums and pushes them to every member (it never waits)
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
@@ -720,17 +719,22 @@ static int prove_body(mfb_set *s, mfb_ssp *ssp, const mfb_set_region *rs, const 
       SET_TRY(grow((void **)&mb.co, &cap, (3 * cnt + 4) * 4, false));
       mb.co_cap = cap / 4;
       SET_CUDA(cudaStreamWaitEvent(mb.stream, s->ev_polys, 0));
-      for (int k = 0; k < 3 && cnt; k++)
-        SET_CUDA(cudaMemcpyPeerAsync(mb.co + k * cnt, mb.device, wvh + k * D + first, p.device, cnt * 4, mb.stream));
+      if (cnt)  // rows w, v, h of the primary's [3][D] array -> the member's [3][cnt]
+        SET_CUDA(cudaMemcpy2DAsync(mb.co, cnt * 4, wvh + first, D * 4, cnt * 4, 3, cudaMemcpyDefault, mb.stream));
       cw = mb.co;
       cv = mb.co + cnt;
       ch = mb.co + 2 * cnt;
     }
     SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(rs->shard[i]), cw, ch, cnt, 0, mb.stream));
     SET_TRY(mfb_lincomb2_partials_dev(mb.ctx, (const uint64_t *)mfb_region_cts(ras->shard[i]), cv, ch, cnt, 1, mb.stream));
-    SET_TRY(mfb_peer_finish4_push_dev(mb.ctx, mb.group, mb.stream));  // never blocks
+    SET_TRY(mfb_peer_finish4_push_dev(mb.ctx, mb.group, mb.stream));
   }
-  for (size_t i = 0; i < world; i++) {  // the waiting halves, after every member's pushes are queued
+  // 4. the incoming accumulators (usually all zero: a proof starts from proof_init) — staged while the devices work
+  const bool any = stage_in(s, host, 4);
+  SET_CUDA(cudaSetDevice(p.device));
+  if (any) SET_CUDA(cudaMemcpyAsync(p.res, s->acc_pin, 4 * SLOT * 8, cudaMemcpyHostToDevice, p.stream));
+  // 5. the waiting halves of the exchange, after every member's pushes are queued
+  for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
     SET_TRY(mfb_peer_wait4_dev(mb.ctx, mb.group, i == 0 && any ? mb.res : nullptr, mb.res, SLOT, mb.stream));
@@ -762,8 +766,7 @@ MFB_API int mfb_set_prove_resident_bw(mfb_set *s, mfb_ssp *ssp, const mfb_set_re
       return set_fail(MFB_EARG, "mfb_set_prove_resident: the two regions are sharded differently");
   SET_TRY(ensure_acc_pin(s));
   uint64_t *host[NACC] = {v_w_flat_inout, h_flat_inout, hat_v_flat_inout, hat_h_flat_inout, b_w_flat_out};
-  const bool any = stage_in(s, host, 4);
-  const int rc = finish_call(s, prove_body(s, ssp, rs, ras, witness_limbs, nlimbs, delta, seed, bt_offset, bt_recs, M, any,
+  const int rc = finish_call(s, prove_body(s, ssp, rs, ras, witness_limbs, nlimbs, delta, seed, bt_offset, bt_recs, M, host,
                                            b_w_flat_out != nullptr));
   if (rc == MFB_OK) stage_out(s, host, b_w_flat_out ? NACC : 4);
   return rc;

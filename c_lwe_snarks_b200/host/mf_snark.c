@@ -486,10 +486,21 @@ void prover(proof_t pi, crs_t crs, ssp_t ssp, mpz_t witness) {
      * only the witness bits and the four accumulators cross PCIe */
     static uint64_t *acc = NULL; /* kept across proofs: 647 KB would be a fresh mmap + page faults every call */
     if (!acc && !(acc = malloc(5 * FLAT_CT * 8))) mf_die("malloc");
-    mf_ct_to_flat(acc, pi->v_w, "prover");
-    mf_ct_to_flat(acc + FLAT_CT, pi->h, "prover");
-    mf_ct_to_flat(acc + 2 * FLAT_CT, pi->hat_v, "prover");
-    mf_ct_to_flat(acc + 3 * FLAT_CT, pi->hat_h, "prover");
+    { /* eval_poly accumulates into rop (lwe.c:176-186) — but a proof normally starts from proof_init: all zero */
+      mpz_t *el[4] = {pi->v_w, pi->h, pi->hat_v, pi->hat_h};
+      int zero = 1;
+      for (int k = 0; k < 4 && zero; k++)
+        for (size_t i = 0; i <= GAMMA_N; i++)
+          if (SIZ(el[k][i]) != 0) {
+            zero = 0;
+            break;
+          }
+      if (zero) {
+        memset(acc, 0, 4 * FLAT_CT * 8);
+      } else {
+        for (int k = 0; k < 4; k++) mf_ct_to_flat(acc + k * FLAT_CT, el[k], "prover");
+      }
+    }
     if (res->ms) {
       if (mfb_set_prove_resident_bw(g_set, rssp, res->ms, res->mas, PTR(witness), (size_t)SIZ(witness), delta, crs->seed, CTR_BT, recs,
                                     M, acc, acc + FLAT_CT, acc + 2 * FLAT_CT, acc + 3 * FLAT_CT, acc + 4 * FLAT_CT) != MFB_OK) {
