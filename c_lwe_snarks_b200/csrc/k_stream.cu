@@ -213,11 +213,15 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
            const uint32_t *__restrict__ coeffs0, const uint32_t *__restrict__ coeffs1,
            const uint32_t *__restrict__ idx, size_t d, int nparts, uint64_t *__restrict__ partial0,
            uint64_t *__restrict__ partial1) {
-  // NVEC = 1: tiles of 490 coordinates, thread t < 490 owns coordinate t.
-  // NVEC = 2: tiles of 245 coordinates, threads [0,245) accumulate vector 0 and [245,490) vector 1 from the same tile.
-  constexpr int TILE = KS_TILE / NVEC;
-  constexpr int NTILES = N / TILE;
-  constexpr int TILE_BYTES = TILE * CT_BYTES;
+  // Tiles of 490 coordinates, thread t < 490 owns coordinate t.  NVEC = 1: one E/O accumulator (43 registers, 22
+  // IMAD.WIDE.X per MAC).  NVEC = 2: TWO scalar vectors over the same keystream tile; the two accumulators are kept
+  // CANONICAL (22 limbs each, 44 registers together — what one E/O accumulator takes), so the kernel keeps the
+  // full-size tile, the 5.5 blocks per thread and the register budget of NVEC = 1; a canonical MAC is the even chain
+  // on the register pairs (r[2i], r[2i+1]) plus the odd chain on (r[2i+1], r[2i+2]) (acc_mad_canon), a few more
+  // instructions than the E/O form in a kernel whose MAC phase is 2-3 % of its instructions.
+  constexpr int TILE = KS_TILE;
+  constexpr int NTILES = KS_NTILES;
+  constexpr int TILE_BYTES = KS_TILE_BYTES;
   extern __shared__ __align__(16) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bars[2 * KS_NBUF];
   KsSmem s = ks_smem_setup(dyn, t0_global);
@@ -232,10 +236,8 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
   const int tile = blockIdx.x % NTILES;
   const int chunk = blockIdx.x / NTILES;
   const int lane = threadIdx.x & 31;
-  const int vec = (NVEC == 2 && threadIdx.x >= TILE) ? 1 : 0;
-  const int lc = threadIdx.x - vec * TILE;
-  const bool is_mac = threadIdx.x < NVEC * TILE;
-  const uint32_t *coeffs = vec ? coeffs1 : coeffs0;
+  const int lc = threadIdx.x;
+  const bool is_mac = threadIdx.x < TILE;
 
   auto geom = [&](size_t m) {
     const size_t k = idx ? idx[m] : m;
@@ -255,16 +257,20 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     const int b = (int)(t % KS_NBUF);
     if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));  // its previous reader is done
     const TileGeom g = geom(m0 + t);
-    // NVEC = 1: 2818 blocks = 5.5 per thread, rotate by half a CTA (5, 6, 5, 6, ...); NVEC = 2: 1409 blocks = 2.75
-    // per thread, rotate by a quarter (3, 3, 3, 2, ...): every warp averages the same work over a few items
-    const int rot = NVEC == 1 ? (int)((t & 1) * (KS_THREADS / 2)) : (int)((t & 3) * (KS_THREADS / 4));
-    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, rot);
+    // 2818 blocks = 5.5 per thread: rotate by half a CTA (5, 6, 5, 6, ...), every warp averages the same work
+    ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * b);
   };
 
-  Acc704 acc;
-  acc_zero(acc);
+  Acc704 acc;            // NVEC = 1
+  uint32_t r0[22], r1[22];  // NVEC = 2
+  if constexpr (NVEC == 1) {
+    acc_zero(acc);
+  } else {
+#pragma unroll
+    for (int l = 0; l < 22; l++) r0[l] = r1[l] = 0;
+  }
   __syncthreads();  // tables and barriers ready
   // warp w runs on scheduler w % 4: warps 4-7 and 12-15 are the late ones, so every scheduler has two of each kind
   const bool late = (threadIdx.x >> 7) & 1;  // late warps: AES of item t+2 before the MAC of item t
@@ -279,7 +285,12 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
       const TileGeom g = geom(m);
       uint32_t a[22];
       ks_read_coord(buf_of(b), g.delta + CT_BYTES * lc, a);
-      acc_mad(acc, a, coeffs[m]);
+      if constexpr (NVEC == 1) {
+        acc_mad(acc, a, coeffs0[m]);
+      } else {
+        acc_mad_canon(r0, a, coeffs0[m]);
+        acc_mad_canon(r1, a, coeffs1[m]);
+      }
     }
     __syncwarp();
     if (lane == 0) ksb_arrive(bbase + 8 * (KS_NBUF + b));
@@ -290,15 +301,22 @@ k_evalpoly(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_g
     // the finish kernel adds `nparts` partials for every coordinate: a tile with one chunk fewer zeroes the last slot
     const int c = tile * TILE + lc;
     if (chunk == nch - 1 && nch < nparts) {
-      uint64_t *z = (vec ? partial1 : partial0) + (size_t)nch * PLANAR_U64;
 #pragma unroll
-      for (int j = 0; j < L64; j++) z[(size_t)j * NCP + c] = 0;
+      for (int v = 0; v < NVEC; v++) {
+        uint64_t *z = (v ? partial1 : partial0) + (size_t)nch * PLANAR_U64;
+#pragma unroll
+        for (int j = 0; j < L64; j++) z[(size_t)j * NCP + c] = 0;
+      }
     }
-    uint64_t *out = (vec ? partial1 : partial0) + (size_t)chunk * PLANAR_U64;
-    uint32_t r[22];
-    acc_fold(acc, r);
+    if constexpr (NVEC == 1) acc_fold(acc, r0);
+    uint64_t *out = partial0 + (size_t)chunk * PLANAR_U64;
 #pragma unroll
-    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r[2 * j] | (uint64_t)r[2 * j + 1] << 32;
+    for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r0[2 * j] | (uint64_t)r0[2 * j + 1] << 32;
+    if constexpr (NVEC == 2) {
+      out = partial1 + (size_t)chunk * PLANAR_U64;
+#pragma unroll
+      for (int j = 0; j < L64; j++) out[(size_t)j * NCP + c] = (uint64_t)r1[2 * j] | (uint64_t)r1[2 * j + 1] << 32;
+    }
   }
 }
 
@@ -772,7 +790,7 @@ cudaError_t launch_bcoord_partials(const uint8_t *c8, const uint32_t *coeffs0, c
 
 int evalpoly2_nchunks(size_t d, int sm_count) {
   int nparts;
-  evalpoly_plan(d, sm_count, 2 * KS_NTILES, EVALPOLY_MAX_PARTS, &nparts);
+  evalpoly_plan(d, sm_count, KS_NTILES, EVALPOLY_MAX_PARTS, &nparts);
   return nparts;
 }
 
@@ -782,7 +800,7 @@ cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uin
                                       uint64_t *partial0, uint64_t *partial1, cudaStream_t st) {
   if (d == 0 || nchunks == 0) return cudaSuccess;
   int nparts;
-  const int ncta = evalpoly_plan(d, sm_count, 2 * KS_NTILES, nchunks, &nparts);
+  const int ncta = evalpoly_plan(d, sm_count, KS_NTILES, nchunks, &nparts);
   if (nparts != nchunks) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void *)k_evalpoly<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;

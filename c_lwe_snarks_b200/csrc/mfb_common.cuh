@@ -91,6 +91,17 @@ __device__ __forceinline__ void acc_mad(AccN<NL> &x, const uint32_t (&a)[NL], ui
   MadChain<NL / 2 - 1, true>::template run<0, 1>(x.O, a, s);  // odd limbs: O[0..NL-3], low half of a[NL-1] * s into O[NL-2]
 }
 
+// r += s * a on a CANONICAL accumulator (NL limbs, value = r): the even chain adds a[2i] * s on the register pairs
+// (r[2i], r[2i+1]), the odd chain a[2i+1] * s on (r[2i+1], r[2i+2]) — half the registers of the E/O form; the odd chain's
+// pairs are not 64-bit aligned, so it costs a few more instructions.  For kernels that need two accumulators in the
+// register budget of one (k_evalpoly<2>).
+template <int NL>
+__device__ __forceinline__ void acc_mad_canon(uint32_t (&r)[NL], const uint32_t (&a)[NL], uint32_t s) {
+  static_assert(NL % 2 == 0, "even limb count");
+  MadChain<NL / 2, false>::template run<0, 0>(r, a, s);
+  MadChain<NL / 2 - 1, true>::template run<1, 1>(r, a, s);
+}
+
 // acc += (a * b) mod 2^(32 NL) for two NL-limb operands (schoolbook low half: NL (NL + 1) / 2 limb products, 253 for 22).
 // Row KB adds a[0..NL-1-KB] * b[KB] at limb offset KB as two carry chains (l even, l odd).  A product at
 // limb position pos = l + KB goes to E[pos], E[pos+1] when pos is even and to O[pos-1], O[pos] when
