@@ -104,6 +104,8 @@ _SIGS = {
     "mfb_eval_poly_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_eval_poly2": (C.c_int, [_vp, _u8p, C.c_uint64, _u8p, _u64p, _u64p, C.c_size_t, _u64p, _u64p]),
     "mfb_eval_poly2_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
+    "mfb_eval_poly2_begin_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "mfb_eval_poly2_end_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "mfb_encrypt": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p]),
     "mfb_encrypt_cb": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
                                 C.c_int, C.c_size_t, _u8p]),
@@ -611,6 +613,15 @@ class Context:
                        rop1_in, rop1_out: int, stream: int = 0):
         self._ck(self.lib.mfb_eval_poly2_dev(self.h, _p8(_seed(seed)), offset, c8_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in,
                                              rop0_out, rop1_in, rop1_out, stream))
+
+    def eval_poly2_begin_dev(self, seed, offset: int, coeffs0_ptr: int, coeffs1_ptr, d: int, records_from_host: bool, stream: int = 0):
+        self._ck(self.lib.mfb_eval_poly2_begin_dev(self.h, _p8(_seed(seed)), offset, coeffs0_ptr, coeffs1_ptr, d,
+                                                   1 if records_from_host else 0, stream))
+
+    def eval_poly2_end_dev(self, c8_dev_ptr: int, c8_host_ptr, coeffs0_ptr: int, coeffs1_ptr, d: int, rop0_in, rop0_out: int,
+                           rop1_in, rop1_out, stream: int = 0):
+        self._ck(self.lib.mfb_eval_poly2_end_dev(self.h, c8_dev_ptr, c8_host_ptr, coeffs0_ptr, coeffs1_ptr, d, rop0_in, rop0_out,
+                                                 rop1_in, rop1_out, stream))
 
     def columns_split_dev(self, flat_ptr: int, cols_ptr: int, stream: int = 0):
         self._ck(self.lib.mfb_columns_split_dev(self.h, flat_ptr, cols_ptr, stream))

@@ -751,26 +751,30 @@ int mfb_columns_carry_dev(mfb_ctx *ctx, const uint64_t *cols_dev, int c0, int nc
   return MFB_OK;
 }
 
-// eval_poly over one region for one or two scalar vectors (coeffs1 / rop1 = nullptr: one): the AES + MAC kernel for the a
-// coordinates, k_bcoord for the b coordinate, the finish kernel(s) (fused with the peer exchange when `g`).  The wire
-// records are either on the device already (c8_host = nullptr) or are copied from c8_host into c8_dev on the context's
-// second stream while the AES kernel — which does not need them — is running.
-static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *c8_dev, const uint8_t *c8_host,
-                          size_t c8_bytes, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, const uint32_t *idx_dev,
-                          size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
-                          uint64_t *rop1_out_dev, cudaStream_t st, mfb_peer_group *g) {
+// eval_poly over one region for one or two scalar vectors (coeffs1 / rop1 = nullptr: one), in two halves:
+//   begin  the AES + MAC kernel for the a coordinates — it needs the seed and the scalars only;
+//   end    k_bcoord for the b coordinate (the ONLY consumer of the wire records) and the finish kernel(s) (fused with the
+//          peer exchange when `g`).  The records are either on the device already (c8_host = nullptr) or are copied from
+//          c8_host into c8_dev on the context's second stream while the AES kernel is running.
+// A caller that drives several contexts from one thread (device sets) queues every context's `begin` before any `end`:
+// staging pageable records blocks the calling thread, and must not delay the other devices' AES kernels.
+static int eval_poly_nchunks(const mfb_ctx *ctx, size_t d, bool two) {
+  int nchunks = d ? (two ? evalpoly2_nchunks(d, ctx->sm_count) : evalpoly_nchunks(d, ctx->sm_count)) : 0;
+  if ((two ? 2 : 1) * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / (two ? 2 : 1);
+  return nchunks;
+}
+
+static int eval_poly_begin(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, bool overlap_records, const uint32_t *coeffs0_dev,
+                           const uint32_t *coeffs1_dev, const uint32_t *idx_dev, size_t d, cudaStream_t st) {
   AesKey key;
   aes_host::expand(seed, &key);
   const bool two = coeffs1_dev != nullptr;
-  int nchunks = d ? (two ? evalpoly2_nchunks(d, ctx->sm_count) : evalpoly_nchunks(d, ctx->sm_count)) : 0;
-  if ((two ? 2 : 1) * nchunks > MAX_CHUNKS) nchunks = MAX_CHUNKS / (two ? 2 : 1);
+  const int nchunks = eval_poly_nchunks(ctx, d, two);
   uint64_t *p0 = ctx->partial_ws, *p1 = two ? ctx->partial_ws + (size_t)nchunks * PLANAR_U64 : nullptr;
-  cudaStream_t st_b = st;
-  if (d && c8_host) {
+  if (d && overlap_records) {
     if (!ctx->stream2) MFB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     if (!ctx->ev_a) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
     if (!ctx->ev_b) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
-    st_b = ctx->stream2;
     MFB_CUDA_TRY(cudaEventRecord(ctx->ev_a, st));  // the scalars (queued on st by the caller) are on the device
   }
   if (d) prof_mark(ctx, 0, st);
@@ -779,7 +783,21 @@ static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset,
   else
     MFB_CUDA_TRY(launch_evalpoly_partials(key, ctx->t0_dev, offset, coeffs0_dev, idx_dev, d, nchunks, ctx->sm_count, p0, st));
   if (d) prof_mark(ctx, 1, st);
+  if (d) ctx->launches += 1;
+  return MFB_OK;
+}
+
+static int eval_poly_end(mfb_ctx *ctx, uint8_t *c8_dev, const uint8_t *c8_host, size_t c8_bytes, const uint32_t *coeffs0_dev,
+                         const uint32_t *coeffs1_dev, const uint32_t *idx_dev, size_t d, const uint64_t *rop0_in_dev,
+                         uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, cudaStream_t st,
+                         mfb_peer_group *g) {
+  const bool two = coeffs1_dev != nullptr;
+  const int nchunks = eval_poly_nchunks(ctx, d, two);
+  uint64_t *p0 = ctx->partial_ws, *p1 = two ? ctx->partial_ws + (size_t)nchunks * PLANAR_U64 : nullptr;
+  cudaStream_t st_b = st;
   if (d && c8_host) {
+    if (!ctx->stream2 || !ctx->ev_a || !ctx->ev_b) return set_err(MFB_EARG, "eval_poly: records from the host need records_from_host in the first half");
+    st_b = ctx->stream2;
     MFB_CUDA_TRY(cudaStreamWaitEvent(st_b, ctx->ev_a, 0));
     MFB_CUDA_TRY(cudaMemcpyAsync(c8_dev, c8_host, c8_bytes, cudaMemcpyHostToDevice, st_b));
   }
@@ -796,8 +814,34 @@ static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset,
   } else {
     MFB_CUDA_TRY(launch_lincomb_finish(p0, 0, 1, nchunks, rop0_in_dev, rop0_out_dev, 0, nullptr, nullptr, st));
   }
-  ctx->launches += (d ? 2 : 0) + 1;
+  ctx->launches += (d ? 1 : 0) + 1;
   return MFB_OK;
+}
+
+static int eval_poly_core(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, uint8_t *c8_dev, const uint8_t *c8_host,
+                          size_t c8_bytes, const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, const uint32_t *idx_dev,
+                          size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev,
+                          uint64_t *rop1_out_dev, cudaStream_t st, mfb_peer_group *g) {
+  MFB_TRY(eval_poly_begin(ctx, seed, offset, c8_host != nullptr, coeffs0_dev, coeffs1_dev, idx_dev, d, st));
+  return eval_poly_end(ctx, c8_dev, c8_host, c8_bytes, coeffs0_dev, coeffs1_dev, idx_dev, d, rop0_in_dev, rop0_out_dev, rop1_in_dev,
+                       rop1_out_dev, st, g);
+}
+
+int mfb_eval_poly2_begin_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint32_t *coeffs0_dev,
+                             const uint32_t *coeffs1_dev, size_t d, int records_from_host, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!seed || (d && !coeffs0_dev)) return set_err(MFB_EARG, "mfb_eval_poly2_begin_dev: null pointer");
+  return eval_poly_begin(ctx, seed, offset, records_from_host != 0, coeffs0_dev, coeffs1_dev, nullptr, d, (cudaStream_t)stream);
+}
+
+int mfb_eval_poly2_end_dev(mfb_ctx *ctx, uint8_t *c8_dev, const uint8_t *c8_host, const uint32_t *coeffs0_dev,
+                           const uint32_t *coeffs1_dev, size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev,
+                           const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, void *stream) {
+  MFB_CHECK_CTX(ctx);
+  if (!rop0_out_dev || (d && (!c8_dev || !coeffs0_dev)) || ((coeffs1_dev == nullptr) != (rop1_out_dev == nullptr)))
+    return set_err(MFB_EARG, "mfb_eval_poly2_end_dev: null pointer");
+  return eval_poly_end(ctx, c8_dev, c8_host, d * CT_BYTES, coeffs0_dev, coeffs1_dev, nullptr, d, rop0_in_dev, rop0_out_dev, rop1_in_dev,
+                       rop1_out_dev, (cudaStream_t)stream, nullptr);
 }
 
 int mfb_eval_poly_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,

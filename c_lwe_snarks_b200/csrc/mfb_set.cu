@@ -406,6 +406,7 @@ MFB_API int mfb_set_region_lincomb2(mfb_set *s, const mfb_set_region *r, const u
 static int eval_poly2_body(mfb_set *s, const uint8_t seed[40], uint64_t offset, const uint8_t *c8, const uint32_t *co32, size_t d,
                            int nvec, bool any) {
   const size_t world = s->m.size();
+  // 1. every member: its scalars, then the AES + MAC kernel over its range — it needs nothing else
   for (size_t i = 0; i < world; i++) {
     Member &mb = s->m[i];
     SET_CUDA(cudaSetDevice(mb.device));
@@ -417,18 +418,24 @@ static int eval_poly2_body(mfb_set *s, const uint8_t seed[40], uint64_t offset, 
       mb.co_cap = cap / 4;
     }
     SET_TRY(grow((void **)&mb.c8, &mb.c8_cap, cnt * MFB_CT_BYTES + 16, false));
-    uint32_t *c0 = mb.co, *c1 = mb.co + cnt;
+    uint32_t *c0 = mb.co, *c1 = nvec == 2 ? mb.co + cnt : nullptr;
     if (cnt) {
       SET_CUDA(cudaMemcpyAsync(c0, co32 + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
       if (nvec == 2) SET_CUDA(cudaMemcpyAsync(c1, co32 + d + first, cnt * 4, cudaMemcpyHostToDevice, mb.stream));
-      SET_CUDA(cudaMemcpyAsync(mb.c8, c8 + first * MFB_CT_BYTES, cnt * MFB_CT_BYTES, cudaMemcpyHostToDevice, mb.stream));
     }
     if (i == 0 && any) SET_CUDA(cudaMemcpyAsync(mb.res, s->acc_pin, (size_t)nvec * SLOT * 8, cudaMemcpyHostToDevice, mb.stream));
-    const uint64_t off = offset + first * (uint64_t)MFB_CTR_CT;
-    if (nvec == 2)
-      SET_TRY(mfb_eval_poly2_dev(mb.ctx, seed, off, mb.c8, c0, c1, cnt, nullptr, mb.part, nullptr, mb.part + SLOT, mb.stream));
-    else
-      SET_TRY(mfb_eval_poly_dev(mb.ctx, seed, off, mb.c8, c0, nullptr, cnt, nullptr, mb.part, mb.stream));
+    SET_TRY(mfb_eval_poly2_begin_dev(mb.ctx, seed, offset + first * (uint64_t)MFB_CTR_CT, c0, c1, cnt, 1, mb.stream));
+  }
+  // 2. the wire records (pageable host memory: staging them blocks this thread) follow on every member's second stream
+  //    while all the AES kernels are already running; then the b coordinate and the finish
+  for (size_t i = 0; i < world; i++) {
+    Member &mb = s->m[i];
+    SET_CUDA(cudaSetDevice(mb.device));
+    size_t first, cnt;
+    split_range(d, world, i, &first, &cnt);
+    uint32_t *c0 = mb.co, *c1 = nvec == 2 ? mb.co + cnt : nullptr;
+    SET_TRY(mfb_eval_poly2_end_dev(mb.ctx, mb.c8, c8 + first * MFB_CT_BYTES, c0, c1, cnt, nullptr, mb.part, nullptr,
+                                   nvec == 2 ? mb.part + SLOT : nullptr, mb.stream));
   }
   SET_TRY(exchange_all(s, nvec, any));
   Member &p = s->m[0];

@@ -290,6 +290,17 @@ MFB_API int mfb_eval_poly2(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
 MFB_API int mfb_eval_poly2_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint8_t *c8_dev,
                        const uint32_t *coeffs0_dev, const uint32_t *coeffs1_dev, size_t d, const uint64_t *rop0_in_dev,
                        uint64_t *rop0_out_dev, const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, void *stream);
+/* mfb_eval_poly2_dev in two halves, for callers that drive SEVERAL contexts from one thread (device sets): `begin` queues
+ * the AES + MAC kernel (it needs the seed and the scalars only), `end` the b-coordinate kernel — the only consumer of the
+ * wire records — and the finish.  With c8_host != NULL (and records_from_host != 0 in `begin`) `end` copies the d records
+ * from host memory into c8_dev on the context's second stream, beside the running AES kernel; staging pageable memory
+ * blocks the calling thread, so queue every context's `begin` before the first `end`.  coeffs1 / rop1 may be NULL (one
+ * scalar vector).  The same (d, coeffs) must be passed to both halves; one begin/end pair at a time per context. */
+MFB_API int mfb_eval_poly2_begin_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint32_t *coeffs0_dev,
+                             const uint32_t *coeffs1_dev, size_t d, int records_from_host, void *stream);
+MFB_API int mfb_eval_poly2_end_dev(mfb_ctx *ctx, uint8_t *c8_dev, const uint8_t *c8_host, const uint32_t *coeffs0_dev,
+                           const uint32_t *coeffs1_dev, size_t d, const uint64_t *rop0_in_dev, uint64_t *rop0_out_dev,
+                           const uint64_t *rop1_in_dev, uint64_t *rop1_out_dev, void *stream);
 
 /* ---- K3+K5: Regev encryption -------------------------------------------------------------- */
 /* out_c8[k] = ct_export(regev_encrypt2(rng at offset + k*MFB_CTR_CT, sk, msg[k], e_k)) for k < count

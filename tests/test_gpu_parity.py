@@ -210,6 +210,31 @@ def test_eval_poly2_vs_oracle(ctx, oracle, d, off):
     assert np.array_equal(got1, ctx.eval_poly(SEED, off, c8, h1))
 
 
+@pytest.mark.parametrize("d,two", [(1, True), (75, True), (75, False), (500, True)])
+def test_eval_poly2_in_two_halves_with_host_records(ctx, oracle, torch, d, two):
+    """mfb_eval_poly2_begin_dev / _end_dev (what a device set queues per member): the AES + MAC kernel first, the wire records
+    copied from PAGEABLE host memory on the second stream behind it — equal to the oracle, one or two scalar vectors"""
+    off = 4 * CTR_CT + 12
+    c8 = np.ascontiguousarray(xof_records(f"halves-c8-{d}", d))
+    h0, h1 = xof_scalars(f"halves-h0-{d}", d), xof_scalars(f"halves-h1-{d}", d)
+    st = torch.cuda.current_stream().cuda_stream
+    d_h0, d_h1 = dev(torch, h0.astype(np.uint32)), dev(torch, h1.astype(np.uint32))
+    d_c8 = torch.zeros(d * CT_BYTES + 16, dtype=torch.uint8, device="cuda")
+    d_r0 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
+    d_r1 = torch.zeros(1472 * L64, dtype=torch.int64, device="cuda")
+    p1 = d_h1.data_ptr() if two else None
+    for _ in range(2):  # twice: the second pair reuses the context's second stream and events
+        ctx.eval_poly2_begin_dev(SEED, off, d_h0.data_ptr(), p1, d, True, st)
+        ctx.eval_poly2_end_dev(d_c8.data_ptr(), c8.ctypes.data, d_h0.data_ptr(), p1, d, None, d_r0.data_ptr(), None,
+                               d_r1.data_ptr() if two else None, st)
+        torch.cuda.synchronize()
+        got0 = d_r0.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64)
+        assert np.array_equal(wide(got0), oracle.eval_poly(SEED, off, c8, h0))
+        if two:
+            got1 = d_r1.cpu().numpy().view(np.uint64)[: NC * L64].reshape(NC, L64)
+            assert np.array_equal(wide(got1), oracle.eval_poly(SEED, off, c8, h1))
+
+
 def test_region(ctx, oracle):
     d, off = 64, 9 * CTR_CT
     c8, h = xof_records("reg-c8", d), xof_scalars("reg-h", d)
