@@ -109,6 +109,8 @@ _SIGS = {
     "mfb_encrypt": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_int, C.c_int, C.c_size_t, _u8p]),
     "mfb_encrypt_cb": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
                                 C.c_int, C.c_size_t, _u8p]),
+    "mfb_encrypt_cb_segs": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
+                                     C.c_int, C.c_size_t, _vp, C.c_int]),
     "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
@@ -539,6 +541,35 @@ class Context:
         self._ck(self.lib.mfb_encrypt_cb(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes, m.size,
                                          _p8(out)))
         return out
+
+    def encrypt_cb_segs(self, seed, offset: int, sk_flat, msg, draw, cuts, ent_stride: int = ENT_BYTES,
+                        ent_nbytes: int = ENT_BYTES - 1):
+        """encrypt_cb() with the records written straight into separate arrays (mfb_encrypt_cb_segs; setup() fills
+        crs->s / as / t / v this way): ``cuts`` = record counts of consecutive segments; returns one array per segment."""
+        s, sk, m = _seed(seed), _arr(sk_flat, np.uint64), _arr(msg, np.uint64)
+        if sk.size != FLAT_SK_U64 or sum(cuts) != m.size:
+            raise ValueError("sk_flat must be (1470, 11) uint64 and the segments must cover the messages")
+
+        class Seg(C.Structure):
+            _fields_ = [("first", C.c_size_t), ("count", C.c_size_t), ("dst", C.c_void_p)]
+
+        outs = [np.zeros((c, CT_BYTES), np.uint8) for c in cuts]
+        segs, first = (Seg * len(cuts))(), 0
+        for i, (c, o) in enumerate(zip(cuts, outs)):
+            segs[i] = Seg(first, c, o.ctypes.data)
+            first += c
+        fn_t = _SIGS["mfb_encrypt_cb_segs"][1][5]
+
+        def _draw(_user, dst, nbytes):
+            data = bytes(draw(nbytes))
+            if len(data) != nbytes:
+                raise ValueError("entropy callback returned the wrong number of bytes")
+            C.memmove(dst, data, nbytes)
+
+        cb = fn_t(_draw)
+        self._ck(self.lib.mfb_encrypt_cb_segs(self.h, _p8(s), offset, _p64(sk), _p64(m), cb, None, ent_stride, ent_nbytes, m.size,
+                                              C.cast(segs, C.c_void_p), len(cuts)))
+        return outs
 
     def decrypt(self, sk_flat, cts_flat, b_neg=None, want_dot: bool = False):
         sk, cts = _arr(sk_flat, np.uint64), _arr(cts_flat, np.uint64)

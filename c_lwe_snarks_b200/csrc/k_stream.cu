@@ -562,11 +562,20 @@ k_encrypt(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_gl
 //   reduced mod q_eff = 2^(64 L), L = floor(log q / 64) (what lwe.h:108-118 does for 736: mask, then drop the top limb);
 //   b_k = (e_k p + <sk, a_k> + m_k) mod q_eff, written as a ctb-byte record.
 // A ciphertext is cut into `ntiles` tiles of at most `tile` coordinates (tile * ctb <= the 45 KB keystream buffer).
+//
+// Bank conflicts of the consumers' reads: lane L reads word l of coordinate c + L, i.e. words ctb/4 apart.  For the
+// reference's width (92 bytes = 23 words) and for 100 bytes (25 words) the stride is odd and the 32 lanes hit 32 banks; for
+// log q = 512 / 768 / 1024 (16 / 24 / 32 words) they hit 2 / 4 / ONE bank(s): 33 reads of 32 wavefronts each per coordinate
+// round, on the LSU pipe the AES lookups are bound by (measured: 0.49 of the lookup bound at log q = 1024).  PADDED layout
+// (pad_wb = ctb / 16 > 0, chosen by the launcher when it lowers the conflict degree): the producers leave one 16-byte
+// block free after every ctb bytes of keystream (block b goes to slot b + b / pad_wb), so the coordinate stride becomes
+// ctb/4 + 4 words — 20 / 28 / 36: 4-way instead of 16 / 8 / 32-way; a 16-byte pad keeps the producers' STS.128 aligned.
 template <int L>
 __global__ void __launch_bounds__(KE_THREADS, 1)
 k_encrypt_g(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_global, uint64_t offset,
             const uint64_t *__restrict__ sk, int sk_stride, const uint64_t *__restrict__ msg, const uint8_t *__restrict__ ent,
-            int ent_stride, int ent_nbytes, size_t count, int n, int ctb, int tile, int ntiles, uint8_t *__restrict__ out_c8) {
+            int ent_stride, int ent_nbytes, size_t count, int n, int ctb, int tile, int ntiles, int pad_wb, uint32_t pad_inv,
+            uint8_t *__restrict__ out_c8) {
   constexpr int NL = 2 * L;
   extern __shared__ __align__(16) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bars[2 * KS_NBUF];
@@ -611,7 +620,15 @@ k_encrypt_g(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_
       const int b = (int)(t % KS_NBUF);
       if (t >= KS_NBUF) ksb_wait(bbase + 8 * (KS_NBUF + b), (uint32_t)((t / KS_NBUF - 1) & 1));
       const TileGeom g = geom(t);
-      ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, (int)((t & 1) * (KS_THREADS / 2)));
+      const int rot = (int)((t & 1) * (KS_THREADS / 2));
+      if (pad_wb == 0) {
+        ks_fill_rot(key, g.first, g.nblk, buf_of(b), s.lut, cache, rot);
+      } else {  // padded layout: block bl -> slot bl + bl / pad_wb (pad_inv: the launcher's exact reciprocal)
+        const uint32_t bufb = buf_of(b);
+        for (int bl = (threadIdx.x + rot) & (KS_THREADS - 1); bl < g.nblk; bl += KS_THREADS)
+          sts128(bufb + 16u * ((uint32_t)bl + (((uint32_t)bl * pad_inv) >> 16)),
+                 aes256_ctr_block_cached<2>(s.lut, key, g.first + bl, cache));
+      }
       __syncwarp();
       if (lane == 0) ksb_arrive(bbase + 8 * b);
     }
@@ -640,13 +657,28 @@ k_encrypt_g(const __grid_constant__ AesKey key, const uint32_t *__restrict__ t0_
       }
       {  // the NL live limbs of the coordinate that starts at byte pos of the keystream buffer
         const uint32_t pos = g.delta + (uint32_t)ctb * lc;
-        const uint32_t wa = buf_of(b) + (pos & ~3u), sh = (pos & 3u) * 8;
-        uint32_t lo = lds32(wa);
+        const uint32_t sh = (pos & 3u) * 8;
+        if (pad_wb == 0) {
+          const uint32_t wa = buf_of(b) + (pos & ~3u);
+          uint32_t lo = lds32(wa);
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-          const uint32_t hi = lds32(wa + 4 * (l + 1));
-          a[l] = __funnelshift_r(lo, hi, sh);
-          lo = hi;
+          for (int l = 0; l < NL; l++) {
+            const uint32_t hi = lds32(wa + 4 * (l + 1));
+            a[l] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+          }
+        } else {
+          // padded layout: the coordinate starts in window lc (16 lc pad bytes before it); its word l lies in the next
+          // window — one more pad block away — once (delta & ~3) + 4 l reaches ctb
+          const uint32_t wa = buf_of(b) + (pos & ~3u) + 16u * (uint32_t)lc;
+          const uint32_t room = (uint32_t)ctb - (g.delta & ~3u);  // bytes of this window from the coordinate's first word on
+          uint32_t lo = lds32(wa);
+#pragma unroll
+          for (int l = 0; l < NL; l++) {
+            const uint32_t hi = lds32(wa + 4 * (l + 1) + (4u * (l + 1) >= room ? 16u : 0u));
+            a[l] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+          }
         }
       }
       acc_mul(acc, a, w);
@@ -827,12 +859,38 @@ static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t
                                  uint8_t *out_c8, int sm_count, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt_g<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const int max_tile = KS_TILE_BYTES / ctb;  // coordinates whose keystream fits one buffer
-  const int ntiles = (n + max_tile - 1) / max_tile;
-  const int tile = (n + ntiles - 1) / ntiles;  // balanced
+  // padded keystream layout (see the kernel): when the coordinate width is a whole number of AES blocks and one pad block
+  // per coordinate lowers the bank-conflict degree gcd(words per coordinate, 32) of the consumers' reads
+  auto gcd32 = [](int v) { int g = 32; while (v % g) g >>= 1; return g; };
+  int pad_wb = 0;
+  uint32_t pad_inv = 0;
+  if (ctb % 16 == 0 && gcd32(ctb / 4 + 4) < gcd32(ctb / 4)) {
+    pad_wb = ctb / 16;
+    pad_inv = 65536u / (uint32_t)pad_wb + 1;
+    for (uint32_t bl = 0; bl <= (uint32_t)KS_MAX_BLK; bl++)  // the reciprocal must be exact for every block of a tile
+      if (((bl * pad_inv) >> 16) != bl / (uint32_t)pad_wb) pad_wb = 0;
+  }
+  const int max_tile = KS_TILE_BYTES / (ctb + (pad_wb ? 16 : 0));  // coordinates whose keystream fits one buffer
+  int ntiles = (n + max_tile - 1) / max_tile;
+  int tile = (n + ntiles - 1) / ntiles;  // balanced
+  // The 128 consumer threads walk a tile in rounds of 128 coordinates, and a partly filled round costs a full one: when
+  // tiles of a whole number of rounds need fewer rounds per ciphertext than the balanced split, take those (log q = 1024
+  // with the padded layout: 7 tiles of 293 = 21 rounds against 8 tiles of 256 = 16).
+  const int t128 = max_tile / KE_CONSUMERS * KE_CONSUMERS;
+  if (t128 >= KE_CONSUMERS) {
+    auto rounds = [&](int tl, int nt) {
+      const int last = n - (nt - 1) * tl;
+      return (nt - 1) * ((tl + KE_CONSUMERS - 1) / KE_CONSUMERS) + (last + KE_CONSUMERS - 1) / KE_CONSUMERS;
+    };
+    const int nt128 = (n + t128 - 1) / t128;
+    if (rounds(t128, nt128) < rounds(tile, ntiles)) {
+      tile = t128;
+      ntiles = nt128;
+    }
+  }
   const size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
   k_encrypt_g<L><<<(unsigned)grid, KE_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, sk_stride, msg, ent, ent_stride, ent_nbytes,
-                                                                      count, n, ctb, tile, ntiles, out_c8);
+                                                                      count, n, ctb, tile, ntiles, pad_wb, pad_inv, out_c8);
   return cudaGetLastError();
 }
 

@@ -1286,8 +1286,27 @@ int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uin
   return rc;
 }
 
+// records [first, first + cnt) of the call, device -> their destination(s): out_c8 (contiguous) or the caller's segments
+static int records_back(const uint8_t *d_out, size_t first, size_t cnt, uint8_t *out_c8, const mfb_c8_segment *segs, int nsegs,
+                        cudaStream_t st) {
+  if (cnt == 0) return MFB_OK;
+  if (out_c8) {
+    MFB_CUDA_TRY(cudaMemcpyAsync(out_c8 + first * CT_BYTES, d_out + first * CT_BYTES, cnt * CT_BYTES, cudaMemcpyDeviceToHost, st));
+    return MFB_OK;
+  }
+  for (int g = 0; g < nsegs; g++) {
+    const size_t lo = segs[g].first > first ? segs[g].first : first;
+    const size_t hi_s = segs[g].first + segs[g].count, hi_p = first + cnt, hi = hi_s < hi_p ? hi_s : hi_p;
+    if (lo >= hi) continue;
+    MFB_CUDA_TRY(cudaMemcpyAsync(segs[g].dst + (lo - segs[g].first) * CT_BYTES, d_out + lo * CT_BYTES, (hi - lo) * CT_BYTES,
+                                 cudaMemcpyDeviceToHost, st));
+  }
+  return MFB_OK;
+}
+
 static int encrypt_cb_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
-                           mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+                           mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8,
+                           const mfb_c8_segment *segs, int nsegs) {
   // pieces: a short first one so that the device starts early, then ~110 ciphertexts per SM and launch
   const size_t piece = (size_t)ctx->sm_count * 110, first_piece = (size_t)ctx->sm_count * 16;
   const size_t cap = piece * (size_t)ent_stride;
@@ -1302,6 +1321,9 @@ static int encrypt_cb_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
   }
   for (int k = 0; k < 2; k++)
     if (!ctx->ent_free[k]) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ent_free[k], cudaEventDisableTiming));
+  if (!ctx->stream2) MFB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  if (!ctx->ev_a) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+  if (!ctx->ev_b) MFB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
   void *d_skf, *d_skp, *d_msg, *d_ent, *d_out;
   MFB_TRY(scratch(ctx, 0, MFB_FLAT_SK_U64 * 8, &d_skf));
   MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &d_skp));
@@ -1313,6 +1335,12 @@ static int encrypt_cb_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
   MFB_TRY(mfb_flat_to_planar_dev(ctx, (const uint64_t *)d_skf, N, 1, (uint64_t *)d_skp, ctx->stream));
   bool used[2] = {false, false};
   int k = 0;
+  // The records of piece i go back on the SECOND stream while piece i + 1 is being encrypted.  The destination is
+  // pageable memory (the CRS arrays), so that copy blocks this thread until piece i's kernel has finished: it is queued
+  // only after piece i + 1 has been launched — the device never waits for the host, the host still draws the entropy of
+  // piece i + 2 within the kernel time of piece i + 1.
+  size_t prev_first = 0, prev_cnt = 0;
+  cudaEvent_t ev[2] = {ctx->ev_a, ctx->ev_b};
   for (size_t done = 0; done < count; k ^= 1) {
     size_t cnt = done == 0 ? first_piece : piece;
     if (cnt > count - done) cnt = count - done;
@@ -1325,27 +1353,53 @@ static int encrypt_cb_body(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset
     used[k] = true;
     MFB_TRY(mfb_encrypt_dev(ctx, seed, offset + done * (uint64_t)CTR_CT, (const uint64_t *)d_skp, (const uint64_t *)d_msg + done,
                             d_e, ent_stride, ent_nbytes, cnt, (uint8_t *)d_out + done * CT_BYTES, ctx->stream));
+    MFB_CUDA_TRY(cudaEventRecord(ev[k], ctx->stream));
+    if (prev_cnt) {
+      MFB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ev[k ^ 1], 0));
+      MFB_TRY(records_back((const uint8_t *)d_out, prev_first, prev_cnt, out_c8, segs, nsegs, ctx->stream2));
+    }
+    prev_first = done;
+    prev_cnt = cnt;
     done += cnt;
   }
-  MFB_CUDA_TRY(cudaMemcpyAsync(out_c8, d_out, count * CT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  MFB_TRY(records_back((const uint8_t *)d_out, prev_first, prev_cnt, out_c8, segs, nsegs, ctx->stream));  // the last piece
+  MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream2));
   MFB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MFB_OK;
 }
 
-int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
-                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+static int encrypt_cb_checked(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                              mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8,
+                              const mfb_c8_segment *segs, int nsegs, const char *who) {
   MFB_CHECK_CTX(ctx);
   if (count == 0) return MFB_OK;
-  if (!seed || !sk_flat || !msg || !draw || !out_c8) return set_err(MFB_EARG, "mfb_encrypt_cb: null pointer");
+  if (!seed || !sk_flat || !msg || !draw || ((out_c8 == nullptr) == (segs == nullptr)) || (segs && nsegs < 1))
+    return set_err(MFB_EARG, "%s: null pointer (give either out_c8 or segments)", who);
   if (ent_nbytes < 0 || ent_nbytes > 88 || ent_stride < ent_nbytes || ent_stride <= 0)
-    return set_err(MFB_EARG, "mfb_encrypt_cb: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)");
-  const int rc = encrypt_cb_body(ctx, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, count, out_c8);
+    return set_err(MFB_EARG, "%s: need 0 <= ent_nbytes <= 88 and ent_stride >= max(1, ent_nbytes)", who);
+  const int rc = encrypt_cb_body(ctx, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, count, out_c8, segs, nsegs);
   // the key and the noise are secret: nothing of them stays in the staging buffers, on error paths either
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);  // (the pinned buffers may still be read by a queued copy after an early return)
   for (int j = 0; j < 2; j++)
     if (ctx->ent_pin[j]) memset(ctx->ent_pin[j], 0, ctx->ent_pin_cap);
   scrub_secrets(ctx, count * (size_t)ent_stride);
   return rc;
+}
+
+int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                   mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8) {
+  if (count && !out_c8) return set_err(MFB_EARG, "mfb_encrypt_cb: null pointer");
+  return encrypt_cb_checked(ctx, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, count, out_c8, nullptr, 0,
+                            "mfb_encrypt_cb");
+}
+
+int mfb_encrypt_cb_segs(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                        mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, const mfb_c8_segment *segs,
+                        int nsegs) {
+  if (count && !segs) return set_err(MFB_EARG, "mfb_encrypt_cb_segs: null pointer");
+  return encrypt_cb_checked(ctx, seed, offset, sk_flat, msg, draw, user, ent_stride, ent_nbytes, count, nullptr, segs, nsegs,
+                            "mfb_encrypt_cb_segs");
 }
 
 static int decrypt_body(mfb_ctx *ctx, const uint64_t *sk_flat, const uint64_t *cts_flat, const uint8_t *b_neg, size_t count,

@@ -348,16 +348,12 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
       abort();
     }
     mf_trace("setup.entropy+encrypt (one thread per GPU)", t0);
-  } else {
+  } else if (set) { /* hooked entropy: drawn by this thread in the reference's order, the pieces spread over the GPUs */
     uint8_t *recs = malloc(count * CT_BYTES);
     if (!recs) mf_die("malloc");
-    if (set) { /* hooked entropy: drawn by this thread in the reference's order, the pieces spread over the GPUs */
-      if (mfb_set_encrypt_cb(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs) != MFB_OK) {
-        fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_cb failed: %s\n", mfb_set_last_error());
-        abort();
-      }
-    } else {
-      MF_GPU(mfb_encrypt_cb(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs));
+    if (mfb_set_encrypt_cb(set, crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, recs) != MFB_OK) {
+      fprintf(stderr, "mangiafuoco_b200: mfb_set_encrypt_cb failed: %s\n", mfb_set_last_error());
+      abort();
     }
     mf_trace("setup.entropy+encrypt", t0);
     memcpy(crs->s, recs, D * CT_BYTES);
@@ -365,6 +361,14 @@ void setup(crs_t crs, vrs_t vrs, ssp_t ssp) {
     memcpy(crs->t, recs + 2 * D * CT_BYTES, CT_BYTES);
     memcpy(crs->v, recs + (2 * D + 1) * CT_BYTES, (M - 1) * CT_BYTES);
     free(recs);
+  } else {
+    /* one GPU: the records of a piece come back on a second stream while the next piece is encrypted, straight into the
+     * CRS arrays */
+    const mfb_c8_segment segs[4] = {{0, D, (uint8_t *)crs->s}, {D, D, (uint8_t *)crs->as}, {2 * D, 1, crs->t},
+                                    {2 * D + 1, M - 1, (uint8_t *)crs->v}};
+    MF_GPU(mfb_encrypt_cb_segs(mf_gpu(), crs->seed, 0, skf, msg, draw_entropy, NULL, MFB_ENT_BYTES, MFB_ENT_BYTES - 1, count, segs,
+                               M > 1 ? 4 : 3));
+    mf_trace("setup.entropy+encrypt", t0);
   }
   explicit_bzero(skf, MFB_FLAT_SK_U64 * 8); /* the flat copy of the secret key does not outlive the call */
   free(skf);

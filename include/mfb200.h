@@ -317,6 +317,12 @@ MFB_API int mfb_encrypt(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, c
  * encrypts the previous piece: setup()'s 2D+M draws (tens of ms of getrandom) hide behind the kernel. */
 MFB_API int mfb_encrypt_cb(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
                    mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8);
+/* The same with the records written straight to nsegs segments of the record index space (record k of segment g goes to
+ * g.dst + (k - g.first) * 92): setup() fills crs->s, crs->as, crs->t, crs->v without an intermediate array.  In both
+ * forms the records of a piece travel back on a second stream while the next piece is being encrypted. */
+MFB_API int mfb_encrypt_cb_segs(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_flat, const uint64_t *msg,
+                        mfb_entropy_fn draw, void *user, int ent_stride, int ent_nbytes, size_t count, const mfb_c8_segment *segs,
+                        int nsegs);
 MFB_API int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const uint64_t *sk_planar_dev,
                     const uint64_t *msg_dev, const uint8_t *ent_dev, int ent_stride, int ent_nbytes, size_t count,
                     uint8_t *out_c8_dev, void *stream);

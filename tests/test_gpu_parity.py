@@ -383,6 +383,26 @@ def test_encrypt_cb_equals_encrypt(ctx, oracle, cnt):
     assert np.array_equal(got[k], want[0])
 
 
+@pytest.mark.parametrize("cuts", [(1,), (3, 0, 2), (148 * 16 - 1, 2, 148 * 110 + 5, 1, 63), (20000, 20000, 1, 63)])
+def test_encrypt_cb_into_segments(ctx, oracle, cuts):
+    """mfb_encrypt_cb_segs (setup(): records straight into crs->s / as / t / v, each piece travelling back while the next
+    one is encrypted): the segments, concatenated, are the records of mfb_encrypt — cuts inside pieces, empty segments"""
+    cnt = sum(cuts)
+    sk = oracle.key_gen(xof("sk-cbs", N * CT_BYTES))
+    m = xof_scalars(f"m-cbs-{cnt}", cnt)
+    ent = xof(f"ent-cbs-{cnt}", cnt * 70)
+    pos = [0]
+
+    def draw(n):
+        out = ent[pos[0]: pos[0] + n].tobytes()
+        pos[0] += n
+        return out
+
+    outs = ctx.encrypt_cb_segs(SEED, 2 * CTR_CT + 9, sk[:, :11], m, draw, cuts)
+    assert pos[0] == cnt * 70 and [o.shape[0] for o in outs] == list(cuts)
+    assert np.array_equal(np.concatenate(outs), ctx.encrypt(SEED, 2 * CTR_CT + 9, sk[:, :11], m, ent))
+
+
 def test_allocation_failure_is_reported_and_does_not_poison_later_calls(ctx, oracle):
     """A region that cannot be allocated (2^21 ciphertexts = 272 GB) fails with MFB_ENOMEM and leaves no stale CUDA
     error behind: the next calls work (mf_crs_make_resident relies on this to fall back to the fused path)."""

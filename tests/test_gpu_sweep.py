@@ -58,10 +58,12 @@ def sk_planar(sk_flat: np.ndarray, stride: int) -> np.ndarray:
 
 
 @pytest.mark.parametrize("L,n,ctb,cnt", [(11, 1470, 92, 3), (8, 1024, 64, 5), (10, 1246, 80, 4), (12, 1470, 100, 3), (14, 1470, 112, 2),
-                                         (16, 2047, 128, 2), (4, 65, 32, 9), (6, 700, 52, 300), (13, 33, 104, 150)])
+                                         (16, 2047, 128, 2), (4, 65, 32, 9), (6, 700, 52, 300), (13, 33, 104, 150),
+                                         (12, 1600, 96, 2), (8, 600, 64, 200), (16, 320, 128, 170)])
 def test_generic_encrypt_vs_python(L, n, ctb, cnt, oracle):
     """b_k = (e_k p + <sk, a_k> + m_k) mod 2^(64 L) with a_k from the AES-CTR stream at coordinate width ctb = log q / 8 —
-    against plain integers over the oracle's keystream (ragged tiles, mid-block stream offsets, maximal noise bytes)."""
+    against plain integers over the oracle's keystream (ragged tiles, mid-block stream offsets, maximal noise bytes; widths of
+    64 / 96 / 128 / 32 bytes take the padded keystream layout of k_encrypt_g, the others the plain one)."""
     import torch
 
     import c_lwe_snarks_b200 as m

@@ -11,6 +11,7 @@ ciphertexts of n + 1 coordinates with q_eff = 2^(64 * floor(log q / 64)).
 Prints one JSON line per point and kernel; run on a B200:  python tools/sweep_params.py > profiles/sweep_params_r02.jsonl
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -22,6 +23,9 @@ sys.path.insert(0, str(ROOT))
 import c_lwe_snarks_b200 as m  # noqa: E402
 
 POINTS = [(1024, 512), (1024, 640), (1246, 640), (1246, 736), (1470, 736), (1470, 800), (1470, 896), (1600, 768), (2047, 1024)]
+if os.environ.get("SWEEP_POINTS"):  # e.g. SWEEP_POINTS=2047:1024,1470:896 SWEEP_KERNELS=encrypt (profiling one point under ncu)
+    POINTS = [tuple(int(v) for v in pt.split(":")) for pt in os.environ["SWEEP_POINTS"].split(",")]
+KERNELS = os.environ.get("SWEEP_KERNELS", "lincomb,encrypt").split(",")
 AES_BOUND = 4.5e10  # blocks/s at 100 % of the LDS pipe, 1.965 GHz
 SEED = bytes(range(40))
 
@@ -50,17 +54,20 @@ def main():
         T = (nc + 63) // 64
         ct_bytes = T * L * 64 * 8
         d = max(1024, int(gb * 1e9 // ct_bytes))
-        cts = torch.randint(-2**62, 2**62, (d * T * L * 64,), dtype=torch.int64, device="cuda")
-        h = torch.randint(0, 2**31 - 1, (d,), dtype=torch.int32, device="cuda")
-        out = torch.zeros(T * L * 64, dtype=torch.int64, device="cuda")
-        ms = timed(lambda: ctx.lincomb_generic_dev(L, nc, cts.data_ptr(), h.data_ptr(), d, out.data_ptr(), st), 10)
-        algo = d * nc * L * 8  # live bytes: (n+1) coordinates x L limbs
-        print(json.dumps({"kernel": "lincomb", "n": n, "logq": logq, "q_eff_bits": 64 * L, "ciphertexts": d,
-                          "resident_GB": d * ct_bytes / 1e9, "ms": ms, "mac_per_s": d / (ms * 1e-3), "algorithmic_GBps": algo / ms / 1e6,
-                          "frac_of_measured_copy_peak": algo / ms / 1e6 / peak}), flush=True)
-        del cts
-        torch.cuda.empty_cache()
-        # encrypt: ~64 ciphertexts per SM
+        if "lincomb" in KERNELS:
+            cts = torch.randint(-2**62, 2**62, (d * T * L * 64,), dtype=torch.int64, device="cuda")
+            h = torch.randint(0, 2**31 - 1, (d,), dtype=torch.int32, device="cuda")
+            out = torch.zeros(T * L * 64, dtype=torch.int64, device="cuda")
+            ms = timed(lambda: ctx.lincomb_generic_dev(L, nc, cts.data_ptr(), h.data_ptr(), d, out.data_ptr(), st), 10)
+            algo = d * nc * L * 8  # live bytes: (n+1) coordinates x L limbs
+            print(json.dumps({"kernel": "lincomb", "n": n, "logq": logq, "q_eff_bits": 64 * L, "ciphertexts": d,
+                              "resident_GB": d * ct_bytes / 1e9, "ms": ms, "mac_per_s": d / (ms * 1e-3), "algorithmic_GBps": algo / ms / 1e6,
+                              "frac_of_measured_copy_peak": algo / ms / 1e6 / peak}), flush=True)
+            del cts
+            torch.cuda.empty_cache()
+        if "encrypt" not in KERNELS:
+            continue
+        # encrypt: ~256 ciphertexts per SM
         ctb = logq // 8
         cnt = 148 * 256
         stride = (n + 63) // 64 * 64
