@@ -306,22 +306,45 @@ MFB_API int mfb_set_region_create(mfb_set *s, const uint8_t seed[40], uint64_t o
   r->first.assign(world, 0);
   r->count.assign(world, 0);
   r->total = count;
-  int rc = MFB_OK;
-  for (size_t i = 0; i < world && rc == MFB_OK; i++) {
-    split_range(count, world, i, &r->first[i], &r->count[i]);
-    // queued on the member's stream: the members' AES expansions run concurrently
-    cudaSetDevice(s->m[i].device);
-    rc = mfb_region_create_async(s->m[i].ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
-                                 r->count[i], s->m[i].stream, &r->shard[i]);
-  }
-  for (size_t i = 0; i < world; i++) {
-    cudaSetDevice(s->m[i].device);
-    const cudaError_t e = cudaStreamSynchronize(s->m[i].stream);
-    if (e != cudaSuccess && rc == MFB_OK) {
-      snprintf(g_set_err, sizeof(g_set_err), "mfb_set_region_create: device %d: %s", s->m[i].device, cudaGetErrorString(e));
-      rc = MFB_ECUDA;
+  // one host thread per member: the device allocation (synchronous, milliseconds for tens of GB) and the staging of the
+  // member's wire records from pageable memory (which blocks the calling thread) run side by side, like the expansions
+  for (size_t i = 0; i < world; i++) split_range(count, world, i, &r->first[i], &r->count[i]);
+  std::vector<int> rcs(world, MFB_OK);
+  std::vector<std::string> errs(world);
+  auto work = [&](size_t i) {
+    g_set_err[0] = 0;
+    Member &mb = s->m[i];
+    int rc1 = MFB_OK;
+    if (cudaSetDevice(mb.device) != cudaSuccess) {
+      rc1 = set_fail(MFB_ECUDA, "mfb_set_region_create: cudaSetDevice failed");
+      cudaGetLastError();
     }
+    if (rc1 == MFB_OK)
+      rc1 = mfb_region_create_async(mb.ctx, seed, offset + r->first[i] * (uint64_t)MFB_CTR_CT, c8 + r->first[i] * MFB_CT_BYTES,
+                                    r->count[i], mb.stream, &r->shard[i]);
+    if (rc1 == MFB_OK) {
+      const cudaError_t e = cudaStreamSynchronize(mb.stream);
+      if (e != cudaSuccess) {
+        snprintf(g_set_err, sizeof(g_set_err), "mfb_set_region_create: device %d: %s", mb.device, cudaGetErrorString(e));
+        cudaGetLastError();
+        rc1 = MFB_ECUDA;
+      }
+    }
+    if (rc1 != MFB_OK) errs[i] = mfb_set_last_error();  // (thread-local: copy it out before the thread ends)
+    rcs[i] = rc1;
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < world; i++) pool.emplace_back(work, i);
+    work(0);
+    for (auto &t : pool) t.join();
   }
+  int rc = MFB_OK;
+  for (size_t i = 0; i < world && rc == MFB_OK; i++)
+    if (rcs[i] != MFB_OK) {
+      snprintf(g_set_err, sizeof(g_set_err), "%s", errs[i].c_str());
+      rc = rcs[i];
+    }
   if (rc != MFB_OK) {  // (no exchange was started: the set itself stays usable)
     char keep[256];
     snprintf(keep, sizeof(keep), "%s", mfb_set_last_error());
