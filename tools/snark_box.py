@@ -24,7 +24,7 @@ t_setup = sn.setup()
 for n in counts:
     sn.set_devices(n)
     sn.setup()  # warm-up of the members' buffers
-    t_setup_set = sn.setup()  # the encryptions spread over the n GPUs (mfb_set_encrypt_cb): entropy-bound
+    t_setup_set = sn.setup()  # the encryptions spread over the n GPUs, one host thread per GPU (mfb_set_encrypt_par)
     t_nonres = float("nan")
     if not os.environ.get("SNARK_BOX_RESIDENT_ONLY"):  # (set when only the resident pipeline is to be profiled)
         sn.prove()  # nothing resident: both fused AES + MAC passes sharded over the n GPUs (mfb_set_eval_poly2)
