@@ -112,6 +112,8 @@ _SIGS = {
     "mfb_encrypt_cb_segs": (C.c_int, [_vp, _u8p, C.c_uint64, _u64p, _u64p, C.CFUNCTYPE(None, _vp, _vp, C.c_size_t), _vp, C.c_int,
                                      C.c_int, C.c_size_t, _vp, C.c_int]),
     "mfb_encrypt_dev": (C.c_int, [_vp, _u8p, C.c_uint64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, _vp]),
+    "mfb_encrypt_generic_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_uint32)]),
     "mfb_decrypt": (C.c_int, [_vp, _u64p, _u64p, _u8p, C.c_size_t, _u64p, _u64p]),
     "mfb_decrypt_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "mfb_ssp_prover_polys": (C.c_int, [_vp, _u64p, C.c_size_t, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p]),

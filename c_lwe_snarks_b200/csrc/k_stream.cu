@@ -853,14 +853,14 @@ cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offse
   return cudaGetLastError();
 }
 
-template <int L>
-static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk, int sk_stride,
-                                 const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, int n, int ctb,
-                                 uint8_t *out_c8, int sm_count, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt_g<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  // padded keystream layout (see the kernel): when the coordinate width is a whole number of AES blocks and one pad block
-  // per coordinate lowers the bank-conflict degree gcd(words per coordinate, 32) of the consumers' reads
+// Tiling of k_encrypt_g for a coordinate width of ctb bytes (host logic; mfb_encrypt_generic_plan exposes it to the tests).
+//  * padded keystream layout (see the kernel): when the width is a whole number of AES blocks and one pad block per
+//    coordinate lowers the bank-conflict degree gcd(words per coordinate, 32) of the consumers' reads;
+//  * tiles: at most the coordinates whose (padded) keystream fits one buffer, balanced — or, when that needs fewer consumer
+//    rounds per ciphertext, tiles of a whole number of rounds: the 128 consumer threads walk a tile in rounds of 128
+//    coordinates and a partly filled round costs a full one (log q = 1024 padded: 7 tiles of 293 = 21 rounds against 8
+//    tiles of 256 = 16).
+void encrypt_generic_plan(int n, int ctb, int *tile_out, int *ntiles_out, int *pad_wb_out, uint32_t *pad_inv_out) {
   auto gcd32 = [](int v) { int g = 32; while (v % g) g >>= 1; return g; };
   int pad_wb = 0;
   uint32_t pad_inv = 0;
@@ -869,13 +869,11 @@ static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t
     pad_inv = 65536u / (uint32_t)pad_wb + 1;
     for (uint32_t bl = 0; bl <= (uint32_t)KS_MAX_BLK; bl++)  // the reciprocal must be exact for every block of a tile
       if (((bl * pad_inv) >> 16) != bl / (uint32_t)pad_wb) pad_wb = 0;
+    if (!pad_wb) pad_inv = 0;
   }
-  const int max_tile = KS_TILE_BYTES / (ctb + (pad_wb ? 16 : 0));  // coordinates whose keystream fits one buffer
+  const int max_tile = KS_TILE_BYTES / (ctb + (pad_wb ? 16 : 0));
   int ntiles = (n + max_tile - 1) / max_tile;
   int tile = (n + ntiles - 1) / ntiles;  // balanced
-  // The 128 consumer threads walk a tile in rounds of 128 coordinates, and a partly filled round costs a full one: when
-  // tiles of a whole number of rounds need fewer rounds per ciphertext than the balanced split, take those (log q = 1024
-  // with the padded layout: 7 tiles of 293 = 21 rounds against 8 tiles of 256 = 16).
   const int t128 = max_tile / KE_CONSUMERS * KE_CONSUMERS;
   if (t128 >= KE_CONSUMERS) {
     auto rounds = [&](int tl, int nt) {
@@ -888,6 +886,21 @@ static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t
       ntiles = nt128;
     }
   }
+  *tile_out = tile;
+  *ntiles_out = ntiles;
+  *pad_wb_out = pad_wb;
+  *pad_inv_out = pad_inv;
+}
+
+template <int L>
+static cudaError_t run_encrypt_g(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk, int sk_stride,
+                                 const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count, int n, int ctb,
+                                 uint8_t *out_c8, int sm_count, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_encrypt_g<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, KS3_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  int tile, ntiles, pad_wb;
+  uint32_t pad_inv;
+  encrypt_generic_plan(n, ctb, &tile, &ntiles, &pad_wb, &pad_inv);
   const size_t grid = count < (size_t)sm_count ? count : (size_t)sm_count;
   k_encrypt_g<L><<<(unsigned)grid, KE_THREADS, KS3_SMEM_BYTES, st>>>(key, t0, offset, sk, sk_stride, msg, ent, ent_stride, ent_nbytes,
                                                                       count, n, ctb, tile, ntiles, pad_wb, pad_inv, out_c8);

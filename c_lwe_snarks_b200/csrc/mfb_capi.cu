@@ -61,6 +61,7 @@ cudaError_t launch_evalpoly2_partials(const AesKey &key, const uint32_t *t0, uin
 cudaError_t launch_encrypt(const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
                            const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes, size_t count,
                            uint8_t *out_c8, int sm_count, cudaStream_t st);
+void encrypt_generic_plan(int n, int ctb, int *tile_out, int *ntiles_out, int *pad_wb_out, uint32_t *pad_inv_out);
 cudaError_t launch_encrypt_generic(int limbs64, const AesKey &key, const uint32_t *t0, uint64_t offset, const uint64_t *sk,
                                    int sk_stride, const uint64_t *msg, const uint8_t *ent, int ent_stride, int ent_nbytes,
                                    size_t count, int n, int ctb, uint8_t *out_c8, int sm_count, cudaStream_t st);
@@ -886,6 +887,14 @@ int mfb_encrypt_dev(mfb_ctx *ctx, const uint8_t seed[40], uint64_t offset, const
   MFB_CUDA_TRY(launch_encrypt(key, ctx->t0_dev, offset, sk_planar_dev, msg_dev, ent_dev, ent_stride, ent_nbytes, count,
                               out_c8_dev, ctx->sm_count, (cudaStream_t)stream));
   if (count) ctx->launches += 1;
+  return MFB_OK;
+}
+
+int mfb_encrypt_generic_plan(int n, int ct_bytes, int *tile, int *ntiles, int *pad_blocks, uint32_t *pad_reciprocal) {
+  if (!tile || !ntiles || !pad_blocks || !pad_reciprocal) return set_err(MFB_EARG, "mfb_encrypt_generic_plan: null pointer");
+  if (n < 1 || n > 4096 || ct_bytes % 4 || ct_bytes < 32 || ct_bytes > 128)
+    return set_err(MFB_EARG, "mfb_encrypt_generic_plan: need 1 <= n <= 4096 and ct_bytes a multiple of 4 in [32, 128]");
+  encrypt_generic_plan(n, ct_bytes, tile, ntiles, pad_blocks, pad_reciprocal);
   return MFB_OK;
 }
 

@@ -155,6 +155,11 @@ MFB_API int mfb_lincomb_generic_dev(mfb_ctx *ctx, int limbs64, int ncoords, cons
 MFB_API int mfb_encrypt_generic_dev(mfb_ctx *ctx, int limbs64, int n, int ct_bytes, const uint8_t seed[40], uint64_t offset,
                             const uint64_t *sk_planar_dev, int sk_stride, const uint64_t *msg_dev, const uint8_t *ent_dev,
                             int ent_stride, int ent_nbytes, size_t count, uint8_t *out_c8_dev, void *stream);
+/* The tiling mfb_encrypt_generic_dev uses for (n, ct_bytes) — host logic, no device needed (the CPU tests check its
+ * invariants): coordinates per tile, tiles per ciphertext, and the padded keystream layout (pad_blocks = ct_bytes / 16 when
+ * one free 16-byte slot per coordinate lowers the bank-conflict degree of the consumers' reads, else 0; pad_reciprocal =
+ * the multiplier with (b * pad_reciprocal) >> 16 == b / pad_blocks for every block index of a tile). */
+MFB_API int mfb_encrypt_generic_plan(int n, int ct_bytes, int *tile, int *ntiles, int *pad_blocks, uint32_t *pad_reciprocal);
 
 /* ---- multi-GPU exchange helpers (one process per GPU; the collective itself is NCCL) ------ */
 /* cols_dev[1472][22] u64 <- the 32-bit limbs of flat_dev, widened, so that an elementwise integer sum over

@@ -175,3 +175,41 @@ int main(void) {
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr[-500:])
+
+
+def test_generic_encrypt_tiling_plan():
+    """Host logic of mfb_encrypt_generic_dev (BASELINE configs[4]; no device needed): the tiles cover the ciphertext, their
+    (padded) keystream fits one 45 KB buffer at any stream alignment, the padded layout is taken exactly when it lowers
+    the bank-conflict degree of the consumers' reads, its reciprocal is exact, and whole-round tiles never need more
+    consumer rounds than the balanced split."""
+    import ctypes as C
+    from math import gcd
+
+    from c_lwe_snarks_b200.api import load_library
+    lib = load_library()
+    KS_TILE_BYTES, CONSUMERS = 490 * 92, 128
+    KS_BUF_BYTES = ((KS_TILE_BYTES + 30) // 16) * 16 + 16
+    for ctb in range(32, 129, 4):
+        for n in (1, 33, 65, 700, 1024, 1246, 1470, 1600, 2047, 4096):
+            tile, ntiles, wb, inv = C.c_int(), C.c_int(), C.c_int(), C.c_uint32()
+            assert lib.mfb_encrypt_generic_plan(n, ctb, C.byref(tile), C.byref(ntiles), C.byref(wb), C.byref(inv)) == 0
+            tile, ntiles, wb, inv = tile.value, ntiles.value, wb.value, inv.value
+            assert tile >= 1 and (ntiles - 1) * tile < n <= ntiles * tile
+            words = ctb // 4
+            want_pad = ctb % 16 == 0 and gcd(words + 4, 32) < gcd(words, 32)
+            assert (wb != 0) == want_pad and (wb == 0 or wb == ctb // 16)
+            slot = ctb + (16 if wb else 0)
+            for delta in (0, 15):  # the tile's first coordinate may start anywhere inside an AES block
+                nblk = (delta + tile * ctb + 15) // 16
+                last_slot = (nblk - 1) + ((nblk - 1) // wb if wb else 0)
+                assert 16 * (last_slot + 1) <= KS_BUF_BYTES
+                assert (delta & ~3) + (tile - 1) * slot + ctb + 16 + 4 <= KS_BUF_BYTES  # the consumers' furthest read
+            if wb:
+                assert all((b * inv) >> 16 == b // wb for b in range(0, KS_BUF_BYTES // 16 + 1))
+            max_tile = KS_TILE_BYTES // slot
+            nt_bal = -(-n // max_tile)
+            t_bal = -(-n // nt_bal)
+            rounds = lambda tl, nt: (nt - 1) * -(-tl // CONSUMERS) + -(-(n - (nt - 1) * tl) // CONSUMERS)  # noqa: E731
+            assert rounds(tile, ntiles) <= rounds(t_bal, nt_bal)
+    bad = C.c_int()
+    assert lib.mfb_encrypt_generic_plan(1470, 90, C.byref(bad), C.byref(bad), C.byref(bad), C.byref(C.c_uint32())) != 0
