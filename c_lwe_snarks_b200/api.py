@@ -54,6 +54,7 @@ _SIGS = {
     "mfb_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "mfb_ctx_destroy": (None, [_vp]),
     "mfb_ctx_warm": (C.c_int, [_vp]),
+    "mfb_ctx_reserve": (C.c_int, [_vp, C.c_size_t, C.c_size_t]),
     "mfb_last_error": (C.c_char_p, []),
     "mfb_device_sm_count": (C.c_int, [_vp]),
     "mfb_launch_count": (C.c_uint64, [_vp]),

