@@ -101,21 +101,11 @@ constexpr int NTTL_T = NTT_B / 4;  // threads: one radix-4 step each per pass
 // twloc: the COMPACT table of the NTT_B / 2 powers of w_NTT_B per prime (k_twiddle_compact): contiguous, so that the
 // 3072 CTAs of a 2^21-point transform read 4 KB each in full lines instead of gathering 1024 sectors from the big table
 // (that gather was two thirds of this kernel's L2 traffic).
+// the local stages of one block held in shared memory (s: blk elements, twl: the blk/2 powers of w_blk or w_blk^-1);
+// ends with a __syncthreads
 template <bool INVERSE>
-__global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ twloc,
-                                                      uint32_t sc0, uint32_t sc1, uint32_t sc2) {
-  __shared__ uint32_t s[NTT_B];
-  __shared__ uint32_t twl[NTT_B / 2];
-  const int k = blockIdx.y;
-  const uint32_t P = c_P[k], pinv = c_PINV[k];
-  const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;  // Montgomery n^-1 when this is the last kernel of an inverse
-  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+__device__ __forceinline__ void ntt_block_stages(uint32_t *s, const uint32_t *twl, uint32_t blk, uint32_t P, uint32_t pinv) {
   const uint32_t bh = blk >> 1;
-  uint32_t *xk = x + (size_t)k * n + (size_t)blockIdx.x * blk;
-  const uint32_t *twk = twloc + (size_t)k * (NTT_B / 2);
-  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) s[i] = xk[i];
-  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twk[(size_t)e * ((NTT_B / 2) / bh)];  // w_blk^e = w_NTT_B^(e NTT_B / blk)
-  __syncthreads();
   auto radix2 = [&](uint32_t half) {  // one plain stage (half = 1 when the stage count is odd)
     const uint32_t ts = bh / half;
     for (uint32_t t = threadIdx.x; t < bh; t += NTTL_T) {
@@ -166,7 +156,6 @@ __global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, c
     uint32_t h = bh;
     for (; h >= 2; h >>= 2) radix4(h);
     if (h == 1) radix2(1);
-    for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = s[i];
   } else {
     int lg = 0;
     while ((2u << lg) <= bh) lg++;          // bh = 2^lg: stages half = 1, 2, ..., 2^lg
@@ -176,8 +165,62 @@ __global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, c
       h = 4;
     }
     for (; h <= bh; h <<= 2) radix4(h);
+  }
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTTL_T) k_ntt_local(uint32_t *x, uint32_t n, const uint32_t *__restrict__ twloc,
+                                                      uint32_t sc0, uint32_t sc1, uint32_t sc2) {
+  __shared__ uint32_t s[NTT_B];
+  __shared__ uint32_t twl[NTT_B / 2];
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;  // Montgomery n^-1 when this is the last kernel of an inverse
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  const uint32_t bh = blk >> 1;
+  uint32_t *xk = x + (size_t)k * n + (size_t)blockIdx.x * blk;
+  const uint32_t *twk = twloc + (size_t)k * (NTT_B / 2);
+  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) s[i] = xk[i];
+  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twk[(size_t)e * ((NTT_B / 2) / bh)];  // w_blk^e = w_NTT_B^(e NTT_B / blk)
+  __syncthreads();
+  ntt_block_stages<INVERSE>(s, twl, blk, P, pinv);
+  if (!INVERSE) {
+    for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = s[i];
+  } else {
     for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = scale ? mont_mul(s[i], scale, P, pinv) : s[i];
   }
+}
+
+// The middle of a product in ONE kernel: the forward transform's local stages, the pointwise product and the inverse
+// transform's local stages all work on the same contiguous blocks of NTT_B elements (DIF leaves a block bit-reversed,
+// DIT takes it bit-reversed), so a block makes one trip through shared memory instead of three kernels and three trips
+// through L2:  x_block <- iNTT_local( NTT_local(x_block) .* (b ? b_block : NTT_local(x_block)) ).  b = the other operand's
+// forward transform (nullptr: a square).  Same operations in the same order as the three kernels: identical results.
+__global__ void __launch_bounds__(NTTL_T) k_ntt_local_mul(uint32_t *x, const uint32_t *__restrict__ b, uint32_t n,
+                                                          const uint32_t *__restrict__ twloc, const uint32_t *__restrict__ twiloc,
+                                                          uint32_t sc0, uint32_t sc1, uint32_t sc2) {
+  __shared__ uint32_t s[NTT_B];
+  __shared__ uint32_t twl[NTT_B / 2];
+  const int k = blockIdx.y;
+  const uint32_t P = c_P[k], pinv = c_PINV[k];
+  const uint32_t scale = k == 0 ? sc0 : k == 1 ? sc1 : sc2;
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  const uint32_t bh = blk >> 1;
+  const size_t base = (size_t)k * n + (size_t)blockIdx.x * blk;
+  uint32_t *xk = x + base;
+  const uint32_t tstep = (NTT_B / 2) / bh;
+  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) s[i] = xk[i];
+  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twloc[(size_t)k * (NTT_B / 2) + (size_t)e * tstep];
+  __syncthreads();
+  ntt_block_stages<false>(s, twl, blk, P, pinv);
+  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) {
+    const uint32_t v = s[i];
+    s[i] = mont_mul(v, b ? b[base + i] : v, P, pinv);
+  }
+  for (uint32_t e = threadIdx.x; e < bh; e += NTTL_T) twl[e] = twiloc[(size_t)k * (NTT_B / 2) + (size_t)e * tstep];
+  __syncthreads();
+  ntt_block_stages<true>(s, twl, blk, P, pinv);
+  for (uint32_t i = threadIdx.x; i < blk; i += NTTL_T) xk[i] = scale ? mont_mul(s[i], scale, P, pinv) : s[i];
 }
 
 // The stages with span >= NTT_B as ONE kernel ("four-step" form).  View x as m = n / NTT_B rows of c = NTT_B columns
@@ -320,15 +363,6 @@ __global__ void k_lift(const uint32_t *__restrict__ in, uint32_t len, uint32_t s
       v = mont_mul(v % P, r2, P, pinv);
     }
     out[(size_t)k * n + i] = v;
-  }
-}
-
-__global__ void k_pointwise(uint32_t *a, const uint32_t *__restrict__ b, uint32_t n) {
-  const int k = blockIdx.y;
-  const uint32_t P = c_P[k], pinv = c_PINV[k];
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const size_t o = (size_t)k * n + i;
-    a[o] = mont_mul(a[o], b[o], P, pinv);
   }
 }
 
@@ -599,21 +633,29 @@ static cudaError_t ntt_forward(PolyEngine &E, uint32_t *x, uint32_t n, cudaStrea
   E.launches++;
   return cudaGetLastError();
 }
-static cudaError_t ntt_inverse(PolyEngine &E, uint32_t *x, uint32_t n, cudaStream_t st) {
+// x <- iNTT( NTT(x) .* (bhat ? bhat : NTT(x)) ): the column stages as their own launches (n > NTT_B), everything between
+// them — local forward stages, pointwise product, local inverse stages — as one launch (k_ntt_local_mul)
+static cudaError_t ntt_product_inplace(PolyEngine &E, uint32_t *x, const uint32_t *bhat, uint32_t n, cudaStream_t st) {
   const uint32_t nh = E.nmax / 2;
+  const uint32_t zero[NPR] = {0, 0, 0};
   uint32_t sc[NPR];
   for (int k = 0; k < NPR; k++) {
     const uint32_t ninv = h_powmod(n % h_P[k], h_P[k] - 2, h_P[k]);
     sc[k] = (uint32_t)(((uint64_t)ninv << 32) % h_P[k]);
   }
-  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
   const bool cols = n > (uint32_t)NTT_B;
-  // the 1/n scaling rides in the last kernel of the transform
-  k_ntt_local<true><<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, n, E.twi_loc, cols ? 0 : sc[0], cols ? 0 : sc[1], cols ? 0 : sc[2]);
-  E.launches++;
+  cudaError_t e;
   if (cols) {
-    cudaError_t e = launch_ntt_cols<true>(x, n, E.twi, nh, sc, st);
-    if (e != cudaSuccess) return e;
+    if ((e = launch_ntt_cols<false>(x, n, E.tw, nh, zero, st)) != cudaSuccess) return e;
+    E.launches++;
+  }
+  const uint32_t blk = n < (uint32_t)NTT_B ? n : (uint32_t)NTT_B;
+  k_ntt_local_mul<<<dim3(n / blk, NPR), NTTL_T, 0, st>>>(x, bhat, n, E.tw_loc, E.twi_loc, cols ? 0 : sc[0], cols ? 0 : sc[1],
+                                                          cols ? 0 : sc[2]);
+  E.launches++;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (cols) {
+    if ((e = launch_ntt_cols<true>(x, n, E.twi, nh, sc, st)) != cudaSuccess) return e;
     E.launches++;
   }
   return cudaGetLastError();
@@ -632,16 +674,13 @@ static cudaError_t poly_mul(PolyEngine &E, const uint32_t *a, uint32_t la, uint3
   const bool square = (a == b && la == lb && a_rev == b_rev && a_src_len == b_src_len);
   k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(a, la, a_src_len, a_rev, E.fa, n);
   E.launches++;
-  cudaError_t ne = ntt_forward(E, E.fa, n, st);
-  if (ne != cudaSuccess) return ne;
+  cudaError_t ne;
   if (!square) {
     k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(b, lb, b_src_len, b_rev, E.fb, n);
     E.launches++;
     if ((ne = ntt_forward(E, E.fb, n, st)) != cudaSuccess) return ne;
   }
-  k_pointwise<<<dim3(gridfor(n), NPR), 256, 0, st>>>(E.fa, square ? E.fa : E.fb, n);
-  E.launches++;
-  if ((ne = ntt_inverse(E, E.fa, n, st)) != cudaSuccess) return ne;
+  if ((ne = ntt_product_inplace(E, E.fa, square ? nullptr : E.fb, n, st)) != cudaSuccess) return ne;
   k_crt<<<gridfor(out_len), 256, 0, st>>>(E.fa, n, lo, out_len, E.crt, mode, out);
   E.launches++;
   return cudaGetLastError();
@@ -654,11 +693,8 @@ static cudaError_t poly_mul_bhat(PolyEngine &E, const uint32_t *a, uint32_t la, 
   if (n > E.nmax) return cudaErrorInvalidValue;
   k_lift<<<dim3(gridfor(n), NPR), 256, 0, st>>>(a, la, a_src_len, a_rev, E.fa, n);
   E.launches++;
-  cudaError_t ne = ntt_forward(E, E.fa, n, st);
+  cudaError_t ne = ntt_product_inplace(E, E.fa, bhat, n, st);
   if (ne != cudaSuccess) return ne;
-  k_pointwise<<<dim3(gridfor(n), NPR), 256, 0, st>>>(E.fa, bhat, n);
-  E.launches++;
-  if ((ne = ntt_inverse(E, E.fa, n, st)) != cudaSuccess) return ne;
   k_crt<<<gridfor(out_len), 256, 0, st>>>(E.fa, n, lo, out_len, E.crt, 0, out);
   E.launches++;
   return cudaGetLastError();
