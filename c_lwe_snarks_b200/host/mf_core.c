@@ -10,24 +10,27 @@ static size_t g_d = 0, g_m = 0;       /* explicit (mf_set_instance) */
 static size_t g_def_d = 0, g_def_m = 0; /* first compile-time default registered by a caller */
 
 void mf_set_instance(size_t D, size_t M) {
-  g_d = D;
-  g_m = M;
+  __atomic_store_n(&g_d, D, __ATOMIC_RELAXED);
+  __atomic_store_n(&g_m, M, __ATOMIC_RELAXED);
 }
+/* (the warm-up thread peeks at these while the program's thread may be registering them: relaxed atomics) */
+#define LD(x) __atomic_load_n(&(x), __ATOMIC_RELAXED)
+#define ST(x, v) __atomic_store_n(&(x), (v), __ATOMIC_RELAXED)
 size_t mf_gamma_d(size_t def) {
-  if (g_d) return g_d;
-  if (!g_def_d) g_def_d = def;
-  return g_def_d;
+  if (LD(g_d)) return LD(g_d);
+  if (!LD(g_def_d)) ST(g_def_d, def);
+  return LD(g_def_d);
 }
 size_t mf_gamma_m(size_t def) {
-  if (g_m) return g_m;
-  if (!g_def_m) g_def_m = def;
-  return g_def_m;
+  if (LD(g_m)) return LD(g_m);
+  if (!LD(g_def_m)) ST(g_def_m, def);
+  return LD(g_def_m);
 }
 /* the instance size if a caller has fixed it already (explicitly or by evaluating GAMMA_D / GAMMA_M), WITHOUT registering
  * a default: the library's own background thread must not decide the instance size for the program */
 static int instance_peek(size_t *d, size_t *m) {
-  *d = g_d ? g_d : g_def_d;
-  *m = g_m ? g_m : g_def_m;
+  *d = LD(g_d) ? LD(g_d) : LD(g_def_d);
+  *m = LD(g_m) ? LD(g_m) : LD(g_def_m);
   return *d != 0 && *m != 0;
 }
 
