@@ -765,6 +765,9 @@ int ctx_enter(mfb_ctx *ctx);
 int ctx_bad_arg(const char *msg);
 int ctx_h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces, cudaStream_t st);
 int ctx_h2d(mfb_ctx *ctx, void *dst_dev, const void *src, size_t bytes, cudaStream_t st);
+void ctx_trace(const char *label);
+int ctx_h2d_narrow_u64(mfb_ctx *ctx, uint32_t *dst_dev, const uint64_t *src, size_t count, uint64_t limit, int *narrow_ok,
+                       cudaStream_t st);
 
 PolyEngine *poly_engine_new() { return new PolyEngine(); }
 void poly_engine_delete(PolyEngine *e) {
@@ -936,20 +939,39 @@ extern "C" int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_
   const uint64_t L0 = E.launches;
   uint32_t n = 2;
   while (n < 2 * D) n <<= 1;
-  PTRY(engine_reserve(E, n, st));
+  ctx_trace("ssp_create: enter");
+  // (twice the product size: the Newton inversion of rev(t) at the first proof needs transforms of up to 2.5 D + 8 points —
+  // reserving that now saves it from freeing and re-allocating the engine's ten buffers inside the first prover() call)
+  PTRY(engine_reserve(E, n <= (1u << 22) ? 2 * n : n, st));
+  ctx_trace("ssp_create: transform engine reserved");
   mfb_ssp *h = new mfb_ssp();
   h->D = D;
   h->M = M;
   const size_t total = (M + 1) * D;
   cudaError_t e = cudaMalloc(&h->blob, total * 4);
+  ctx_trace("ssp_create: blob allocated");
   if (e != cudaSuccess) {
     delete h;
     return ctx_fail(e, "cudaMalloc of the resident SSP", __FILE__, __LINE__);
   }
+  // The reference's blob stores residues < p in 8 bytes each (ssp.h:6-9): the host threads that pack the pinned bounce
+  // buffers narrow them to u32 on the way, so half the bytes cross PCIe and no device pass is needed.  A blob with a value
+  // >= p somewhere (legal for this API: coefficients are reduced mod p) takes the full-width path below from the start.
+  int narrow_ok = 0;
+  if (total >= ((size_t)1 << 20)) {
+    rc = ctx_h2d_narrow_u64(ctx, h->blob, ssp, total, (uint64_t)FP, &narrow_ok, st);
+    if (rc != MFB_OK) {
+      cudaStreamSynchronize(st);
+      cudaFree(h->blob);
+      delete h;
+      return rc;
+    }
+  }
+  ctx_trace("ssp_create: narrow upload queued");
   const size_t STAGE = (size_t)32 << 20;  // u64 coefficients per upload batch (256 MB)
-  void *d_stage;
-  rc = ctx_scratch(ctx, 3, (total < STAGE ? total : STAGE) * 8, &d_stage);
-  for (size_t o = 0; rc == MFB_OK && o < total; o += STAGE) {
+  void *d_stage = nullptr;
+  if (!narrow_ok) rc = ctx_scratch(ctx, 3, (total < STAGE ? total : STAGE) * 8, &d_stage);
+  for (size_t o = 0; !narrow_ok && rc == MFB_OK && o < total; o += STAGE) {
     const size_t cnt = total - o < STAGE ? total - o : STAGE;
     if ((rc = ctx_h2d(ctx, d_stage, ssp + o, cnt * 8, st)) != MFB_OK) break;
     // (no synchronisation between batches: the staging area is reused in stream order, and the host packs the next
@@ -965,6 +987,7 @@ extern "C" int mfb_ssp_create(mfb_ctx *ctx, const uint64_t *ssp, size_t D, size_
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h->lt, E.d_len, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
+  ctx_trace("ssp_create: upload complete");
   ctx_count_launches(ctx, E.launches - L0);
   if (rc != MFB_OK || e != cudaSuccess) {
     cudaFree(h->blob);

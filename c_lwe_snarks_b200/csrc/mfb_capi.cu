@@ -246,7 +246,97 @@ static int h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_
   return MFB_OK;
 }
 
+// dst_dev[i] = (uint32_t)src[i] for i < count, provided EVERY src[i] < limit (<= 2^32): the host threads narrow the u64
+// values to u32 while they pack the pinned bounce buffers, so only half the bytes cross PCIe (the reference's dense SSP blob
+// stores residues < p = 2^32 - 5 in 8 bytes each: 5.7 GB at its default instance).  *narrow_ok = 0 as soon as a value
+// >= limit is met (the caller then falls back to the full-width path; what was copied so far is garbage).
+// The workers are spawned once per call and meet the coordinating thread at a barrier twice per chunk.
+#include <pthread.h>
+static int h2d_narrow_u64(mfb_ctx *ctx, uint32_t *dst_dev, const uint64_t *src, size_t count, uint64_t limit, int *narrow_ok,
+                          cudaStream_t st) {
+  *narrow_ok = 1;
+  if (count == 0) return MFB_OK;
+  MFB_TRY(bounce_ready(ctx));
+  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned nthreads = hw >= 16 ? 16 : hw >= 8 ? 8 : hw >= 4 ? 4 : 1;
+  const size_t CH = BOUNCE_BYTES / 4;  // u32 elements per chunk
+  const size_t nchunks = (count + CH - 1) / CH;
+  struct Shared {
+    pthread_barrier_t bar;
+    const uint64_t *src;
+    uint32_t *bb;
+    size_t n;       // elements of the current chunk
+    uint64_t limit;
+    unsigned nthreads;
+    bool stop;
+    bool bad[64];
+  } sh;
+  sh.limit = limit;
+  sh.nthreads = nthreads;
+  sh.stop = false;
+  for (unsigned t = 0; t < 64; t++) sh.bad[t] = false;
+  if (pthread_barrier_init(&sh.bar, nullptr, nthreads) != 0) return set_err(MFB_ENOMEM, "pthread_barrier_init failed");
+  auto pack = [](Shared *s, unsigned t) {  // this thread's slice of the current chunk
+    const size_t per = (s->n + s->nthreads - 1) / s->nthreads;
+    const size_t lo = (size_t)t * per, hi = lo + per < s->n ? lo + per : s->n;
+    uint64_t over = 0;
+    const uint64_t lim = s->limit;
+    for (size_t i = lo; i < hi; i++) {
+      const uint64_t v = s->src[i];
+      over |= (uint64_t)(v >= lim);
+      s->bb[i] = (uint32_t)v;
+    }
+    if (over) s->bad[t] = true;
+  };
+  auto worker = [&pack](Shared *s, unsigned t) {
+    for (;;) {
+      pthread_barrier_wait(&s->bar);  // chunk published (or stop)
+      if (s->stop) return;
+      pack(s, t);
+      pthread_barrier_wait(&s->bar);  // chunk packed
+    }
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(worker, &sh, t);
+  int rc = MFB_OK;
+  int k = 0;
+  for (size_t c = 0; c < nchunks && rc == MFB_OK && *narrow_ok; c++, k ^= 1) {
+    if (ctx->bounce_used[k]) {
+      const cudaError_t e = cudaEventSynchronize(ctx->bounce_free[k]);  // also across calls
+      if (e != cudaSuccess) {
+        rc = fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
+        break;
+      }
+    }
+    sh.src = src + c * CH;
+    sh.bb = (uint32_t *)ctx->bounce[k];
+    sh.n = count - c * CH < CH ? count - c * CH : CH;
+    if (nthreads > 1) pthread_barrier_wait(&sh.bar);
+    pack(&sh, 0);
+    if (nthreads > 1) pthread_barrier_wait(&sh.bar);
+    for (unsigned t = 0; t < nthreads; t++)
+      if (sh.bad[t]) *narrow_ok = 0;
+    if (!*narrow_ok) break;
+    cudaError_t e = cudaMemcpyAsync(dst_dev + c * CH, sh.bb, sh.n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->bounce_free[k], st);
+    if (e != cudaSuccess) {
+      rc = fail(e, "H2D", __FILE__, __LINE__);
+      break;
+    }
+    ctx->bounce_used[k] = true;
+  }
+  sh.stop = true;
+  if (nthreads > 1) pthread_barrier_wait(&sh.bar);
+  for (auto &th : pool) th.join();
+  pthread_barrier_destroy(&sh.bar);
+  return rc;
+}
+
 namespace mfb {  // hooks for k_poly.cu
+int ctx_h2d_narrow_u64(mfb_ctx *ctx, uint32_t *dst_dev, const uint64_t *src, size_t count, uint64_t limit, int *narrow_ok,
+                       cudaStream_t st) {
+  return h2d_narrow_u64(ctx, dst_dev, src, count, limit, narrow_ok, st);
+}
 int ctx_h2d_pieces(mfb_ctx *ctx, void *dst_dev, const void *const *src, size_t piece_bytes, size_t npieces, cudaStream_t st) {
   return h2d_pieces(ctx, dst_dev, src, piece_bytes, npieces, st);
 }
@@ -271,6 +361,7 @@ int ctx_enter(mfb_ctx *ctx) {
   return MFB_OK;
 }
 int ctx_bad_arg(const char *msg) { return set_err(MFB_EARG, "%s", msg); }
+void ctx_trace(const char *label) { trace_pt(label); }
 }  // namespace mfb
 
 extern "C" {
@@ -1483,8 +1574,8 @@ int mfb_ctx_reserve(mfb_ctx *ctx, size_t D, size_t M) {
   MFB_TRY(scratch(ctx, 1, mx(count * 8, 2 * D * 4), &p));
   MFB_TRY(scratch(ctx, 2, 5 * FL * 8, &p));
   MFB_TRY(scratch(ctx, 3, mx(count * (size_t)ENT_BYTES, D * 4), &p));
-  MFB_TRY(scratch(ctx, 4, PLANAR_U64 * 8, &p));
-  MFB_TRY(scratch(ctx, 5, mx(count * CT_BYTES, 5 * FL * 8), &p));
+  MFB_TRY(scratch(ctx, 4, mx(PLANAR_U64 * 8, 16 * D), &p));  // (also the polynomial step's product buffer: 2 D -> 4 D u32)
+  MFB_TRY(scratch(ctx, 5, mx(mx(count * CT_BYTES, 5 * FL * 8), 12 * D), &p));
   MFB_TRY(scratch(ctx, 6, 5 * L64 * 8, &p));
   MFB_TRY(scratch(ctx, 7, (M + 1) * CT_BYTES, &p));
   // one-element dry runs: stream2 / events / pinned entropy buffers are created, every kernel of the path is loaded

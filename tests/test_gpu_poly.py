@@ -204,6 +204,27 @@ def test_ssp_eval_resident_equals_host_blob_eval(ctx, D, M):
         res.close()
 
 
+@pytest.mark.parametrize("wide_at", [None, 0, -3])
+def test_resident_ssp_upload_narrow_and_full_width(ctx, wide_at):
+    """mfb_ssp_create narrows the 8-byte wire coefficients to u32 on the host while it packs the upload (half the PCIe
+    bytes) when every coefficient is < p, and falls back to the full-width path when one is not — here over a blob of two
+    upload chunks (17 M coefficients), with the offending value in the first or in the last chunk: the evaluations from
+    the resident blob equal those from the host blob (which always takes the full-width path)."""
+    D, M = 1 << 18, 64
+    rng = np.random.Generator(np.random.PCG64(2018))
+    blob = rng.integers(0, P, size=(M + 1) * D, dtype=np.uint64)
+    blob[1] = np.uint64(P - 1)  # the largest value the narrow path takes
+    if wide_at is not None:
+        blob[wide_at] = np.uint64(P) if wide_at else np.uint64(2**40 + 7)
+    x = 0x0BADF00D % P
+    want = ctx.ssp_eval(blob, D, x)
+    res = ctx.ssp_resident(blob.view(np.uint8), D, M)
+    try:
+        assert np.array_equal(res.eval(0, M + 1, x), want)
+    finally:
+        res.close()
+
+
 def test_prover_polys_2_20_identity_at_random_points(ctx):
     """D = 2^20 (BASELINE configs[3]): v = w + v_0 and v^2 - 1 = h*t + r with deg r < deg t, checked by evaluating both
     sides at random points — with delta = 1 the instance is exact (r = 0), so v(x)^2 - 1 == h(x) t(x) mod p."""
