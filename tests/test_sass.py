@@ -80,3 +80,33 @@ def test_encrypt_tail_uses_redux_and_shared_atomics():
     assert "REDUX" in s and "ATOMS" in s
     assert "USETMAXREG.DEALLOC" in s and "USETMAXREG.TRY_ALLOC" in s, "producer / consumer register re-balancing missing"
     assert len(re.findall(r"IMAD\.WIDE\.U32", s)) >= 250, "low-half 22x22 product is 253 limb products"
+
+
+def test_two_vector_fused_pass_keeps_the_full_tile_budget(usage):
+    """k_evalpoly<2> (round 2): two CANONICAL accumulators in the register budget of one E/O accumulator — at most a few
+    registers more than k_evalpoly<1>, no spills, and both carry chains of both vectors as IMAD.WIDE.U32.X"""
+    r1 = next(u for n, u in usage.items() if "k_evalpolyILi1" in n)
+    r2 = next(u for n, u in usage.items() if "k_evalpolyILi2" in n)
+    assert r2["REG"] <= r1["REG"] + 8 and r2["REG"] <= 128 and r2["STACK"] == 0
+    s1, s2 = sass_of(r"_ZN3mfb10k_evalpolyILi1"), sass_of(r"_ZN3mfb10k_evalpolyILi2")
+    x1, x2 = len(re.findall(r"IMAD\.WIDE\.U32\.X", s1)), len(re.findall(r"IMAD\.WIDE\.U32\.X", s2))
+    assert x1 >= 20 and x2 >= 2 * x1 - 4, (x1, x2)
+    # the same AES per tile: the lookups (LDS) of the two kernels differ only by a handful
+    assert abs(s1.count("LDS") - s2.count("LDS")) <= 8
+
+
+def test_polynomial_step_has_the_fused_middle_kernel(usage):
+    """forward local stages + pointwise product + inverse local stages of a product are ONE kernel (k_ntt_local_mul); the
+    separate pointwise kernel is gone"""
+    names = list(usage)
+    assert any("k_ntt_local_mul" in n for n in names)
+    assert not any("k_pointwise" in n for n in names)
+    u = next(u for n, u in usage.items() if "k_ntt_local_mul" in n)
+    assert u["STACK"] == 0 and u["REG"] <= 40 and u["SHARED"] <= 12288 + 1024  # one block + one twiddle table (+ the driver's 1 KB)
+
+
+def test_generic_encrypt_kernels_do_not_spill(usage):
+    gen = [(n, u) for n, u in usage.items() if "k_encrypt_gILi" in n]
+    assert len(gen) == 9  # limb counts 4, 6, 8, 10, 11, 12, 13, 14, 16
+    for n, u in gen:
+        assert u["STACK"] == 0 and u["LOCAL"] == 0 and u["REG"] <= 102, (n, u)
